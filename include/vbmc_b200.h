@@ -1,0 +1,217 @@
+/*
+ * vbmc_b200.h — C ABI of libvbmc_b200.so: the B200 (sm_100a) implementation of the VBMC
+ * variational-optimisation hot path (negelcbo_vbmc + gradient, gplogjoint, entmc_vbmc,
+ * vpbndloss) and of the GP-surrogate refit (gplite_post / gplite_nlZ -> gplite_core).
+ *
+ * The reference (acerbilab/vbmc) is pure MATLAB and has no FFI; the only replaceable seam is
+ * the MATLAB function call itself (a MEX file shadows a same-named .m).  Every entry point
+ * below therefore names the MATLAB function (reference file:line) whose body it replaces, and
+ * INTEGRATION.md shows the MEX gateway that binds it.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all arrays are HOST pointers unless the
+ *     name ends in _dev; all matrices are MATLAB column-major FP64 (double).
+ *   - every function returns 0 on success or a VBMC_B200_E* code; vbmc_b200_last_error()
+ *     returns a thread-local message that starts with the MATLAB error identifier the
+ *     reference would raise (e.g. "negelcbo_vbmc:vargrad: ...").
+ *   - a context owns ONE GPU (one process per GPU, or several contexts in one process);
+ *     calls on one context are serialised by the caller (MATLAB's interpreter thread).
+ *   - there is NO CPU fallback: without a usable sm_100 device vbmc_b200_create() fails.
+ */
+#ifndef VBMC_B200_H
+#define VBMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBMC_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+  VBMC_B200_OK = 0,
+  VBMC_B200_EINVAL = 1,      /* bad argument / dimension mismatch                           */
+  VBMC_B200_ECUDA = 2,       /* CUDA runtime / driver error                                 */
+  VBMC_B200_ENODEV = 3,      /* no usable sm_100 device                                     */
+  VBMC_B200_ESTATE = 4,      /* call order: e.g. negelcbo before gp_attach / vp_set         */
+  VBMC_B200_EUNSUPPORTED = 5,/* reference feature outside this build's scope */
+  VBMC_B200_EREFERENCE = 6,  /* the reference itself would raise error(...): id in message  */
+  VBMC_B200_ENCCL = 7        /* NCCL error                                                  */
+};
+
+typedef struct vbmc_b200_ctx vbmc_b200_ctx;
+
+/* ---------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------- */
+int vbmc_b200_version(void);
+const char* vbmc_b200_last_error(void);
+/* device: CUDA ordinal; fails with ENODEV when the device is not compute capability 10.x. */
+int vbmc_b200_create(vbmc_b200_ctx** out, int device);
+int vbmc_b200_destroy(vbmc_b200_ctx* ctx);
+int vbmc_b200_sync(vbmc_b200_ctx* ctx);
+/* number of kernels this library launched on the context since creation (bench: gpu_launches) */
+int vbmc_b200_launch_count(vbmc_b200_ctx* ctx, long long* count);
+
+/* ---------------------------------------------------------------------------------------
+ * multi-GPU: one context per rank, one NCCL all-reduce per negelcbo step.
+ * The MC pair axis of entmc_vbmc and the hyper-parameter-sample axis of gplogjoint are
+ * sharded over ranks; results are replicated on every rank after the all-reduce.
+ * ------------------------------------------------------------------------------------- */
+#define VBMC_B200_UNIQUE_ID_BYTES 128
+int vbmc_b200_comm_unique_id(void* id128);                                  /* rank 0, then broadcast out of band */
+int vbmc_b200_comm_init(vbmc_b200_ctx* ctx, int nranks, int rank, const void* id128);
+int vbmc_b200_comm_info(vbmc_b200_ctx* ctx, int* nranks, int* rank);
+
+/* ---------------------------------------------------------------------------------------
+ * GP struct (reference type: gplite/gplite_post.m:94-151; consumed by misc/gplogjoint.m:32-45)
+ * ------------------------------------------------------------------------------------- */
+typedef struct vbmc_b200_gp_desc {
+  int N, D, S;        /* training points, dimension, hyper-parameter samples numel(gp.post)      */
+  int Nhyp;           /* rows of hyp = Ncov + Nnoise + Nmean                                      */
+  int covfun;         /* gp.covfun(1); only 1 (SE-ARD) (gplite_core.m:52)                         */
+  int meanfun;        /* gp.meanfun; 0 zero, 1 const, 4 negquad (gplite_meanfun.m cases 0,1,4)    */
+  int noisefun[3];    /* gp.noisefun, gplite_noisefun.m:176-210                                   */
+  const double* X;    /* N x D  (gp.X)                                                            */
+  const double* y;    /* N      (gp.y)                 — gp_post / gp_nlz only                    */
+  const double* s2;   /* N or NULL (gp.s2)             — gp_post / gp_nlz only                    */
+  const double* hyp;  /* Nhyp x S (gp.post(s).hyp)                                                */
+} vbmc_b200_gp_desc;
+
+/* Adopt a posterior MATLAB already computed (needed when only negelcbo_vbmc is shadowed).
+ * alpha: N x S (gp.post(s).alpha); sW1: S values gp.post(s).sW(1); Lchol: S flags;
+ * L: N x N x S upper factors (gp.post(s).L) or NULL when variances are never requested. */
+int vbmc_b200_gp_attach(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const double* alpha,
+                        const double* sW1, const int* Lchol, const double* L);
+
+/* gplite_post(hyp,X,y,covfun,meanfun,noisefun,s2)  — gplite/gplite_post.m:94-172, i.e. S x
+ * gplite_core(hyp,gp,0,0) (gplite/private/gplite_core.m:33-102,278-285): SE-ARD Gram, Cholesky
+ * with the x10 jitter retry, alpha.  The posterior stays resident on the device (it becomes the
+ * attached GP); any non-NULL output is also copied to the host:
+ *   alpha N x S, L N x N x S (upper; -inv(K+Sigma) when Lchol==0), sW1 S, sn2_mult S, Lchol S. */
+int vbmc_b200_gp_post(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, double* alpha, double* L,
+                      double* sW1, double* sn2_mult, int* Lchol);
+
+/* Hyper-prior of gplite_nlZ (gplite/gplite_hypprior.m:18-58); arrays of length Nhyp. */
+typedef struct vbmc_b200_hprior {
+  const double* mu;
+  const double* sigma;
+  const double* df;   /* NULL => 7 for every hyper-parameter (gplite_hypprior.m:33-35) */
+} vbmc_b200_hprior;
+
+/* [nlZ,dnlZ] = gplite_nlZ(hyp,gp,hprior) — gplite/gplite_nlZ.m:27-66 -> gplite_core(hyp,gp,1,grad)
+ * (gplite_core.m:193,226-261).  gp->S must be 1 and gp->hyp one column; dnlZ (Nhyp) may be NULL
+ * (no gradient, like nargout==1).  hprior may be NULL. */
+int vbmc_b200_gp_nlz(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const vbmc_b200_hprior* hprior,
+                     double* nlZ, double* dnlZ);
+
+/* ---------------------------------------------------------------------------------------
+ * VP struct (reference type: misc/setupvars_vbmc.m:78-99)
+ * ------------------------------------------------------------------------------------- */
+typedef struct vbmc_b200_vp_desc {
+  int D, K;
+  const double* mu;      /* D x K                                                        */
+  const double* sigma;   /* K                                                            */
+  const double* lambda;  /* D                                                            */
+  const double* w;       /* K                                                            */
+  const double* eta;     /* K or NULL (then log(w)); vp.eta is what J_w uses             */
+  const double* delta;   /* D, or NULL for vp.delta empty/0 (gplogjoint.m:86-90)         */
+  int optimize_mu, optimize_sigma, optimize_lambda, optimize_weights;
+} vbmc_b200_vp_desc;
+
+int vbmc_b200_vp_set(vbmc_b200_ctx* ctx, const vbmc_b200_vp_desc* vp);
+
+/* thetabnd struct of misc/vpbounds.m:32-52; pass n == 0 to clear (thetabnd == []). */
+int vbmc_b200_thetabnd_set(vbmc_b200_ctx* ctx, int n, const double* lb, const double* ub, double TolCon,
+                           double WeightThreshold, double WeightPenalty);
+
+/* ---------------------------------------------------------------------------------------
+ * entropy draws.  The reference draws epsilon = randn(D,1,Ns/2) per component from MATLAB's
+ * global stream (ent/entmc_vbmc.m:53).  Two sources:
+ *   parity mode : the caller supplies the draws (host buffer, D x Ns/2 x K column-major);
+ *   device mode : counter-based Philox4x32-10 + Box-Muller keyed by (seed, call counter,
+ *                 element index) — independent of the number of GPUs and of the sharding.
+ * ------------------------------------------------------------------------------------- */
+enum { VBMC_B200_EPS_HOST = 0, VBMC_B200_EPS_RESIDENT = 1, VBMC_B200_EPS_PHILOX = 2 };
+/* copy draws to the device once; later calls may use VBMC_B200_EPS_RESIDENT */
+int vbmc_b200_eps_upload(vbmc_b200_ctx* ctx, int D, int K, int Ns, const double* eps);
+/* fill the resident buffer with Philox draws and (optionally, eps_out != NULL) read them back */
+int vbmc_b200_eps_philox(vbmc_b200_ctx* ctx, int D, int K, int Ns, uint64_t seed, uint64_t stream,
+                         double* eps_out);
+
+/* ---------------------------------------------------------------------------------------
+ * [F,dF,G,H,varF,dH,varGss,varG,varH,I_sk,J_sjk] =
+ *     negelcbo_vbmc(theta,beta,vp,gp,Ns,compute_grad,compute_var,altent_flag,thetabnd,entropy_alpha)
+ * misc/negelcbo_vbmc.m:1-164 -> misc/gplogjoint.m:1-413, ent/entmc_vbmc.m:1-125,
+ * misc/vpbndloss.m:1-72, utils/softbndloss.m:9-28.
+ * The MEX gateway resolves MATLAB's nargin/nargout defaults (negelcbo_vbmc.m:9-17) and fills
+ * this struct; vp / gp / thetabnd are the ones last set on the context.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vbmc_b200_negelcbo_args {
+  /* inputs */
+  const double* theta;   /* ntheta (host)                                                 */
+  int ntheta;
+  double beta;           /* 0 or non-finite => 0 (negelcbo_vbmc.m:15)                      */
+  int Ns;                /* MC draws per component; made even like entmc_vbmc.m:45; must be > 0 */
+  int compute_grad;      /* 0/1                                                            */
+  int compute_var;       /* 0 none, 1 full, 2 diagonal (gplogjoint.m:273,306)              */
+  int separate_K;        /* nargout > 9: fill I_sk (and J_sjk when compute_var)            */
+  int use_thetabnd;      /* 0 => thetabnd == [] for this call (negelcbo_vbmc.m:136)        */
+  int eps_mode;          /* VBMC_B200_EPS_*                                                */
+  const double* eps;     /* EPS_HOST: D x Ns/2 x K draws                                   */
+  uint64_t seed, stream; /* EPS_PHILOX: key and call counter                               */
+  /* outputs (host; NULL = not wanted) */
+  double* F;             /* 1      */
+  double* dF;            /* ntheta */
+  double* G;             /* 1      */
+  double* H;             /* 1      */
+  double* varF;          /* 1      */
+  double* dH;            /* ntheta */
+  double* varGss;        /* 1      */
+  double* varG;          /* 1      */
+  double* varH;          /* 1      */
+  double* I_sk;          /* S x K  */
+  double* J_sjk;         /* S x K x K */
+} vbmc_b200_negelcbo_args;
+
+int vbmc_b200_negelcbo(vbmc_b200_ctx* ctx, const vbmc_b200_negelcbo_args* args);
+
+/* [H,dH] = entmc_vbmc(vp,Ns,grad_flags,jacobian_flag) — ent/entmc_vbmc.m:1-125.
+ * Uses the vp last set (no theta unpacking).  grad_flags[4]; dH length = D*K*gf0 + K*gf1 + D*gf2 + K*gf3. */
+int vbmc_b200_entmc(vbmc_b200_ctx* ctx, int Ns, const int grad_flags[4], int jacobian_flag, int eps_mode,
+                    const double* eps, uint64_t seed, uint64_t stream, double* H, double* dH);
+
+/* [F,dF,varF,dvarF,varss,I_sk,J_sjk] = gplogjoint(vp,gp,grad_flags,avg_flag,jacobian_flag,compute_var,separate_K)
+ * misc/gplogjoint.m:1-413.  avg_flag must be 1 when S > 1.  dvarF: compute_var == 2 only
+ * (else the reference raises gplogjoint:FullVarianceGradient). */
+int vbmc_b200_gplogjoint(vbmc_b200_ctx* ctx, const int grad_flags[4], int avg_flag, int jacobian_flag,
+                         int compute_var, double* F, double* dF, double* varF, double* dvarF, double* varss,
+                         double* I_sk, double* J_sjk);
+
+/* ---------------------------------------------------------------------------------------
+ * benchmark / profiling hooks (not part of the reference surface)
+ * ------------------------------------------------------------------------------------- */
+/* Run `steps` consecutive negelcbo evaluations entirely on the device (theta, eps already
+ * resident; no host copies) and return the CUDA-event time of the whole region in ms. */
+int vbmc_b200_negelcbo_resident_loop(vbmc_b200_ctx* ctx, const vbmc_b200_negelcbo_args* args, int steps,
+                                     float* ms_total);
+/* per-kernel CUDA-event timing: when enabled each kernel of a step is bracketed by events on
+ * the launch stream (graph replay is bypassed).  names: "entmc","gplogjoint","vp_unpack",
+ * "reduce","finalize","philox","gram","potrf",...  returns accumulated ms and launch count. */
+int vbmc_b200_profile_enable(vbmc_b200_ctx* ctx, int on);
+int vbmc_b200_profile_get(vbmc_b200_ctx* ctx, const char* name, double* ms_sum, long long* launches);
+int vbmc_b200_profile_reset(vbmc_b200_ctx* ctx);
+/* measured FP64 FMA peak of this device (DFMA micro-benchmark, TFLOP/s) and copy bandwidth (GB/s) */
+int vbmc_b200_measure_fp64_peak(vbmc_b200_ctx* ctx, double* tflops);
+int vbmc_b200_measure_hbm_copy(vbmc_b200_ctx* ctx, double* gbs);
+/* raw Philox4x32-10 block for the known-answer test (Random123 vectors) */
+int vbmc_b200_philox_raw(vbmc_b200_ctx* ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* write >126 MB to flush L2 between timed iterations */
+int vbmc_b200_flush_l2(vbmc_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBMC_B200_H */

@@ -1,0 +1,252 @@
+"""CUDA path vs the CPU oracle through the C ABI (host NumPy buffers in, host buffers out).
+FP64 tolerance (BASELINE.json north_star): 1e-10 relative on F, dF, G, H, dH (max-norm relative)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import vbmc_oracle as orc
+from vbmc_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def mk(D, N, K, S, Ns, seed=0, target="rosenbrock", **kw):
+    cfg = dict(D=D, N=N, K=K, S=S, Ns=Ns, target=target, noisy=False, **kw)
+    return workloads.build(cfg, orc.gplite_post, seeds=(seed + 1, seed + 2, seed + 3, seed + 4))
+
+
+SHAPES = [
+    dict(D=2, N=50, K=2, S=8, Ns=100),          # c1 (rosenbrock_test plumbing case)
+    dict(D=1, N=20, K=1, S=1, Ns=2),            # smallest legal problem
+    dict(D=3, N=33, K=5, S=2, Ns=37),           # odd D, odd Ns (made even), ragged tiles
+    dict(D=5, N=100, K=7, S=3, Ns=1000),
+    dict(D=6, N=400, K=20, S=8, Ns=4096),       # c2
+    dict(D=9, N=64, K=33, S=2, Ns=130),         # K > 32: second round of the column sums
+    dict(D=10, N=300, K=50, S=4, Ns=512, target="lumpy"),   # c3 shape, reduced N/Ns/S
+    dict(D=20, N=128, K=12, S=2, Ns=96, target="lumpy"),    # c5 dimension
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "D{D}N{N}K{K}S{S}Ns{Ns}".format(**s))
+def test_negelcbo_matches_oracle(gpu_ctx, shape):
+    import vbmc_b200
+    w = mk(**shape)
+    vp, gp, theta, eps, Ns = w["vp"], w["gp"], w["theta"], w["epsilon"], shape["Ns"]
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+    ref = orc.negelcbo_vbmc(theta, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+    F, dF, G, H, varF, dH = got
+    Fo, dFo, Go, Ho, _, dHo = ref[:6]
+    assert rel(H, Ho) < TOL and rel(dH, dHo) < TOL
+    assert rel(G, Go) < TOL
+    assert rel(F, Fo) < TOL and rel(dF, dFo) < TOL
+    assert varF == 0.0
+
+
+def test_negelcbo_no_grad_and_no_bounds(gpu_ctx):
+    import vbmc_b200
+    w = mk(D=4, N=60, K=6, S=3, Ns=200)
+    vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
+    (F,) = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 200, epsilon=eps, nargout=1)
+    Fo = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 200, epsilon=eps, nargout=1)[0]
+    assert rel(F, Fo) < TOL
+    F4 = vbmc_b200.negelcbo_vbmc(theta, float("nan"), vp, gp, 200, 0, 0, epsilon=eps, nargout=4)
+    assert F4[1] is None and rel(F4[0], Fo) < TOL  # beta NaN -> 0 (negelcbo_vbmc.m:15)
+
+
+def test_soft_bound_and_weight_penalties(gpu_ctx):
+    """theta outside the soft bounds + small weights below WeightThreshold (negelcbo_vbmc.m:136-164)."""
+    import vbmc_b200
+    w = mk(D=3, N=40, K=6, S=2, Ns=64)
+    vp, gp, theta, eps = w["vp"], w["gp"], w["theta"].copy(), w["epsilon"]
+    D, K = 3, 6
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    theta[0] = tb["ub"][0] + 0.4
+    theta[5] = tb["lb"][5] - 0.2
+    theta[D * K + 1] = -20.0            # log sigma far below the lnscale lower bounds
+    theta[D * K + K] = 3.0              # log lambda large: above lnscale upper bound for some k
+    theta[-1] = 0.7                     # eta above 0
+    theta[-2] = -9.0                    # tiny weight -> w < WeightThreshold
+    got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 64, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)
+    ref = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 64, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)
+    assert rel(got[0], ref[0]) < TOL and rel(got[1], ref[1]) < TOL
+    # the penalty must be active in this case
+    nob = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 64, 1, 0, 0, None, 0, epsilon=eps, nargout=2)
+    assert abs(ref[0] - nob[0]) > 1.0
+
+
+@pytest.mark.parametrize("flags", [(1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (1, 1, 0, 0), (1, 0, 1, 1)])
+def test_optimize_flag_subsets(gpu_ctx, flags):
+    """theta layout depends on vp.optimize_* (negelcbo_vbmc.m:32-48, vpbndloss.m:9-38)."""
+    import vbmc_b200
+    if flags == (0, 0, 0, 1):
+        pytest.skip("weights-only path = gplogjoint_weights.m, out of scope (SURVEY.md 2 #5)")
+    w = mk(D=3, N=40, K=4, S=2, Ns=50)
+    vp, gp, eps = dict(w["vp"]), w["gp"], w["epsilon"]
+    for f, v in zip(("optimize_mu", "optimize_sigma", "optimize_lambda", "optimize_weights"), flags):
+        vp[f] = bool(v)
+    parts = []
+    if flags[0]: parts.append(vp["mu"].T.ravel() + 0.05)
+    if flags[1]: parts.append(np.log(vp["sigma"]) - 0.1)
+    if flags[2]: parts.append(np.log(vp["lambda"]) + 0.02)
+    if flags[3]: parts.append(np.asarray(vp["eta"]) + 0.1)
+    theta = np.concatenate(parts)
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 50, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)
+    ref = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 50, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)
+    assert got[1].shape == ref[1].shape
+    assert rel(got[0], ref[0]) < TOL and rel(got[1], ref[1]) < TOL
+
+
+@pytest.mark.parametrize("meanfun", [0, 1, 4])
+def test_gplogjoint_meanfuns_and_Isk(gpu_ctx, meanfun):
+    import vbmc_b200
+    rng = np.random.default_rng(7)
+    D, N, K, S = 3, 45, 5, 3
+    X = rng.standard_normal((N, D)) * 1.5
+    y = workloads.rosenbrock_logpost(X)
+    Nmean = {0: 0, 1: 1, 4: 1 + 2 * D}[meanfun]
+    hyp = np.zeros((D + 2 + Nmean, S))
+    for s in range(S):
+        hyp[:D, s] = np.log(1.0 + 0.3 * rng.random(D))
+        hyp[D, s] = math.log(np.std(y))
+        hyp[D + 1, s] = math.log(0.05)
+        if meanfun >= 1:
+            hyp[D + 2, s] = np.max(y)
+        if meanfun == 4:
+            hyp[D + 3 : 2 * D + 3, s] = X.mean(axis=0) + 0.1 * rng.standard_normal(D)
+            hyp[2 * D + 3 :, s] = np.log(2 * X.std(axis=0))
+    gp = orc.gplite_post(hyp, X, y, 1, meanfun, [1, 0, 0], None)
+    vp = workloads.make_vp(dict(D=D, K=K), X, y, seed=11)
+    vp["delta"] = 0.05 * np.ones(D) if meanfun == 4 else None
+    got = vbmc_b200.gplogjoint(vp, gp, True, True, True, 0, nargout=6)
+    ref = orc.gplogjoint(vp, gp, True, True, True, 0, nargout=6)
+    assert rel(got[0], ref[0]) < TOL and rel(got[1], ref[1]) < TOL
+    assert got[5].shape == (S, K) and rel(got[5], ref[5]) < TOL
+    # jacobian_flag = 0
+    got = vbmc_b200.gplogjoint(vp, gp, [1, 1, 1, 1], True, False, 0, nargout=2)
+    ref = orc.gplogjoint(vp, gp, [1, 1, 1, 1], True, False, 0, nargout=2)
+    assert rel(got[1], ref[1]) < TOL
+
+
+@pytest.mark.parametrize("gf", [(1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 1, 0), (0, 0, 0, 1), (0, 0, 0, 0)])
+@pytest.mark.parametrize("jac", [True, False])
+def test_entmc_grad_flags(gpu_ctx, gf, jac):
+    import vbmc_b200
+    w = mk(D=4, N=30, K=6, S=1, Ns=300)
+    vp, eps = w["vp"], w["epsilon"]
+    H, dH = vbmc_b200.entmc_vbmc(vp, 300, list(gf), jac, epsilon=eps)
+    Ho, dHo = orc.entmc_vbmc(vp, 300, list(gf), jac, epsilon=eps)
+    assert rel(H, Ho) < TOL
+    assert dH.shape == dHo.shape
+    if dHo.size:
+        assert rel(dH, dHo) < TOL
+
+
+def test_entmc_K1_known_answer(gpu_ctx):
+    """K=1 closed form (entmc_vbmc.m:60-67 / entlb_vbmc.m:34) evaluated by the CUDA path itself."""
+    import vbmc_b200
+    rng = np.random.default_rng(1)
+    D, Ns = 6, 4096
+    vp = dict(D=D, K=1, mu=rng.standard_normal((D, 1)), sigma=np.array([0.3]), w=np.array([1.0]), eta=np.array([0.0]),
+              optimize_mu=True, optimize_sigma=True, optimize_lambda=True, optimize_weights=True, delta=None)
+    vp["lambda"] = np.exp(0.3 * rng.standard_normal(D))
+    eps = rng.standard_normal((1, Ns // 2, D))
+    H, dH = vbmc_b200.entmc_vbmc(vp, Ns, True, True, epsilon=eps)
+    expect = 0.5 * D * math.log(2 * math.pi) + D * math.log(0.3) + np.sum(np.log(vp["lambda"])) + 0.5 * D * np.mean(eps**2)
+    assert abs(H - expect) < 1e-12 * abs(expect)
+    assert np.max(np.abs(dH[:D])) < 1e-12
+    assert abs(dH[D] - np.mean(np.sum(eps**2, axis=2))) < 1e-11 * abs(dH[D])
+
+
+def test_exp_underflow_matches_reference_semantics(gpu_ctx):
+    """Far-apart tiny components: cross terms underflow to exactly 0 as in MATLAB's direct exp (entmc_vbmc.m:63)."""
+    import vbmc_b200
+    rng = np.random.default_rng(2)
+    D, K, Ns = 3, 4, 64
+    vp = dict(D=D, K=K, mu=50.0 * rng.standard_normal((D, K)), sigma=0.01 * np.ones(K), w=np.ones(K) / K,
+              eta=np.log(np.ones(K) / K), optimize_mu=True, optimize_sigma=True, optimize_lambda=True,
+              optimize_weights=True, delta=None)
+    vp["lambda"] = np.ones(D)
+    eps = rng.standard_normal((K, Ns // 2, D))
+    H, dH = vbmc_b200.entmc_vbmc(vp, Ns, True, True, epsilon=eps)
+    Ho, dHo = orc.entmc_vbmc(vp, Ns, True, True, epsilon=eps)
+    assert np.isfinite(H) and rel(H, Ho) < TOL and rel(dH, dHo) < TOL
+
+
+def test_device_rng_equals_parity_mode_on_dumped_draws(gpu_ctx):
+    """Device Philox mode == parity mode fed with the draws it dumped; draws are standard normal."""
+    import vbmc_b200
+    w = mk(D=5, N=40, K=8, S=2, Ns=2048)
+    vp, gp, theta = w["vp"], w["gp"], w["theta"]
+    eps = gpu_ctx.eps_philox(5, 8, 2048, seed=1234, stream=7, readback=True)
+    assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1) < 0.02 and abs(np.mean(eps**3)) < 0.05
+    assert abs(np.mean(eps**4) - 3) < 0.15
+    a = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 2048, 1, 0, rng=(1234, 7), nargout=2)
+    b = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 2048, 1, 0, epsilon=eps, nargout=2)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    c = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 2048, 1, 0, epsilon=eps, nargout=2)
+    assert rel(a[0], c[0]) < TOL and rel(a[1], c[1]) < TOL
+    # a different stream gives different draws
+    eps2 = gpu_ctx.eps_philox(5, 8, 2048, seed=1234, stream=8, readback=True)
+    assert not np.array_equal(eps, eps2)
+
+
+def test_philox_known_answers(gpu_ctx):
+    """Random123 known-answer vectors for philox4x32-10."""
+    import ctypes as C
+    from vbmc_b200 import _lib
+    lib = _lib.load()
+
+    def run(ctr, key):
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        _lib.check(lib.vbmc_b200_philox_raw(gpu_ctx.handle, c, k, o))
+        return list(o)
+
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = 0xFFFFFFFF
+    assert run([f, f, f, f], [f, f]) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert run([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_reference_error_identifiers(gpu_ctx):
+    import vbmc_b200
+    w = mk(D=2, N=20, K=2, S=2, Ns=10)
+    with pytest.raises(vbmc_b200.VbmcB200Error) as ei:
+        vbmc_b200.negelcbo_vbmc(w["theta"], 1.0, w["vp"], w["gp"], 10, 1, 1, epsilon=w["epsilon"])
+    assert ei.value.identifier == "negelcbo_vbmc:vargrad"
+    gp = dict(w["gp"], meanfun=7)
+    with pytest.raises(vbmc_b200.VbmcB200Error) as ei:
+        vbmc_b200.gplogjoint(w["vp"], gp)
+    assert ei.value.identifier == "gplogjoint:UnsupportedMeanFun"
+    with pytest.raises(vbmc_b200.VbmcB200Error):
+        vbmc_b200.negelcbo_vbmc(w["theta"][:-1], 0.0, w["vp"], w["gp"], 10, epsilon=w["epsilon"])
+
+
+def test_full_size_properties_c3(gpu_ctx):
+    """c3 shape at full K, Ns (oracle too slow there): size-independent properties.
+    (1) linearity in the draws: H over [eps_a; eps_b] == mean of H over eps_a and eps_b;
+    (2) the eta-gradient of G+H sums to ~0 (J_w rows sum to zero);
+    (3) run-to-run bit reproducibility."""
+    import vbmc_b200
+    w = mk(D=10, N=256, K=50, S=2, Ns=32768, target="lumpy")
+    vp = w["vp"]
+    rng = np.random.Generator(np.random.Philox(9))
+    ea = rng.standard_normal((50, 8192, 10))
+    eb = rng.standard_normal((50, 8192, 10))
+    Ha, dHa = vbmc_b200.entmc_vbmc(vp, 16384, True, True, epsilon=ea)
+    Hb, dHb = vbmc_b200.entmc_vbmc(vp, 16384, True, True, epsilon=eb)
+    Hab, dHab = vbmc_b200.entmc_vbmc(vp, 32768, True, True, epsilon=np.concatenate([ea, eb], axis=1))
+    assert abs(Hab - 0.5 * (Ha + Hb)) < 1e-12 * abs(Hab)
+    assert rel(dHab, 0.5 * (dHa + dHb)) < 1e-11
+    assert abs(np.sum(dHab[-50:])) < 1e-10 * np.max(np.abs(dHab[-50:]))
+    H2, dH2 = vbmc_b200.entmc_vbmc(vp, 32768, True, True, epsilon=np.concatenate([ea, eb], axis=1))
+    assert H2 == Hab and np.array_equal(dH2, dHab)

@@ -1,0 +1,11 @@
+"""vbmc_b200 — B200 (sm_100a) implementation of the VBMC variational-optimisation hot path.
+
+Public surface = the reference's MATLAB function names for this path (see vbmc_b200/api.py);
+the numerics live in vbmc_b200/lib/libvbmc_b200.so (C ABI: include/vbmc_b200.h).
+"""
+from .api import (Context, VbmcB200Error, default_context, entmc_vbmc, get_vptheta, gplite_nlZ, gplite_post,
+                  gplogjoint, negelcbo_vbmc, rescale_params, vpbounds)
+
+__all__ = ["Context", "VbmcB200Error", "default_context", "entmc_vbmc", "get_vptheta", "gplite_nlZ", "gplite_post",
+           "gplogjoint", "negelcbo_vbmc", "rescale_params", "vpbounds"]
+__version__ = "0.1.0"

@@ -1,0 +1,491 @@
+"""Host-side mirror of the reference's MATLAB functions for the hot path, on top of the C ABI.
+
+Same names, argument order/meaning and error identifiers as the reference:
+
+    negelcbo_vbmc(theta,beta,vp,gp,Ns,compute_grad,compute_var,altent_flag,thetabnd,entropy_alpha)
+        misc/negelcbo_vbmc.m:1
+    gplogjoint(vp,gp,grad_flags,avg_flag,jacobian_flag,compute_var,separate_K)   misc/gplogjoint.m:1
+    entmc_vbmc(vp,Ns,grad_flags,jacobian_flag)                                   ent/entmc_vbmc.m:1
+    gplite_post(hyp,X,y,covfun,meanfun,noisefun,s2)                              gplite/gplite_post.m:1
+    gplite_nlZ(hyp,gp,hprior)                                                    gplite/gplite_nlZ.m:1
+
+MATLAB structs are dicts (``vp``: D,K,mu(D,K),sigma(K),lambda(D),w(K),eta,delta,optimize_*;
+``gp``: X(N,D),y,s2,covfun,meanfun,noisefun,Ncov,Nnoise,Nmean,post=[{hyp,alpha,sW,L,sn2_mult,Lchol}]).
+MATLAB's ``nargout`` is an explicit keyword.  The reference draws the entropy samples from
+MATLAB's global ``randn`` stream (entmc_vbmc.m:53); here they come either from ``epsilon``
+(shape (K, Ns/2, D), parity mode) or from the device Philox generator (``rng=(seed, stream)``).
+
+All numerics run in libvbmc_b200.so on the GPU; nothing here computes the path on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import VbmcB200Error, dptr, f64
+
+__all__ = [
+    "Context", "default_context", "negelcbo_vbmc", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ",
+    "vpbounds", "rescale_params", "get_vptheta", "VbmcB200Error",
+]
+
+
+def _fingerprint(*arrays):
+    return hash(tuple(a.tobytes() if isinstance(a, np.ndarray) else repr(a) for a in arrays))
+
+
+class Context:
+    """One GPU context (vbmc_b200_create).  Caches which gp / vp / thetabnd are resident."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self.lib.vbmc_b200_create(C.byref(self._h), int(device)))
+        self.device = device
+        self._gp_key = None
+        self._vp_key = None
+        self._bnd_key = None
+        self._keep = []  # host arrays referenced by in-flight descriptors
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.lib.vbmc_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        _lib.check(self.lib.vbmc_b200_sync(self._h))
+
+    def launch_count(self) -> int:
+        n = C.c_longlong()
+        _lib.check(self.lib.vbmc_b200_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # -- multi-GPU --------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        _lib.check(_lib.load().vbmc_b200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes | None):
+        buf = C.create_string_buffer(uid, _lib.UNIQUE_ID_BYTES) if uid is not None else None
+        _lib.check(self.lib.vbmc_b200_comm_init(self._h, nranks, rank, buf))
+
+    # -- GP ---------------------------------------------------------------------------------
+    @staticmethod
+    def _gp_desc(gp, hyp, keep):
+        X = f64(gp["X"])
+        N, D = X.shape
+        Xc = np.ascontiguousarray(X.T)  # column-major N x D
+        hyp = f64(hyp)
+        if hyp.ndim == 1:
+            hyp = hyp[None, :]
+        S, Nhyp = hyp.shape
+        d = _lib.GpDesc()
+        d.N, d.D, d.S, d.Nhyp = N, D, S, Nhyp
+        cov = gp.get("covfun", 1)
+        d.covfun = int(cov[0] if isinstance(cov, (list, tuple, np.ndarray)) else cov)
+        d.meanfun = int(gp.get("meanfun", 1))
+        nf = list(gp.get("noisefun", [1, 0, 0]))
+        d.noisefun = (C.c_int * 3)(*[int(v) for v in nf])
+        y = f64(gp["y"]).ravel() if gp.get("y") is not None else None
+        s2 = f64(gp["s2"]).ravel() if gp.get("s2") is not None else None
+        d.X, d.y, d.s2, d.hyp = dptr(Xc), dptr(y), dptr(s2), dptr(hyp)
+        keep += [Xc, hyp, y, s2]
+        return d, (N, D, S, Nhyp)
+
+    def gp_attach(self, gp, want_L=False):
+        """Make ``gp`` (with a posterior computed elsewhere) resident; no-op when unchanged."""
+        post = gp["post"]
+        hyp = np.stack([f64(p["hyp"]).ravel() for p in post])
+        alpha = np.ascontiguousarray(np.stack([f64(p["alpha"]).ravel() for p in post]))
+        key = (id(gp), gp["X"].shape, len(post), float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
+               float(hyp[-1, -1]), bool(want_L))
+        if key == self._gp_key:
+            return
+        keep = []
+        d, (N, D, S, _) = self._gp_desc(gp, hyp, keep)
+        sW1 = f64([np.asarray(p["sW"]).ravel()[0] for p in post])
+        Lchol = np.ascontiguousarray([int(bool(p.get("Lchol", True))) for p in post], dtype=np.int32)
+        L = None
+        if want_L:
+            L = np.ascontiguousarray(np.stack([f64(p["L"]).T for p in post]))  # each column-major
+        _lib.check(self.lib.vbmc_b200_gp_attach(self._h, C.byref(d), dptr(alpha), dptr(sW1),
+                                                Lchol.ctypes.data_as(_lib.c_int_p), dptr(L)))
+        self._gp_key = key
+
+    # -- VP ---------------------------------------------------------------------------------
+    def vp_set(self, vp):
+        D, K = int(vp["D"]), int(vp["K"])
+        mu = np.ascontiguousarray(f64(vp["mu"]).reshape(D, K).T)  # column-major D x K
+        sigma = f64(vp["sigma"]).ravel()
+        lam = f64(vp["lambda"]).ravel()
+        w = f64(vp["w"]).ravel()
+        eta = f64(vp["eta"]).ravel() if vp.get("eta") is not None else None
+        delta = vp.get("delta")
+        if delta is not None and np.size(delta) > 0:
+            delta = f64(delta).ravel() * np.ones(D)
+        else:
+            delta = None
+        flags = tuple(int(bool(vp[f])) for f in ("optimize_mu", "optimize_sigma", "optimize_lambda", "optimize_weights"))
+        key = (D, K, flags, _fingerprint(mu, sigma, lam, w, eta, delta))
+        if key == self._vp_key:
+            return
+        d = _lib.VpDesc()
+        d.D, d.K = D, K
+        d.mu, d.sigma, d.lambda_, d.w, d.eta, d.delta = dptr(mu), dptr(sigma), dptr(lam), dptr(w), dptr(eta), dptr(delta)
+        d.optimize_mu, d.optimize_sigma, d.optimize_lambda, d.optimize_weights = flags
+        _lib.check(self.lib.vbmc_b200_vp_set(self._h, C.byref(d)))
+        self._vp_key = key
+
+    def thetabnd_set(self, thetabnd):
+        if thetabnd is None:
+            if self._bnd_key is not None:
+                _lib.check(self.lib.vbmc_b200_thetabnd_set(self._h, 0, None, None, 0.0, 0.0, 0.0))
+                self._bnd_key = None
+            return
+        lb, ub = f64(thetabnd["lb"]).ravel(), f64(thetabnd["ub"]).ravel()
+        wt, wp = float(thetabnd.get("WeightThreshold", 0.0)), float(thetabnd.get("WeightPenalty", 0.0))
+        key = (_fingerprint(lb, ub), float(thetabnd["TolCon"]), wt, wp)
+        if key == self._bnd_key:
+            return
+        _lib.check(self.lib.vbmc_b200_thetabnd_set(self._h, lb.size, dptr(lb), dptr(ub), float(thetabnd["TolCon"]), wt, wp))
+        self._bnd_key = key
+
+    # -- draws ------------------------------------------------------------------------------
+    def eps_upload(self, epsilon):
+        e = f64(epsilon)
+        K, half, D = e.shape
+        _lib.check(self.lib.vbmc_b200_eps_upload(self._h, D, K, 2 * half, dptr(e)))
+
+    def eps_philox(self, D, K, Ns, seed, stream, readback=False):
+        Ns = int(math.ceil(Ns / 2) * 2)
+        out = np.empty((K, Ns // 2, D)) if readback else None
+        _lib.check(self.lib.vbmc_b200_eps_philox(self._h, D, K, Ns, int(seed), int(stream), dptr(out)))
+        return out
+
+    # -- profiling hooks --------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        _lib.check(self.lib.vbmc_b200_profile_enable(self._h, int(bool(on))))
+
+    def profile_get(self, name):
+        ms, n = C.c_double(), C.c_longlong()
+        _lib.check(self.lib.vbmc_b200_profile_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def profile_reset(self):
+        _lib.check(self.lib.vbmc_b200_profile_reset(self._h))
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        _lib.check(self.lib.vbmc_b200_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_hbm_copy(self):
+        v = C.c_double()
+        _lib.check(self.lib.vbmc_b200_measure_hbm_copy(self._h, C.byref(v)))
+        return v.value
+
+    def flush_l2(self):
+        _lib.check(self.lib.vbmc_b200_flush_l2(self._h))
+
+
+_default = None
+
+
+def default_context() -> Context:
+    """Library-static context, the analogue of the MEX file's mexLock()'d state."""
+    global _default
+    if _default is None:
+        _default = Context(0)
+    return _default
+
+
+# ------------------------------------------------------------------------------------------
+# host-side helpers the callers of the hot path use (plain O(DK) NumPy; no GPU work)
+# ------------------------------------------------------------------------------------------
+def rescale_params(vp, theta=None):
+    """misc/rescale_params.m:6-40: assign theta, rescale so that mean(lambda^2) == 1, sum(w) == 1."""
+    vp = dict(vp)
+    D, K = vp["D"], vp["K"]
+    if theta is not None:
+        t = f64(theta).ravel()
+        i = 0
+        if vp["optimize_mu"]:
+            vp["mu"] = t[: D * K].reshape(K, D).T.copy()
+            i = D * K
+        if vp["optimize_sigma"]:
+            vp["sigma"] = np.exp(t[i:i + K])
+            i += K
+        if vp["optimize_lambda"]:
+            vp["lambda"] = np.exp(t[i:i + D])
+        if vp["optimize_weights"]:
+            eta = t[-K:] - np.max(t[-K:])
+            vp["w"] = np.exp(eta)
+    lam = f64(vp["lambda"]).ravel()
+    nl = math.sqrt(float(np.sum(lam * lam)) / D)
+    vp["lambda"] = lam / nl
+    vp["sigma"] = f64(vp["sigma"]).ravel() * nl
+    if vp["optimize_weights"]:
+        w = f64(vp["w"]).ravel()
+        vp["w"] = w / np.sum(w)
+        vp.pop("eta", None)
+    vp.pop("mode", None)
+    return vp
+
+
+def get_vptheta(vp):
+    """misc/get_vptheta.m:17-21 -> (theta, vp)."""
+    vp = rescale_params(vp)
+    blocks = []
+    if vp["optimize_mu"]:
+        blocks.append(f64(vp["mu"]).T.ravel())
+    if vp["optimize_sigma"]:
+        blocks.append(np.log(vp["sigma"]))
+    if vp["optimize_lambda"]:
+        blocks.append(np.log(vp["lambda"]))
+    if vp["optimize_weights"]:
+        blocks.append(np.log(vp["w"]))
+    return np.concatenate(blocks), vp
+
+
+def vpbounds(vp, gp, options, K=None):
+    """misc/vpbounds.m:8-52 -> (vp, thetabnd).  options: TolLength, TolWeight, TolConLoss, WeightPenalty."""
+    vp = dict(vp)
+    K = vp["K"] if K is None else K
+    D = vp["D"]
+    X = f64(gp["X"])
+    lo, hi = X.min(axis=0), X.max(axis=0)
+    b = dict(vp.get("bounds") or {"mu_lb": np.full(D, np.inf), "mu_ub": np.full(D, -np.inf),
+                                   "lnscale_lb": np.full(D, np.inf), "lnscale_ub": np.full(D, -np.inf)})
+    b["mu_lb"] = np.minimum(lo, b["mu_lb"])
+    b["mu_ub"] = np.maximum(hi, b["mu_ub"])
+    lnrange = np.log(hi - lo)
+    b["lnscale_lb"] = np.minimum(b["lnscale_lb"], lnrange + math.log(options["TolLength"]))
+    b["lnscale_ub"] = np.maximum(b["lnscale_ub"], lnrange)
+    if vp["optimize_weights"]:
+        b["eta_lb"], b["eta_ub"] = math.log(0.5 * options["TolWeight"]), 0.0
+    vp["bounds"] = b
+    lbs, ubs = [], []
+    if vp["optimize_mu"]:
+        lbs.append(np.tile(b["mu_lb"], K)); ubs.append(np.tile(b["mu_ub"], K))
+    if vp["optimize_sigma"] or vp["optimize_lambda"]:
+        lbs.append(np.tile(b["lnscale_lb"], K)); ubs.append(np.tile(b["lnscale_ub"], K))
+    if vp["optimize_weights"]:
+        lbs.append(np.full(K, b["eta_lb"])); ubs.append(np.full(K, b["eta_ub"]))
+    tb = {"lb": np.concatenate(lbs), "ub": np.concatenate(ubs), "TolCon": options["TolConLoss"]}
+    if vp["optimize_weights"]:
+        tb["WeightThreshold"] = max(1.0 / (4 * K), options["TolWeight"])
+        tb["WeightPenalty"] = options["WeightPenalty"]
+    return vp, tb
+
+
+# ------------------------------------------------------------------------------------------
+# the hot-path functions
+# ------------------------------------------------------------------------------------------
+def _eps_args(vp, Ns, epsilon, rng):
+    Ns2 = int(math.ceil(Ns / 2) * 2)
+    if epsilon is not None and not isinstance(epsilon, str):
+        e = f64(epsilon)
+        want = (vp["K"], Ns2 // 2, vp["D"])
+        if e.shape != want:
+            raise VbmcB200Error(_lib.EINVAL, f"vbmc_b200:epsilon: epsilon must have shape (K,Ns/2,D)={want}, got {e.shape}")
+        return _lib.EPS_HOST, e, 0, 0
+    if isinstance(epsilon, str) and epsilon == "resident":
+        return _lib.EPS_RESIDENT, None, 0, 0
+    if rng is None:
+        raise VbmcB200Error(_lib.EINVAL, "vbmc_b200:epsilon: pass epsilon (parity mode), epsilon='resident', or rng=(seed, stream)")
+    return _lib.EPS_PHILOX, None, int(rng[0]), int(rng[1])
+
+
+def negelcbo_vbmc(theta, beta, vp, gp, Ns=0, compute_grad=None, compute_var=None, altent_flag=False,
+                  thetabnd=None, entropy_alpha=0, *, epsilon=None, rng=None, nargout=2, ctx=None):
+    """[F,dF,G,H,varF,dH,varGss,varG,varH,I_sk,J_sjk] = negelcbo_vbmc(...), misc/negelcbo_vbmc.m:1-164.
+
+    Defaults follow negelcbo_vbmc.m:9-17 (``compute_grad = nargout > 1`` etc.).  ``altent_flag`` and
+    ``entropy_alpha`` are accepted and ignored, like the reference (:19).  Returns a tuple of
+    ``nargout`` values.
+    """
+    ctx = ctx or default_context()
+    if Ns is None:
+        Ns = 0
+    if compute_grad is None:
+        compute_grad = nargout > 1
+    if beta is None or not np.isfinite(beta):
+        beta = 0.0
+    if compute_var is None:
+        compute_var = (beta != 0) or nargout > 4
+    separate_K = nargout > 9
+    theta = f64(theta).ravel()
+    ctx.vp_set(vp)
+    ctx.gp_attach(gp, want_L=bool(compute_var))
+    ctx.thetabnd_set(thetabnd)
+    S, K = len(gp["post"]), int(vp["K"])
+    a = _lib.NegelcboArgs()
+    a.theta, a.ntheta = dptr(theta), theta.size
+    a.beta, a.Ns = float(beta), int(Ns)
+    a.compute_grad, a.compute_var, a.separate_K = int(bool(compute_grad)), int(compute_var), int(separate_K)
+    a.use_thetabnd = int(thetabnd is not None)
+    if Ns > 0:
+        mode, e, seed, stream = _eps_args(vp, Ns, epsilon, rng)
+    else:
+        mode, e, seed, stream = _lib.EPS_RESIDENT, None, 0, 0
+    a.eps_mode, a.eps, a.seed, a.stream = mode, dptr(e), seed, stream
+    sc = np.zeros(8)
+    dF = np.zeros(theta.size) if compute_grad else None
+    dH = np.zeros(theta.size) if compute_grad else None
+    Isk = np.zeros((K, S)) if separate_K else None
+    Jsjk = np.zeros((K, K, S)) if (separate_K and compute_var) else None
+    p = sc.ctypes.data_as(_lib.c_double_p)
+    off = lambda i: C.cast(C.addressof(p.contents) + 8 * i, _lib.c_double_p)
+    a.F, a.G, a.H, a.varF, a.varGss, a.varG, a.varH = off(0), off(1), off(2), off(3), off(4), off(5), off(6)
+    a.dF, a.dH, a.I_sk, a.J_sjk = dptr(dF), dptr(dH), dptr(Isk), dptr(Jsjk)
+    _lib.check(ctx.lib.vbmc_b200_negelcbo(ctx.handle, C.byref(a)))
+    out = (float(sc[0]), dF, float(sc[1]), float(sc[2]), float(sc[3]), dH, float(sc[4]), float(sc[5]), float(sc[6]),
+           None if Isk is None else Isk.T.copy(), None if Jsjk is None else Jsjk.transpose(2, 1, 0).copy())
+    return out[:max(1, nargout)]
+
+
+def entmc_vbmc(vp, Ns=10, grad_flags=None, jacobian_flag=True, *, epsilon=None, rng=None, nargout=2, ctx=None):
+    """[H,dH] = entmc_vbmc(vp,Ns,grad_flags,jacobian_flag), ent/entmc_vbmc.m:1-125."""
+    ctx = ctx or default_context()
+    if nargout < 2:
+        grad_flags = False
+    elif grad_flags is None:
+        grad_flags = True
+    if np.isscalar(grad_flags):
+        grad_flags = [bool(grad_flags)] * 4
+    gf = (C.c_int * 4)(*[int(bool(g)) for g in grad_flags])
+    ctx.vp_set(vp)
+    mode, e, seed, stream = _eps_args(vp, Ns, epsilon, rng)
+    D, K = int(vp["D"]), int(vp["K"])
+    n = D * K * gf[0] + K * gf[1] + D * gf[2] + K * gf[3]
+    H = C.c_double()
+    dH = np.zeros(n) if nargout > 1 else None
+    _lib.check(ctx.lib.vbmc_b200_entmc(ctx.handle, int(Ns), gf, int(bool(jacobian_flag)), mode, dptr(e), seed, stream,
+                                       C.byref(H), dptr(dH)))
+    return (H.value, dH)[:max(1, nargout)]
+
+
+def gplogjoint(vp, gp, grad_flags=None, avg_flag=True, jacobian_flag=True, compute_var=None, separate_K=None, *,
+               nargout=2, ctx=None):
+    """[F,dF,varF,dvarF,varss,I_sk,J_sjk] = gplogjoint(...), misc/gplogjoint.m:1-413."""
+    ctx = ctx or default_context()
+    if separate_K is None:
+        separate_K = nargout > 5
+    if compute_var is None:
+        compute_var = nargout > 2
+    if nargout < 2:
+        grad_flags = False
+    elif grad_flags is None:
+        grad_flags = True
+    if np.isscalar(grad_flags):
+        grad_flags = [bool(grad_flags)] * 4
+    gf = (C.c_int * 4)(*[int(bool(g)) for g in grad_flags])
+    ctx.vp_set(vp)
+    ctx.gp_attach(gp, want_L=bool(compute_var))
+    D, K, S = int(vp["D"]), int(vp["K"]), len(gp["post"])
+    n = D * K * gf[0] + K * gf[1] + D * gf[2] + K * gf[3]
+    F, varss = C.c_double(), C.c_double()
+    dF = np.zeros(n) if nargout > 1 else None
+    varF = C.c_double() if compute_var else None
+    compute_vargrad = nargout > 3 and compute_var and any(gf)
+    dvarF = np.zeros(n) if compute_vargrad else None
+    Isk = np.zeros((K, S)) if separate_K else None
+    Jsjk = np.zeros((K, K, S)) if (separate_K and compute_var) else None
+    _lib.check(ctx.lib.vbmc_b200_gplogjoint(ctx.handle, gf, int(bool(avg_flag)), int(bool(jacobian_flag)), int(compute_var),
+                                            C.byref(F), dptr(dF), None if varF is None else C.byref(varF), dptr(dvarF),
+                                            C.byref(varss), dptr(Isk), dptr(Jsjk)))
+    out = (F.value, dF, None if varF is None else varF.value, dvarF, varss.value,
+           None if Isk is None else Isk.T.copy(), None if Jsjk is None else Jsjk.transpose(2, 1, 0).copy())
+    return out[:max(1, nargout)]
+
+
+def _noise_count(noisefun):
+    return int(noisefun[0] == 1) + int(noisefun[1] == 2) + 2 * int(noisefun[2] == 1)
+
+
+def _mean_count(D, meanfun):
+    return {0: 0, 1: 1, 4: 1 + 2 * D}.get(meanfun)
+
+
+def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *, ctx=None, want_L=True):
+    """gp = gplite_post(hyp,X,y,covfun,meanfun,noisefun,s2), gplite/gplite_post.m:94-172 (full refit).
+
+    The S Cholesky factorisations run on the GPU and the posterior stays resident (it becomes the
+    attached GP of ``ctx``); the returned dict mirrors the MATLAB struct.  ``want_L=False`` skips the
+    N x N x S device->host copy of the factors (gp.post(s).L is then None).
+    """
+    ctx = ctx or default_context()
+    X = f64(X)
+    y = f64(y).ravel()
+    N, D = X.shape
+    hyp = f64(hyp)
+    if hyp.ndim == 1:
+        hyp = hyp[:, None]
+    Nhyp, S = hyp.shape
+    covfun = 1 if covfun is None else covfun
+    meanfun = 1 if meanfun is None else meanfun
+    if noisefun is None:
+        noisefun = [1, 0, 0] if s2 is None else [1, 1, 0]
+    gp = {"X": X, "y": y, "s2": None if s2 is None else f64(s2).ravel(), "covfun": covfun, "meanfun": meanfun,
+          "noisefun": list(noisefun), "Ncov": D + 1, "Nnoise": _noise_count(noisefun), "Nmean": _mean_count(D, meanfun),
+          "meanfun_extras": None, "intmeanfun": 0}
+    keep = []
+    d, _ = ctx._gp_desc(gp, np.ascontiguousarray(hyp.T), keep)
+    alpha = np.zeros((S, N))
+    L = np.zeros((S, N, N)) if want_L else None
+    sW1, mult = np.zeros(S), np.zeros(S)
+    Lchol = np.zeros(S, dtype=np.int32)
+    _lib.check(ctx.lib.vbmc_b200_gp_post(ctx.handle, C.byref(d), dptr(alpha), dptr(L), dptr(sW1), dptr(mult),
+                                         Lchol.ctypes.data_as(_lib.c_int_p)))
+    gp["post"] = [{"hyp": hyp[:, s].copy(), "alpha": alpha[s].copy(), "sW": np.full(N, sW1[s]),
+                   "L": None if L is None else L[s].T.copy(), "sn2_mult": float(mult[s]), "Lchol": bool(Lchol[s])}
+                  for s in range(S)]
+    ctx._gp_key = (id(gp), gp["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
+                   float(hyp[-1, -1]), bool(want_L))
+    return gp
+
+
+def gplite_nlZ(hyp, gp, hprior=None, *, nargout=1, ctx=None):
+    """[nlZ,dnlZ] = gplite_nlZ(hyp,gp,hprior), gplite/gplite_nlZ.m:27-66."""
+    ctx = ctx or default_context()
+    hyp = f64(hyp)
+    if hyp.ndim == 1:
+        hyp = hyp[:, None]
+    Nhyp, Ns = hyp.shape
+    D = gp["X"].shape[1]
+    Ncov, Nnoise, Nmean = D + 1, _noise_count(gp["noisefun"]), _mean_count(D, gp["meanfun"])
+    if Nmean is None or Nhyp != Ncov + Nnoise + Nmean:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_nlZ:dimmismatch: Number of hyperparameters mismatched with dimension of training inputs.")
+    if nargout > 1 and Ns > 1:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_nlZ:NoSampling: Computation of the log marginal likelihood is available only for one-sample hyperparameter inputs.")
+    keep = []
+    d, _ = ctx._gp_desc(gp, np.ascontiguousarray(hyp[:, :1].T), keep)
+    hp = None
+    if hprior is not None:
+        hp = _lib.HPrior()
+        mu, sg = f64(hprior["mu"]).ravel(), f64(hprior["sigma"]).ravel()
+        df = hprior.get("df")
+        df = None if df is None or np.size(df) == 0 else f64(df).ravel()
+        hp.mu, hp.sigma, hp.df = dptr(mu), dptr(sg), dptr(df)
+        keep += [mu, sg, df]
+    nlZ = C.c_double()
+    dnlZ = np.zeros(Nhyp) if nargout > 1 else None
+    _lib.check(ctx.lib.vbmc_b200_gp_nlz(ctx.handle, C.byref(d), None if hp is None else C.byref(hp), C.byref(nlZ), dptr(dnlZ)))
+    ctx._gp_key = None  # gp_nlz reuses the GP work buffers
+    return (nlZ.value, dnlZ)[:max(1, nargout)]

@@ -1,0 +1,630 @@
+// C ABI of libvbmc_b200 (see include/vbmc_b200.h): context, GP/VP residency, one negelcbo step.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void shard_range(int total, int nranks, int rank, int* begin, int* end) {
+  // contiguous balanced split: the first (total % nranks) ranks get one extra unit
+  const int base = total / nranks, rem = total % nranks;
+  const int b = rank * base + (rank < rem ? rank : rem);
+  *begin = b;
+  *end = b + base + (rank < rem ? 1 : 0);
+}
+
+KernelScope::KernelScope(vbmc_b200_ctx* ctx, const char* nm, cudaStream_t s) : c(ctx), name(nm), st(s) {
+  c->launches++;
+  if (c->profiling) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+}
+KernelScope::~KernelScope() {
+  if (c->profiling && e0) {
+    cudaEventRecord(e1, st);
+    c->prof_events.push_back(e0);
+    c->prof_events.push_back(e1);
+    c->prof[name].n += 1;
+    c->prof_names.push_back(name);
+  }
+}
+int profile_collect(vbmc_b200_ctx* c) {
+  VB_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < c->prof_events.size(); i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]);
+    c->prof[c->prof_names[i / 2]].ms += ms;
+    cudaEventDestroy(c->prof_events[i]);
+    cudaEventDestroy(c->prof_events[i + 1]);
+  }
+  c->prof_events.clear();
+  c->prof_names.clear();
+  return VBMC_B200_OK;
+}
+
+static int ensure_pinned(double** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return VBMC_B200_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  VB_CUDA(cudaMallocHost(reinterpret_cast<void**>(p), bytes));
+  *cap = bytes;
+  return VBMC_B200_OK;
+}
+
+static int grad_mask_len(const vbmc_b200_ctx* c, int mask) {
+  int n = 0;
+  if (mask & 1) n += c->D * c->K;
+  if (mask & 2) n += c->K;
+  if (mask & 4) n += c->D;
+  if (mask & 8) n += c->K;
+  return n;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vbmc_b200_version(void) { return VBMC_B200_VERSION; }
+const char* vbmc_b200_last_error(void) { return vb::g_err; }
+
+int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
+  if (!out) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    VB_FAIL(VBMC_B200_ENODEV, "vbmc_b200:nodevice: no CUDA device (%s); this library has no CPU fallback",
+            e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_create: device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  VB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    VB_FAIL(VBMC_B200_ENODEV, "vbmc_b200:nodevice: device %d (%s) is sm_%d%d; this library is built for sm_100a only",
+            device, prop.name, prop.major, prop.minor);
+  VB_CUDA(cudaSetDevice(device));
+  vbmc_b200_ctx* c = new vbmc_b200_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  VB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreate(&c->ev_t0));
+  VB_CUDA(cudaEventCreate(&c->ev_t1));
+  *out = c;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_destroy(vbmc_b200_ctx* c) {
+  if (!c) return VBMC_B200_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  vb::comm_destroy(c);
+  vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
+                        &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
+                        &c->ent_partial, &c->glj_out, &c->flush};
+  for (auto* b : bufs) b->release();
+  if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
+  if (c->out_pinned) cudaFreeHost(c->out_pinned);
+  for (auto ev : c->prof_events) cudaEventDestroy(ev);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaEventDestroy(c->ev_t0);
+  cudaEventDestroy(c->ev_t1);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream2);
+  delete c;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_sync(vbmc_b200_ctx* c) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_CUDA(cudaStreamSynchronize(c->stream2));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_launch_count(vbmc_b200_ctx* c, long long* count) {
+  if (!c || !count) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  *count = c->launches;
+  return VBMC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GP
+// ---------------------------------------------------------------------------------------------
+static int gp_check_desc(const vbmc_b200_gp_desc* g, int* Ncov, int* Nnoise, int* Nmean) {
+  if (!g || !g->X || !g->hyp) VB_FAIL(VBMC_B200_EINVAL, "gp descriptor: X and hyp are required");
+  if (g->N <= 0 || g->D <= 0 || g->S <= 0) VB_FAIL(VBMC_B200_EINVAL, "gp descriptor: N, D, S must be positive");
+  if (g->covfun != 1)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:UnsupportedCovFun: only covfun=1 (SE-ARD) is in scope (got %d)", g->covfun);
+  *Ncov = g->D + 1;  // gplite_covfun('info'): SE-ARD
+  int nn = 0;
+  if (g->noisefun[0] == 1) nn += 1;
+  if (g->noisefun[1] == 2) nn += 1;
+  if (g->noisefun[2] == 1) nn += 2;
+  *Nnoise = nn;
+  switch (g->meanfun) {
+    case 0: *Nmean = 0; break;
+    case 1: *Nmean = 1; break;
+    case 4: *Nmean = 1 + 2 * g->D; break;
+    default:
+      VB_FAIL(VBMC_B200_EREFERENCE,
+              "gplogjoint:UnsupportedMeanFun: this build supports meanfun 0 (zero), 1 (const), 4 (negquad); got %d",
+              g->meanfun);
+  }
+  if (g->Nhyp != *Ncov + *Nnoise + *Nmean)
+    VB_FAIL(VBMC_B200_EREFERENCE,
+            "gplite_post:dimmismatch: Number of hyperparameters mismatched with GP model specification (Nhyp=%d, expected %d).",
+            g->Nhyp, *Ncov + *Nnoise + *Nmean);
+  return VBMC_B200_OK;
+}
+
+// derived per-sample constants used by gplogjoint (gplogjoint.m:99-122)
+static int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1) {
+  const int D = g->D, S = g->S;
+  std::vector<double> h(static_cast<size_t>(S) * (3 * D + 3));
+  double* ell = h.data();
+  double* lnc = ell + S * D;
+  double* m0 = lnc + S;
+  double* xm = m0 + S;
+  double* iom2 = xm + S * D;
+  double* sn2eff = iom2 + S * D;
+  for (int s = 0; s < S; ++s) {
+    const double* hyp = g->hyp + static_cast<size_t>(s) * g->Nhyp;
+    double sum_lnell = 0.0;
+    for (int d = 0; d < D; ++d) {
+      ell[s * D + d] = exp(hyp[d]);
+      sum_lnell += hyp[d];
+    }
+    lnc[s] = 2.0 * hyp[D] + sum_lnell;  // ln_sf2 + sum_lnell
+    m0[s] = g->meanfun > 0 ? hyp[Ncov + Nnoise] : 0.0;
+    for (int d = 0; d < D; ++d) {
+      if (g->meanfun == 4) {
+        xm[s * D + d] = hyp[Ncov + Nnoise + 1 + d];
+        const double om = exp(hyp[Ncov + Nnoise + D + 1 + d]);
+        iom2[s * D + d] = 1.0 / (om * om);
+      } else {
+        xm[s * D + d] = 0.0;
+        iom2[s * D + d] = 0.0;
+      }
+    }
+    sn2eff[s] = sW1 ? 1.0 / (sW1[s] * sW1[s]) : 1.0;
+  }
+  VB_TRY(c->gpDerived.reserve(h.size() * sizeof(double)));
+  VB_CUDA(cudaMemcpyAsync(c->gpDerived.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  double* base = c->gpDerived.d();
+  c->gp.ell = base;
+  c->gp.lnc = base + S * D;
+  c->gp.m0 = base + S * D + S;
+  c->gp.xm = base + S * D + 2 * S;
+  c->gp.iom2 = base + 2 * S * D + 2 * S;
+  c->gp.sn2eff = base + 3 * S * D + 2 * S;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const double* alpha, const double* sW1,
+                        const int* Lchol, const double* L) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  int Ncov, Nnoise, Nmean;
+  VB_TRY(gp_check_desc(g, &Ncov, &Nnoise, &Nmean));
+  if (!alpha) VB_FAIL(VBMC_B200_EINVAL, "gp_attach: alpha is required");
+  VB_CUDA(cudaSetDevice(c->device));
+  c->gp_ready = false;
+  const size_t N = g->N, D = g->D, S = g->S;
+  VB_TRY(c->gpX.reserve(N * D * sizeof(double)));
+  VB_TRY(c->gpHyp.reserve(S * g->Nhyp * sizeof(double)));
+  VB_TRY(c->gpAlpha.reserve(S * N * sizeof(double)));
+  VB_CUDA(cudaMemcpyAsync(c->gpX.p, g->X, N * D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaMemcpyAsync(c->gpHyp.p, g->hyp, S * g->Nhyp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaMemcpyAsync(c->gpAlpha.p, alpha, S * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->gpHasL = false;
+  if (L) {
+    VB_TRY(c->gpL.reserve(S * N * N * sizeof(double)));
+    VB_CUDA(cudaMemcpyAsync(c->gpL.p, L, S * N * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->gpHasL = true;
+  }
+  c->gpLchol.assign(S, 1);
+  if (Lchol)
+    for (size_t s = 0; s < S; ++s) c->gpLchol[s] = Lchol[s];
+  c->gp.N = g->N; c->gp.D = g->D; c->gp.S = g->S; c->gp.Nhyp = g->Nhyp;
+  c->gp.Ncov = Ncov; c->gp.Nnoise = Nnoise; c->gp.Nmean = Nmean; c->gp.meanfun = g->meanfun;
+  c->gp.X = c->gpX.d();
+  c->gp.hyp = c->gpHyp.d();
+  c->gp.alpha = c->gpAlpha.d();
+  VB_TRY(gp_upload_derived(c, g, Ncov, Nnoise, sW1));
+  c->gp_ready = true;
+  return VBMC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VP / thetabnd
+// ---------------------------------------------------------------------------------------------
+int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
+  if (!c || !v) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  if (v->D <= 0 || v->K <= 0 || !v->mu || !v->sigma || !v->lambda || !v->w)
+    VB_FAIL(VBMC_B200_EINVAL, "vp descriptor: D, K > 0 and mu, sigma, lambda, w are required");
+  VB_CUDA(cudaSetDevice(c->device));
+  const int D = v->D, K = v->K;
+  c->vp_ready = false;
+  c->D = D; c->K = K;
+  c->opt[0] = v->optimize_mu != 0; c->opt[1] = v->optimize_sigma != 0;
+  c->opt[2] = v->optimize_lambda != 0; c->opt[3] = v->optimize_weights != 0;
+  c->ntheta = (c->opt[0] ? D * K : 0) + (c->opt[1] ? K : 0) + (c->opt[2] ? D : 0) + (c->opt[3] ? K : 0);
+  // base: mu[DK] sigma[K] lambda[D] w[K] eta[K] ; cur: mu[DK] sigma[K] lambda[D] w[K] eta[K] lnsigma[K]
+  //       lnlambda[D] delta[D] ck[K] ak[K] cn[K+1]
+  const size_t nbase = static_cast<size_t>(D) * K + 3 * K + D;
+  std::vector<double> h(nbase);
+  double* p = h.data();
+  memcpy(p, v->mu, sizeof(double) * D * K); p += D * K;
+  memcpy(p, v->sigma, sizeof(double) * K); p += K;
+  memcpy(p, v->lambda, sizeof(double) * D); p += D;
+  memcpy(p, v->w, sizeof(double) * K); p += K;
+  for (int k = 0; k < K; ++k) p[k] = v->eta ? v->eta[k] : log(v->w[k]);
+  VB_TRY(c->vpBase.reserve(nbase * sizeof(double)));
+  VB_CUDA(cudaMemcpyAsync(c->vpBase.p, h.data(), nbase * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  double* b = c->vpBase.d();
+  c->base_mu = b; b += D * K;
+  c->base_sigma = b; b += K;
+  c->base_lambda = b; b += D;
+  c->base_w = b; b += K;
+  c->base_eta = b;
+  const size_t ncur = static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K;
+  VB_TRY(c->vpCur.reserve(ncur * sizeof(double)));
+  double* q = c->vpCur.d();
+  c->vp.D = D; c->vp.K = K;
+  c->vp.mu = q; q += D * K;
+  c->vp.sigma = q; q += K;
+  c->vp.lambda = q; q += D;
+  c->vp.w = q; q += K;
+  c->vp.eta = q; q += K;
+  c->vp.lnsigma = q; q += K;
+  c->vp.lnlambda = q; q += D;
+  c->vp.delta = q; q += D;
+  c->vp.ck = q; q += K;
+  c->vp.ak = q; q += K;
+  c->vp.cn = q; q += K + 1;
+  std::vector<double> dl(D, 0.0);
+  if (v->delta)
+    for (int d = 0; d < D; ++d) dl[d] = v->delta[d];
+  VB_CUDA(cudaMemcpyAsync(c->vp.delta, dl.data(), sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  c->vp_ready = true;
+  c->eps_ready = c->eps_ready && c->epsD == D && c->epsK == K;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_thetabnd_set(vbmc_b200_ctx* c, int n, const double* lb, const double* ub, double TolCon,
+                           double WeightThreshold, double WeightPenalty) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  if (n <= 0) {
+    c->nbnd = 0;
+    return VBMC_B200_OK;
+  }
+  if (!lb || !ub) VB_FAIL(VBMC_B200_EINVAL, "thetabnd_set: lb/ub required");
+  VB_TRY(c->bnd.reserve(sizeof(double) * 2 * n));
+  VB_CUDA(cudaMemcpyAsync(c->bnd.d(), lb, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaMemcpyAsync(c->bnd.d() + n, ub, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  c->nbnd = n;
+  c->TolCon = TolCon;
+  c->WeightThreshold = WeightThreshold;
+  c->WeightPenalty = WeightPenalty;
+  return VBMC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// eps
+// ---------------------------------------------------------------------------------------------
+static int eps_reserve(vbmc_b200_ctx* c, int D, int K, int Ns) {
+  if (D <= 0 || K <= 0 || Ns <= 0 || (Ns & 1)) VB_FAIL(VBMC_B200_EINVAL, "eps: D, K > 0 and Ns even > 0 required");
+  VB_TRY(c->eps.reserve(sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2)));
+  c->epsD = D; c->epsK = K; c->epsNs = Ns;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_eps_upload(vbmc_b200_ctx* c, int D, int K, int Ns, const double* eps) {
+  if (!c || !eps) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  VB_CUDA(cudaSetDevice(c->device));
+  Ns = (Ns + 1) / 2 * 2;
+  VB_TRY(eps_reserve(c, D, K, Ns));
+  VB_CUDA(cudaMemcpyAsync(c->eps.p, eps, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2), cudaMemcpyHostToDevice,
+                          c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  c->eps_ready = true;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_eps_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream, double* eps_out) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  Ns = (Ns + 1) / 2 * 2;
+  VB_TRY(eps_reserve(c, D, K, Ns));
+  if (c->nranks > 1 && eps_out)  // a read-back must see every element, not only this rank's shard
+    VB_CUDA(cudaMemsetAsync(c->eps.p, 0, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2), c->stream));
+  VB_TRY(launch_philox(c, D, K, Ns, seed, stream, c->stream));
+  if (eps_out)
+    VB_CUDA(cudaMemcpyAsync(eps_out, c->eps.p, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2),
+                            cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  c->eps_ready = true;
+  return VBMC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one step
+// ---------------------------------------------------------------------------------------------
+static int prepare_eps(vbmc_b200_ctx* c, int Ns, int mode, const double* eps, uint64_t seed, uint64_t stream_id) {
+  const int D = c->D, K = c->K;
+  const size_t n = static_cast<size_t>(D) * K * (Ns / 2);
+  switch (mode) {
+    case VBMC_B200_EPS_HOST:
+      if (!eps) VB_FAIL(VBMC_B200_EINVAL, "eps_mode EPS_HOST requires the eps pointer");
+      VB_TRY(eps_reserve(c, D, K, Ns));
+      VB_CUDA(cudaMemcpyAsync(c->eps.p, eps, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+      c->eps_ready = true;
+      return VBMC_B200_OK;
+    case VBMC_B200_EPS_RESIDENT:
+      if (!c->eps_ready || c->epsD != D || c->epsK != K || c->epsNs != Ns)
+        VB_FAIL(VBMC_B200_ESTATE, "eps_mode EPS_RESIDENT: no resident draws of shape D=%d K=%d Ns=%d (have %d %d %d)", D,
+                K, Ns, c->epsD, c->epsK, c->epsNs);
+      return VBMC_B200_OK;
+    case VBMC_B200_EPS_PHILOX:
+      VB_TRY(eps_reserve(c, D, K, Ns));
+      VB_TRY(launch_philox(c, D, K, Ns, seed, stream_id, c->stream));
+      c->eps_ready = true;
+      return VBMC_B200_OK;
+  }
+  VB_FAIL(VBMC_B200_EINVAL, "unknown eps_mode %d", mode);
+}
+
+// enqueue the device part of one evaluation; `what` selects negelcbo / entmc / gplogjoint
+static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int jacobian, int what, bool have_theta) {
+  const bool doH = what != FIN_GPLOGJOINT, doG = what != FIN_ENTMC;
+  RLayout rl;
+  rl.init(c->D, c->K, (doG || c->gp_ready) ? c->gp.S : 0);
+  if (what == FIN_ENTMC) rl.init(c->D, c->K, 0);
+  VB_TRY(c->R_dev.reserve(sizeof(double) * rl.total));
+  VB_CUDA(cudaMemsetAsync(c->R_dev.p, 0, sizeof(double) * rl.total, c->stream));
+  VB_TRY(launch_vp_unpack(c, have_theta));
+  if (doG) {
+    VB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    VB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    VB_TRY(launch_gplogjoint(c, gmask != 0, c->stream2));
+    VB_TRY(launch_glj_reduce(c, c->stream2));
+    VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+  }
+  if (doH) {
+    int need = 0;
+    if (gmask & 1) need |= NEED_MU;
+    if (gmask & (2 | 4)) need |= NEED_E;
+    if (gmask & 8) need |= NEED_W;
+    VB_TRY(launch_entmc(c, Ns, need, c->stream));
+    VB_TRY(launch_entmc_reduce(c, Ns, rl.S, c->stream));
+  }
+  if (doG) VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if (c->nranks > 1) VB_TRY(allreduce_R(c, rl.total, c->stream));
+  VB_TRY(launch_finalize(c, Ns, gmask, use_bnd, jacobian, what, c->stream));
+  return VBMC_B200_OK;
+}
+
+static int fetch_out(vbmc_b200_ctx* c, int nout_theta, int S) {
+  OutLayout ol;
+  ol.init(nout_theta, S, c->K);
+  VB_TRY(ensure_pinned(&c->out_pinned, &c->out_pinned_cap, sizeof(double) * ol.total));
+  VB_CUDA(cudaMemcpyAsync(c->out_pinned, c->out_dev.p, sizeof(double) * ol.total, cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBMC_B200_OK;
+}
+
+static int negelcbo_validate(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, double* beta, int* Ns, int* gmask) {
+  if (!c || !a) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  if (!c->vp_ready) VB_FAIL(VBMC_B200_ESTATE, "negelcbo: call vbmc_b200_vp_set first");
+  if (!c->gp_ready) VB_FAIL(VBMC_B200_ESTATE, "negelcbo: call vbmc_b200_gp_attach or vbmc_b200_gp_post first");
+  if (c->gp.D != c->D) VB_FAIL(VBMC_B200_EINVAL, "negelcbo: vp.D=%d but gp.D=%d", c->D, c->gp.D);
+  if (a->ntheta != c->ntheta)
+    VB_FAIL(VBMC_B200_EINVAL, "negelcbo: numel(theta)=%d but the optimize_* flags imply %d", a->ntheta, c->ntheta);
+  if (!a->theta) VB_FAIL(VBMC_B200_EINVAL, "negelcbo: theta is required");
+  double b = a->beta;
+  if (!isfinite(b)) b = 0.0;  // negelcbo_vbmc.m:15
+  *beta = b;
+  if (a->compute_grad && b != 0.0 && a->compute_var != 2)
+    VB_FAIL(VBMC_B200_EREFERENCE,
+            "negelcbo_vbmc:vargrad: Computation of the gradient of ELBO with full variance not supported.");
+  if (a->separate_K && a->compute_grad)
+    VB_FAIL(VBMC_B200_EREFERENCE,
+            "negelcbo_vbmc:separateK: Computing the gradient of variational parameters and requesting per-component "
+            "results at the same time.");
+  if (c->opt[3] && !c->opt[0] && !c->opt[1] && !c->opt[2])
+    VB_FAIL(VBMC_B200_EUNSUPPORTED,
+            "vbmc_b200:OutOfScope: weights-only optimisation (gplogjoint_weights.m) is outside this build (SURVEY.md 2 #5)");
+  if (a->Ns <= 0)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED,
+            "vbmc_b200:OutOfScope: Ns == 0 selects entlb_vbmc (deterministic entropy bound), outside this build");
+  if (a->compute_var != 0 || b != 0.0)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED,
+            "vbmc_b200:NotYet: compute_var/beta != 0 (gplogjoint.m:273-339 variance) is not built in this round");
+  if (a->use_thetabnd && c->nbnd > 0) {
+    const int expect = (c->opt[0] ? c->D * c->K : 0) + ((c->opt[1] || c->opt[2]) ? c->D * c->K : 0) + (c->opt[3] ? c->K : 0);
+    if (expect != c->nbnd)
+      VB_FAIL(VBMC_B200_EINVAL, "negelcbo: thetabnd has %d entries, expected %d (vpbounds.m:34-46)", c->nbnd, expect);
+  }
+  *Ns = (a->Ns + 1) / 2 * 2;  // entmc_vbmc.m:45
+  int m = 0;
+  if (a->compute_grad)
+    for (int i = 0; i < 4; ++i)
+      if (c->opt[i]) m |= 1 << i;
+  *gmask = m;
+  return VBMC_B200_OK;
+}
+
+static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int nth) {
+  OutLayout ol;
+  ol.init(nth, c->gp.S, c->K);
+  const double* o = c->out_pinned;
+  if (a->F) *a->F = o[ol.oF];
+  if (a->G) *a->G = o[ol.oG];
+  if (a->H) *a->H = o[ol.oH];
+  if (a->varF) *a->varF = 0.0;
+  if (a->varGss) *a->varGss = 0.0;
+  if (a->varG) *a->varG = 0.0;
+  if (a->varH) *a->varH = 0.0;
+  if (a->dF && nth) memcpy(a->dF, o + ol.oDF, sizeof(double) * nth);
+  if (a->dH && nth) memcpy(a->dH, o + ol.oDH, sizeof(double) * nth);
+  if (a->I_sk) {  // S x K column-major
+    const int S = c->gp.S, K = c->K;
+    for (int s = 0; s < S; ++s)
+      for (int k = 0; k < K; ++k) a->I_sk[s + static_cast<size_t>(k) * S] = o[ol.oIsk + s * K + k];
+  }
+}
+
+int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
+  double beta;
+  int Ns, gmask;
+  VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_TRY(c->theta_dev.reserve(sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
+  VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
+  memcpy(c->theta_pinned, a->theta, sizeof(double) * c->ntheta);
+  VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * c->ntheta, cudaMemcpyHostToDevice, c->stream));
+  VB_TRY(prepare_eps(c, Ns, a->eps_mode, a->eps, a->seed, a->stream));
+  VB_TRY(enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true));
+  const int nth = grad_mask_len(c, gmask);
+  VB_TRY(fetch_out(c, nth, c->gp.S));
+  scatter_negelcbo(c, a, nth);
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_negelcbo_resident_loop(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int steps, float* ms_total) {
+  double beta;
+  int Ns, gmask;
+  VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
+  if (steps <= 0 || !ms_total) VB_FAIL(VBMC_B200_EINVAL, "resident_loop: steps > 0 and ms_total required");
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_TRY(c->theta_dev.reserve(sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
+  VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, a->theta, sizeof(double) * c->ntheta, cudaMemcpyHostToDevice, c->stream));
+  if (a->eps_mode == VBMC_B200_EPS_HOST) {
+    VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_HOST, a->eps, 0, 0));
+  }
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  VB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+  for (int i = 0; i < steps; ++i) {
+    if (a->eps_mode == VBMC_B200_EPS_PHILOX)
+      VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, a->seed, a->stream + i));
+    else
+      VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_RESIDENT, nullptr, 0, 0));
+    VB_TRY(enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true));
+  }
+  VB_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+  VB_CUDA(cudaEventSynchronize(c->ev_t1));
+  VB_CUDA(cudaEventElapsedTime(ms_total, c->ev_t0, c->ev_t1));
+  const int nth = grad_mask_len(c, gmask);
+  VB_TRY(fetch_out(c, nth, c->gp.S));
+  scatter_negelcbo(c, a, nth);
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_entmc(vbmc_b200_ctx* c, int Ns, const int grad_flags[4], int jacobian_flag, int eps_mode, const double* eps,
+                    uint64_t seed, uint64_t stream, double* H, double* dH) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  if (!c->vp_ready) VB_FAIL(VBMC_B200_ESTATE, "entmc: call vbmc_b200_vp_set first");
+  if (Ns <= 0) VB_FAIL(VBMC_B200_EINVAL, "entmc: Ns must be positive");
+  VB_CUDA(cudaSetDevice(c->device));
+  Ns = (Ns + 1) / 2 * 2;
+  int gmask = 0;
+  if (grad_flags && dH)
+    for (int i = 0; i < 4; ++i)
+      if (grad_flags[i]) gmask |= 1 << i;
+  VB_TRY(prepare_eps(c, Ns, eps_mode, eps, seed, stream));
+  VB_TRY(enqueue_step(c, Ns, gmask, 0, jacobian_flag, FIN_ENTMC, false));
+  const int nth = grad_mask_len(c, gmask);
+  VB_TRY(fetch_out(c, nth, 0));
+  OutLayout ol;
+  ol.init(nth, 0, c->K);
+  if (H) *H = c->out_pinned[ol.oH];
+  if (dH && nth) memcpy(dH, c->out_pinned + ol.oDH, sizeof(double) * nth);
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_gplogjoint(vbmc_b200_ctx* c, const int grad_flags[4], int avg_flag, int jacobian_flag, int compute_var,
+                         double* F, double* dF, double* varF, double* dvarF, double* varss, double* I_sk, double* J_sjk) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  if (!c->vp_ready) VB_FAIL(VBMC_B200_ESTATE, "gplogjoint: call vbmc_b200_vp_set first");
+  if (!c->gp_ready) VB_FAIL(VBMC_B200_ESTATE, "gplogjoint: call vbmc_b200_gp_attach or vbmc_b200_gp_post first");
+  if (c->gp.D != c->D) VB_FAIL(VBMC_B200_EINVAL, "gplogjoint: vp.D=%d but gp.D=%d", c->D, c->gp.D);
+  if (dvarF && compute_var && compute_var != 2)
+    VB_FAIL(VBMC_B200_EREFERENCE,
+            "gplogjoint:FullVarianceGradient: Computation of gradient of log joint variance is currently available only "
+            "for diagonal approximation of the variance.");
+  if (compute_var != 0 || varF || dvarF || J_sjk)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: gplogjoint variance (gplogjoint.m:273-339) is not built in this round");
+  if (!avg_flag && c->gp.S > 1)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:OutOfScope: avg_flag=0 with several hyper-parameter samples");
+  VB_CUDA(cudaSetDevice(c->device));
+  int gmask = 0;
+  if (grad_flags && dF)
+    for (int i = 0; i < 4; ++i)
+      if (grad_flags[i]) gmask |= 1 << i;
+  VB_TRY(enqueue_step(c, 2, gmask, 0, jacobian_flag, FIN_GPLOGJOINT, false));
+  const int nth = grad_mask_len(c, gmask);
+  VB_TRY(fetch_out(c, nth, c->gp.S));
+  OutLayout ol;
+  ol.init(nth, c->gp.S, c->K);
+  const double* o = c->out_pinned;
+  if (F) *F = o[ol.oG];
+  if (dF && nth) memcpy(dF, o + ol.oDG, sizeof(double) * nth);
+  if (varss) *varss = 0.0;
+  if (I_sk) {
+    const int S = c->gp.S, K = c->K;
+    for (int s = 0; s < S; ++s)
+      for (int k = 0; k < K; ++k) I_sk[s + static_cast<size_t>(k) * S] = o[ol.oIsk + s * K + k];
+  }
+  return VBMC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// profiling hooks
+// ---------------------------------------------------------------------------------------------
+int vbmc_b200_profile_enable(vbmc_b200_ctx* c, int on) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  if (!on && c->profiling) VB_TRY(profile_collect(c));
+  c->profiling = on != 0;
+  return VBMC_B200_OK;
+}
+int vbmc_b200_profile_get(vbmc_b200_ctx* c, const char* name, double* ms_sum, long long* launches) {
+  if (!c || !name) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_TRY(profile_collect(c));
+  auto it = c->prof.find(name);
+  if (ms_sum) *ms_sum = it == c->prof.end() ? 0.0 : it->second.ms;
+  if (launches) *launches = it == c->prof.end() ? 0 : it->second.n;
+  return VBMC_B200_OK;
+}
+int vbmc_b200_profile_reset(vbmc_b200_ctx* c) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_TRY(profile_collect(c));
+  c->prof.clear();
+  return VBMC_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// Shared declarations of libvbmc_b200 (sm_100a only).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vbmc_b200.h"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define VB_FAIL(code, ...)      \
+  do {                          \
+    vb::set_error(__VA_ARGS__); \
+    return (code);              \
+  } while (0)
+#define VB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      vb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                    cudaGetErrorString(_e));                                               \
+      return VBMC_B200_ECUDA;                                                              \
+    }                                                                                      \
+  } while (0)
+#define VB_TRY(expr)                     \
+  do {                                   \
+    int _rc = (expr);                    \
+    if (_rc != VBMC_B200_OK) return _rc; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// growable device buffer of doubles / bytes
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return VBMC_B200_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return VBMC_B200_ECUDA;
+    }
+    cap = bytes;
+    return VBMC_B200_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  double* d() const { return static_cast<double*>(p); }
+  int* i() const { return static_cast<int*>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// device-side views passed to kernels
+// ------------------------------------------------------------------------------------------------
+struct VpDev {  // unpacked variational posterior (filled by vp_unpack_kernel each step)
+  int D, K;
+  double* mu;        // [K][D]  (== MATLAB D x K column-major)
+  double* sigma;     // [K]
+  double* lambda;    // [D]
+  double* w;         // [K]
+  double* eta;       // [K]
+  double* lnsigma;   // [K]
+  double* lnlambda;  // [D]
+  double* delta;     // [D] (zeros when vp.delta empty)
+  double* ck;        // [K]  w_k*nf/sigma_k^D      (entmc_vbmc.m:40,63)
+  double* ak;        // [K]  ck_k/sigma_k
+  double* cn;        // [K+1] nf/sigma_k^D, cn[K] = nf
+};
+
+struct GpDev {  // attached GP posterior
+  int N, D, S, Nhyp, Ncov, Nnoise, Nmean, meanfun;
+  const double* X;      // [D][N] (N x D column-major)
+  const double* hyp;    // [S][Nhyp]
+  const double* alpha;  // [S][N]
+  const double* ell;    // [S][D]  exp(hyp(1:D))
+  const double* lnc;    // [S]     2*hyp(D+1) + sum(hyp(1:D))
+  const double* m0;     // [S]
+  const double* xm;     // [S][D]
+  const double* iom2;   // [S][D]  1/omega^2
+  const double* sn2eff; // [S]     1/sW(1)^2
+};
+
+// partial-sum vector R that is all-reduced across ranks
+struct RLayout {
+  int D, K, S;
+  int oHs, oM, oE, oWc, oI, oGmu, oGsig, oGlam, total;
+  __host__ __device__ void init(int D_, int K_, int S_) {
+    D = D_; K = K_; S = S_;
+    oHs = 0;
+    oM = oHs + K;
+    oE = oM + K * D;
+    oWc = oE + K * D;
+    oI = oWc + K * K;  // per-source column sums W_jl (weighted by w_j in finalize)
+    oGmu = oI + S * K;
+    oGsig = oGmu + K * D;
+    oGlam = oGsig + K;
+    total = oGlam + D;
+  }
+};
+
+// output block written by finalize_kernel (device), copied to the host in one memcpy
+struct OutLayout {
+  int ntheta, S, K;
+  int oF, oG, oH, oVarF, oVarGss, oVarG, oVarH, oDF, oDH, oDG, oIsk, total;
+  __host__ __device__ void init(int ntheta_, int S_, int K_) {
+    ntheta = ntheta_; S = S_; K = K_;
+    oF = 0; oG = 1; oH = 2; oVarF = 3; oVarGss = 4; oVarG = 5; oVarH = 6;
+    oDF = 8;
+    oDH = oDF + ntheta;
+    oDG = oDH + ntheta;
+    oIsk = oDG + ntheta;
+    total = oIsk + S * K;
+  }
+};
+
+struct Prof {
+  double ms = 0;
+  long long n = 0;
+};
+
+}  // namespace vb
+
+// ------------------------------------------------------------------------------------------------
+// the context
+// ------------------------------------------------------------------------------------------------
+struct ncclComm;
+struct vbmc_b200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // gplogjoint branch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  long long launches = 0;
+
+  // multi-GPU
+  int nranks = 1, rank = 0;
+  ncclComm* comm = nullptr;
+
+  // GP
+  bool gp_ready = false;
+  vb::GpDev gp{};
+  vb::DevBuf gpX, gpHyp, gpAlpha, gpDerived, gpL, gpY, gpS2, gpWork;
+  std::vector<int> gpLchol;
+  std::vector<double> gpSn2mult;
+  bool gpHasL = false;
+
+  // VP
+  bool vp_ready = false;
+  int D = 0, K = 0;
+  int opt[4] = {0, 0, 0, 0};
+  int ntheta = 0;
+  vb::DevBuf vpBase;  // base vp as set by vp_set: mu, sigma, lambda, w, eta, delta
+  vb::DevBuf vpCur;   // unpacked vp of the current step
+  vb::VpDev vp{};
+  double* base_mu = nullptr; double* base_sigma = nullptr; double* base_lambda = nullptr;
+  double* base_w = nullptr; double* base_eta = nullptr;
+
+  // thetabnd
+  int nbnd = 0;
+  vb::DevBuf bnd;  // lb[n], ub[n]
+  double TolCon = 0, WeightThreshold = 0, WeightPenalty = 0;
+
+  // eps
+  vb::DevBuf eps;
+  int epsD = 0, epsK = 0, epsNs = 0;
+  bool eps_ready = false;
+
+  // step buffers
+  vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out;
+  double* theta_pinned = nullptr;
+  double* out_pinned = nullptr;
+  size_t theta_pinned_cap = 0, out_pinned_cap = 0;
+  vb::DevBuf flush;  // L2 flush scratch
+
+  // profiling
+  bool profiling = false;
+  std::map<std::string, vb::Prof> prof;
+  std::vector<cudaEvent_t> prof_events;  // pending (start, stop) pairs
+  std::vector<std::string> prof_names;   // kernel name of each pending pair
+};
+
+namespace vb {
+
+// launch bookkeeping: every kernel launch goes through KernelScope so that launches are counted
+// and (when profiling) bracketed by CUDA events on the launch stream.
+struct KernelScope {
+  vbmc_b200_ctx* c;
+  const char* name;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelScope(vbmc_b200_ctx* ctx, const char* nm, cudaStream_t s);
+  ~KernelScope();
+};
+int profile_collect(vbmc_b200_ctx* c);  // sync + fold pending event pairs into c->prof
+
+// ---- step pieces (each defined in its own .cu) ----
+int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);
+int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st);
+int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st);
+int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st);
+int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
+int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
+int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st);
+int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
+void comm_destroy(vbmc_b200_ctx* c);
+int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
+void shard_range(int total, int nranks, int rank, int* begin, int* end);
+
+enum { NEED_MU = 1, NEED_E = 2, NEED_W = 4 };
+enum { FIN_NEGELCBO = 0, FIN_ENTMC = 1, FIN_GPLOGJOINT = 2 };
+
+}  // namespace vb

@@ -1,0 +1,362 @@
+// Small single-CTA kernels around the two hot kernels of a negelcbo step:
+//   vp_unpack_kernel : theta -> vp.mu/sigma/lambda/eta/w          (misc/negelcbo_vbmc.m:32-48)
+//   finalize_kernel  : reduced sums R -> H,dH (ent/entmc_vbmc.m:67,82-125), G,dG
+//                      (misc/gplogjoint.m:352-413), soft-bound + weight penalties
+//                      (misc/vpbndloss.m:9-71, utils/softbndloss.m:9-28, negelcbo_vbmc.m:136-164),
+//                      F = -G - H + L, dF = -dG - dH + dL (negelcbo_vbmc.m:116-117).
+// O(DK) work; they exist so that a step needs no host round trip between kernels.
+#include "common.cuh"
+
+namespace vb {
+
+struct UnpackArgs {
+  int D, K, ntheta, have_theta;
+  int opt[4];
+  const double* theta;
+  const double *base_mu, *base_sigma, *base_lambda, *base_w, *base_eta;
+  VpDev vp;
+  double* cn;  // [K] nf/sigma_k^D ; cn[K] = nf
+};
+
+__global__ void vp_unpack_kernel(const UnpackArgs a) {
+  const int D = a.D, K = a.K, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double s_es, s_nf;
+  const bool ht = a.have_theta != 0;
+  int idx = 0;
+  const int o_mu = 0;
+  if (ht && a.opt[0]) idx += D * K;
+  const int o_sig = idx;
+  if (ht && a.opt[1]) idx += K;
+  const int o_lam = idx;
+  const int o_eta = a.ntheta - K;
+  for (int i = tid; i < D * K; i += nt) a.vp.mu[i] = (ht && a.opt[0]) ? a.theta[o_mu + i] : a.base_mu[i];
+  for (int k = tid; k < K; k += nt) {
+    if (ht && a.opt[1]) {
+      const double ls = a.theta[o_sig + k];
+      a.vp.lnsigma[k] = ls;
+      a.vp.sigma[k] = exp(ls);  // vp.sigma(1,:) = exp(theta(idx_start+(1:K)))  (:39-42)
+    } else {
+      a.vp.sigma[k] = a.base_sigma[k];
+      a.vp.lnsigma[k] = log(a.base_sigma[k]);
+    }
+    a.vp.eta[k] = (ht && a.opt[3]) ? a.theta[o_eta + k] : a.base_eta[k];
+  }
+  for (int d = tid; d < D; d += nt) {
+    if (ht && a.opt[2]) {
+      const double ll = a.theta[o_lam + d];
+      a.vp.lnlambda[d] = ll;
+      a.vp.lambda[d] = exp(ll);  // (:43)
+    } else {
+      a.vp.lambda[d] = a.base_lambda[d];
+      a.vp.lnlambda[d] = log(a.base_lambda[d]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double es = 0.0;
+    for (int k = 0; k < K; ++k) es += exp(a.vp.eta[k]);  // (:46-47) no max-shift, like the reference
+    s_es = es;
+    double pl = 1.0;
+    for (int d = 0; d < D; ++d) pl *= a.vp.lambda[d];
+    s_nf = 1.0 / pow(2.0 * 3.14159265358979323846, 0.5 * D) / pl;  // nf (entmc_vbmc.m:40)
+    a.cn[K] = s_nf;
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) {
+    const double w = (ht && a.opt[3]) ? exp(a.vp.eta[k]) / s_es : a.base_w[k];
+    a.vp.w[k] = w;
+    const double sg = a.vp.sigma[k];
+    const double cn = s_nf / pow(sg, static_cast<double>(D));  // nf/sigma(k)^D  (:63)
+    a.cn[k] = cn;
+    a.vp.ck[k] = w * cn;
+    a.vp.ak[k] = w * cn / sg;
+  }
+}
+
+struct FinArgs {
+  int D, K, S, Ns, ntheta_out;
+  int gf[4];       // which gradient blocks are produced
+  int jacobian;    // jacobian_flag
+  int what;        // FIN_*
+  int use_bnd, nbnd, opt[4];
+  double TolCon, WThresh, WPen;
+  const double* R;
+  const double* lb;
+  const double* ub;
+  const double* cn;  // [K+1]
+  VpDev vp;
+  double* out;
+};
+
+__device__ __forceinline__ double soft_pen(double x, double lb, double ub, double tol, double* dy) {
+  // utils/softbndloss.m:12-27
+  const double ell = (ub - lb) * tol;
+  double y = 0.0;
+  *dy = 0.0;
+  if (x < lb) {
+    const double t = (lb - x) / ell;
+    y = 0.5 * t * t;
+    *dy = (x - lb) / (ell * ell);
+  } else if (x > ub) {
+    const double t = (x - ub) / ell;
+    y = 0.5 * t * t;
+    *dy = (x - ub) / (ell * ell);
+  }
+  return y;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
+  extern __shared__ double sm[];
+  const int D = a.D, K = a.K, S = a.S, tid = threadIdx.x, nt = blockDim.x;
+  RLayout rl;
+  rl.init(D, K, S);
+  OutLayout ol;
+  ol.init(a.ntheta_out, S, K);
+  const double* R = a.R;
+  double* out = a.out;
+  double* wsm = sm;            // [K]   softmax(eta)
+  double* gHw = wsm + K;       // [K]   entropy w-grad (before J_w)
+  double* gGw = gHw + K;       // [K]   log-joint w-grad (before J_w)
+  double* gPw = gGw + K;       // [K]   weight-penalty w-grad (before J_w)
+  double* dls = gPw + K;       // [D*K] d(penalty)/d(lnscale)
+  double* part = dls + D * K;  // [256]
+  double* sc = part + 256;     // scalars: 0 es, 1 H, 2 G, 3 L, 4 Lw, 5 dotH, 6 dotG, 7 dotP
+  const bool doH = a.what != FIN_GPLOGJOINT, doG = a.what != FIN_ENTMC;
+  const double invNs = 1.0 / static_cast<double>(a.Ns > 0 ? a.Ns : 1);
+  const double invS = 1.0 / static_cast<double>(S > 0 ? S : 1);
+
+  // output offsets of the gradient blocks
+  int o_mu = 0, o_sig = 0, o_lam = 0, o_w = 0, n = 0;
+  o_mu = n; if (a.gf[0]) n += D * K;
+  o_sig = n; if (a.gf[1]) n += K;
+  o_lam = n; if (a.gf[2]) n += D;
+  o_w = n; if (a.gf[3]) n += K;
+
+  if (tid == 0) {
+    double es = 0.0;
+    for (int k = 0; k < K; ++k) es += exp(a.vp.eta[k]);
+    sc[0] = es;
+    sc[3] = 0.0;
+    sc[4] = 0.0;
+  }
+  for (int i = tid; i < 8; i += nt) out[i] = 0.0;
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) {
+    wsm[k] = exp(a.vp.eta[k]) / sc[0];
+    gPw[k] = 0.0;
+  }
+  for (int i = tid; i < 3 * a.ntheta_out; i += nt) out[ol.oDF + i] = 0.0;
+  __syncthreads();
+
+  // ------------------------------------------------------------------ entropy (entmc_vbmc.m)
+  if (doH) {
+    if (tid == 0) {
+      double H = 0.0;
+      for (int j = 0; j < K; ++j) H -= a.vp.w[j] * R[rl.oHs + j] * invNs;  // :67
+      sc[1] = H;
+      out[ol.oH] = H;
+    }
+    if (a.gf[0])
+      for (int i = tid; i < D * K; i += nt) {
+        const int j = i / D, d = i - j * D;
+        out[ol.oDH + o_mu + i] = a.vp.w[j] * R[rl.oM + i] * invNs / a.vp.lambda[d];  // :82
+      }
+    if (a.gf[1])
+      for (int j = tid; j < K; j += nt) {
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc += R[rl.oE + j * D + d];  // :87-88
+        double g = a.vp.w[j] * acc * invNs;
+        if (a.jacobian) g *= a.vp.sigma[j];  // :112-114
+        out[ol.oDH + o_sig + j] = g;
+      }
+    if (a.gf[2])
+      for (int d = tid; d < D; d += nt) {
+        double acc = 0.0;
+        for (int j = 0; j < K; ++j) acc += a.vp.w[j] * a.vp.sigma[j] * R[rl.oE + j * D + d];  // :93, :106-108
+        double g = acc * invNs;
+        if (!a.jacobian) g /= a.vp.lambda[d];  // :116-118
+        out[ol.oDH + o_lam + d] = g;
+      }
+    if (a.gf[3])
+      for (int l = tid; l < K; l += nt) {
+        double acc = 0.0;
+        for (int j = 0; j < K; ++j) acc += a.vp.w[j] * R[rl.oWc + j * K + l];
+        gHw[l] = -R[rl.oHs + l] * invNs - a.cn[l] * acc * invNs;  // :97, :100
+      }
+  }
+  // ------------------------------------------------------------------ expected log joint
+  if (doG) {
+    if (tid == 0) {
+      double G = 0.0;
+      for (int s = 0; s < S; ++s) {
+        double Fs = 0.0;
+        for (int k = 0; k < K; ++k) Fs += a.vp.w[k] * R[rl.oI + s * K + k];  // F(s) += w(k)*I_k  (:203)
+        G += Fs;
+      }
+      G *= invS;  // :398-399
+      sc[2] = G;
+      out[ol.oG] = G;
+    }
+    for (int i = tid; i < S * K; i += nt) out[ol.oIsk + i] = R[rl.oI + i];
+    if (a.gf[0])
+      for (int i = tid; i < D * K; i += nt) out[ol.oDG + o_mu + i] = a.vp.w[i / D] * R[rl.oGmu + i] * invS;
+    if (a.gf[1])
+      for (int k = tid; k < K; k += nt) {
+        double g = a.vp.w[k] * R[rl.oGsig + k] * invS;
+        if (a.jacobian) g *= a.vp.sigma[k];  // :357-359
+        out[ol.oDG + o_sig + k] = g;
+      }
+    if (a.gf[2])
+      for (int d = tid; d < D; d += nt) {
+        double g = R[rl.oGlam + d] * invS;
+        if (a.jacobian) g *= a.vp.lambda[d];  // :361-363
+        out[ol.oDG + o_lam + d] = g;
+      }
+    if (a.gf[3])
+      for (int k = tid; k < K; k += nt) {
+        double acc = 0.0;
+        for (int s = 0; s < S; ++s) acc += R[rl.oI + s * K + k];
+        gGw[k] = acc * invS;  // w_grad(k,s) = I_k  (:269-271), mean over s
+      }
+  }
+  // ------------------------------------------------------------------ penalties (FIN_NEGELCBO only)
+  const bool doP = a.what == FIN_NEGELCBO && a.use_bnd && a.nbnd > 0;
+  if (doP) {
+    // theta_ext = [mu(:); lnscale(:); eta(:)]   (vpbndloss.m:34-38)
+    int b_mu = 0, b_ls = 0, b_eta = 0, nb = 0;
+    b_mu = nb; if (a.opt[0]) nb += D * K;
+    b_ls = nb; if (a.opt[1] || a.opt[2]) nb += D * K;
+    b_eta = nb; if (a.opt[3]) nb += K;
+    double lacc = 0.0;
+    if (a.opt[0])
+      for (int i = tid; i < D * K; i += nt) {
+        double dy;
+        lacc += soft_pen(a.vp.mu[i], a.lb[b_mu + i], a.ub[b_mu + i], a.TolCon, &dy);
+        if (a.gf[0]) out[ol.oDF + o_mu + i] = dy;
+      }
+    if (a.opt[1] || a.opt[2])
+      for (int i = tid; i < D * K; i += nt) {
+        const int k = i / D, d = i - k * D;
+        double dy;
+        lacc += soft_pen(a.vp.lnsigma[k] + a.vp.lnlambda[d], a.lb[b_ls + i], a.ub[b_ls + i], a.TolCon, &dy);
+        dls[i] = dy;
+      }
+    if (a.opt[3])
+      for (int k = tid; k < K; k += nt) {
+        double dy;
+        lacc += soft_pen(a.vp.eta[k], a.lb[b_eta + k], a.ub[b_eta + k], a.TolCon, &dy);
+        if (a.gf[3]) out[ol.oDF + o_w + k] = dy;
+      }
+    part[tid] = lacc;
+    __syncthreads();
+    if (tid == 0) {
+      double L = 0.0;
+      for (int t = 0; t < nt; ++t) L += part[t];
+      sc[3] = L;
+      if (a.opt[3]) {  // negelcbo_vbmc.m:146-151
+        double Lw = 0.0;
+        for (int k = 0; k < K; ++k) Lw += (a.vp.w[k] < a.WThresh) ? a.vp.w[k] : a.WThresh;
+        sc[4] = Lw * a.WPen;
+      }
+    }
+    if (a.opt[1] && a.gf[1])
+      for (int k = tid; k < K; k += nt) {
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc += dls[k * D + d];  // dsigma = sum(dlnscale,1)  (:52)
+        out[ol.oDF + o_sig + k] = acc;
+      }
+    if (a.opt[2] && a.gf[2])
+      for (int d = tid; d < D; d += nt) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc += dls[k * D + d];  // dlambda = sum(dlnscale,2)  (:57)
+        out[ol.oDF + o_lam + d] = acc;
+      }
+    if (a.opt[3] && a.gf[3])
+      for (int k = tid; k < K; k += nt) gPw[k] = a.WPen * ((a.vp.w[k] < a.WThresh) ? 1.0 : 0.0);  // :155
+  }
+  __syncthreads();
+  // ------------------------------------------------------------------ softmax Jacobian J_w * g
+  // J_w = diag(e/es) - e e'/es^2  =>  (J_w g)_i = wsm_i (g_i - sum_l wsm_l g_l)   (gplogjoint.m:366-368)
+  if (a.gf[3]) {
+    if (tid == 0) {
+      double dh = 0.0, dg = 0.0, dp = 0.0;
+      for (int l = 0; l < K; ++l) {
+        if (doH) dh += wsm[l] * gHw[l];
+        if (doG) dg += wsm[l] * gGw[l];
+        dp += wsm[l] * gPw[l];
+      }
+      sc[5] = dh; sc[6] = dg; sc[7] = dp;
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) {
+      if (doH) out[ol.oDH + o_w + k] = a.jacobian ? wsm[k] * (gHw[k] - sc[5]) : gHw[k];
+      if (doG) out[ol.oDG + o_w + k] = a.jacobian ? wsm[k] * (gGw[k] - sc[6]) : gGw[k];
+      if (doP) out[ol.oDF + o_w + k] += wsm[k] * (gPw[k] - sc[7]);  // negelcbo_vbmc.m:156-160
+    }
+  }
+  __syncthreads();
+  // ------------------------------------------------------------------ F, dF
+  if (a.what == FIN_NEGELCBO) {
+    for (int i = tid; i < a.ntheta_out; i += nt)
+      out[ol.oDF + i] = -out[ol.oDG + i] - out[ol.oDH + i] + out[ol.oDF + i];  // dF = -dG - dH (+ dL)
+    if (tid == 0) out[ol.oF] = -sc[2] - sc[1] + sc[3] + sc[4];               // F = -G - H (+ L)
+  } else if (a.what == FIN_ENTMC) {
+    if (tid == 0) out[ol.oF] = sc[1];
+  } else {
+    if (tid == 0) out[ol.oF] = sc[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
+  UnpackArgs a;
+  a.D = c->D; a.K = c->K; a.ntheta = c->ntheta; a.have_theta = have_theta ? 1 : 0;
+  for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
+  a.theta = c->theta_dev.d();
+  a.base_mu = c->base_mu; a.base_sigma = c->base_sigma; a.base_lambda = c->base_lambda;
+  a.base_w = c->base_w; a.base_eta = c->base_eta;
+  a.vp = c->vp;
+  a.cn = c->vp.cn;
+  KernelScope ks(c, "vp_unpack", c->stream);
+  vp_unpack_kernel<<<1, 256, 0, c->stream>>>(a);
+  VB_CUDA(cudaGetLastError());
+  return VBMC_B200_OK;
+}
+
+int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st) {
+  // compute_grad: bit mask of gradient blocks (bit i = grad_flags(i+1))
+  FinArgs a;
+  a.D = c->D; a.K = c->K; a.S = c->gp_ready ? c->gp.S : 0; a.Ns = Ns;
+  if (what == FIN_ENTMC) a.S = 0;
+  int n = 0;
+  for (int i = 0; i < 4; ++i) a.gf[i] = (compute_grad >> i) & 1;
+  if (a.gf[0]) n += c->D * c->K;
+  if (a.gf[1]) n += c->K;
+  if (a.gf[2]) n += c->D;
+  if (a.gf[3]) n += c->K;
+  a.ntheta_out = n;
+  a.jacobian = jacobian;
+  a.what = what;
+  a.use_bnd = use_bnd;
+  a.nbnd = c->nbnd;
+  for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
+  a.TolCon = c->TolCon; a.WThresh = c->WeightThreshold; a.WPen = c->WeightPenalty;
+  a.R = c->R_dev.d();
+  a.lb = c->bnd.d();
+  a.ub = c->bnd.d() + c->nbnd;
+  a.cn = c->vp.cn;
+  a.vp = c->vp;
+  OutLayout ol;
+  ol.init(n, a.S, c->K);
+  VB_TRY(c->out_dev.reserve(sizeof(double) * ol.total));
+  a.out = c->out_dev.d();
+  const size_t smem = sizeof(double) * (4 * c->K + static_cast<size_t>(c->D) * c->K + 256 + 16);
+  if (smem > 48 * 1024)
+    VB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  KernelScope ks(c, "finalize", st);
+  finalize_kernel<<<1, 256, smem, st>>>(a);
+  VB_CUDA(cudaGetLastError());
+  return VBMC_B200_OK;
+}
+
+}  // namespace vb

@@ -1,0 +1,95 @@
+// Device-side source of the entropy draws: counter-based Philox4x32-10 (Salmon et al., SC'11)
+// + Box-Muller.  Replaces MATLAB's global randn stream (ent/entmc_vbmc.m:53), which cannot be
+// reproduced outside MATLAB; draws depend only on (seed, stream, element index), never on the
+// number of GPUs or on the sharding, so any rank can regenerate any slice.
+#include "common.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  // 53 random bits -> (0,1), never 0 or 1
+  const double x = static_cast<double>(hi >> 5) * 67108864.0 + static_cast<double>(lo >> 6);
+  return (x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct PhiloxArgs {
+  int D, K, half, pair_begin, pair_end;
+  uint64_t seed, stream;
+  double* eps;  // [K][half][D]
+};
+
+// one thread per Philox counter = two consecutive elements (2c, 2c+1) of the flat eps array
+__global__ void philox_normal_kernel(const PhiloxArgs a) {
+  const int j = blockIdx.y;
+  const long long e_begin = (static_cast<long long>(j) * a.half + a.pair_begin) * a.D;
+  const long long e_end = (static_cast<long long>(j) * a.half + a.pair_end) * a.D;
+  const long long c_begin = e_begin >> 1, c_end = (e_end + 1) >> 1;
+  for (long long c = c_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; c < c_end;
+       c += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 ctr = make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
+                                 static_cast<uint32_t>(a.stream), static_cast<uint32_t>(a.stream >> 32));
+    const uint2 key = make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+    const uint4 r = philox4x32_10(ctr, key);
+    const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    const long long e0 = 2 * c, e1 = 2 * c + 1;
+    if (e0 >= e_begin && e0 < e_end) a.eps[e0] = rad * cs;
+    if (e1 >= e_begin && e1 < e_end) a.eps[e1] = rad * sn;
+  }
+}
+
+// raw generator output for the known-answer test (tests/test_philox.py)
+__global__ void philox_raw_kernel(uint4 ctr, uint2 key, uint32_t* out) {
+  const uint4 r = philox4x32_10(ctr, key);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+  PhiloxArgs a;
+  a.D = D; a.K = K; a.half = Ns / 2;
+  shard_range(a.half, c->nranks, c->rank, &a.pair_begin, &a.pair_end);
+  a.seed = seed; a.stream = stream_id;
+  a.eps = c->eps.d();
+  if (a.pair_end <= a.pair_begin) return VBMC_B200_OK;
+  const long long per_comp = (static_cast<long long>(a.pair_end - a.pair_begin) * D + 2) / 2;
+  int bx = static_cast<int>((per_comp + 255) / 256);
+  const int cap = (c->num_sms * 8 + K - 1) / K;
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  dim3 grid(bx, K);
+  KernelScope ks(c, "philox", st);
+  philox_normal_kernel<<<grid, 256, 0, st>>>(a);
+  VB_CUDA(cudaGetLastError());
+  return VBMC_B200_OK;
+}
+
+}  // namespace vb
+
+extern "C" int vbmc_b200_philox_raw(vbmc_b200_ctx* ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  if (!ctx || !ctr || !key || !out) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_philox_raw: null argument");
+  VB_CUDA(cudaSetDevice(ctx->device));
+  uint32_t* d = nullptr;
+  VB_CUDA(cudaMalloc(&d, 16));
+  {
+    vb::KernelScope ks(ctx, "philox_raw", ctx->stream);
+    vb::philox_raw_kernel<<<1, 1, 0, ctx->stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+  }
+  VB_CUDA(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  VB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return VBMC_B200_OK;
+}
