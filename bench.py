@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — negelcbo_vbmc grad-steps/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # reference CPU path (oracle port, host cores)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one [F,dF] = negelcbo_vbmc(theta, 0, vp, gp, Ns, 1, 0, 0, thetabnd) evaluation with fresh
+entropy draws (the reference draws randn inside entmc_vbmc every call), i.e. one fminadam iteration's
+objective call (utils/fminadam.m:48).  Workload: synthetic config c3 (D=10, N=2000, K=50, Ns=32768 per
+component, S=20) at N=1, c4 (Ns=131072, strong-sharded MC axis) is available with --config c4.
+
+Timed quantities
+  value : steps/s with theta, GP posterior and draws resident in HBM; every step is timed with CUDA
+          events on the library's launch stream (L2 flushed between steps, outside the events);
+          max over ranks.
+  e2e   : steps/s through the public host API vbmc_b200.negelcbo_vbmc (host theta in, F/dF out,
+          Adam update of fminadam.m:51-60 on the host), wall clock between device syncs.
+  roofline : entmc kernel (dominant): algorithmic FLOPs / CUDA-event duration vs the FP64 FMA peak
+          measured live on the same device; HBM fraction of the algorithmic bytes reported beside it.
+  cpu_baseline : the oracle's C/OpenMP port on the host cores, bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=40)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--config", default=None, help="c2|c3|c4 (default: c3 at 1 GPU, c4 at >1)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scipy_gp_post(hyp, X, y, covfun, meanfun, noisefun, s2):
+    """Workload set-up only (NOT the timed path, NOT the oracle): GP posterior via LAPACK."""
+    import scipy.linalg as sla
+    N, D = X.shape
+    S = hyp.shape[1]
+    post = []
+    for s in range(S):
+        h = hyp[:, s]
+        ell, sf2, sn2 = np.exp(h[:D]), math.exp(2 * h[D]), math.exp(2 * h[D + 1])
+        Z = X / ell
+        sq = np.maximum(np.sum(Z * Z, 1)[:, None] + np.sum(Z * Z, 1)[None, :] - 2 * Z @ Z.T, 0)
+        Kmat = sf2 * np.exp(-0.5 * sq)
+        sn2v = sn2 + (s2 if s2 is not None else 0.0) * np.ones(N)
+        m = h[D + 2] - 0.5 * np.sum(((X - h[D + 3:2 * D + 3]) / np.exp(h[2 * D + 3:])) ** 2, axis=1)
+        sdiv = float(np.min(sn2v))
+        L = sla.cholesky(Kmat / sdiv + np.diag(sn2v / sdiv), lower=False)
+        alpha = sla.cho_solve((L, False), y - m) / sdiv
+        post.append({"hyp": h.copy(), "alpha": alpha, "sW": np.ones(N) / math.sqrt(sdiv), "L": None, "sn2_mult": 1.0, "Lchol": True})
+    return {"X": X, "y": y, "s2": s2, "covfun": 1, "meanfun": 4, "noisefun": noisefun, "Ncov": D + 1, "Nnoise": 1,
+            "Nmean": 2 * D + 1, "post": post}
+
+
+def algorithmic_counts(cfg):
+    """per grad-step."""
+    D, K, Ns, N, S = cfg["D"], cfg["K"], cfg["Ns"], cfg["N"], cfg["S"]
+    return {"entmc_triples": K * K * Ns, "entmc_flops": K * K * Ns * (5 * D + 12), "entmc_exp": K * K * Ns,
+            "entmc_bytes": K * (Ns // 2) * D * 8 + (1 + 2 * D + K) * K * 8,
+            "glj_flops": S * K * N * (7 * D + 10), "glj_bytes": (N * D + S * N) * 8}
+
+
+def adam_update(state, x, grad):
+    """utils/fminadam.m:51-60."""
+    state["it"] += 1
+    it = state["it"]
+    state["m"] = 0.9 * state["m"] + 0.1 * grad
+    state["v"] = 0.999 * state["v"] + 0.001 * grad * grad
+    mhat = state["m"] / (1 - 0.9 ** it)
+    vhat = state["v"] / (1 - 0.999 ** it)
+    step = 0.001 + (0.1 - 0.001) * math.exp(-it / 200.0)
+    return x - step * mhat / (np.sqrt(vhat) + math.sqrt(np.finfo(float).eps))
+
+
+def run_reference(args, cfg_name):
+    """Reference arm: the reference's CPU algorithm (oracle C/OpenMP port) on the host cores."""
+    from vbmc_b200 import workloads
+    from oracle import cport
+    cfg = dict(workloads.CONFIGS[cfg_name])
+    w = workloads.build(cfg, scipy_gp_post, with_eps=False)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cport.time_negelcbo(w, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "negelcbo_vbmc grad-steps/sec", "value": res["steps_per_s"], "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["steps_per_s"],
+            "higher_is_better": True, "scaling": "strong" if cfg_name == "c4" else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")}},
+            "cpu_baseline": {"value": res["steps_per_s"], "unit": "steps/s", "cores": res["threads"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name = args.config or ("c3" if max(world, args.gpus) == 1 else "c4")
+    if args.impl == "reference":
+        run_reference(args, cfg_name)
+        return
+
+    import vbmc_b200
+    from vbmc_b200 import _lib, workloads
+    import ctypes as C
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = vbmc_b200.Context(local)
+    if world > 1:
+        import torch
+        uid = torch.zeros(_lib.UNIQUE_ID_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(vbmc_b200.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+    cfg = dict(workloads.CONFIGS[cfg_name])
+    t_setup = time.time()
+    gp_fn = (lambda *a: vbmc_b200.gplite_post(*a, ctx=ctx, want_L=False)) if os.environ.get("VBMC_B200_BENCH_GPU_GP", "1") == "1" \
+        else scipy_gp_post
+    try:
+        w = workloads.build(cfg, gp_fn, with_eps=False)
+        gp_source = "vbmc_b200.gplite_post (GPU)"
+    except vbmc_b200.VbmcB200Error as e:
+        if "NotYet" not in str(e):
+            raise
+        w = workloads.build(cfg, scipy_gp_post, with_eps=False)
+        gp_source = "scipy LAPACK (set-up only)"
+    t_setup = time.time() - t_setup
+    vp, gp, theta0 = w["vp"], w["gp"], w["theta"]
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    Ns = cfg["Ns"]
+    counts = algorithmic_counts(cfg)
+
+    # ---- make everything resident, build the args struct for the device-resident loop ----
+    ctx.vp_set(vp)
+    ctx.gp_attach(gp)
+    ctx.thetabnd_set(tb)
+    theta = np.ascontiguousarray(theta0)
+    F = C.c_double()
+    dF = np.zeros_like(theta)
+    a = _lib.NegelcboArgs()
+    a.theta, a.ntheta, a.beta, a.Ns = _lib.dptr(theta), theta.size, 0.0, Ns
+    a.compute_grad, a.compute_var, a.separate_K, a.use_thetabnd = 1, 0, 0, 1
+    a.eps_mode, a.seed, a.stream = _lib.EPS_PHILOX, 20260925, 0
+    a.F, a.dF = C.pointer(F), _lib.dptr(dF)
+    ms = C.c_float()
+
+    def resident_step(i):
+        a.stream = i
+        _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
+        return ms.value
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        resident_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    t_wall0 = time.perf_counter()
+    tot_ms = 0.0
+    for i in range(args.steps):
+        ctx.flush_l2()               # outside the timed events
+        tot_ms += resident_step(args.warmup + i)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - l0 - args.steps  # minus the flush memsets? (memset is not a counted kernel)
+    launches = ctx.launch_count() - l0
+    if dist is not None:
+        import torch
+        t = torch.tensor([tot_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = float(t.item())
+    ms_per_step = tot_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    nprof = max(3, min(10, args.steps))
+    for i in range(nprof):
+        ctx.flush_l2()
+        resident_step(10_000 + i)
+    ctx.profile_enable(False)
+    prof = {}
+    for name in ("entmc", "gplogjoint", "philox", "reduce", "finalize", "vp_unpack"):
+        t_ms, n = ctx.profile_get(name)
+        prof[name] = {"ms_per_step": t_ms / nprof, "launches_per_step": n / nprof}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e through the public host API: host theta -> F, dF on the host + host Adam ----
+    def e2e_loop(nsteps, warm, host_eps=None):
+        x = theta0.copy()
+        st = {"it": 0, "m": np.zeros_like(x), "v": np.zeros_like(x)}
+        for i in range(warm + nsteps):
+            if i == warm:
+                barrier()
+                t0 = time.perf_counter()
+            if host_eps is None:
+                Fh, dFh = vbmc_b200.negelcbo_vbmc(x, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, rng=(777, i), nargout=2, ctx=ctx)
+            else:
+                Fh, dFh = vbmc_b200.negelcbo_vbmc(x, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=host_eps, nargout=2, ctx=ctx)
+            x = adam_update(st, x, dFh)
+        barrier()
+        return (time.perf_counter() - t0) / nsteps
+
+    e2e_s = e2e_loop(args.steps, max(3, args.warmup))
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_host_eps = None
+    if world == 1:
+        heps = workloads.make_epsilon(cfg)
+        e2e_host_eps = 1.0 / e2e_loop(max(3, args.steps // 4), 2, host_eps=heps)
+
+    if rank != 0:
+        return
+    # ---- roofline ----
+    peaks, peak_src = measured_peaks()
+    fp64_peak = ctx.measure_fp64_peak()
+    ent_ms = prof["entmc"]["ms_per_step"]
+    shard = 1.0 / world
+    ent_tflops = counts["entmc_flops"] * shard / (ent_ms * 1e-3) / 1e12 if ent_ms > 0 else None
+    ent_gbs = counts["entmc_bytes"] * shard / (ent_ms * 1e-3) / 1e9 if ent_ms > 0 else None
+    roofline = {"kernel": "entmc_kernel", "bound": "fp64", "achieved": ent_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ent_tflops / fp64_peak if ent_tflops else None, "traffic": None,
+                "peak_source": "DFMA micro-benchmark run live on this device (MEASURED_PEAKS.json has no FP64 entry)",
+                "hbm": {"achieved": ent_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ent_gbs / peaks["hbm_gbs"] if ent_gbs else None,
+                        "peak_source": peak_src + " MEASURED_PEAKS.json"},
+                "algorithmic": {"flops_per_launch": counts["entmc_flops"] * shard, "bytes_per_launch": counts["entmc_bytes"] * shard,
+                                "ms_per_launch": ent_ms},
+                "note": "entmc at K=50 has ~78 flop/B: FP64-pipe bound, not HBM bound (SURVEY.md 8d); both fractions reported"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import cport
+            r = cport.time_negelcbo(w, steps=2, warmup=1)
+            cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+        except Exception as e:  # the baseline is reporting only; never let it kill the bench line
+            cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
+    nth = theta.size
+    line = {
+        "metric": "negelcbo_vbmc grad-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")},
+                   "parallelism": f"mc-pair-shard x{world} + hyp-sample shard, 1 all-reduce/step" if world > 1 else "single GPU",
+                   "eps": "device Philox4x32-10, fresh draws every step (reference: randn per call)",
+                   "l2": "flushed (256 MB memset) between timed steps, outside the CUDA events",
+                   "gp_posterior_from": gp_source, "setup_s": round(t_setup, 2)},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": nth * 8, "d2h_bytes_per_step": (nth + 8) * 8,
+                "includes": "host theta H2D, F/dF D2H, host Adam update (fminadam.m:51-60); draws from the device generator",
+                "host_eps_variant_steps_per_s": e2e_host_eps,
+                "host_eps_variant_h2d_bytes_per_step": counts["entmc_bytes"] if e2e_host_eps else None},
+        "gpu_launches": launches,
+        "wall_s_timed_region": t_wall,
+        "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in prof.items()},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
