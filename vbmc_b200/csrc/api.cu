@@ -1,6 +1,7 @@
 // C ABI of libvbmc_b200 (see include/vbmc_b200.h): context, GP/VP residency, one negelcbo step.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -106,6 +107,10 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreate(&c->ev_t0));
   VB_CUDA(cudaEventCreate(&c->ev_t1));
+  if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
+    if (!strcmp(f, "expanded")) c->entmc_form = 0;
+    if (!strcmp(f, "direct")) c->entmc_form = 1;
+  }
   *out = c;
   return VBMC_B200_OK;
 }
@@ -286,7 +291,7 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   c->base_lambda = b; b += D;
   c->base_w = b; b += K;
   c->base_eta = b;
-  const size_t ncur = static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K;
+  const size_t ncur = 2 * static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K + 2;
   VB_TRY(c->vpCur.reserve(ncur * sizeof(double)));
   double* q = c->vpCur.d();
   c->vp.D = D; c->vp.K = K;
@@ -301,6 +306,8 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   c->vp.ck = q; q += K;
   c->vp.ak = q; q += K;
   c->vp.cn = q; q += K + 1;
+  c->vp.form_flag = reinterpret_cast<int*>(q); q += 2;
+  c->vp.scratch = q; q += D * K;
   std::vector<double> dl(D, 0.0);
   if (v->delta)
     for (int d = 0; d < D; ++d) dl[d] = v->delta[d];
@@ -387,9 +394,11 @@ static int prepare_eps(vbmc_b200_ctx* c, int Ns, int mode, const double* eps, ui
         VB_FAIL(VBMC_B200_ESTATE, "eps_mode EPS_RESIDENT: no resident draws of shape D=%d K=%d Ns=%d (have %d %d %d)", D,
                 K, Ns, c->epsD, c->epsK, c->epsNs);
       return VBMC_B200_OK;
-    case VBMC_B200_EPS_PHILOX:
+    case VBMC_B200_EPS_PHILOX:  // generated inside enqueue_step, after the gplogjoint branch has been forked
       VB_TRY(eps_reserve(c, D, K, Ns));
-      VB_TRY(launch_philox(c, D, K, Ns, seed, stream_id, c->stream));
+      c->philox_pending = true;
+      c->philox_seed = seed;
+      c->philox_stream = stream_id;
       c->eps_ready = true;
       return VBMC_B200_OK;
   }
@@ -413,6 +422,10 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
   }
   if (doH) {
+    if (c->philox_pending) {
+      c->philox_pending = false;
+      VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream));
+    }
     int need = 0;
     if (gmask & 1) need |= NEED_MU;
     if (gmask & (2 | 4)) need |= NEED_E;

@@ -81,6 +81,8 @@ struct VpDev {  // unpacked variational posterior (filled by vp_unpack_kernel ea
   double* ck;        // [K]  w_k*nf/sigma_k^D      (entmc_vbmc.m:40,63)
   double* ak;        // [K]  ck_k/sigma_k
   double* cn;        // [K+1] nf/sigma_k^D, cn[K] = nf
+  double* scratch;   // [K*D] work array of vp_unpack_kernel
+  int* form_flag;    // entmc formulation of this step: 0 expanded, 1 direct (set by vp_unpack_kernel)
 };
 
 struct GpDev {  // attached GP posterior
@@ -148,6 +150,7 @@ struct vbmc_b200_ctx {
   cudaStream_t stream2 = nullptr;  // gplogjoint branch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   long long launches = 0;
+  int entmc_form = -1;  // -1 auto (device guard), 0 force expanded, 1 force direct (VBMC_B200_ENTMC_FORM)
 
   // multi-GPU
   int nranks = 1, rank = 0;
@@ -181,6 +184,8 @@ struct vbmc_b200_ctx {
   vb::DevBuf eps;
   int epsD = 0, epsK = 0, epsNs = 0;
   bool eps_ready = false;
+  bool philox_pending = false;
+  uint64_t philox_seed = 0, philox_stream = 0;
 
   // step buffers
   vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out;

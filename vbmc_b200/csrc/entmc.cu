@@ -2,39 +2,47 @@
 // reparameterisation gradient (reference: ent/entmc_vbmc.m:49-104).
 //
 // Work unit = antithetic PAIR (j, p): source component j, draw eps_p (D doubles) and its mirror
-// -eps_p (entmc_vbmc.m:53-54).  One thread owns one pair and scores it against all K components
-// in two sequential passes (sign = +1, -1); one warp owns 32 consecutive pairs of one component,
-// one CTA tile = nwarps*32 pairs of one component.  Persistent CTAs (one per SM) stride over tiles.
+// -eps_p (entmc_vbmc.m:53-54).  One thread owns one pair and scores BOTH signs against all K
+// components in one sweep (two independent dependency chains per thread); one warp owns 32
+// consecutive pairs of one component, one CTA tile = nwarps*32 pairs of one component.  Persistent
+// CTAs (one per SM) stride over the tiles.
 //
-// Per (pair, sign, k):  z_d = u_jkd + sign*r_jk*eps_d,  u_jkd = (mu_jd-mu_kd)/(sigma_k lambda_d),
-//                       r_jk = sigma_j/sigma_k         (== (xi-mu_k)/(sigma_k lambda), :55,:62)
-//   e_k  = exp(-0.5*sum_d z_d^2)                        (:63, direct exp like the reference)
-//   q   += ck_k*e_k,    ck_k = w_k*nf/sigma_k^D         (:63-64)
-//   T_d += (ck_k/sigma_k)*e_k*z_d                       (lsum_d*lambda_d, :77-79)
-// The e_k of a warp's 32 samples are staged in shared memory (XOR-swizzled [K][32] plane) so that
-// the w-gradient column sums  W_jl = sum_s e_l(x_s)/q_s  (:100) can be formed after q_s is known.
-// eps tiles are staged global->shared with TMA bulk copies (cp.async.bulk + mbarrier), one
-// prefetch ahead.  All reductions run in a fixed order => results are bit-reproducible.
+// Per (pair, k):  z(+-)_d = u_jkd +- r_jk*eps_d,  u_jkd = (mu_jd-mu_kd)/(sigma_k lambda_d),
+//                 r_jk = sigma_j/sigma_k            (== (xi-mu_k)/(sigma_k lambda), :55,:62)
+//   e(+-)_k = exp(-0.5*||z(+-)||^2)                 (:63, direct exp, no max-shift, like the reference)
+//   q(+-)  += ck_k*e(+-)_k,   ck_k = w_k*nf/sigma_k^D   (:63-64)
+//   T(+-)_d = sum_k ak_k e(+-)_k z(+-)_d = A(+-)_d +- eps_d*B(+-),  ak = ck/sigma_k   (lsum*lambda, :77-79)
+// Two formulations of ||z||^2, chosen on the device per step (flag written by vp_unpack_kernel):
+//   EXPANDED : ||z(+-)||^2 = ||u||^2 + r^2||eps||^2 +- 2r(eps.u): one D-long dot product serves both
+//              signs (the antithetic pair shares everything but the sign of the cross term);
+//   DIRECT   : the reference's own subtraction-then-square; used when ||u||^2 is so large that the
+//              expanded form's cancellation error (~eps_mach*||u||^2) could matter.
+// The e(+-)_k of a warp's 32 pairs are staged in shared memory ([K][32] x {+,-}, XOR-swizzled) so
+// that the w-gradient column sums W_jl = sum_s e_l(x_s)/q_s (:100) can be formed once q_s is known.
+// eps tiles are staged global->shared with TMA bulk copies (cp.async.bulk + mbarrier), one tile
+// ahead.  All reductions run in a fixed order => results are bit-reproducible run to run.
 #include "common.cuh"
 
 namespace vb {
 
 struct EntmcArgs {
-  int D, K, half;          // half = Ns/2 pairs per component
+  int D, K, half;            // half = Ns/2 pairs per component
   int pair_begin, pair_end;  // this rank's shard of the pair axis (same range for every component)
   int tiles_per_comp, pairs_per_tile, ntiles;
-  int need;                // NEED_* mask
-  int pstride;             // 1 + 2*D + K doubles per tile partial
-  const double* eps;       // [K][half][D]
-  const double* mu;        // [K][D]
-  const double* sigma;     // [K]
-  const double* lambda;    // [D]
-  const double* ck;        // [K]  w_k*nf/sigma_k^D
-  const double* ak;        // [K]  ck_k/sigma_k
-  double* partial;         // [ntiles][pstride]
+  int need;                  // NEED_* mask
+  int pstride;               // 1 + 2*D + K doubles per tile partial
+  int iq_in_smem;            // 1: 1/q broadcast through shared memory, 0: through shuffles
+  const int* form_flag;      // device flag: 0 -> expanded form, 1 -> direct form
+  const double* eps;         // [K][half][D]
+  const double* mu;          // [K][D]
+  const double* sigma;       // [K]
+  const double* lambda;      // [D]
+  const double* ck;          // [K]  w_k*nf/sigma_k^D
+  const double* ak;          // [K]  ck_k/sigma_k
+  double* partial;           // [ntiles][pstride]
   // shared-memory carve-up (byte offsets, computed on the host)
-  int off_u, off_r, off_ck, off_ak, off_bar, off_warp, warp_bytes;
-  int woff_eps, woff_iq, woff_wsum, woff_res, woff_stage;  // offsets inside a warp region
+  int off_u, off_s, off_t16, off_bar, off_warp, warp_bytes;
+  int woff_eps, woff_iq, woff_stage;  // offsets inside a warp region
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk => SASS UBLKCP) ----
@@ -83,38 +91,65 @@ __device__ __forceinline__ bool eps_stage(double* dst, const double* src, int nd
   return tma_ok;
 }
 
-template <int DP, int MAXW>
+// exp(x) for x <= ~0: 2^(m + j/16) * p(r), 16-entry table in shared memory + degree-6 polynomial
+// (|r| <= ln2/32, truncation 4e-16).  Arguments below -708 return 0 (denormals flushed; q always
+// contains the source component's own term exp(-||eps||^2/2), so this is invisible in q, T, W).
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t16) {
+  const double L2E16 = 23.083120654223414;        // 16/ln2
+  const double MAGIC = 6755399441055744.0;        // 1.5*2^52
+  const double LN2_16_HI = 0.043321698783984175;  // ln2/16, low 18 bits zero
+  const double LN2_16_LO = 1.0124068866660351e-12;
+  const double kf = fma(x, L2E16, MAGIC);
+  const int ki = __double2loint(kf);
+  const double kd = kf - MAGIC;
+  double r = fma(kd, -LN2_16_HI, x);
+  r = fma(kd, -LN2_16_LO, r);
+  const double r2 = r * r;
+  const double a0 = 1.0 + r;
+  const double a1 = fma(r, 1.0 / 6.0, 0.5);
+  double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  a2 = fma(r2, 1.0 / 720.0, a2);
+  double p = fma(r2, a2, a1);
+  p = fma(r2, p, a0);
+  p *= t16[ki & 15];
+  const int hi = __double2hiint(p) + ((ki >> 4) << 20);
+  p = __hiloint2double(hi, __double2loint(p));
+  return x < -708.0 ? 0.0 : p;
+}
+
+__constant__ double c_t16[16] = {1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
+                                 1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
+                                 1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
+                                 1.7562521603732995, 1.8340080864093424, 1.9152065613971474};  // 2^(j/16)
+
+template <int DP, int MAXW, bool EXPANDED>
 __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) {
+  if ((*a.form_flag != 0) == EXPANDED) return;  // the other instantiation handles this step
   extern __shared__ __align__(16) unsigned char smem[];
   const int D = a.D, K = a.K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = blockDim.x >> 5;
 
-  double* tab_u = reinterpret_cast<double*>(smem + a.off_u);    // [K][DP]
-  double* tab_r = reinterpret_cast<double*>(smem + a.off_r);    // [K]
-  double* tab_ck = reinterpret_cast<double*>(smem + a.off_ck);  // [K]
-  double* tab_ak = reinterpret_cast<double*>(smem + a.off_ak);  // [K]
+  double* tab_u = reinterpret_cast<double*>(smem + a.off_u);      // [K][DP]
+  double4* tab_s = reinterpret_cast<double4*>(smem + a.off_s);    // [K] {r, -0.5||u||^2, ck, ak}
+  double* t16 = reinterpret_cast<double*>(smem + a.off_t16);      // [16] 2^(j/16)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + warp;
   unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
-  double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);    // [32*D]
-  double* iq_s = reinterpret_cast<double*>(wbase + a.woff_iq);      // [32]
-  double* wsum = reinterpret_cast<double*>(wbase + a.woff_wsum);    // [K]
-  double* wres = reinterpret_cast<double*>(wbase + a.woff_res);     // [pstride]
-  double* stage = reinterpret_cast<double*>(wbase + a.woff_stage);  // [K][32] (aliased by red[][33])
+  double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);      // [32*D]
+  double2* iq_s = reinterpret_cast<double2*>(wbase + a.woff_iq);      // [32] {1/q+, 1/q-} (optional)
+  double2* stage = reinterpret_cast<double2*>(wbase + a.woff_stage);  // [K][32] {e+, e-}, swizzled
+  double* wres = reinterpret_cast<double*>(wbase + a.woff_stage);     // [pstride]   (aliases stage)
+  double* red = wres + ((a.pstride + 1) & ~1);                        // [1+2D][33]  (aliases stage)
 
   const bool needT = (a.need & (NEED_MU | NEED_E)) != 0;
   const bool needW = (a.need & NEED_W) != 0;
 
   if (lane == 0) mbar_init(bar, 1);
-  for (int k = tid; k < K; k += blockDim.x) {
-    tab_ck[k] = a.ck[k];
-    tab_ak[k] = a.ak[k];
-  }
+  if (tid < 16) t16[tid] = c_t16[tid];
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
   uint32_t phase = 0;
-  // prefetch eps of the first tile
   int tile = blockIdx.x;
   bool tma_pending = false;
   auto issue_eps = [&](int t) -> bool {
@@ -136,7 +171,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     np = np < 0 ? 0 : (np > 32 ? 32 : np);
 
     // ---- per-component tables (shared by all warps of the CTA) ----
-    __syncthreads();  // previous tile finished with the tables and with wres
+    __syncthreads();  // previous tile: tables and the wres/stage regions are free again
     {
       const double sj = a.sigma[j];
       for (int i = tid; i < K * DP; i += blockDim.x) {
@@ -145,7 +180,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
         if (d < D) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
         tab_u[i] = u;
       }
-      for (int k = tid; k < K; k += blockDim.x) tab_r[k] = sj / a.sigma[k];
+      __syncthreads();
+      for (int k = tid; k < K; k += blockDim.x) {
+        double uu = 0.0;
+        for (int d = 0; d < D; ++d) uu = fma(tab_u[k * DP + d], tab_u[k * DP + d], uu);
+        tab_s[k] = make_double4(sj / a.sigma[k], -0.5 * uu, a.ck[k], a.ak[k]);
+      }
     }
     // ---- this thread's draw ----
     if (tma_pending) {
@@ -162,106 +202,144 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     tma_pending = issue_eps(tile + gridDim.x);
     __syncthreads();  // tables ready
 
-    double Hs = 0.0;
-    double Tkeep[DP];  // (A_d + eps_d*B)/q of the +pass
-#pragma unroll
-    for (int d = 0; d < DP; ++d) Tkeep[d] = 0.0;
-    if (needW)
-      for (int l = lane; l < K; l += 32) wsum[l] = 0.0;
-
     if (np > 0) {
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const double sgn = pass == 0 ? 1.0 : -1.0;
-        double q = 0.0, B = 0.0;
-        double A[DP];
+      double qp = 0.0, qm = 0.0, Bp = 0.0, Bm = 0.0;
+      double Ap[DP], Am[DP];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) A[d] = 0.0;
-        const int sw = lane;  // swizzled column = lane ^ (k & 15)
+      for (int d = 0; d < DP; ++d) Ap[d] = Am[d] = 0.0;
+      double mhee = 0.0;  // -0.5*||eps||^2
+      if (EXPANDED) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) mhee = fma(e[d], e[d], mhee);
+        mhee *= -0.5;
+      }
 #pragma unroll 2
-        for (int k = 0; k < K; ++k) {
-          const double r = sgn * tab_r[k];
-          const double* uk = tab_u + k * DP;
-          double d2a = 0.0, d2b = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double4 s4 = tab_s[k];  // {r, -0.5||u||^2, ck, ak}
+        const double r = s4.x;
+        const double* uk = tab_u + k * DP;
+        double xp, xm;
+        if (EXPANDED) {
+          double t0 = 0.0, t1 = 0.0;
 #pragma unroll
           for (int d = 0; d < DP; d += 2) {
             const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
-            const double z0 = fma(r, e[d], u2.x);
-            const double z1 = fma(r, e[d + 1], u2.y);
-            d2a = fma(z0, z0, d2a);
-            d2b = fma(z1, z1, d2b);
+            t0 = fma(e[d], u2.x, t0);
+            t1 = fma(e[d + 1], u2.y, t1);
           }
-          const double ex = exp(-0.5 * (d2a + d2b));
-          if (needW) stage[k * 32 + (sw ^ (k & 15))] = ex;
-          q = fma(tab_ck[k], ex, q);
-          if (needT) {
-            const double t = tab_ak[k] * ex;
-            B = fma(t, r, B);
+          const double rt = r * (t0 + t1);
+          const double xb = fma(r * r, mhee, s4.y);
+          xp = xb - rt;
+          xm = xb + rt;
+        } else {
+          double dpa = 0.0, dpb = 0.0, dma = 0.0, dmb = 0.0;
 #pragma unroll
-            for (int d = 0; d < DP; d += 2) {
-              const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
-              A[d] = fma(t, u2.x, A[d]);
-              A[d + 1] = fma(t, u2.y, A[d + 1]);
-            }
+          for (int d = 0; d < DP; d += 2) {
+            const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
+            const double zp0 = fma(r, e[d], u2.x), zm0 = fma(-r, e[d], u2.x);
+            const double zp1 = fma(r, e[d + 1], u2.y), zm1 = fma(-r, e[d + 1], u2.y);
+            dpa = fma(zp0, zp0, dpa);
+            dma = fma(zm0, zm0, dma);
+            dpb = fma(zp1, zp1, dpb);
+            dmb = fma(zm1, zm1, dmb);
           }
+          xp = -0.5 * (dpa + dpb);
+          xm = -0.5 * (dma + dmb);
         }
-        const double iq = valid ? 1.0 / q : 0.0;
-        Hs += valid ? log(q) : 0.0;
+        const double ep = exp_neg(xp, t16);
+        const double em = exp_neg(xm, t16);
+        if (needW) stage[k * 32 + (lane ^ (k & 7))] = make_double2(ep, em);
+        qp = fma(s4.z, ep, qp);
+        qm = fma(s4.z, em, qm);
         if (needT) {
-          if (pass == 0) {
+          const double tp = s4.w * ep, tm = s4.w * em;
+          Bp = fma(tp, r, Bp);
+          Bm = fma(tm, r, Bm);
 #pragma unroll
-            for (int d = 0; d < DP; ++d) Tkeep[d] = fma(e[d], B, A[d]) * iq;
-          } else {
-            // fold both signs:  M_d = T+ + T-,  E_d = eps_d (T+ - T-)   (eps of the mirror is -eps)
-#pragma unroll
-            for (int d = 0; d < DP; ++d) {
-              const double tm = fma(e[d], B, A[d]) * iq;
-              const double tp = Tkeep[d];
-              Tkeep[d] = tp + tm;
-              A[d] = e[d] * (tp - tm);
-            }
-            // A[] now holds E_d; stash into the reduction scratch below
+          for (int d = 0; d < DP; d += 2) {
+            const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
+            Ap[d] = fma(tp, u2.x, Ap[d]);
+            Am[d] = fma(tm, u2.x, Am[d]);
+            Ap[d + 1] = fma(tp, u2.y, Ap[d + 1]);
+            Am[d + 1] = fma(tm, u2.y, Am[d + 1]);
           }
         }
-        if (needW) {
-          iq_s[lane] = iq;
-          __syncwarp();
-          for (int l = lane; l < K; l += 32) {
-            const double* row = stage + l * 32;
-            const int x = l & 15;
-            double acc = 0.0;
+      }
+      const double iqp = valid ? 1.0 / qp : 0.0;
+      const double iqm = valid ? 1.0 / qm : 0.0;
+      const double Hs = valid ? log(qp) + log(qm) : 0.0;
+      if (needT) {
+        // T+ = (A+ + eps*B+)/q+,  T- = (A- - eps*B-)/q-;  M_d = T+ + T-,  E_d = eps_d (T+ - T-)
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const double tp = fma(e[d], Bp, Ap[d]) * iqp;
+          const double tm = fma(-e[d], Bm, Am[d]) * iqm;
+          Ap[d] = tp + tm;
+          Am[d] = e[d] * (tp - tm);
+        }
+      }
+      // ---- column sums W_l = sum_p e+_l/q+ + e-_l/q-  (lanes over l, p serial) ----
+      double wacc[4] = {0.0, 0.0, 0.0, 0.0};
+      if (needW) {
+        if (a.iq_in_smem) iq_s[lane] = make_double2(iqp, iqm);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int l = lane + 32 * rr;
+          const bool act = l < K;
+          const double2* row = stage + (act ? l : 0) * 32;
+          const int x = l & 7;
+          double acc = 0.0;
+          if (32 * rr < K) {  // warp-uniform
+            if (a.iq_in_smem) {
+              if (act) {
 #pragma unroll 8
-            for (int p = 0; p < 32; ++p) acc = fma(row[p ^ x], iq_s[p], acc);
-            wsum[l] += acc;
-          }
-          __syncwarp();  // stage / iq_s free for the next pass
-        }
-        if (pass == 1) {
-          // ---- warp reduction in fixed order via transposed scratch red[i][33] (aliases stage) ----
-          double* red = stage;
-          red[0 * 33 + lane] = Hs;
-          if (needT) {
-#pragma unroll
-            for (int d = 0; d < DP; ++d) {
-              if (d < D) {
-                red[(1 + d) * 33 + lane] = Tkeep[d];
-                red[(1 + D + d) * 33 + lane] = A[d];
+                for (int p = 0; p < 32; ++p) {
+                  const double2 ee = row[p ^ x];
+                  const double2 iq = iq_s[p];
+                  acc = fma(ee.x, iq.x, acc);
+                  acc = fma(ee.y, iq.y, acc);
+                }
+              }
+            } else {
+#pragma unroll 8
+              for (int p = 0; p < 32; ++p) {
+                const double2 ee = row[p ^ x];
+                acc = fma(ee.x, __shfl_sync(0xffffffffu, iqp, p), acc);
+                acc = fma(ee.y, __shfl_sync(0xffffffffu, iqm, p), acc);
               }
             }
           }
-          __syncwarp();
-          const int nval = needT ? 1 + 2 * D : 1;
-          for (int i = lane; i < nval; i += 32) {
-            const double* rr = red + i * 33;
-            double s = 0.0;
-            for (int p = 0; p < 32; ++p) s += rr[p];
-            wres[i] = s;
-          }
-          if (!needT)
-            for (int i = 1 + lane; i < 1 + 2 * D; i += 32) wres[i] = 0.0;
-          for (int l = lane; l < K; l += 32) wres[1 + 2 * D + l] = needW ? wsum[l] : 0.0;
-          __syncwarp();
+          wacc[rr] = act ? acc : 0.0;
         }
+        __syncwarp();  // stage is free: reuse it as reduction scratch
+      }
+      // ---- warp reduction in fixed order via transposed scratch red[i][33] ----
+      red[0 * 33 + lane] = Hs;
+      if (needT) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          if (d < D) {
+            red[(1 + d) * 33 + lane] = Ap[d];
+            red[(1 + D + d) * 33 + lane] = Am[d];
+          }
+        }
+      }
+      __syncwarp();
+      const int nval = needT ? 1 + 2 * D : 1;
+      for (int i = lane; i < nval; i += 32) {
+        const double* rr = red + i * 33;
+        double s = 0.0;
+#pragma unroll 8
+        for (int p = 0; p < 32; ++p) s += rr[p];
+        wres[i] = s;
+      }
+      if (!needT)
+        for (int i = 1 + lane; i < 1 + 2 * D; i += 32) wres[i] = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int l = lane + 32 * rr;
+        if (l < K) wres[1 + 2 * D + l] = wacc[rr];
       }
     } else {
       for (int i = lane; i < a.pstride; i += 32) wres[i] = 0.0;
@@ -271,7 +349,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     for (int i = tid; i < a.pstride; i += blockDim.x) {
       double s = 0.0;
       for (int w = 0; w < nw; ++w)
-        s += reinterpret_cast<const double*>(smem + a.off_warp + static_cast<size_t>(w) * a.warp_bytes + a.woff_res)[i];
+        s += reinterpret_cast<const double*>(smem + a.off_warp + static_cast<size_t>(w) * a.warp_bytes + a.woff_stage)[i];
       a.partial[static_cast<size_t>(tile) * a.pstride + i] = s;
     }
   }
@@ -286,6 +364,7 @@ __global__ void entmc_reduce_kernel(const double* __restrict__ partial, int tile
   for (int i = threadIdx.x; i < pstride; i += blockDim.x) {
     double s = 0.0;
     const double* p = partial + static_cast<size_t>(j) * tiles_per_comp * pstride + i;
+#pragma unroll 8
     for (int t = 0; t < tiles_per_comp; ++t) s += p[static_cast<size_t>(t) * pstride];
     if (i == 0)
       Hs[j] = s;
@@ -321,7 +400,8 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   const int half = Ns / 2;
   pl->DP = pick_dp(D);
   if (pl->DP < 0) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: D=%d > 24 is not supported by this build", D);
-  pl->maxw = pl->DP <= 12 ? 12 : 8;
+  if (K > 128) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: K=%d > 128 is not supported by this build", K);
+  pl->maxw = 8;
   shard_range(half, c->nranks, c->rank, &pl->pair_begin, &pl->pair_end);
   pl->npairs_local = pl->pair_end - pl->pair_begin;
   const int DP = pl->DP;
@@ -333,29 +413,38 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   // CTA-shared region
   int off = 0;
   a.off_u = off; off += K * DP * 8;
-  a.off_r = off; off += K * 8;
-  a.off_ck = off; off += K * 8;
-  a.off_ak = off; off += K * 8;
-  a.off_bar = off; off += 16 * 8;
+  off = round_up(off, 32);
+  a.off_s = off; off += K * 32;
+  a.off_t16 = off; off += 16 * 8;
+  a.off_bar = off; off += 8 * 8;
   off = round_up(off, 16);
   a.off_warp = off;
-  // per-warp region
+  // per-warp region; the stage planes double as [wres | red] scratch after the column sums
+  const int stage_bytes = K * 32 * 16;
+  const int scratch_bytes = (round_up(a.pstride, 2) + (1 + 2 * D) * 33) * 8;
+  const int stage_alloc = round_up(stage_bytes > scratch_bytes ? stage_bytes : scratch_bytes, 16);
+  const size_t avail = c->smem_optin;
+  int best_nw = 0, best_iq = 0;
+  for (int iq = 1; iq >= 0; --iq) {
+    const int wb = round_up(32 * D * 8, 16) + (iq ? 32 * 16 : 0) + stage_alloc;
+    int nw_fit = static_cast<int>((avail - a.off_warp) / wb);
+    if (nw_fit > pl->maxw) nw_fit = pl->maxw;
+    if (nw_fit >= 4) nw_fit = nw_fit / 4 * 4;  // equal load on the 4 SM sub-partitions
+    if (nw_fit > best_nw) {
+      best_nw = nw_fit;
+      best_iq = iq;
+    }
+  }
+  if (best_nw < 1)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: K=%d, D=%d needs more shared memory per warp than the %zu B available",
+            K, D, avail - a.off_warp);
+  a.iq_in_smem = best_iq;
   int w = 0;
   a.woff_eps = w; w += round_up(32 * D * 8, 16);
-  a.woff_iq = w; w += 32 * 8;
-  a.woff_wsum = w; w += round_up(K * 8, 16);
-  a.woff_res = w; w += round_up(a.pstride * 8, 16);
-  a.woff_stage = w;
-  const int stage_dbl = (K * 32 > (1 + 2 * D) * 33) ? K * 32 : (1 + 2 * D) * 33;
-  w += round_up(stage_dbl * 8, 16);
+  a.woff_iq = w; w += best_iq ? 32 * 16 : 0;
+  a.woff_stage = w; w += stage_alloc;
   a.warp_bytes = w;
-  const size_t avail = c->smem_optin;
-  int nw_fit = static_cast<int>((avail - a.off_warp) / a.warp_bytes);
-  if (nw_fit < 1)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: K=%d, D=%d needs %d B shared memory per warp (> %zu available)", K,
-            D, a.warp_bytes, avail - a.off_warp);
-  int nw = nw_fit < pl->maxw ? nw_fit : pl->maxw;
-  if (nw >= 4) nw = nw / 4 * 4;  // equal load on the 4 SM sub-partitions
+  int nw = best_nw;
   // small problems: prefer more, smaller tiles so that every SM gets work
   const long long total_pairs = static_cast<long long>(pl->npairs_local) * K;
   while (nw > 1 && total_pairs / (nw * 32) < 2LL * c->num_sms) nw = (nw > 4) ? nw - 4 : nw - 1;
@@ -380,14 +469,23 @@ int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_pe
   return VBMC_B200_OK;
 }
 
-template <int DP, int MAXW>
+template <int DP>
 static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
-  auto kern = entmc_kernel<DP, MAXW>;
-  VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  auto kexp = entmc_kernel<DP, 8, true>;
+  auto kdir = entmc_kernel<DP, 8, false>;
+  VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   const int grid = pl.ntiles < c->num_sms ? pl.ntiles : c->num_sms;
-  KernelScope ks(c, "entmc", st);
-  kern<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
-  VB_CUDA(cudaGetLastError());
+  {
+    KernelScope ks(c, "entmc", st);
+    kexp<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+    VB_CUDA(cudaGetLastError());
+  }
+  {
+    KernelScope ks(c, "entmc_direct", st);
+    kdir<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+    VB_CUDA(cudaGetLastError());
+  }
   return VBMC_B200_OK;
 }
 
@@ -398,6 +496,7 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   VB_TRY(c->ent_partial.reserve(static_cast<size_t>(pl.ntiles) * pl.a.pstride * sizeof(double)));
   EntmcArgs& a = pl.a;
   a.need = need_mask;
+  a.form_flag = c->vp.form_flag;
   a.eps = c->eps.d();
   a.mu = c->vp.mu;
   a.sigma = c->vp.sigma;
@@ -406,15 +505,15 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   a.ak = c->vp.ak;
   a.partial = c->ent_partial.d();
   switch (pl.DP) {
-    case 2: return launch_one<2, 12>(c, pl, st);
-    case 4: return launch_one<4, 12>(c, pl, st);
-    case 6: return launch_one<6, 12>(c, pl, st);
-    case 8: return launch_one<8, 12>(c, pl, st);
-    case 10: return launch_one<10, 12>(c, pl, st);
-    case 12: return launch_one<12, 12>(c, pl, st);
-    case 16: return launch_one<16, 8>(c, pl, st);
-    case 20: return launch_one<20, 8>(c, pl, st);
-    case 24: return launch_one<24, 8>(c, pl, st);
+    case 2: return launch_one<2>(c, pl, st);
+    case 4: return launch_one<4>(c, pl, st);
+    case 6: return launch_one<6>(c, pl, st);
+    case 8: return launch_one<8>(c, pl, st);
+    case 10: return launch_one<10>(c, pl, st);
+    case 12: return launch_one<12>(c, pl, st);
+    case 16: return launch_one<16>(c, pl, st);
+    case 20: return launch_one<20>(c, pl, st);
+    case 24: return launch_one<24>(c, pl, st);
   }
   VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: unsupported padded dimension %d", pl.DP);
 }

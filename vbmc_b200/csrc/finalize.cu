@@ -10,12 +10,13 @@
 namespace vb {
 
 struct UnpackArgs {
-  int D, K, ntheta, have_theta;
+  int D, K, ntheta, have_theta, force_form;
   int opt[4];
   const double* theta;
   const double *base_mu, *base_sigma, *base_lambda, *base_w, *base_eta;
   VpDev vp;
   double* cn;  // [K] nf/sigma_k^D ; cn[K] = nf
+  double* scratch;  // [K*D]
 };
 
 __global__ void vp_unpack_kernel(const UnpackArgs a) {
@@ -52,16 +53,56 @@ __global__ void vp_unpack_kernel(const UnpackArgs a) {
     }
   }
   __syncthreads();
-  if (tid == 0) {
+  {
+    __shared__ double part[256];
     double es = 0.0;
-    for (int k = 0; k < K; ++k) es += exp(a.vp.eta[k]);  // (:46-47) no max-shift, like the reference
-    s_es = es;
+    for (int k = tid; k < K; k += nt) es += exp(a.vp.eta[k]);  // (:46-47) no max-shift, like the reference
+    part[tid] = es;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) part[tid] += part[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) s_es = part[0];
+  }
+  if (tid == 0) {
     double pl = 1.0;
     for (int d = 0; d < D; ++d) pl *= a.vp.lambda[d];
     s_nf = 1.0 / pow(2.0 * 3.14159265358979323846, 0.5 * D) / pl;  // nf (entmc_vbmc.m:40)
     a.cn[K] = s_nf;
   }
   __syncthreads();
+  // ---- choose the entmc formulation for this step (see entmc.cu) ----
+  // expanded form error ~ eps_mach * (||u_jk||^2 + r_jk^2 ||eps||^2); keep it below ~1e-10 absolute in d^2.
+  // ||u_jk||^2 = sum_d (mu_jd - mu_kd)^2 * isl2_kd with isl2_kd = 1/(sigma_k lambda_d)^2 (a.scratch, [K][D])
+  {
+    __shared__ double pmax[256];
+    for (int i = tid; i < K * D; i += nt) {
+      const double sl = a.vp.sigma[i / D] * a.vp.lambda[i % D];
+      a.scratch[i] = 1.0 / (sl * sl);
+    }
+    __syncthreads();
+    const double eemax = D + 12.0 * sqrt(2.0 * D) + 72.0;  // > 12 sigma bound on ||eps||^2
+    double m = 0.0;
+    for (int i = tid; i < K * K; i += nt) {
+      const int j = i / K, k = i - j * K;
+      double uu = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double dm = a.vp.mu[j * D + d] - a.vp.mu[k * D + d];
+        uu = fma(dm * dm, a.scratch[k * D + d], uu);
+      }
+      const double r2 = a.vp.sigma[j] * a.vp.sigma[j] * a.scratch[k * D] * a.vp.lambda[0] * a.vp.lambda[0];
+      const double v = fma(r2, eemax, uu);
+      m = (v > m || !(v == v)) ? v : m;
+    }
+    pmax[tid] = m;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) pmax[tid] = (pmax[tid + off] > pmax[tid] || !(pmax[tid + off] == pmax[tid + off])) ? pmax[tid + off] : pmax[tid];
+      __syncthreads();
+    }
+    if (tid == 0) *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((pmax[0] <= 2.0e5) ? 0 : 1);
+  }
   for (int k = tid; k < K; k += nt) {
     const double w = (ht && a.opt[3]) ? exp(a.vp.eta[k]) / s_es : a.base_w[k];
     a.vp.w[k] = w;
@@ -105,6 +146,20 @@ __device__ __forceinline__ double soft_pen(double x, double lb, double ub, doubl
   return y;
 }
 
+// deterministic block-wide sum (fixed tree) of one value per thread; blockDim.x == 256
+__device__ __forceinline__ double block_sum256(double v, double* part) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  part[tid] = v;
+  __syncthreads();
+#pragma unroll
+  for (int off = 128; off > 0; off >>= 1) {
+    if (tid < off) part[tid] += part[tid + off];
+    __syncthreads();
+  }
+  return part[0];
+}
+
 __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   extern __shared__ double sm[];
   const int D = a.D, K = a.K, S = a.S, tid = threadIdx.x, nt = blockDim.x;
@@ -132,12 +187,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   o_lam = n; if (a.gf[2]) n += D;
   o_w = n; if (a.gf[3]) n += K;
 
-  if (tid == 0) {
+  {
     double es = 0.0;
-    for (int k = 0; k < K; ++k) es += exp(a.vp.eta[k]);
-    sc[0] = es;
-    sc[3] = 0.0;
-    sc[4] = 0.0;
+    for (int k = tid; k < K; k += nt) es += exp(a.vp.eta[k]);
+    es = block_sum256(es, part);
+    if (tid == 0) {
+      sc[0] = es;
+      sc[1] = sc[2] = sc[3] = sc[4] = 0.0;
+    }
   }
   for (int i = tid; i < 8; i += nt) out[i] = 0.0;
   __syncthreads();
@@ -150,11 +207,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
 
   // ------------------------------------------------------------------ entropy (entmc_vbmc.m)
   if (doH) {
-    if (tid == 0) {
+    {
       double H = 0.0;
-      for (int j = 0; j < K; ++j) H -= a.vp.w[j] * R[rl.oHs + j] * invNs;  // :67
-      sc[1] = H;
-      out[ol.oH] = H;
+      for (int j = tid; j < K; j += nt) H -= a.vp.w[j] * R[rl.oHs + j] * invNs;  // :67
+      H = block_sum256(H, part);
+      if (tid == 0) {
+        sc[1] = H;
+        out[ol.oH] = H;
+      }
     }
     if (a.gf[0])
       for (int i = tid; i < D * K; i += nt) {
@@ -186,16 +246,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   }
   // ------------------------------------------------------------------ expected log joint
   if (doG) {
-    if (tid == 0) {
+    {
       double G = 0.0;
-      for (int s = 0; s < S; ++s) {
-        double Fs = 0.0;
-        for (int k = 0; k < K; ++k) Fs += a.vp.w[k] * R[rl.oI + s * K + k];  // F(s) += w(k)*I_k  (:203)
-        G += Fs;
+      for (int i = tid; i < S * K; i += nt) G += a.vp.w[i % K] * R[rl.oI + i];  // F(s) += w(k)*I_k  (:203)
+      G = block_sum256(G, part) * invS;                                          // mean over s (:398-399)
+      if (tid == 0) {
+        sc[2] = G;
+        out[ol.oG] = G;
       }
-      G *= invS;  // :398-399
-      sc[2] = G;
-      out[ol.oG] = G;
     }
     for (int i = tid; i < S * K; i += nt) out[ol.oIsk + i] = R[rl.oI + i];
     if (a.gf[0])
@@ -247,15 +305,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
         lacc += soft_pen(a.vp.eta[k], a.lb[b_eta + k], a.ub[b_eta + k], a.TolCon, &dy);
         if (a.gf[3]) out[ol.oDF + o_w + k] = dy;
       }
-    part[tid] = lacc;
-    __syncthreads();
-    if (tid == 0) {
-      double L = 0.0;
-      for (int t = 0; t < nt; ++t) L += part[t];
-      sc[3] = L;
-      if (a.opt[3]) {  // negelcbo_vbmc.m:146-151
-        double Lw = 0.0;
-        for (int k = 0; k < K; ++k) Lw += (a.vp.w[k] < a.WThresh) ? a.vp.w[k] : a.WThresh;
+    {
+      const double L = block_sum256(lacc, part);
+      double Lw = 0.0;
+      if (a.opt[3])  // negelcbo_vbmc.m:146-151
+        for (int k = tid; k < K; k += nt) Lw += (a.vp.w[k] < a.WThresh) ? a.vp.w[k] : a.WThresh;
+      Lw = block_sum256(Lw, part);
+      if (tid == 0) {
+        sc[3] = L;
         sc[4] = Lw * a.WPen;
       }
     }
@@ -278,13 +335,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   // ------------------------------------------------------------------ softmax Jacobian J_w * g
   // J_w = diag(e/es) - e e'/es^2  =>  (J_w g)_i = wsm_i (g_i - sum_l wsm_l g_l)   (gplogjoint.m:366-368)
   if (a.gf[3]) {
+    double dh = 0.0, dg = 0.0, dp = 0.0;
+    for (int l = tid; l < K; l += nt) {
+      if (doH) dh += wsm[l] * gHw[l];
+      if (doG) dg += wsm[l] * gGw[l];
+      dp += wsm[l] * gPw[l];
+    }
+    dh = block_sum256(dh, part);
+    dg = block_sum256(dg, part);
+    dp = block_sum256(dp, part);
     if (tid == 0) {
-      double dh = 0.0, dg = 0.0, dp = 0.0;
-      for (int l = 0; l < K; ++l) {
-        if (doH) dh += wsm[l] * gHw[l];
-        if (doG) dg += wsm[l] * gGw[l];
-        dp += wsm[l] * gPw[l];
-      }
       sc[5] = dh; sc[6] = dg; sc[7] = dp;
     }
     __syncthreads();
@@ -311,12 +371,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
 int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   UnpackArgs a;
   a.D = c->D; a.K = c->K; a.ntheta = c->ntheta; a.have_theta = have_theta ? 1 : 0;
+  a.force_form = c->entmc_form;
   for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
   a.theta = c->theta_dev.d();
   a.base_mu = c->base_mu; a.base_sigma = c->base_sigma; a.base_lambda = c->base_lambda;
   a.base_w = c->base_w; a.base_eta = c->base_eta;
   a.vp = c->vp;
   a.cn = c->vp.cn;
+  a.scratch = c->vp.scratch;
   KernelScope ks(c, "vp_unpack", c->stream);
   vp_unpack_kernel<<<1, 256, 0, c->stream>>>(a);
   VB_CUDA(cudaGetLastError());

@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
 }
 
 // R.I[s][k] (all S rows: zero outside the local shard), R.Gmu[k][d], R.Gsig[k], R.Glam[d]
-__global__ void glj_reduce_kernel(const double* __restrict__ out, int ostride, int D, int K, int S, int s_begin,
-                                  int s_count, const double* __restrict__ w, double* __restrict__ RI,
-                                  double* __restrict__ Gmu, double* __restrict__ Gsig, double* __restrict__ Glam) {
+__global__ void __launch_bounds__(256) glj_reduce_kernel(const double* __restrict__ out, int ostride, int D, int K, int S,
+                                                         int s_begin, int s_count, const double* __restrict__ w,
+                                                         double* __restrict__ RI, double* __restrict__ Gmu,
+                                                         double* __restrict__ Gsig, double* __restrict__ Glam) {
+  extern __shared__ double tmp[];  // [K*D]  w_k * sum_s glam[s][k][d]
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < S * K; i += nt) {
     const int s = i / K;
@@ -156,19 +158,26 @@ __global__ void glj_reduce_kernel(const double* __restrict__ out, int ostride, i
   }
   for (int i = tid; i < K * D; i += nt) {
     const int k = i / D, d = i - k * D;
-    double acc = 0.0;
-    for (int s = s_begin; s < s_begin + s_count; ++s) acc += out[(static_cast<size_t>(s) * K + k) * ostride + 2 + d];
-    Gmu[i] = acc;
+    double gm = 0.0, gl = 0.0;
+#pragma unroll 4
+    for (int s = s_begin; s < s_begin + s_count; ++s) {
+      const double* o = out + (static_cast<size_t>(s) * K + k) * ostride;
+      gm += o[2 + d];
+      gl += o[2 + D + d];
+    }
+    Gmu[i] = gm;
+    tmp[i] = w[k] * gl;
   }
   for (int k = tid; k < K; k += nt) {
     double acc = 0.0;
+#pragma unroll 4
     for (int s = s_begin; s < s_begin + s_count; ++s) acc += out[(static_cast<size_t>(s) * K + k) * ostride + 1];
     Gsig[k] = acc;
   }
+  __syncthreads();
   for (int d = tid; d < D; d += nt) {
     double acc = 0.0;
-    for (int s = s_begin; s < s_begin + s_count; ++s)
-      for (int k = 0; k < K; ++k) acc += w[k] * out[(static_cast<size_t>(s) * K + k) * ostride + 2 + D + d];
+    for (int k = 0; k < K; ++k) acc += tmp[k * D + d];
     Glam[d] = acc;
   }
 }
@@ -227,7 +236,7 @@ int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st) {
   shard_range(c->gp.S, c->nranks, c->rank, &sb, &se);
   double* R = c->R_dev.d();
   KernelScope ks(c, "reduce", st);
-  glj_reduce_kernel<<<1, 256, 0, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w,
+  glj_reduce_kernel<<<1, 256, sizeof(double) * c->K * c->D, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w,
                                        R + rl.oI, R + rl.oGmu, R + rl.oGsig, R + rl.oGlam);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
