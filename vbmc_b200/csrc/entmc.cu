@@ -117,6 +117,49 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
   return x < -708.0 ? 0.0 : p;
 }
 
+// four independent exponentials evaluated stage by stage (keeps four dependency chains in flight)
+__device__ __forceinline__ void exp_neg4(const double (&x)[4], double (&y)[4], const double* __restrict__ t16) {
+  const double L2E16 = 23.083120654223414, MAGIC = 6755399441055744.0;
+  const double LN2_16_HI = 0.043321698783984175, LN2_16_LO = 1.0124068866660351e-12;
+  double kf[4], r[4], r2[4], a2[4], p[4];
+  int ki[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) kf[i] = fma(x[i], L2E16, MAGIC);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ki[i] = __double2loint(kf[i]);
+    kf[i] -= MAGIC;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma(kf[i], -LN2_16_HI, x[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = fma(kf[i], -LN2_16_LO, r[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r2[i] = r[i] * r[i];
+    a2[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a2[i] = fma(r2[i], 1.0 / 720.0, a2[i]);
+    p[i] = fma(r[i], 1.0 / 6.0, 0.5);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    p[i] = fma(r2[i], a2[i], p[i]);
+    a2[i] = 1.0 + r[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = fma(r2[i], p[i], a2[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] *= t16[ki[i] & 15];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int hi = __double2hiint(p[i]) + ((ki[i] >> 4) << 20);
+    y[i] = x[i] < -708.0 ? 0.0 : __hiloint2double(hi, __double2loint(p[i]));
+  }
+}
+
 __constant__ double c_t16[16] = {1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721,
                                  1.241857812073484, 1.2968395546510096, 1.3542555469368927, 1.4142135623730951,
                                  1.4768261459394993, 1.5422108254079407, 1.6104903319492543, 1.681792830507429,
@@ -127,6 +170,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
   if ((*a.form_flag != 0) == EXPANDED) return;  // the other instantiation handles this step
   extern __shared__ __align__(16) unsigned char smem[];
   const int D = a.D, K = a.K;
+  const int K2 = (K + 1) & ~1;  // tables are padded to an even number of components (dummy: ck = ak = 0)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = blockDim.x >> 5;
 
@@ -174,17 +218,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     __syncthreads();  // previous tile: tables and the wres/stage regions are free again
     {
       const double sj = a.sigma[j];
-      for (int i = tid; i < K * DP; i += blockDim.x) {
+      for (int i = tid; i < K2 * DP; i += blockDim.x) {
         const int k = i / DP, d = i - k * DP;
         double u = 0.0;
-        if (d < D) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
+        if (d < D && k < K) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
         tab_u[i] = u;
       }
       __syncthreads();
-      for (int k = tid; k < K; k += blockDim.x) {
+      for (int k = tid; k < K2; k += blockDim.x) {
         double uu = 0.0;
         for (int d = 0; d < D; ++d) uu = fma(tab_u[k * DP + d], tab_u[k * DP + d], uu);
-        tab_s[k] = make_double4(sj / a.sigma[k], -0.5 * uu, a.ck[k], a.ak[k]);
+        tab_s[k] = k < K ? make_double4(sj / a.sigma[k], -0.5 * uu, a.ck[k], a.ak[k]) : make_double4(0.0, 0.0, 0.0, 0.0);
       }
     }
     // ---- this thread's draw ----
@@ -213,55 +257,72 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
         for (int d = 0; d < DP; ++d) mhee = fma(e[d], e[d], mhee);
         mhee *= -0.5;
       }
-#pragma unroll 2
-      for (int k = 0; k < K; ++k) {
-        const double4 s4 = tab_s[k];  // {r, -0.5||u||^2, ck, ak}
-        const double r = s4.x;
-        const double* uk = tab_u + k * DP;
-        double xp, xm;
-        if (EXPANDED) {
-          double t0 = 0.0, t1 = 0.0;
+      // two components per iteration => four independent exp chains (k, k+1) x (+, -) per thread
+#pragma unroll 1
+      for (int k = 0; k < K2; k += 2) {
+        const double4 sa = tab_s[k], sb = tab_s[k + 1];  // {r, -0.5||u||^2, ck, ak}
+        double ua[DP], ub[DP];
 #pragma unroll
-          for (int d = 0; d < DP; d += 2) {
-            const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
-            t0 = fma(e[d], u2.x, t0);
-            t1 = fma(e[d + 1], u2.y, t1);
-          }
-          const double rt = r * (t0 + t1);
-          const double xb = fma(r * r, mhee, s4.y);
-          xp = xb - rt;
-          xm = xb + rt;
-        } else {
-          double dpa = 0.0, dpb = 0.0, dma = 0.0, dmb = 0.0;
-#pragma unroll
-          for (int d = 0; d < DP; d += 2) {
-            const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
-            const double zp0 = fma(r, e[d], u2.x), zm0 = fma(-r, e[d], u2.x);
-            const double zp1 = fma(r, e[d + 1], u2.y), zm1 = fma(-r, e[d + 1], u2.y);
-            dpa = fma(zp0, zp0, dpa);
-            dma = fma(zm0, zm0, dma);
-            dpb = fma(zp1, zp1, dpb);
-            dmb = fma(zm1, zm1, dmb);
-          }
-          xp = -0.5 * (dpa + dpb);
-          xm = -0.5 * (dma + dmb);
+        for (int d = 0; d < DP; d += 2) {
+          const double2 a2 = *reinterpret_cast<const double2*>(tab_u + k * DP + d);
+          const double2 b2 = *reinterpret_cast<const double2*>(tab_u + (k + 1) * DP + d);
+          ua[d] = a2.x; ua[d + 1] = a2.y;
+          ub[d] = b2.x; ub[d + 1] = b2.y;
         }
-        const double ep = exp_neg(xp, t16);
-        const double em = exp_neg(xm, t16);
-        if (needW) stage[k * 32 + (lane ^ (k & 7))] = make_double2(ep, em);
-        qp = fma(s4.z, ep, qp);
-        qm = fma(s4.z, em, qm);
-        if (needT) {
-          const double tp = s4.w * ep, tm = s4.w * em;
-          Bp = fma(tp, r, Bp);
-          Bm = fma(tm, r, Bm);
+        double x[4], ex[4];
+        if (EXPANDED) {
+          double ta0 = 0.0, ta1 = 0.0, tb0 = 0.0, tb1 = 0.0;
 #pragma unroll
           for (int d = 0; d < DP; d += 2) {
-            const double2 u2 = *reinterpret_cast<const double2*>(uk + d);
-            Ap[d] = fma(tp, u2.x, Ap[d]);
-            Am[d] = fma(tm, u2.x, Am[d]);
-            Ap[d + 1] = fma(tp, u2.y, Ap[d + 1]);
-            Am[d + 1] = fma(tm, u2.y, Am[d + 1]);
+            ta0 = fma(e[d], ua[d], ta0);
+            tb0 = fma(e[d], ub[d], tb0);
+            ta1 = fma(e[d + 1], ua[d + 1], ta1);
+            tb1 = fma(e[d + 1], ub[d + 1], tb1);
+          }
+          const double rta = sa.x * (ta0 + ta1), rtb = sb.x * (tb0 + tb1);
+          const double xba = fma(sa.x * sa.x, mhee, sa.y), xbb = fma(sb.x * sb.x, mhee, sb.y);
+          x[0] = xba - rta; x[1] = xba + rta;
+          x[2] = xbb - rtb; x[3] = xbb + rtb;
+        } else {
+          double da[4] = {0.0, 0.0, 0.0, 0.0}, db[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int d = 0; d < DP; d += 2) {
+            const double zap0 = fma(sa.x, e[d], ua[d]), zam0 = fma(-sa.x, e[d], ua[d]);
+            const double zbp0 = fma(sb.x, e[d], ub[d]), zbm0 = fma(-sb.x, e[d], ub[d]);
+            const double zap1 = fma(sa.x, e[d + 1], ua[d + 1]), zam1 = fma(-sa.x, e[d + 1], ua[d + 1]);
+            const double zbp1 = fma(sb.x, e[d + 1], ub[d + 1]), zbm1 = fma(-sb.x, e[d + 1], ub[d + 1]);
+            da[0] = fma(zap0, zap0, da[0]); da[1] = fma(zam0, zam0, da[1]);
+            db[0] = fma(zbp0, zbp0, db[0]); db[1] = fma(zbm0, zbm0, db[1]);
+            da[2] = fma(zap1, zap1, da[2]); da[3] = fma(zam1, zam1, da[3]);
+            db[2] = fma(zbp1, zbp1, db[2]); db[3] = fma(zbm1, zbm1, db[3]);
+          }
+          x[0] = -0.5 * (da[0] + da[2]); x[1] = -0.5 * (da[1] + da[3]);
+          x[2] = -0.5 * (db[0] + db[2]); x[3] = -0.5 * (db[1] + db[3]);
+        }
+        exp_neg4(x, ex, t16);
+        if (needW) {
+          stage[k * 32 + (lane ^ (k & 7))] = make_double2(ex[0], ex[1]);
+          stage[(k + 1) * 32 + (lane ^ ((k + 1) & 7))] = make_double2(ex[2], ex[3]);
+        }
+        qp = fma(sa.z, ex[0], qp);
+        qm = fma(sa.z, ex[1], qm);
+        qp = fma(sb.z, ex[2], qp);
+        qm = fma(sb.z, ex[3], qm);
+        if (needT) {
+          const double tpa = sa.w * ex[0], tma = sa.w * ex[1], tpb = sb.w * ex[2], tmb = sb.w * ex[3];
+          Bp = fma(tpa, sa.x, Bp);
+          Bm = fma(tma, sa.x, Bm);
+          Bp = fma(tpb, sb.x, Bp);
+          Bm = fma(tmb, sb.x, Bm);
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            Ap[d] = fma(tpa, ua[d], Ap[d]);
+            Am[d] = fma(tma, ua[d], Am[d]);
+          }
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            Ap[d] = fma(tpb, ub[d], Ap[d]);
+            Am[d] = fma(tmb, ub[d], Am[d]);
           }
         }
       }
@@ -412,15 +473,16 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   a.pstride = 1 + 2 * D + K;
   // CTA-shared region
   int off = 0;
-  a.off_u = off; off += K * DP * 8;
+  const int K2 = (K + 1) & ~1;
+  a.off_u = off; off += K2 * DP * 8;
   off = round_up(off, 32);
-  a.off_s = off; off += K * 32;
+  a.off_s = off; off += K2 * 32;
   a.off_t16 = off; off += 16 * 8;
   a.off_bar = off; off += 8 * 8;
   off = round_up(off, 16);
   a.off_warp = off;
   // per-warp region; the stage planes double as [wres | red] scratch after the column sums
-  const int stage_bytes = K * 32 * 16;
+  const int stage_bytes = K2 * 32 * 16;
   const int scratch_bytes = (round_up(a.pstride, 2) + (1 + 2 * D) * 33) * 8;
   const int stage_alloc = round_up(stage_bytes > scratch_bytes ? stage_bytes : scratch_bytes, 16);
   const size_t avail = c->smem_optin;
