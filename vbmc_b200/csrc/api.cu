@@ -181,8 +181,10 @@ static int gp_check_desc(const vbmc_b200_gp_desc* g, int* Ncov, int* Nnoise, int
   return VBMC_B200_OK;
 }
 
+}  // extern "C"
+namespace vb {
 // derived per-sample constants used by gplogjoint (gplogjoint.m:99-122)
-static int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1) {
+int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1) {
   const int D = g->D, S = g->S;
   std::vector<double> h(static_cast<size_t>(S) * (3 * D + 3));
   double* ell = h.data();
@@ -224,6 +226,8 @@ static int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int N
   c->gp.sn2eff = base + 3 * S * D + 2 * S;
   return VBMC_B200_OK;
 }
+}  // namespace vb
+extern "C" {
 
 int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const double* alpha, const double* sW1,
                         const int* Lchol, const double* L) {
@@ -241,6 +245,7 @@ int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const doub
   VB_CUDA(cudaMemcpyAsync(c->gpHyp.p, g->hyp, S * g->Nhyp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   VB_CUDA(cudaMemcpyAsync(c->gpAlpha.p, alpha, S * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->gpHasL = false;
+  c->gpLd = g->N;
   if (L) {
     VB_TRY(c->gpL.reserve(S * N * N * sizeof(double)));
     VB_CUDA(cudaMemcpyAsync(c->gpL.p, L, S * N * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));

@@ -163,6 +163,7 @@ struct vbmc_b200_ctx {
   std::vector<int> gpLchol;
   std::vector<double> gpSn2mult;
   bool gpHasL = false;
+  int gpLd = 0;  // leading dimension of the factors in gpL (N when attached from the host, Np after gp_post)
 
   // VP
   bool vp_ready = false;
@@ -213,7 +214,8 @@ struct KernelScope {
   KernelScope(vbmc_b200_ctx* ctx, const char* nm, cudaStream_t s);
   ~KernelScope();
 };
-int profile_collect(vbmc_b200_ctx* c);  // sync + fold pending event pairs into c->prof
+int profile_collect(vbmc_b200_ctx* c);
+int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1);  // sync + fold pending event pairs into c->prof
 
 // ---- step pieces (each defined in its own .cu) ----
 int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);
