@@ -202,6 +202,27 @@ def main():
         gp_source = "scipy LAPACK (set-up only)"
     t_setup = time.time() - t_setup
     vp, gp, theta0 = w["vp"], w["gp"], w["theta"]
+    # ---- secondary path: GP refit (gplite_post = S x gplite_core), timed per kernel with CUDA events ----
+    refit = None
+    if gp_source.startswith("vbmc_b200") and rank == 0:
+        noisefun = [1, 1, 0] if w["s2"] is not None else [1, 0, 0]
+        vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)  # warm
+        ctx.sync()
+        t0 = time.perf_counter()
+        vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
+        ctx.sync()
+        t_refit = time.perf_counter() - t0
+        ctx.profile_reset(); ctx.profile_enable(True)
+        gp = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
+        ctx.profile_enable(False)
+        kt = {k: ctx.profile_get(k)[0] for k in ("gram", "potrf_panel", "potrf_update", "trsv", "gp_prep")}
+        N_, S_ = cfg["N"], cfg["S"]
+        Np_ = (N_ + 1 + 63) // 64 * 64
+        nb_ = Np_ // 64
+        upd_flops = S_ * sum((nb_ - kb - 1) * (nb_ - kb) // 2 for kb in range(nb_)) * 2.0 * 64 ** 3
+        refit = {"gplite_post_wall_ms": t_refit * 1e3, "S": S_, "N": N_, "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
+                 "potrf_update_dmma_tflops": upd_flops / (kt["potrf_update"] * 1e-3) / 1e12 if kt["potrf_update"] > 0 else None,
+                 "chol_flops_N3_over_3_x_S": S_ * N_ ** 3 / 3.0}
     _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
     Ns = cfg["Ns"]
     counts = algorithmic_counts(cfg)
@@ -341,6 +362,7 @@ def main():
         "wall_s_timed_region": t_wall,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in prof.items()},
         "roofline": roofline,
+        "refit": refit,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -139,82 +139,96 @@ __global__ void __launch_bounds__(256) gp_gram_kernel(const GpBatch g) {
   }
 }
 
-// ---- panel step kb: factor the diagonal block, then R_kJ = R_kk^-T A_kJ for the blocks to the right -----
-// grid (max(1, nb-kb-1), nact).  Every CTA refactors the 64x64 diagonal block (cheap) so that no
-// inter-CTA dependency exists inside the launch; CTA x==0 writes it back.
-__global__ void __launch_bounds__(256) gp_panel_kernel(const GpBatch g, int kb) {
-  extern __shared__ __align__(16) double psm[];
-  typedef double (*Blk)[TB + 1];
-  Blk A = reinterpret_cast<Blk>(psm);                            // A[c][r]: column c, row r (upper part), unscaled
-  Blk R = reinterpret_cast<Blk>(psm + TB * (TB + 1));            // factor
-  Blk Bx = reinterpret_cast<Blk>(psm + 2 * TB * (TB + 1));       // right-hand block, Bx[c][r]
+// ---- panel step kb, part 1: factor the 64x64 diagonal block (one CTA per sample) -----------------------
+// Right-looking elimination in shared memory, 16x16 threads x 4x4 entries, two barriers per pivot.
+// Rows >= N (rhs / padding rows) are unit rows.  A non-positive pivot is reported in info[s].
+__global__ void __launch_bounds__(256) gp_potf2_kernel(const GpBatch g, int kb) {
+  __shared__ double A[TB][TB + 1];  // A[c][r]: column c, row r
+  __shared__ double lrow[TB];       // scaled pivot row
   __shared__ int bad;
-  const int s = g.active[blockIdx.y];
+  const int s = g.active[blockIdx.x];
   const int Np = g.Np, N = g.N, tid = threadIdx.x;
   double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
   const int k0 = kb * TB;
   if (tid == 0) bad = 0;
   for (int i = tid; i < TB * TB; i += 256) {
-    const int c = i / TB, r = i - c * TB;
+    const int c = i >> 6, r = i & 63;
     A[c][r] = Ms[static_cast<size_t>(k0 + c) * Np + k0 + r];
-    R[c][r] = 0.0;
   }
-  const int nJ = Np / TB - kb - 1;
-  const int jb = kb + 1 + blockIdx.x;
-  const bool have_rhs = blockIdx.x < nJ;
-  if (have_rhs)
-    for (int i = tid; i < TB * TB; i += 256) {
-      const int c = i / TB, r = i - c * TB;
-      Bx[c][r] = Ms[static_cast<size_t>(jb * TB + c) * Np + k0 + r];
-    }
   __syncthreads();
-  // right-looking elimination, one barrier per pivot: rows >= N (rhs/padding rows) are unit rows
+  const int tx = tid & 15, ty = tid >> 4;  // thread owns columns tx+16a, rows ty+16b
   for (int p = 0; p < TB; ++p) {
     const bool unit = (k0 + p) >= N;
     const double d = A[p][p];
-    if (!unit && !(d > 0.0) && tid == 0 && bad == 0) bad = k0 + p + 1;
-    const double id = unit ? 0.0 : 1.0 / d;
+    if (tid == 0 && !unit && !(d > 0.0) && bad == 0) bad = k0 + p + 1;
     const double isq = unit ? 0.0 : rsqrt(d);
-    // R[p][j] = a_pj / sqrt(d)
     if (tid < TB) {
       const int j = tid;
-      if (j >= p) R[j][p] = unit ? (j == p ? 1.0 : 0.0) : A[j][p] * isq;
+      double v = 0.0;
+      if (j >= p) v = unit ? (j == p ? 1.0 : 0.0) : A[j][p] * isq;   // R(p, j)
+      lrow[j] = v;
     }
-    // trailing update of the diagonal block: A[i][j] -= a_pi a_pj / d,  p < i <= j
-    const int rem = TB - 1 - p;
-    for (int e = tid; e < rem * rem; e += 256) {
-      const int ii = e / rem, jj = e - ii * rem;
-      if (ii <= jj) {
-        const int i = p + 1 + ii, j = p + 1 + jj;
-        A[j][i] -= A[i][p] * A[j][p] * id;
+    __syncthreads();
+    if (tid < TB) A[tid][p] = lrow[tid];                              // store row p of R in place
+    if (!unit) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int j = tx + 16 * a;
+        const double lj = lrow[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = ty + 16 * b;
+          if (i > p && i <= j) A[j][i] = fma(-lrow[i], lj, A[j][i]);
+        }
       }
     }
     __syncthreads();
   }
   if (tid == 0 && bad != 0) atomicCAS(&g.info[s], 0, bad);
-  if (blockIdx.x == 0)
-    for (int i = tid; i < TB * TB; i += 256) {
-      const int c = i / TB, r = i - c * TB;
-      if (r <= c) Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] = R[c][r];
-    }
-  if (!have_rhs) return;
-  // forward substitution R' X = B, row by row; one barrier per row
-  for (int p = 0; p < TB; ++p) {
-    const double ir = 1.0 / R[p][p];
-    if (tid < TB) Bx[tid][p] *= ir;  // x_p for column tid
-    __syncthreads();
-    const int rem = TB - 1 - p;
-    for (int e = tid; e < rem * TB; e += 256) {
-      const int rr = e / TB, c = e - rr * TB;
-      const int r = p + 1 + rr;
-      Bx[c][r] -= R[r][p] * Bx[c][p];
-    }
-    __syncthreads();
-  }
   for (int i = tid; i < TB * TB; i += 256) {
-    const int c = i / TB, r = i - c * TB;
-    Ms[static_cast<size_t>(jb * TB + c) * Np + k0 + r] = Bx[c][r];
+    const int c = i >> 6, r = i & 63;
+    if (r <= c) Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] = A[c][r];
   }
+}
+
+// ---- panel step kb, part 2: R_kJ = R_kk^-T A_kJ for every block J to the right ---------------------------
+// grid (nb-kb-1, nact).  Thread (c = tid/4, q = tid%4) owns rows q, q+4, ... of column c in registers; the
+// four owners of a column sit in one warp, so the forward substitution needs no block barrier.
+__global__ void __launch_bounds__(256) gp_trsm_kernel(const GpBatch g, int kb) {
+  __shared__ double R[TB][TB + 1];  // R[c][r] = R_kk(r, c)
+  __shared__ double ird[TB];        // 1 / R(p, p)
+  const int s = g.active[blockIdx.y];
+  const int Np = g.Np, tid = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  const int k0 = kb * TB;
+  const int jb = kb + 1 + blockIdx.x;
+  for (int i = tid; i < TB * TB; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    R[c][r] = (r <= c) ? Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] : 0.0;
+  }
+  __syncthreads();
+  if (tid < TB) ird[tid] = 1.0 / R[tid][tid];
+  __syncthreads();
+  const int c = tid >> 2, q = tid & 3;
+  double* col = Ms + static_cast<size_t>(jb * TB + c) * Np + k0;
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = col[q + 4 * i];
+  const unsigned lane = tid & 31;
+#pragma unroll
+  for (int p = 0; p < TB; ++p) {
+    // owner of row p: q == p % 4, register index p / 4
+    double xp = x[p >> 2] * ird[p];
+    xp = __shfl_sync(0xffffffffu, xp, (lane & ~3u) | (p & 3));
+    if (q == (p & 3)) x[p >> 2] = xp;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = q + 4 * i;
+      if (r > p) x[i] = fma(-R[r][p], xp, x[i]);   // b_r -= R(p, r) x_p
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) col[q + 4 * i] = x[i];
 }
 
 // ---- trailing update on the FP64 tensor path:  C_IJ -= P_I' P_J  (I <= J, blocks right of kb) ----
@@ -224,69 +238,116 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-// grid (ntile_pairs, nact), 256 threads = 8 warps; warp (wm, wn) owns a 16 x 32 patch of the 64x64 tile.
+// One CTA owns a strip of up to UPD_CHUNK tiles (I fixed, J = J0..J0+len-1): P_I stays in shared memory,
+// the P_J blocks stream through a 2-stage cp.async ring, and the C tile is prefetched into registers before
+// the DMMA loop, so that global-memory latency overlaps the tensor work.
+// grid (nwork, nact), 256 threads = 8 warps; warp (wm, wn) owns a 16 x 32 patch of the 64x64 tile.
+constexpr int UPD_CHUNK = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
+
+// copy a 64(k) x 64(cols) block (column-major, leading dim Np) into dst[c*TLD + k]
+__device__ __forceinline__ void load_pblock_async(double* dst, const double* src, int Np, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = tid + it * 256;       // 2048 chunks of 16 B
+    const int c = idx >> 5, ch = idx & 31;
+    cp_async16(dst + c * TLD + ch * 2, src + static_cast<size_t>(c) * Np + ch * 2);
+  }
+}
+
 __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kb) {
   extern __shared__ __align__(16) double usm[];
-  double* PI = usm;             // PI[m*TLD + k] = P_I(k, m)
-  double* PJ = usm + TB * TLD;
+  double* PI = usm;                 // PI[m*TLD + k] = P_I(k, m)
+  double* PJ0 = usm + TB * TLD;     // two stages
+  double* PJ1 = usm + 2 * TB * TLD;
   const int s = g.active[blockIdx.y];
   const int Np = g.Np, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nr = Np / TB - kb - 1;  // blocks to the right of kb
+  // decode work item -> (ii, chunk): row ii has ceil((nr-ii)/UPD_CHUNK) chunks
   int t = blockIdx.x, ii = 0;
-  while (t >= nr - ii) { t -= nr - ii; ++ii; }
-  const int I = kb + 1 + ii, J = I + t;
-  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
-  const int k0 = kb * TB;
-  for (int i = tid; i < TB * TB; i += 256) {
-    const int c = i / TB, k = i - c * TB;
-    PI[c * TLD + k] = Ms[static_cast<size_t>(I * TB + c) * Np + k0 + k];
-    PJ[c * TLD + k] = Ms[static_cast<size_t>(J * TB + c) * Np + k0 + k];
+  for (;;) {
+    const int nch = (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
+    if (t < nch) break;
+    t -= nch;
+    ++ii;
   }
-  __syncthreads();
+  const int I = kb + 1 + ii;
+  const int J0 = I + t * UPD_CHUNK;
+  int len = kb + 1 + nr - J0;
+  len = len > UPD_CHUNK ? UPD_CHUNK : len;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  const double* prow = Ms + static_cast<size_t>(kb) * TB;  // row offset of the panel
+  load_pblock_async(PI, prow + static_cast<size_t>(I * TB) * Np, Np, tid);
+  load_pblock_async(PJ0, prow + static_cast<size_t>(J0 * TB) * Np, Np, tid);
+  cp_async_commit();
   const int wm = warp >> 1, wn = warp & 1;
   const int g4 = lane >> 2, t4 = lane & 3;
-  double acc[2][4][2];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < TB; k += 4) {
-    double af[2], bf[4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) af[a] = PI[(wm * 16 + a * 8 + g4) * TLD + k + t4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) bf[b] = PJ[(wn * 32 + b * 8 + g4) * TLD + k + t4];
+  for (int jj = 0; jj < len; ++jj) {
+    const int J = J0 + jj;
+    double* PJ = (jj & 1) ? PJ1 : PJ0;
+    if (jj + 1 < len) load_pblock_async((jj & 1) ? PJ0 : PJ1, prow + static_cast<size_t>((J + 1) * TB) * Np, Np, tid);
+    cp_async_commit();
+    // prefetch the C tile
+    double cold[2][4][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-  }
-  // C(m, n) at column-major (I*64+m) + (J*64+n)*Np ; thread holds rows g4, cols 2*t4+{0,1} of each 8x8 tile
+      for (int b = 0; b < 4; ++b) {
+        const int m = I * TB + wm * 16 + a * 8 + g4;
+        const int n = J * TB + wn * 32 + b * 8 + 2 * t4;
+        const double* c0 = Ms + static_cast<size_t>(n) * Np + m;
+        cold[a][b][0] = c0[0];
+        cold[a][b][1] = c0[Np];
+      }
+    cp_async_wait<1>();
+    __syncthreads();
+    double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int m = I * TB + wm * 16 + a * 8 + g4;
-      const int n = J * TB + wn * 32 + b * 8 + 2 * t4;
-      double* c0 = Ms + static_cast<size_t>(n) * Np + m;
-      c0[0] -= acc[a][b][0];
-      c0[Np] -= acc[a][b][1];
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < TB; k += 4) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) af[a] = PI[(wm * 16 + a * 8 + g4) * TLD + k + t4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = PJ[(wn * 32 + b * 8 + g4) * TLD + k + t4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int m = I * TB + wm * 16 + a * 8 + g4;
+        const int n = J * TB + wn * 32 + b * 8 + 2 * t4;
+        double* c0 = Ms + static_cast<size_t>(n) * Np + m;
+        c0[0] = cold[a][b][0] - acc[a][b][0];
+        c0[Np] = cold[a][b][1] - acc[a][b][1];
+      }
+    __syncthreads();  // all warps done with PJ before the ring slot is refilled
+  }
 }
 
-// ---- back substitution R x = z (z = column N of the factored buffer), alpha = x * ascale; one CTA per sample.
-// Also returns sum(log(diag R)) and z'z (nlZ ingredients, gplite_core.m:193).
-__global__ void __launch_bounds__(256) gp_backsolve_kernel(const GpBatch g, const double* ascale, double* alpha,
-                                                           double* logdet, double* zz) {
-  __shared__ double Rk[TB][TB + 1];
-  __shared__ double xk[TB];
+// ---- back substitution R x = z (z = column N of the factored buffer), blocked like the factorisation ----
+// nlZ ingredients: sum(log(diag R)) and z'z  (gplite_core.m:193); one CTA per sample.
+__global__ void __launch_bounds__(256) gp_nlzparts_kernel(const GpBatch g, double* logdet, double* zz) {
   __shared__ double part[256];
-  const int s = g.active[blockIdx.x];
+  const int s = blockIdx.x;
   const int Np = g.Np, N = g.N, tid = threadIdx.x;
-  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
-  double* z = Ms + static_cast<size_t>(N) * Np;  // column N (overwritten by the solution)
-  // nlZ ingredients
+  const double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  const double* z = Ms + static_cast<size_t>(N) * Np;
   double ld = 0.0, q = 0.0;
   for (int i = tid; i < N; i += 256) {
     ld += log(Ms[static_cast<size_t>(i) * Np + i]);
@@ -307,35 +368,68 @@ __global__ void __launch_bounds__(256) gp_backsolve_kernel(const GpBatch g, cons
     __syncthreads();
   }
   if (tid == 0) zz[s] = part[0];
-  __syncthreads();
-  const int nbN = (N + TB - 1) / TB;
-  for (int kb = nbN - 1; kb >= 0; --kb) {
-    const int k0 = kb * TB;
-    for (int i = tid; i < TB * TB; i += 256) {
-      const int c = i / TB, r = i - c * TB;
-      Rk[c][r] = (k0 + c < N && k0 + r < N) ? Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] : (c == r ? 1.0 : 0.0);
-    }
-    if (tid < TB) xk[tid] = (k0 + tid < N) ? z[k0 + tid] : 0.0;
-    __syncthreads();
-    // 64x64 upper back substitution by one warp-sized group of threads, column oriented
-    for (int p = TB - 1; p >= 0; --p) {
-      if (tid == 0) xk[p] = xk[p] / Rk[p][p];
-      __syncthreads();
-      if (tid < p) xk[tid] -= Rk[p][tid] * xk[p];
-      __syncthreads();
-    }
-    if (tid < TB && k0 + tid < N) z[k0 + tid] = xk[tid];
-    // z_i -= sum_{j in block} R(i, j) x_j   for i < k0   (coalesced over i)
-    for (int i = tid; i < k0; i += 256) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int j = 0; j < TB; ++j) acc = fma(Ms[static_cast<size_t>(k0 + j) * Np + i], xk[j], acc);
-      z[i] -= acc;
-    }
-    __syncthreads();
+}
+
+// solve the 64x64 diagonal block kb for x_k (in place in column N); one warp per sample, lane owns rows
+// lane and lane+32; the pivot value is broadcast by shuffle.
+__global__ void __launch_bounds__(32) gp_bsolve_diag_kernel(const GpBatch g, int kb) {
+  __shared__ double Rk[TB][TB + 1];  // Rk[c][r]
+  const int s = blockIdx.x;
+  const int Np = g.Np, N = g.N, lane = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* z = Ms + static_cast<size_t>(N) * Np;
+  const int k0 = kb * TB;
+  for (int i = lane; i < TB * TB; i += 32) {
+    const int c = i >> 6, r = i & 63;
+    Rk[c][r] = (k0 + c < N && k0 + r < N && r <= c) ? Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] : (c == r ? 1.0 : 0.0);
   }
-  const double sc = ascale[s];
-  for (int i = tid; i < N; i += 256) alpha[static_cast<size_t>(s) * N + i] = z[i] * sc;
+  double x0 = (k0 + lane < N) ? z[k0 + lane] : 0.0;
+  double x1 = (k0 + lane + 32 < N) ? z[k0 + lane + 32] : 0.0;
+  __syncwarp();
+  for (int p = TB - 1; p >= 0; --p) {
+    double xp = (p >= 32 ? x1 : x0) / Rk[p][p];
+    xp = __shfl_sync(0xffffffffu, xp, p & 31);
+    if (p >= 32) {
+      if (lane == (p & 31)) x1 = xp;
+      if (lane + 32 < p) x1 = fma(-Rk[p][lane + 32], xp, x1);
+      x0 = fma(-Rk[p][lane], xp, x0);
+    } else {
+      if (lane == p) x0 = xp;
+      if (lane < p) x0 = fma(-Rk[p][lane], xp, x0);
+    }
+  }
+  if (k0 + lane < N) z[k0 + lane] = x0;
+  if (k0 + lane + 32 < N) z[k0 + lane + 32] = x1;
+}
+
+// z_i -= sum_{j<64} R(i, k0+j) x_{k0+j}   for i < k0;  grid (ceil(k0/256), S), coalesced over i
+__global__ void __launch_bounds__(256) gp_bsolve_update_kernel(const GpBatch g, int kb) {
+  __shared__ double xk[TB];
+  const int s = blockIdx.y;
+  const int Np = g.Np, N = g.N, tid = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* z = Ms + static_cast<size_t>(N) * Np;
+  const int k0 = kb * TB;
+  if (tid < TB) xk[tid] = (k0 + tid < N) ? z[k0 + tid] : 0.0;
+  __syncthreads();
+  const int i = blockIdx.x * 256 + tid;
+  if (i >= k0) return;
+  double acc0 = 0.0, acc1 = 0.0;
+  const double* col = Ms + static_cast<size_t>(k0) * Np + i;
+#pragma unroll 8
+  for (int j = 0; j < TB; j += 2) {
+    acc0 = fma(col[static_cast<size_t>(j) * Np], xk[j], acc0);
+    acc1 = fma(col[static_cast<size_t>(j + 1) * Np], xk[j + 1], acc1);
+  }
+  z[i] -= acc0 + acc1;
+}
+
+__global__ void gp_alpha_kernel(const GpBatch g, const double* ascale, double* alpha) {
+  const int s = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.N) return;
+  const double* z = g.M + static_cast<size_t>(s) * g.Np * g.Np + static_cast<size_t>(g.N) * g.Np;
+  alpha[static_cast<size_t>(s) * g.N + i] = z[i] * ascale[s];
 }
 
 // copy the N x N factor out of the padded buffer, zeroing the strictly lower part (MATLAB's chol output)
@@ -420,8 +514,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   std::vector<double> h_scale(S), h_dscale(S), h_ascale(S);
   std::vector<int> h_info(S);
   const int nb = Np / TB;
-  const int PANEL_SMEM = 3 * TB * (TB + 1) * sizeof(double), UPDATE_SMEM = 2 * TB * TLD * sizeof(double);
-  VB_CUDA(cudaFuncSetAttribute(gp_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
+  const int UPDATE_SMEM = 3 * TB * TLD * sizeof(double);
   VB_CUDA(cudaFuncSetAttribute(gp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM));
   for (int attempt = 0; attempt < 10 && !active.empty(); ++attempt) {
     for (int s : active) {
@@ -450,12 +543,18 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
     for (int kb = 0; kb < nb; ++kb) {
       const int nr = nb - kb - 1;
       {
-        dim3 grid(nr > 0 ? nr : 1, nact);
         KernelScope ks(c, "potrf_panel", st);
-        gp_panel_kernel<<<grid, 256, PANEL_SMEM, st>>>(g, kb);
+        gp_potf2_kernel<<<nact, 256, 0, st>>>(g, kb);
       }
       if (nr > 0) {
-        dim3 grid(nr * (nr + 1) / 2, nact);
+        dim3 grid(nr, nact);
+        KernelScope ks(c, "potrf_panel", st);
+        gp_trsm_kernel<<<grid, 256, 0, st>>>(g, kb);
+      }
+      if (nr > 0) {
+        int nwork = 0;
+        for (int ii = 0; ii < nr; ++ii) nwork += (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
+        dim3 grid(nwork, nact);
         KernelScope ks(c, "potrf_update", st);
         gp_update_kernel<<<grid, 256, UPDATE_SMEM, st>>>(g, kb);
       }
@@ -475,11 +574,25 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
     active.swap(next);
   }
   // back substitution + nlZ ingredients for all samples
-  for (int s = 0; s < S; ++s) h_info[s] = s;
-  VB_CUDA(cudaMemcpyAsync(d_active, h_info.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
   {
     KernelScope ks(c, "trsv", st);
-    gp_backsolve_kernel<<<S, 256, 0, st>>>(g, d_ascale, c->gpAlpha.d(), d_logdet, d_zz);
+    gp_nlzparts_kernel<<<S, 256, 0, st>>>(g, d_logdet, d_zz);
+  }
+  for (int kb = (N + TB - 1) / TB - 1; kb >= 0; --kb) {
+    {
+      KernelScope ks(c, "trsv", st);
+      gp_bsolve_diag_kernel<<<S, 32, 0, st>>>(g, kb);
+    }
+    if (kb > 0) {
+      dim3 grid((kb * TB + 255) / 256, S);
+      KernelScope ks(c, "trsv", st);
+      gp_bsolve_update_kernel<<<grid, 256, 0, st>>>(g, kb);
+    }
+  }
+  {
+    dim3 grid((N + 255) / 256, S);
+    KernelScope ks(c, "trsv", st);
+    gp_alpha_kernel<<<grid, 256, 0, st>>>(g, d_ascale, c->gpAlpha.d());
   }
   VB_CUDA(cudaGetLastError());
   rr->logdet.assign(S, 0.0);
