@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=40)
+    p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--config", default=None, help="c2|c3|c4 (default: c3 at 1 GPU, c4 at >1)")
@@ -65,7 +65,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -253,12 +253,12 @@ def main():
             import torch
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # runs through the timed region, the per-kernel pass and the e2e loop
     for i in range(args.warmup):
         resident_step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = ctx.launch_count()
     t_wall0 = time.perf_counter()
     tot_ms = 0.0
@@ -267,7 +267,6 @@ def main():
         tot_ms += resident_step(args.warmup + i)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = ctx.launch_count() - l0 - args.steps  # minus the flush memsets? (memset is not a counted kernel)
     launches = ctx.launch_count() - l0
     if dist is not None:
         import torch
@@ -289,7 +288,6 @@ def main():
     for name in ("entmc", "gplogjoint", "philox", "reduce", "finalize", "vp_unpack"):
         t_ms, n = ctx.profile_get(name)
         prof[name] = {"ms_per_step": t_ms / nprof, "launches_per_step": n / nprof}
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the public host API: host theta -> F, dF on the host + host Adam ----
     def e2e_loop(nsteps, warm, host_eps=None):
@@ -318,7 +316,10 @@ def main():
         heps = workloads.make_epsilon(cfg)
         e2e_host_eps = 1.0 / e2e_loop(max(3, args.steps // 4), 2, host_eps=heps)
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     # ---- roofline ----
     peaks, peak_src = measured_peaks()

@@ -64,6 +64,8 @@ int vbmc_b200_launch_count(vbmc_b200_ctx* ctx, long long* count);
 int vbmc_b200_comm_unique_id(void* id128);                                  /* rank 0, then broadcast out of band */
 int vbmc_b200_comm_init(vbmc_b200_ctx* ctx, int nranks, int rank, const void* id128);
 int vbmc_b200_comm_info(vbmc_b200_ctx* ctx, int* nranks, int* rank);
+/* contiguous balanced split of `total` units (MC pairs per component, hyper-parameter samples) over ranks */
+int vbmc_b200_shard_range(int total, int nranks, int rank, int* begin, int* end);
 
 /* ---------------------------------------------------------------------------------------
  * GP struct (reference type: gplite/gplite_post.m:94-151; consumed by misc/gplogjoint.m:32-45)

@@ -4,6 +4,7 @@ bench.py's cpu_baseline / --impl reference legs only."""
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 import time
@@ -18,9 +19,23 @@ dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
 
+def host_threads():
+    """Threads the CPU baseline should use: the cgroup CPU quota (x2 for SMT) capped by the affinity mask.
+    (On the gpurun boxes nproc = 128 but cpu.max = 16 CPUs; 128 OpenMP threads thrash there.)"""
+    aff = len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            return max(1, min(aff, 2 * int(math.ceil(int(q) / int(per)))))
+    except Exception:
+        pass
+    return aff
+
+
 def load():
     global _lib
     if _lib is None:
+        os.environ.setdefault("OMP_NUM_THREADS", str(host_threads()))
         if not _LIB.exists():
             subprocess.check_call(["make", "-C", str(_DIR)])
         _lib = C.CDLL(str(_LIB))

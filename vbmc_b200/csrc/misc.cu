@@ -108,6 +108,12 @@ int vbmc_b200_comm_init(vbmc_b200_ctx* c, int nranks, int rank, const void* id12
   return VBMC_B200_OK;
 }
 
+int vbmc_b200_shard_range(int total, int nranks, int rank, int* begin, int* end) {
+  if (total < 0 || nranks < 1 || rank < 0 || rank >= nranks || !begin || !end) VB_FAIL(VBMC_B200_EINVAL, "shard_range: bad arguments");
+  shard_range(total, nranks, rank, begin, end);
+  return VBMC_B200_OK;
+}
+
 int vbmc_b200_comm_info(vbmc_b200_ctx* c, int* nranks, int* rank) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
   if (nranks) *nranks = c->nranks;
