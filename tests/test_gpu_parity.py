@@ -250,3 +250,46 @@ def test_full_size_properties_c3(gpu_ctx):
     assert abs(np.sum(dHab[-50:])) < 1e-10 * np.max(np.abs(dHab[-50:]))
     H2, dH2 = vbmc_b200.entmc_vbmc(vp, 32768, True, True, epsilon=np.concatenate([ea, eb], axis=1))
     assert H2 == Hab and np.array_equal(dH2, dHab)
+
+
+# ---- variance of the expected log-joint (gplogjoint.m:273-339) and the eval_fullelcbo call pattern ----
+def _var_problem(K=5, S=3, N=70, D=3):
+    import math as _m
+    return mk(D=D, N=N, K=K, S=S, Ns=64, log_sn=_m.log(0.1))
+
+
+@pytest.mark.parametrize("compute_var", [1, 2])
+@pytest.mark.parametrize("source", ["attach", "refit"])
+def test_gplogjoint_variance(gpu_ctx, compute_var, source):
+    """varF, varss, J_sjk.  J = prior term - z K^-1 z suffers cancellation (the GP is confident near its data),
+    so the comparison is relative to max|J| with a looser bound than the 1e-10 used for F and dF."""
+    import vbmc_b200
+    w = _var_problem()
+    vp, gp = w["vp"], w["gp"]
+    if source == "refit":   # factors computed by the GPU refit and left resident
+        gp = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, [1, 0, 0], None)
+    got = vbmc_b200.gplogjoint(vp, gp, False, True, True, compute_var, nargout=7)
+    ref = orc.gplogjoint(vp, w["gp"], False, True, True, compute_var, nargout=7)
+    assert rel(got[0], ref[0]) < 1e-9
+    assert got[6].shape == ref[6].shape == (3, 5, 5)
+    assert rel(got[6], ref[6]) < 1e-7
+    assert rel(got[2], ref[2]) < 1e-7 and rel(got[4], ref[4]) < 1e-7
+    assert got[2] > 0
+
+
+def test_eval_fullelcbo_call_pattern(gpu_ctx):
+    """vpoptimize_vbmc.m:288-289: negelcbo_vbmc(theta,0,vp,gp,NSentFineK,0,1,...) with 11 outputs."""
+    import vbmc_b200
+    w = _var_problem(K=6, S=4)
+    vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
+    got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 64, 0, 1, epsilon=eps, nargout=11)
+    ref = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 64, 0, 1, epsilon=eps, nargout=11)
+    F, dF, G, H, varF, dH, varGss, varG, varH, I_sk, J_sjk = got
+    assert dF is None and dH is None and varH == 0.0
+    assert rel(F, ref[0]) < 1e-9 and rel(G, ref[2]) < 1e-9 and rel(H, ref[3]) < TOL
+    assert rel(varF, ref[4]) < 1e-7 and rel(varGss, ref[6]) < 1e-7 and rel(varG, ref[7]) < 1e-7
+    assert rel(I_sk, ref[9]) < 1e-9 and rel(J_sjk, ref[10]) < 1e-7
+    # beta ~= 0 without gradient: F = -G - H + beta*sqrt(varF)  (negelcbo_vbmc.m:126)
+    gb = vbmc_b200.negelcbo_vbmc(theta, 1.5, vp, gp, 64, 0, 2, epsilon=eps, nargout=5)
+    rb = orc.negelcbo_vbmc(theta, 1.5, vp, gp, 64, 0, 2, epsilon=eps, nargout=5)
+    assert rel(gb[0], rb[0]) < 1e-8 and rel(gb[4], rb[4]) < 1e-7

@@ -115,8 +115,11 @@ class Context:
         alpha = np.ascontiguousarray(np.stack([f64(p["alpha"]).ravel() for p in post]))
         key = (id(gp), gp["X"].shape, len(post), float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
                float(hyp[-1, -1]), bool(want_L))
-        if key == self._gp_key:
+        if self._gp_key is not None and key[:-1] == self._gp_key[:-1] and (self._gp_key[-1] or not want_L):
             return
+        if want_L and any(p.get("L") is None for p in post):
+            raise VbmcB200Error(_lib.ESTATE, "vbmc_b200:noL: the variance path needs gp.post(s).L (call gplite_post with want_L=True, "
+                                             "or keep the posterior resident)")
         keep = []
         d, (N, D, S, _) = self._gp_desc(gp, hyp, keep)
         sW1 = f64([np.asarray(p["sW"]).ravel()[0] for p in post])
@@ -457,7 +460,7 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
                    "L": None if L is None else L[s].T.copy(), "sn2_mult": float(mult[s]), "Lchol": bool(Lchol[s])}
                   for s in range(S)]
     ctx._gp_key = (id(gp), gp["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
-                   float(hyp[-1, -1]), bool(want_L))
+                   float(hyp[-1, -1]), True)   # the factors stay on the device whether or not they were copied out
     return gp
 
 

@@ -122,7 +122,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   vb::comm_destroy(c);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -477,9 +477,11 @@ static int negelcbo_validate(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
   if (a->Ns <= 0)
     VB_FAIL(VBMC_B200_EUNSUPPORTED,
             "vbmc_b200:OutOfScope: Ns == 0 selects entlb_vbmc (deterministic entropy bound), outside this build");
-  if (a->compute_var != 0 || b != 0.0)
+  if (a->compute_var != 0 && a->compute_var != 1 && a->compute_var != 2)
+    VB_FAIL(VBMC_B200_EINVAL, "negelcbo: compute_var must be 0, 1 (full) or 2 (diagonal)");
+  if (a->compute_grad && b != 0.0)
     VB_FAIL(VBMC_B200_EUNSUPPORTED,
-            "vbmc_b200:NotYet: compute_var/beta != 0 (gplogjoint.m:273-339 variance) is not built in this round");
+            "vbmc_b200:NotYet: gradient of the variance term (beta ~= 0 with compute_grad, gplogjoint.m:289-303) is not built yet");
   if (a->use_thetabnd && c->nbnd > 0) {
     const int expect = (c->opt[0] ? c->D * c->K : 0) + ((c->opt[1] || c->opt[2]) ? c->D * c->K : 0) + (c->opt[3] ? c->K : 0);
     if (expect != c->nbnd)
@@ -492,6 +494,30 @@ static int negelcbo_validate(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
       if (c->opt[i]) m |= 1 << i;
   *gmask = m;
   return VBMC_B200_OK;
+}
+
+// Average over hyper-parameter samples (gplogjoint.m:398-407): varF, varss from F(s), varF(s)
+static void combine_variance(const double* Fs, const std::vector<double>& vF, int S, double* varF, double* varss) {
+  if (S > 1) {
+    double Fbar = 0.0, vm = 0.0;
+    for (int s = 0; s < S; ++s) { Fbar += Fs[s]; vm += vF[s]; }
+    Fbar /= S; vm /= S;
+    double ss = 0.0, sv = 0.0;
+    for (int s = 0; s < S; ++s) { ss += (Fs[s] - Fbar) * (Fs[s] - Fbar); sv += (vF[s] - vm) * (vF[s] - vm); }
+    const double varFss = ss / (S - 1);          // :402
+    *varss = varFss + sqrt(sv / (S - 1));       // varFss + std(varF) (:403)
+    *varF = vm + varFss;                         // :404
+  } else {
+    *varF = vF[0];
+    *varss = 0.0;
+  }
+}
+
+static void scatter_J(const std::vector<double>& J, int S, int K, double* out) {
+  // device J[s][j][k] -> MATLAB J_sjk(s,j,k) column-major
+  for (int s = 0; s < S; ++s)
+    for (int j = 0; j < K; ++j)
+      for (int k = 0; k < K; ++k) out[s + static_cast<size_t>(j) * S + static_cast<size_t>(k) * S * K] = J[(static_cast<size_t>(s) * K + j) * K + k];
 }
 
 static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int nth) {
@@ -528,6 +554,21 @@ int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
   const int nth = grad_mask_len(c, gmask);
   VB_TRY(fetch_out(c, nth, c->gp.S));
   scatter_negelcbo(c, a, nth);
+  if (a->compute_var) {
+    // varG (and J_sjk) from the factors; F = F + beta*sqrt(varF)   (negelcbo_vbmc.m:119-130)
+    std::vector<double> vF, J;
+    VB_TRY(run_variance(c, a->compute_var, &vF, (a->separate_K && a->J_sjk) ? &J : nullptr));
+    OutLayout ol;
+    ol.init(nth, c->gp.S, c->K);
+    double varG, varGss;
+    combine_variance(c->out_pinned + ol.oFs, vF, c->gp.S, &varG, &varGss);
+    if (a->varG) *a->varG = varG;
+    if (a->varGss) *a->varGss = varGss;
+    if (a->varH) *a->varH = 0.0;
+    if (a->varF) *a->varF = varG;
+    if (beta != 0.0 && a->F) *a->F += beta * sqrt(varG);
+    if (a->separate_K && a->J_sjk) scatter_J(J, c->gp.S, c->K, a->J_sjk);
+  }
   return VBMC_B200_OK;
 }
 
@@ -592,8 +633,9 @@ int vbmc_b200_gplogjoint(vbmc_b200_ctx* c, const int grad_flags[4], int avg_flag
     VB_FAIL(VBMC_B200_EREFERENCE,
             "gplogjoint:FullVarianceGradient: Computation of gradient of log joint variance is currently available only "
             "for diagonal approximation of the variance.");
-  if (compute_var != 0 || varF || dvarF || J_sjk)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: gplogjoint variance (gplogjoint.m:273-339) is not built in this round");
+  if (dvarF)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: gradient of the log-joint variance (gplogjoint.m:289-303) is not built yet");
+  if (compute_var != 0 && compute_var != 1 && compute_var != 2) VB_FAIL(VBMC_B200_EINVAL, "gplogjoint: compute_var must be 0, 1 or 2");
   if (!avg_flag && c->gp.S > 1)
     VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:OutOfScope: avg_flag=0 with several hyper-parameter samples");
   VB_CUDA(cudaSetDevice(c->device));
@@ -614,6 +656,15 @@ int vbmc_b200_gplogjoint(vbmc_b200_ctx* c, const int grad_flags[4], int avg_flag
     const int S = c->gp.S, K = c->K;
     for (int s = 0; s < S; ++s)
       for (int k = 0; k < K; ++k) I_sk[s + static_cast<size_t>(k) * S] = o[ol.oIsk + s * K + k];
+  }
+  if (compute_var) {
+    std::vector<double> vF, J;
+    VB_TRY(run_variance(c, compute_var, &vF, J_sjk ? &J : nullptr));
+    double vG, vss;
+    combine_variance(c->out_pinned + ol.oFs, vF, c->gp.S, &vG, &vss);
+    if (varF) *varF = vG;
+    if (varss) *varss = vss;
+    if (J_sjk) scatter_J(J, c->gp.S, c->K, J_sjk);
   }
   return VBMC_B200_OK;
 }

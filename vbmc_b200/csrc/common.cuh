@@ -119,7 +119,7 @@ struct RLayout {
 // output block written by finalize_kernel (device), copied to the host in one memcpy
 struct OutLayout {
   int ntheta, S, K;
-  int oF, oG, oH, oVarF, oVarGss, oVarG, oVarH, oDF, oDH, oDG, oIsk, total;
+  int oF, oG, oH, oVarF, oVarGss, oVarG, oVarH, oDF, oDH, oDG, oIsk, oFs, total;
   __host__ __device__ void init(int ntheta_, int S_, int K_) {
     ntheta = ntheta_; S = S_; K = K_;
     oF = 0; oG = 1; oH = 2; oVarF = 3; oVarGss = 4; oVarG = 5; oVarH = 6;
@@ -127,7 +127,8 @@ struct OutLayout {
     oDH = oDF + ntheta;
     oDG = oDH + ntheta;
     oIsk = oDG + ntheta;
-    total = oIsk + S * K;
+    oFs = oIsk + S * K;   // F(s) = sum_k w_k I_sk per hyper-parameter sample (gplogjoint.m:203)
+    total = oFs + S;
   }
 };
 
@@ -194,6 +195,7 @@ struct vbmc_b200_ctx {
   double* out_pinned = nullptr;
   size_t theta_pinned_cap = 0, out_pinned_cap = 0;
   vb::DevBuf flush;  // L2 flush scratch
+  vb::DevBuf varWork;  // variance path: Z/V, Gram, J, varF(s)
 
   // profiling
   bool profiling = false;
@@ -227,6 +229,7 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
+int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);
 

@@ -256,6 +256,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       }
     }
     for (int i = tid; i < S * K; i += nt) out[ol.oIsk + i] = R[rl.oI + i];
+    for (int s = tid; s < S; s += nt) {
+      double Fs = 0.0;
+      for (int k = 0; k < K; ++k) Fs += a.vp.w[k] * R[rl.oI + s * K + k];
+      out[ol.oFs + s] = Fs;
+    }
     if (a.gf[0])
       for (int i = tid; i < D * K; i += nt) out[ol.oDG + o_mu + i] = a.vp.w[i / D] * R[rl.oGmu + i] * invS;
     if (a.gf[1])
