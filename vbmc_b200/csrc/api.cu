@@ -108,8 +108,9 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaEventCreate(&c->ev_t0));
   VB_CUDA(cudaEventCreate(&c->ev_t1));
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
-    if (!strcmp(f, "expanded")) c->entmc_form = 0;
+    if (!strcmp(f, "separable")) c->entmc_form = 0;
     if (!strcmp(f, "direct")) c->entmc_form = 1;
+    if (!strcmp(f, "expanded")) c->entmc_form = 2;
   }
   *out = c;
   return VBMC_B200_OK;
@@ -296,7 +297,11 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   c->base_lambda = b; b += D;
   c->base_w = b; b += K;
   c->base_eta = b;
-  const size_t ncur = 2 * static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K + 2;
+  const int DPc = vb::entmc_pick_dp(D) > 0 ? vb::entmc_pick_dp(D) : D + (D & 1);
+  const int K2c = (K + 1) & ~1;
+  c->vp_cblob_dp = DPc;
+  c->vp_cblob_len = K2c * DPc + 2 * K2c + DPc;
+  const size_t ncur = 2 * static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K + 2 + c->vp_cblob_len;
   VB_TRY(c->vpCur.reserve(ncur * sizeof(double)));
   double* q = c->vpCur.d();
   c->vp.D = D; c->vp.K = K;
@@ -313,6 +318,7 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   c->vp.cn = q; q += K + 1;
   c->vp.form_flag = reinterpret_cast<int*>(q); q += 2;
   c->vp.scratch = q; q += D * K;
+  c->vp.cblob = q; q += c->vp_cblob_len;
   std::vector<double> dl(D, 0.0);
   if (v->delta)
     for (int d = 0; d < D; ++d) dl[d] = v->delta[d];

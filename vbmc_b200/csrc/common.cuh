@@ -82,6 +82,7 @@ struct VpDev {  // unpacked variational posterior (filled by vp_unpack_kernel ea
   double* ak;        // [K]  ck_k/sigma_k
   double* cn;        // [K+1] nf/sigma_k^D, cn[K] = nf
   double* scratch;   // [K*D] work array of vp_unpack_kernel
+  double* cblob;     // [K2*DP | K2 | K2 | DP] centred mu, ck, ak/sigma, 1/lambda: source of entmc's constant-bank tables
   int* form_flag;    // entmc formulation of this step: 0 expanded, 1 direct (set by vp_unpack_kernel)
 };
 
@@ -171,6 +172,7 @@ struct vbmc_b200_ctx {
   int D = 0, K = 0;
   int opt[4] = {0, 0, 0, 0};
   int ntheta = 0;
+  int vp_cblob_len = 0, vp_cblob_dp = 0;
   vb::DevBuf vpBase;  // base vp as set by vp_set: mu, sigma, lambda, w, eta, delta
   vb::DevBuf vpCur;   // unpacked vp of the current step
   vb::VpDev vp{};
@@ -232,6 +234,7 @@ void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);
+int entmc_pick_dp(int D);
 
 enum { NEED_MU = 1, NEED_E = 2, NEED_W = 4 };
 enum { FIN_NEGELCBO = 0, FIN_ENTMC = 1, FIN_GPLOGJOINT = 2 };

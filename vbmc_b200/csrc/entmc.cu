@@ -32,7 +32,8 @@ struct EntmcArgs {
   int need;                  // NEED_* mask
   int pstride;               // 1 + 2*D + K doubles per tile partial
   int iq_in_smem;            // 1: 1/q broadcast through shared memory, 0: through shuffles
-  const int* form_flag;      // device flag: 0 -> expanded form, 1 -> direct form
+  const int* form_flag;      // device flag: 2 -> expanded form (default), 1 -> direct, 0 -> separable (experimental)
+  int c_mu, c_ck, c_akis, c_ilam;  // offsets (doubles) inside the __constant__ blob c_ent
   const double* eps;         // [K][half][D]
   const double* mu;          // [K][D]
   const double* sigma;       // [K]
@@ -167,7 +168,7 @@ __constant__ double c_t16[16] = {1.0, 1.0442737824274138, 1.0905077326652577, 1.
 
 template <int DP, int MAXW, bool EXPANDED>
 __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) {
-  if ((*a.form_flag != 0) == EXPANDED) return;  // the other instantiation handles this step
+  if (*a.form_flag != (EXPANDED ? 2 : 1)) return;  // another kernel handles this step
   extern __shared__ __align__(16) unsigned char smem[];
   const int D = a.D, K = a.K;
   const int K2 = (K + 1) & ~1;  // tables are padded to an even number of components (dummy: ck = ak = 0)
@@ -416,6 +417,247 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SEPARABLE form (experimental, VBMC_B200_ENTMC_FORM=separable).  u_jkd = (mu_jd - mu_kd)/(sigma_k lambda_d) factorises, so with et_d = eps_d/lambda_d
+//   eps.u_jk = (et.mu_j - et.mu_k)/sigma_k,        A(+-)_d = (mu_jd S(+-) - Q(+-)_d)/lambda_d,   B(+-) = sigma_j S(+-),
+//   S(+-) = sum_k s_k,  Q(+-)_d = sum_k s_k mu_kd,  s_k = ak_k e(+-)_k / sigma_k.
+// All D-vectors the inner loop needs (mu_k, centred) are now independent of the source component j: they live in
+// the constant bank (c_ent) and reach the FP64 pipe through LDC, not through the shared-memory -> register path that
+// bounded the table-in-shared-memory version (broadcast LDS.128 cost as many SM cycles as the DFMAs they fed).
+// Only three scalars per (j,k) stay in shared memory: -0.5||u_jk||^2, r_jk^2 and sigma_j/sigma_k^2.
+__constant__ double c_ent[4096];
+
+template <int DP, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) entmc_sep_kernel(const EntmcArgs a) {
+  if (*a.form_flag != 0) return;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int D = a.D, K = a.K;
+  const int K2 = (K + 1) & ~1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = blockDim.x >> 5;
+  double2* tab_a = reinterpret_cast<double2*>(smem + a.off_u);   // [K2] {-0.5||u_jk||^2, r_jk^2}
+  double* tab_b = reinterpret_cast<double*>(smem + a.off_s);     // [K2] sigma_j / sigma_k^2
+  double* t16 = reinterpret_cast<double*>(smem + a.off_t16);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + warp;
+  unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
+  double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);
+  double2* iq_s = reinterpret_cast<double2*>(wbase + a.woff_iq);
+  double2* stage = reinterpret_cast<double2*>(wbase + a.woff_stage);
+  double* wres = reinterpret_cast<double*>(wbase + a.woff_stage);
+  double* red = wres + ((a.pstride + 1) & ~1);
+  const double* cmu = c_ent + a.c_mu;      // [K2][DP] centred means
+  const double* cck = c_ent + a.c_ck;      // [K2]
+  const double* cak = c_ent + a.c_akis;    // [K2] ak_k / sigma_k
+  const double* cil = c_ent + a.c_ilam;    // [DP] 1 / lambda_d
+
+  const bool needT = (a.need & (NEED_MU | NEED_E)) != 0;
+  const bool needW = (a.need & NEED_W) != 0;
+  if (lane == 0) mbar_init(bar, 1);
+  if (tid < 16) t16[tid] = c_t16[tid];
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  uint32_t phase = 0;
+  int tile = blockIdx.x;
+  bool tma_pending = false;
+  auto issue_eps = [&](int t) -> bool {
+    if (t >= a.ntiles) return false;
+    const int j = t / a.tiles_per_comp, tt = t - j * a.tiles_per_comp;
+    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
+    int np = a.pair_end - p0;
+    np = np < 0 ? 0 : (np > 32 ? 32 : np);
+    if (np == 0) return false;
+    const double* src = a.eps + (static_cast<size_t>(j) * a.half + p0) * D;
+    return eps_stage(eps_s, src, np * D, bar, lane);
+  };
+  tma_pending = issue_eps(tile);
+
+  for (; tile < a.ntiles; tile += gridDim.x) {
+    const int j = tile / a.tiles_per_comp, tt = tile - j * a.tiles_per_comp;
+    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
+    int np = a.pair_end - p0;
+    np = np < 0 ? 0 : (np > 32 ? 32 : np);
+    const double sj = a.sigma[j];
+    __syncthreads();  // previous tile: tables and the wres/stage regions are free again
+    for (int k = tid; k < K2; k += blockDim.x) {
+      double2 ta = make_double2(0.0, 0.0);
+      double tb = 0.0;
+      if (k < K) {
+        const double isg = 1.0 / a.sigma[k];
+        double uu = 0.0;
+        for (int d = 0; d < D; ++d) {
+          const double df = (cmu[j * DP + d] - cmu[k * DP + d]) * cil[d];
+          uu = fma(df, df, uu);
+        }
+        ta = make_double2(-0.5 * uu * isg * isg, sj * sj * isg * isg);
+        tb = sj * isg * isg;
+      }
+      tab_a[k] = ta;
+      tab_b[k] = tb;
+    }
+    if (tma_pending) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+    } else {
+      __syncwarp();
+    }
+    double et[DP];  // eps_d / lambda_d
+    const bool valid = lane < np;
+    double mhee = 0.0, cj = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      const double e = (valid && d < D) ? eps_s[lane * D + d] : 0.0;
+      mhee = fma(e, e, mhee);
+      et[d] = e * cil[d];
+      cj = fma(et[d], cmu[j * DP + d], cj);
+    }
+    mhee *= -0.5;
+    __syncwarp();
+    tma_pending = issue_eps(tile + gridDim.x);
+    __syncthreads();  // tables ready
+
+    if (np > 0) {
+      double qp = 0.0, qm = 0.0, Sp = 0.0, Sm = 0.0;
+      double Qp[DP], Qm[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) Qp[d] = Qm[d] = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < K2; k += 2) {
+        const double* mua = cmu + k * DP;
+        const double* mub = mua + DP;
+        double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DP; d += 2) {
+          da0 = fma(et[d], mua[d], da0);
+          db0 = fma(et[d], mub[d], db0);
+          da1 = fma(et[d + 1], mua[d + 1], da1);
+          db1 = fma(et[d + 1], mub[d + 1], db1);
+        }
+        const double2 ta = tab_a[k], tb = tab_a[k + 1];
+        const double rta = tab_b[k] * (cj - (da0 + da1));      // r_jk * (eps.u_jk)
+        const double rtb = tab_b[k + 1] * (cj - (db0 + db1));
+        const double xba = fma(ta.y, mhee, ta.x), xbb = fma(tb.y, mhee, tb.x);
+        double x[4], ex[4];
+        x[0] = xba - rta; x[1] = xba + rta;
+        x[2] = xbb - rtb; x[3] = xbb + rtb;
+        exp_neg4(x, ex, t16);
+        if (needW) {
+          stage[k * 32 + (lane ^ (k & 7))] = make_double2(ex[0], ex[1]);
+          stage[(k + 1) * 32 + (lane ^ ((k + 1) & 7))] = make_double2(ex[2], ex[3]);
+        }
+        const double cka = cck[k], ckb = cck[k + 1];
+        qp = fma(cka, ex[0], qp);
+        qm = fma(cka, ex[1], qm);
+        qp = fma(ckb, ex[2], qp);
+        qm = fma(ckb, ex[3], qm);
+        if (needT) {
+          const double aka = cak[k], akb = cak[k + 1];
+          const double spa = aka * ex[0], sma = aka * ex[1], spb = akb * ex[2], smb = akb * ex[3];
+          Sp += spa + spb;
+          Sm += sma + smb;
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            Qp[d] = fma(spa, mua[d], Qp[d]);
+            Qm[d] = fma(sma, mua[d], Qm[d]);
+          }
+#pragma unroll
+          for (int d = 0; d < DP; ++d) {
+            Qp[d] = fma(spb, mub[d], Qp[d]);
+            Qm[d] = fma(smb, mub[d], Qm[d]);
+          }
+        }
+      }
+      const double iqp = valid ? 1.0 / qp : 0.0;
+      const double iqm = valid ? 1.0 / qm : 0.0;
+      const double Hs = valid ? log(qp) + log(qm) : 0.0;
+      if (needT) {
+        // T+ = (A+ + eps B+)/q+, T- = (A- - eps B-)/q-;  A = (mu_j S - Q)/lambda, B = sigma_j S, eps = et*lambda
+        const double Bp = sj * Sp, Bm = sj * Sm;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const double il = cil[d];
+          const double e = (d < D) ? et[d] / il : 0.0;
+          const double mj = cmu[j * DP + d];
+          const double tp = fma(e, Bp, (mj * Sp - Qp[d]) * il) * iqp;
+          const double tm = fma(-e, Bm, (mj * Sm - Qm[d]) * il) * iqm;
+          Qp[d] = tp + tm;
+          Qm[d] = e * (tp - tm);
+        }
+      }
+      double wacc[4] = {0.0, 0.0, 0.0, 0.0};
+      if (needW) {
+        if (a.iq_in_smem) iq_s[lane] = make_double2(iqp, iqm);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int l = lane + 32 * rr;
+          const bool act = l < K;
+          const double2* row = stage + (act ? l : 0) * 32;
+          const int x = l & 7;
+          double acc = 0.0;
+          if (32 * rr < K) {
+            if (a.iq_in_smem) {
+              if (act) {
+#pragma unroll 8
+                for (int p = 0; p < 32; ++p) {
+                  const double2 ee = row[p ^ x];
+                  const double2 iq = iq_s[p];
+                  acc = fma(ee.x, iq.x, acc);
+                  acc = fma(ee.y, iq.y, acc);
+                }
+              }
+            } else {
+#pragma unroll 8
+              for (int p = 0; p < 32; ++p) {
+                const double2 ee = row[p ^ x];
+                acc = fma(ee.x, __shfl_sync(0xffffffffu, iqp, p), acc);
+                acc = fma(ee.y, __shfl_sync(0xffffffffu, iqm, p), acc);
+              }
+            }
+          }
+          wacc[rr] = act ? acc : 0.0;
+        }
+        __syncwarp();
+      }
+      red[0 * 33 + lane] = Hs;
+      if (needT) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          if (d < D) {
+            red[(1 + d) * 33 + lane] = Qp[d];
+            red[(1 + D + d) * 33 + lane] = Qm[d];
+          }
+        }
+      }
+      __syncwarp();
+      const int nval = needT ? 1 + 2 * D : 1;
+      for (int i = lane; i < nval; i += 32) {
+        const double* rr = red + i * 33;
+        double sacc = 0.0;
+#pragma unroll 8
+        for (int p = 0; p < 32; ++p) sacc += rr[p];
+        wres[i] = sacc;
+      }
+      if (!needT)
+        for (int i = 1 + lane; i < 1 + 2 * D; i += 32) wres[i] = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int l = lane + 32 * rr;
+        if (l < K) wres[1 + 2 * D + l] = wacc[rr];
+      }
+    } else {
+      for (int i = lane; i < a.pstride; i += 32) wres[i] = 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < a.pstride; i += blockDim.x) {
+      double sacc = 0.0;
+      for (int w = 0; w < nw; ++w)
+        sacc += reinterpret_cast<const double*>(smem + a.off_warp + static_cast<size_t>(w) * a.warp_bytes + a.woff_stage)[i];
+      a.partial[static_cast<size_t>(tile) * a.pstride + i] = sacc;
+    }
+  }
+}
+
 // Sum the tile partials of each component in tile order.  grid = K CTAs.
 // R.Hs[j], R.M[j][d], R.E[j][d], Wj[j][l] (Wj goes to R.oWc region sized K*K)
 __global__ void entmc_reduce_kernel(const double* __restrict__ partial, int tiles_per_comp, int pstride, int D, int K,
@@ -449,6 +691,8 @@ static int pick_dp(int D) {
     if (D <= o) return o;
   return -1;
 }
+
+int entmc_pick_dp(int D) { return pick_dp(D); }
 
 struct EntmcPlan {
   int DP, maxw, nw, pairs_per_tile, tiles_per_comp, ntiles, npairs_local, pair_begin, pair_end;
@@ -533,19 +777,29 @@ int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_pe
 
 template <int DP>
 static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
-  auto kexp = entmc_kernel<DP, 8, true>;
+  auto ksep = entmc_sep_kernel<DP, 8>;
   auto kdir = entmc_kernel<DP, 8, false>;
-  VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  auto kexp = entmc_kernel<DP, 8, true>;
+  VB_CUDA(cudaFuncSetAttribute(ksep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   const int grid = pl.ntiles < c->num_sms ? pl.ntiles : c->num_sms;
+  VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   {
-    KernelScope ks(c, "entmc", st);
+    KernelScope ks(c, "entmc", st);  // expanded form, tables in shared memory (default when the guard allows)
     kexp<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
     VB_CUDA(cudaGetLastError());
   }
   {
     KernelScope ks(c, "entmc_direct", st);
     kdir<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+    VB_CUDA(cudaGetLastError());
+  }
+  if (c->entmc_form == 0) {
+    // experimental separable form with constant-bank tables (VBMC_B200_ENTMC_FORM=separable): measured slower
+    // on B200 (0.56 ms vs 0.35 ms at c3) — LDC latency is exposed with two warps per sub-partition.
+    VB_CUDA(cudaMemcpyToSymbolAsync(c_ent, c->vp.cblob, sizeof(double) * c->vp_cblob_len, 0, cudaMemcpyDeviceToDevice, st));
+    KernelScope ks(c, "entmc_separable", st);
+    ksep<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
     VB_CUDA(cudaGetLastError());
   }
   return VBMC_B200_OK;
@@ -559,6 +813,12 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   EntmcArgs& a = pl.a;
   a.need = need_mask;
   a.form_flag = c->vp.form_flag;
+  {
+    const int K2 = (c->K + 1) & ~1;
+    a.c_mu = 0; a.c_ck = K2 * pl.DP; a.c_akis = a.c_ck + K2; a.c_ilam = a.c_akis + K2;
+    if (a.c_ilam + pl.DP > 4096) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: K=%d, D=%d exceed the constant-bank table", c->K, c->D);
+    if (c->vp_cblob_dp != pl.DP) VB_FAIL(VBMC_B200_ESTATE, "entmc: constant tables were built for another padded dimension");
+  }
   a.eps = c->eps.d();
   a.mu = c->vp.mu;
   a.sigma = c->vp.sigma;

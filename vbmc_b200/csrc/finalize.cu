@@ -10,7 +10,7 @@
 namespace vb {
 
 struct UnpackArgs {
-  int D, K, ntheta, have_theta, force_form;
+  int D, K, ntheta, have_theta, force_form, DPc;
   int opt[4];
   const double* theta;
   const double *base_mu, *base_sigma, *base_lambda, *base_w, *base_eta;
@@ -101,16 +101,37 @@ __global__ void vp_unpack_kernel(const UnpackArgs a) {
       if (tid < off) pmax[tid] = (pmax[tid + off] > pmax[tid] || !(pmax[tid + off] == pmax[tid + off])) ? pmax[tid + off] : pmax[tid];
       __syncthreads();
     }
-    if (tid == 0) *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((pmax[0] <= 2.0e5) ? 0 : 1);
+    if (tid == 0) *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((pmax[0] <= 2.0e5) ? 2 : 1);
   }
-  for (int k = tid; k < K; k += nt) {
-    const double w = (ht && a.opt[3]) ? exp(a.vp.eta[k]) / s_es : a.base_w[k];
-    a.vp.w[k] = w;
-    const double sg = a.vp.sigma[k];
-    const double cn = s_nf / pow(sg, static_cast<double>(D));  // nf/sigma(k)^D  (:63)
-    a.cn[k] = cn;
-    a.vp.ck[k] = w * cn;
-    a.vp.ak[k] = w * cn / sg;
+  const int K2 = (K + 1) & ~1, DPc = a.DPc;
+  double* b_mu = a.vp.cblob;              // [K2][DPc] means centred on their average (only differences matter)
+  double* b_ck = b_mu + K2 * DPc;         // [K2]
+  double* b_ak = b_ck + K2;               // [K2] ak_k / sigma_k
+  double* b_il = b_ak + K2;               // [DPc] 1/lambda_d
+  for (int k = tid; k < K2; k += nt) {
+    double ck = 0.0, aks = 0.0;
+    if (k < K) {
+      const double w = (ht && a.opt[3]) ? exp(a.vp.eta[k]) / s_es : a.base_w[k];
+      a.vp.w[k] = w;
+      const double sg = a.vp.sigma[k];
+      const double cn = s_nf / pow(sg, static_cast<double>(D));  // nf/sigma(k)^D  (:63)
+      a.cn[k] = cn;
+      ck = w * cn;
+      a.vp.ck[k] = ck;
+      a.vp.ak[k] = ck / sg;
+      aks = ck / (sg * sg);
+    }
+    b_ck[k] = ck;
+    b_ak[k] = aks;
+  }
+  for (int d = tid; d < DPc; d += nt) {
+    double mean = 0.0;
+    if (d < D) {
+      for (int k = 0; k < K; ++k) mean += a.vp.mu[k * D + d];
+      mean /= K;
+    }
+    b_il[d] = d < D ? 1.0 / a.vp.lambda[d] : 0.0;
+    for (int k = 0; k < K2; ++k) b_mu[k * DPc + d] = (d < D && k < K) ? a.vp.mu[k * D + d] - mean : 0.0;
   }
 }
 
@@ -377,6 +398,7 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   UnpackArgs a;
   a.D = c->D; a.K = c->K; a.ntheta = c->ntheta; a.have_theta = have_theta ? 1 : 0;
   a.force_form = c->entmc_form;
+  a.DPc = c->vp_cblob_dp;
   for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
   a.theta = c->theta_dev.d();
   a.base_mu = c->base_mu; a.base_sigma = c->base_sigma; a.base_lambda = c->base_lambda;
