@@ -151,3 +151,46 @@ def test_refit_then_negelcbo_end_to_end(gpu_ctx):
     got = vbmc_b200.negelcbo_vbmc(wg["theta"], 0.0, wg["vp"], wg["gp"], 128, 1, 0, epsilon=wg["epsilon"], nargout=4)
     ref = orc.negelcbo_vbmc(wo["theta"], 0.0, wo["vp"], wo["gp"], 128, 1, 0, epsilon=wo["epsilon"], nargout=4)
     assert rel(got[0], ref[0]) < 1e-8 and rel(got[1], ref[1]) < 1e-7 and rel(got[2], ref[2]) < 1e-8
+
+
+@pytest.mark.parametrize("meanfun,noisy,N", [(4, False, 150), (1, False, 70), (0, False, 64), (4, True, 200)])
+def test_gplite_nlZ_gradient(gpu_ctx, meanfun, noisy, N):
+    """[nlZ,dnlZ] = gplite_nlZ(hyp,gp,hprior): gradient through inv(K+Sigma) (gplite_core.m:226-261).
+    inv(A) entries carry cond(A)*eps relative error in any implementation -> cond-scaled bound + FD cross-check."""
+    import vbmc_b200
+    D = 3
+    X, y, s2, hyp = problem(N, D, 1, meanfun=meanfun, noisy=noisy)
+    if noisy:
+        s2 = 0.05 * (1 + np.arange(N) % 3)
+    nf = [1, 1, 0] if noisy else [1, 0, 0]
+    gp = orc.gplite_post(hyp, X, y, 1, meanfun, nf, s2)
+    Nh = hyp.shape[0]
+    hp = dict(mu=np.zeros(Nh), sigma=3.0 * np.ones(Nh), df=np.array([0.0, 3.0] * Nh)[:Nh])
+    nlZ, dnlZ = vbmc_b200.gplite_nlZ(hyp[:, 0], gp, hp, nargout=2)
+    ref = orc.gplite_nlZ(hyp[:, 0], gp, hp, nargout=2)
+    A = gp["post"][0]["L"].T @ gp["post"][0]["L"]
+    bound = max(1e-10, 200 * np.linalg.cond(A) * np.finfo(float).eps)
+    assert rel(nlZ, ref[0]) < 1e-10
+    assert dnlZ.shape == ref[1].shape and rel(dnlZ, ref[1]) < bound
+
+
+def test_gplite_post_low_noise_branch(gpu_ctx):
+    """min(sn2) < 1e-6: post.L = -inv(K + sn2_mult*diag(sn2)), sl = 1 (gplite_core.m:86-100)."""
+    import vbmc_b200
+    rng = np.random.default_rng(6)
+    N, D = 90, 2
+    X = rng.standard_normal((N, D)) * 2
+    y = rng.standard_normal(N)
+    hyp = np.array([[0.0], [0.0], [0.0], [math.log(3e-4)], [0.1]])
+    ref = orc.gplite_post(hyp, X, y, 1, 1, [1, 0, 0], None)
+    gp = vbmc_b200.gplite_post(hyp, X, y, 1, 1, [1, 0, 0], None)
+    a, b = gp["post"][0], ref["post"][0]
+    assert (not a["Lchol"]) and (not b["Lchol"])
+    assert a["sn2_mult"] in (b["sn2_mult"], b["sn2_mult"] * 10, b["sn2_mult"] / 10)
+    if a["sn2_mult"] == b["sn2_mult"]:
+        K = np.exp(-0.5 * orc.sq_dist(X.T))
+        Amat = K + a["sn2_mult"] * math.exp(2 * hyp[3, 0]) * np.eye(N)
+        cond = np.linalg.cond(Amat)
+        assert np.max(np.abs(a["L"] @ Amat + np.eye(N))) < 100 * cond * np.finfo(float).eps
+        assert rel(a["alpha"], b["alpha"]) < 100 * cond * np.finfo(float).eps
+        assert rel(a["sW"], b["sW"]) < 1e-14

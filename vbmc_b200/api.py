@@ -111,15 +111,18 @@ class Context:
     def gp_attach(self, gp, want_L=False):
         """Make ``gp`` (with a posterior computed elsewhere) resident; no-op when unchanged."""
         post = gp["post"]
-        hyp = np.stack([f64(p["hyp"]).ravel() for p in post])
-        alpha = np.ascontiguousarray(np.stack([f64(p["alpha"]).ravel() for p in post]))
-        key = (id(gp), gp["X"].shape, len(post), float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
-               float(hyp[-1, -1]), bool(want_L))
+        a0, a1 = np.asarray(post[0]["alpha"]), np.asarray(post[-1]["alpha"])
+        h0, h1 = np.asarray(post[0]["hyp"]), np.asarray(post[-1]["hyp"])
+        # cheap fingerprint (no copies): identity of the struct + first/last values (SURVEY.md 8b)
+        key = (id(gp), gp["X"].shape, len(post), float(a0.flat[0]), float(a1.flat[-1]), float(h0.flat[0]),
+               float(h1.flat[-1]), bool(want_L))
         if self._gp_key is not None and key[:-1] == self._gp_key[:-1] and (self._gp_key[-1] or not want_L):
             return
         if want_L and any(p.get("L") is None for p in post):
             raise VbmcB200Error(_lib.ESTATE, "vbmc_b200:noL: the variance path needs gp.post(s).L (call gplite_post with want_L=True, "
                                              "or keep the posterior resident)")
+        hyp = np.stack([f64(p["hyp"]).ravel() for p in post])
+        alpha = np.ascontiguousarray(np.stack([f64(p["alpha"]).ravel() for p in post]))
         keep = []
         d, (N, D, S, _) = self._gp_desc(gp, hyp, keep)
         sW1 = f64([np.asarray(p["sW"]).ravel()[0] for p in post])

@@ -232,6 +232,7 @@ int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J);
+int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);
 int entmc_pick_dp(int D);

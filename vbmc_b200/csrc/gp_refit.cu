@@ -432,6 +432,128 @@ __global__ void gp_alpha_kernel(const GpBatch g, const double* ascale, double* a
   alpha[static_cast<size_t>(s) * g.N + i] = z[i] * ascale[s];
 }
 
+// ---- inverse tiles on the tensor path: inv(A) = X'X with X = R^-T (lower), fused epilogues --------------------
+//   mode 0 (gplite_core.m:226-234): Q = inv(A)/sl - alpha*alpha';  S_i = sum sum Q.*K_mat.*sq_dist(X(:,i)'/ell_i),
+//           S_D = sum sum Q.*K_mat, diag(Q)   — inv(A) is never stored;
+//   mode 1 (gplite_core.m:96-99): pL = -inv(A) written out (low-noise posterior).
+// grid = upper 64x64 tiles (I <= J); X(c,a) at Xinv[a*N + c].
+struct InvArgs {
+  int N, D, mode;
+  const double* Xinv;
+  const double* Xc;     // [D][N] training inputs
+  const double* hyp;    // [Nhyp]
+  const double* alpha;  // [N]
+  double inv_sl;
+  double* partial;      // [ntiles][D+1]
+  double* diagQ;        // [N]
+  double* outL;         // [N][N] (mode 1)
+};
+
+__global__ void __launch_bounds__(256) gp_invtile_kernel(const InvArgs g) {
+  extern __shared__ __align__(16) double ism[];
+  double* PI = ism;
+  double* PJ = ism + TB * TLD;
+  double* xi = PJ + TB * TLD;      // [D][64]
+  double* xj = xi + g.D * TB;      // [D][64]
+  double* red = xj + g.D * TB;     // [(D+1)][256]
+  const int N = g.N, D = g.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = (N + TB - 1) / TB;
+  int t = blockIdx.x, I = 0;
+  while (t >= nb - I) { t -= nb - I; ++I; }
+  const int J = I + t;
+  const int wm = warp >> 1, wn = warp & 1, g4 = lane >> 2, t4 = lane & 3;
+  double acc[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int cb = J; cb < nb; ++cb) {
+    __syncthreads();
+    for (int i = tid; i < TB * TB; i += 256) {
+      const int col = i >> 6, k = i & 63;
+      const int c = cb * TB + k, a = I * TB + col, b = J * TB + col;
+      PI[col * TLD + k] = (c < N && a < N) ? g.Xinv[static_cast<size_t>(a) * N + c] : 0.0;
+      PJ[col * TLD + k] = (c < N && b < N) ? g.Xinv[static_cast<size_t>(b) * N + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < TB; k += 4) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) af[a] = PI[(wm * 16 + a * 8 + g4) * TLD + k + t4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = PJ[(wn * 32 + b * 8 + g4) * TLD + k + t4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+  if (g.mode == 1) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int m = I * TB + wm * 16 + a * 8 + g4, n = J * TB + wn * 32 + b * 8 + 2 * t4 + e;
+          if (m < N && n < N) {
+            g.outL[static_cast<size_t>(n) * N + m] = -acc[a][b][e];
+            g.outL[static_cast<size_t>(m) * N + n] = -acc[a][b][e];
+          }
+        }
+    return;
+  }
+  // ---- mode 0: fused Hadamard reductions ----
+  __syncthreads();
+  for (int i = tid; i < D * TB; i += 256) {
+    const int d = i / TB, r = i - d * TB;
+    const double il = exp(-g.hyp[d]);
+    const int ri = I * TB + r, rj = J * TB + r;
+    xi[i] = ri < N ? g.Xc[static_cast<size_t>(d) * N + ri] * il : 0.0;
+    xj[i] = rj < N ? g.Xc[static_cast<size_t>(d) * N + rj] * il : 0.0;
+  }
+  __syncthreads();
+  const double sf2 = exp(2.0 * g.hyp[D]);
+  const double wgt = (I == J) ? 1.0 : 2.0;  // the strictly upper tiles stand for their mirror images as well
+  double sums[25];
+#pragma unroll
+  for (int d = 0; d < 25; ++d) sums[d] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int rm = wm * 16 + a * 8 + g4, rn = wn * 32 + b * 8 + 2 * t4 + e;
+        const int m = I * TB + rm, n = J * TB + rn;
+        if (m < N && n < N) {
+          const double Q = acc[a][b][e] * g.inv_sl - g.alpha[m] * g.alpha[n];   // (:226)
+          double sq = 0.0;
+          for (int d = 0; d < D; ++d) {
+            const double df = xi[d * TB + rm] - xj[d * TB + rn];
+            sq = fma(df, df, sq);
+          }
+          const double QK = wgt * Q * sf2 * exp(-0.5 * sq);
+          sums[D] += QK;                                                          // (:234)
+          for (int d = 0; d < D; ++d) {
+            const double df = xi[d * TB + rm] - xj[d * TB + rn];
+            sums[d] = fma(QK, df * df, sums[d]);                                  // (:230-232)
+          }
+          if (m == n) g.diagQ[m] = Q;
+        }
+      }
+  for (int d = 0; d <= D; ++d) red[d * 256 + tid] = sums[d];
+  __syncthreads();
+  for (int d = warp; d <= D; d += 8) {
+    double v = 0.0;
+    for (int i = lane; i < 256; i += 32) v += red[d * 256 + i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) g.partial[static_cast<size_t>(blockIdx.x) * (D + 1) + d] = v;
+  }
+}
+
 // copy the N x N factor out of the padded buffer, zeroing the strictly lower part (MATLAB's chol output)
 __global__ void gp_extract_kernel(const double* M, int Np, int N, double* out, int negate_full) {
   const int s = blockIdx.z;
@@ -603,6 +725,47 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   return VBMC_B200_OK;
 }
 
+// inv(A) tiles of sample `s` of the last refit: mode 0 -> (S_0..S_D, diagQ) on the host, mode 1 -> -inv(A) into dev_out
+int run_invtiles(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int s, double sl, int mode, std::vector<double>* sums,
+                 std::vector<double>* diagQ, double* dev_out) {
+  const int N = gd->N, D = gd->D;
+  const int Np = (N + 1 + TB - 1) / TB * TB;
+  const int nb = (N + TB - 1) / TB, ntiles = nb * (nb + 1) / 2;
+  if (D > 24) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:nlz_grad: D=%d > 24 is not supported by this build", D);
+  vb::DevBuf& wk = c->varWork;
+  const size_t nX = static_cast<size_t>(N) * N;
+  VB_TRY(wk.reserve(sizeof(double) * (nX + static_cast<size_t>(ntiles) * (D + 1) + N)));
+  double* X = wk.d();
+  double* partial = X + nX;
+  double* dq = partial + static_cast<size_t>(ntiles) * (D + 1);
+  const double* R = c->gpL.d() + static_cast<size_t>(s) * Np * Np;
+  VB_TRY(vb::run_factor_inverse(c, N, Np, R, X));
+  InvArgs a;
+  a.N = N; a.D = D; a.mode = mode;
+  a.Xinv = X; a.Xc = c->gpX.d(); a.hyp = c->gpHyp.d() + static_cast<size_t>(s) * gd->Nhyp;
+  a.alpha = c->gpAlpha.d() + static_cast<size_t>(s) * N;
+  a.inv_sl = 1.0 / sl;
+  a.partial = partial; a.diagQ = dq; a.outL = dev_out;
+  const size_t smem = sizeof(double) * (2 * TB * TLD + 2 * static_cast<size_t>(D) * TB + static_cast<size_t>(D + 1) * 256);
+  VB_CUDA(cudaFuncSetAttribute(gp_invtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  {
+    KernelScope ks(c, "potri_tiles", c->stream);
+    gp_invtile_kernel<<<ntiles, 256, smem, c->stream>>>(a);
+  }
+  VB_CUDA(cudaGetLastError());
+  if (mode == 0) {
+    std::vector<double> hp(static_cast<size_t>(ntiles) * (D + 1));
+    diagQ->assign(N, 0.0);
+    VB_CUDA(cudaMemcpyAsync(hp.data(), partial, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, c->stream));
+    VB_CUDA(cudaMemcpyAsync(diagQ->data(), dq, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    VB_CUDA(cudaStreamSynchronize(c->stream));
+    sums->assign(D + 1, 0.0);
+    for (int t = 0; t < ntiles; ++t)
+      for (int d = 0; d <= D; ++d) (*sums)[d] += hp[static_cast<size_t>(t) * (D + 1) + d];
+  }
+  return VBMC_B200_OK;
+}
+
 int check_desc(const vbmc_b200_gp_desc* g, int* Ncov, int* Nnoise, int* Nmean, const char* who) {
   if (!g || !g->X || !g->hyp || !g->y) VB_FAIL(VBMC_B200_EINVAL, "%s: X, y and hyp are required", who);
   if (g->N <= 0 || g->D <= 0 || g->S <= 0) VB_FAIL(VBMC_B200_EINVAL, "%s: N, D, S must be positive", who);
@@ -637,10 +800,6 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
   RefitResult rr;
   VB_TRY(refit_core(c, gd, Ncov, Nnoise, Nmean, &rr));
   const int N = gd->N, S = gd->S;
-  for (int s = 0; s < S; ++s)
-    if (!rr.Lchol[s])
-      VB_FAIL(VBMC_B200_EUNSUPPORTED,
-              "vbmc_b200:NotYet: min(sn2) < 1e-6 selects the explicit-inverse posterior (gplite_core.m:86-100), not built yet");
   const int Np = (N + 1 + TB - 1) / TB * TB;
   std::vector<double> h_sw(S);
   for (int s = 0; s < S; ++s) h_sw[s] = 1.0 / sqrt(rr.minsn2[s] * rr.mult[s]);  // post.sW (:281)
@@ -654,6 +813,9 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
       KernelScope ks(c, "extract", c->stream);
       gp_extract_kernel<<<grid, 256, 0, c->stream>>>(c->gpL.d(), Np, N, tmp.d(), 0);
     }
+    // low-noise samples: post.L = -inv(K + sn2_mult*diag(sn2))  (gplite_core.m:96-99)
+    for (int s = 0; s < S; ++s)
+      if (!rr.Lchol[s]) VB_TRY(run_invtiles(c, gd, s, 1.0, 1, nullptr, nullptr, tmp.d() + static_cast<size_t>(s) * N * N));
     VB_CUDA(cudaMemcpyAsync(L, tmp.p, sizeof(double) * static_cast<size_t>(S) * N * N, cudaMemcpyDeviceToHost, c->stream));
     VB_CUDA(cudaStreamSynchronize(c->stream));
     tmp.release();
@@ -687,15 +849,11 @@ int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b
     VB_FAIL(VBMC_B200_EREFERENCE,
             "gplite_nlZ:NoSampling: Computation of the log marginal likelihood is available only for one-sample "
             "hyperparameter inputs.");
-  if (dnlZ)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: gplite_nlZ gradient (gplite_core.m:226-261) is not built yet");
   VB_CUDA(cudaSetDevice(c->device));
   c->gp_ready = false;  // the GP buffers are reused
   RefitResult rr;
   VB_TRY(refit_core(c, gd, Ncov, Nnoise, Nmean, &rr));
-  if (!rr.Lchol[0])
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: low-noise branch (gplite_core.m:86-100) is not built yet");
-  const int N = gd->N;
+  const int N = gd->N, D = gd->D;
   // nlZ = (y-m)'*alpha/2 + sum(log(diag(L))) + N*log(2*pi*sl)/2   (:193);  (y-m)'alpha = z'z/sl
   double v = 0.5 * rr.zz[0] / rr.sl[0] + rr.logdet[0] + 0.5 * N * log(2.0 * 3.14159265358979323846 * rr.sl[0]);
   if (hprior && hprior->mu && hprior->sigma) {  // gplite_hypprior.m:24-58 (host: O(Nhyp))
@@ -714,6 +872,80 @@ int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b
     v -= lp;
   }
   *nlZ = v;
+  if (!dnlZ) return VBMC_B200_OK;
+  // ---- gradient (gplite_core.m:226-261) ----
+  std::vector<double> sums, dq, al(N);
+  VB_TRY(run_invtiles(c, gd, 0, rr.sl[0], 0, &sums, &dq, nullptr));
+  VB_CUDA(cudaMemcpyAsync(al.data(), c->gpAlpha.p, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  const double* h = gd->hyp;
+  for (int i = 0; i < gd->Nhyp; ++i) dnlZ[i] = 0.0;
+  for (int i = 0; i < D; ++i) dnlZ[i] = 0.5 * sums[i];   // sum(sum(Q.*K_mat.*sq_dist(X(:,i)'/ell(i))))/2
+  dnlZ[D] = sums[D];                                      // sum(sum(Q.*(2*K_mat)))/2
+  // noise hyper-parameters: 0.5*sn2_mult*sum(dsn2(:,i).*diag(Q))  (:242-251; the scalar case is the same sum)
+  {
+    const double* hn = h + Ncov;
+    int idx = 0;
+    const double mult = rr.mult[0];
+    if (gd->noisefun[0] == 1) {
+      const double d1 = 2.0 * exp(2.0 * hn[idx]);
+      double acc = 0.0;
+      for (int n = 0; n < N; ++n) acc += dq[n];
+      dnlZ[Ncov + idx] = 0.5 * mult * d1 * acc;
+      ++idx;
+    }
+    if (gd->noisefun[1] == 2) {
+      double acc = 0.0;
+      for (int n = 0; n < N; ++n) acc += exp(hn[idx]) * gd->s2[n] * dq[n];
+      dnlZ[Ncov + idx] = 0.5 * mult * acc;
+      ++idx;
+    }
+    if (gd->noisefun[2] == 1) {
+      const double yth = hn[idx], w2 = exp(2.0 * hn[idx + 1]);
+      double a0 = 0.0, a1 = 0.0;
+      for (int n = 0; n < N; ++n) {
+        const double zz = fmax(0.0, yth - gd->y[n]);
+        a0 += 2.0 * w2 * (yth - gd->y[n]) * (zz > 0.0 ? 1.0 : 0.0) * dq[n];
+        a1 += 2.0 * w2 * zz * zz * dq[n];
+      }
+      dnlZ[Ncov + idx] = 0.5 * mult * a0;
+      dnlZ[Ncov + idx + 1] = 0.5 * mult * a1;
+    }
+  }
+  // mean function: -dm'*alpha  (:254-261; gplite_meanfun.m cases 1 and 4)
+  {
+    const double* hm = h + Ncov + Nnoise;
+    double* g = dnlZ + Ncov + Nnoise;
+    if (gd->meanfun == 1 || gd->meanfun == 4) {
+      double acc = 0.0;
+      for (int n = 0; n < N; ++n) acc += al[n];
+      g[0] = -acc;
+    }
+    if (gd->meanfun == 4)
+      for (int d = 0; d < D; ++d) {
+        const double xm = hm[1 + d], om = exp(hm[1 + D + d]);
+        double a1 = 0.0, a2 = 0.0;
+        for (int n = 0; n < N; ++n) {
+          const double df = gd->X[static_cast<size_t>(d) * N + n] - xm;
+          a1 += df / (om * om) * al[n];
+          a2 += (df / om) * (df / om) * al[n];
+        }
+        g[1 + d] = -a1;
+        g[1 + D + d] = -a2;
+      }
+  }
+  if (hprior && hprior->mu && hprior->sigma) {  // dnlZ = dnlZ - dP
+    for (int i = 0; i < gd->Nhyp; ++i) {
+      const double mu = hprior->mu[i], sg = fabs(hprior->sigma[i]);
+      const double df = hprior->df ? hprior->df[i] : 7.0;
+      if (!isfinite(mu) || !isfinite(sg)) continue;
+      const double dlt = gd->hyp[i] - mu, z2 = (dlt / sg) * (dlt / sg);
+      double dlp = 0.0;
+      if (df == 0.0 || !isfinite(df)) dlp = -dlt / (sg * sg);
+      else if (df > 0.0) dlp = -(df + 1.0) / df / (1.0 + z2 / df) * dlt / (sg * sg);
+      dnlZ[i] -= dlp;
+    }
+  }
   return VBMC_B200_OK;
 }
 

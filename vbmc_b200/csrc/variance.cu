@@ -24,6 +24,7 @@ struct VarArgs {
   double* J;          // [S][K][K]  J_sjk (j fastest == MATLAB (s,j,k) after host transpose)
   double* varFs;      // [S]
   int full;           // 1: full matrix, 0: diagonal only
+  int unit_rhs;       // 1: right-hand sides are the identity columns k0.. (inverse of the factor), Z is output only
 };
 
 // z_k(n) = exp(lnnf_k - 0.5*sum_d ((mu_kd - X_nd)/tau_kd)^2)   (gplogjoint.m:164-167); grid (K, S)
@@ -67,11 +68,20 @@ __global__ void __launch_bounds__(256) var_fwd_kernel(const VarArgs a) {
   double* pd = Rb + 64 * 65;       // [64][VR]  partial dots of the current block
   const double* R = a.L + static_cast<size_t>(s) * a.Lstride;
   double* Zs = a.Z + (static_cast<size_t>(s) * a.K + k0) * N;
-  for (int i = tid; i < nrhs * N; i += 256) v[i] = Zs[i];
-  for (int i = nrhs * N + tid; i < VR * N; i += 256) v[i] = 0.0;
+  if (a.unit_rhs) {
+    for (int i = tid; i < VR * N; i += 256) {
+      const int cc = i / N, r = i - cc * N;
+      v[i] = (cc < nrhs && r == k0 + cc) ? 1.0 : 0.0;
+    }
+  } else {
+    for (int i = tid; i < nrhs * N; i += 256) v[i] = Zs[i];
+    for (int i = nrhs * N + tid; i < VR * N; i += 256) v[i] = 0.0;
+  }
   __syncthreads();
   const int nb = (N + 63) / 64;
-  for (int b = 0; b < nb; ++b) {
+  const int bfirst = a.unit_rhs ? k0 / 64 : 0;   // e_a has no entries above row a: the solution is zero there
+  const int jfirst = bfirst * 64;
+  for (int b = bfirst; b < nb; ++b) {
     const int b0 = b * 64;
     // (1) pd[i][c] = sum_{j<b0} R(j, b0+i) v_c[j]   — column b0+i of R is contiguous over j
     for (int i = warp; i < 64; i += 8) {
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(256) var_fwd_kernel(const VarArgs a) {
       for (int c = 0; c < VR; ++c) acc[c] = 0.0;
       if (b0 + i < N) {
         const double* col = R + static_cast<size_t>(b0 + i) * ld;
-        for (int j = lane; j < b0; j += 32) {
+        for (int j = jfirst + lane; j < b0; j += 32) {
           const double r = col[j];
 #pragma unroll
           for (int c = 0; c < VR; ++c) acc[c] = fma(r, v[c * N + j], acc[c]);
@@ -210,6 +220,7 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
   a.L = c->gpL.d();
   a.gp = c->gp; a.vp = c->vp;
   a.full = compute_var == 1 ? 1 : 0;
+  a.unit_rhs = 0;
   const size_t nz = static_cast<size_t>(S) * K * N, ng = static_cast<size_t>(S) * K * K;
   VB_TRY(c->varWork.reserve(sizeof(double) * (nz + 2 * ng + S)));
   a.Z = c->varWork.d(); a.G = a.Z + nz; a.J = a.G + ng; a.varFs = a.J + ng;
@@ -247,6 +258,27 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
     VB_CUDA(cudaMemcpyAsync(J->data(), a.J, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
   }
   VB_CUDA(cudaStreamSynchronize(st));
+  return VBMC_B200_OK;
+}
+
+
+// X = R^-T (lower triangular) of sample `s`, written column-major with leading dimension N into `out`.
+int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out) {
+  VarArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.D = 1; a.K = N; a.S = 1; a.ld = ld;
+  a.Lstride = 0;
+  a.L = R;
+  a.Z = out;
+  a.unit_rhs = 1;
+  const size_t smem = sizeof(double) * (static_cast<size_t>(VR) * N + 64 * 65 + 64 * VR);
+  if (smem > c->smem_optin)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:inverse: N=%d needs %zu B shared memory for the solve (> %zu)", N, smem, c->smem_optin);
+  VB_CUDA(cudaFuncSetAttribute(var_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid((N + VR - 1) / VR, 1);
+  KernelScope ks(c, "trtri", c->stream);
+  var_fwd_kernel<<<grid, 256, smem, c->stream>>>(a);
+  VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
 
