@@ -293,3 +293,25 @@ def test_eval_fullelcbo_call_pattern(gpu_ctx):
     gb = vbmc_b200.negelcbo_vbmc(theta, 1.5, vp, gp, 64, 0, 2, epsilon=eps, nargout=5)
     rb = orc.negelcbo_vbmc(theta, 1.5, vp, gp, 64, 0, 2, epsilon=eps, nargout=5)
     assert rel(gb[0], rb[0]) < 1e-8 and rel(gb[4], rb[4]) < 1e-7
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_variance_gradient_elcbo(gpu_ctx, S):
+    """beta ~= 0 with gradient: dF += 0.5*beta*dvarG/sqrt(varF), diagonal variance only (negelcbo_vbmc.m:21-24,128-130;
+    gplogjoint.m:289-303,370-385,407-410)."""
+    import vbmc_b200
+    w = _var_problem(K=4, S=S, N=60, D=3)
+    vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    got = vbmc_b200.negelcbo_vbmc(theta, 0.7, vp, gp, 64, 1, 2, 0, tb, 0, epsilon=eps, nargout=5)
+    ref = orc.negelcbo_vbmc(theta, 0.7, vp, gp, 64, 1, 2, 0, tb, 0, epsilon=eps, nargout=5)
+    assert rel(got[0], ref[0]) < 1e-8 and rel(got[4], ref[4]) < 1e-7
+    assert rel(got[1], ref[1]) < 1e-7
+    # gplogjoint's own 4th output
+    v = dict(vp)
+    g = vbmc_b200.gplogjoint(v, gp, True, True, True, 2, nargout=5)
+    r = orc.gplogjoint(v, gp, True, True, True, 2, nargout=5)
+    assert rel(g[3], r[3]) < 1e-6 and rel(g[2], r[2]) < 1e-7 and rel(g[4], r[4]) < 1e-7
+    with pytest.raises(vbmc_b200.VbmcB200Error) as ei:
+        vbmc_b200.gplogjoint(v, gp, True, True, True, 1, nargout=4)
+    assert ei.value.identifier == "gplogjoint:FullVarianceGradient"

@@ -485,9 +485,7 @@ static int negelcbo_validate(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
             "vbmc_b200:OutOfScope: Ns == 0 selects entlb_vbmc (deterministic entropy bound), outside this build");
   if (a->compute_var != 0 && a->compute_var != 1 && a->compute_var != 2)
     VB_FAIL(VBMC_B200_EINVAL, "negelcbo: compute_var must be 0, 1 (full) or 2 (diagonal)");
-  if (a->compute_grad && b != 0.0)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED,
-            "vbmc_b200:NotYet: gradient of the variance term (beta ~= 0 with compute_grad, gplogjoint.m:289-303) is not built yet");
+
   if (a->use_thetabnd && c->nbnd > 0) {
     const int expect = (c->opt[0] ? c->D * c->K : 0) + ((c->opt[1] || c->opt[2]) ? c->D * c->K : 0) + (c->opt[3] ? c->K : 0);
     if (expect != c->nbnd)
@@ -546,6 +544,112 @@ static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
   }
 }
 
+// Gradient of the (diagonal) log-joint variance, averaged over hyper-parameter samples
+// (gplogjoint.m:289-303 per sample, :370-385 Jacobians, :407-410 average).  O(S K D) host work on small
+// device read-backs; the N-long contractions were done on the device (run_variance with vgrad).
+static int assemble_vargrad(vbmc_b200_ctx* c, int gmask, int jacobian, const std::vector<double>& vF, const std::vector<double>& J,
+                            const std::vector<double>& vg, const double* Fs, std::vector<double>* dvarF) {
+  const int D = c->D, K = c->K, S = c->gp.S, os = 2 + 2 * D;
+  std::vector<double> vpc(static_cast<size_t>(D) * K + 3 * K + D + 2 * K + 2 * D), der(static_cast<size_t>(S) * (3 * D + 3)),
+      go(static_cast<size_t>(S) * K * os);
+  VB_CUDA(cudaMemcpyAsync(vpc.data(), c->vp.mu, sizeof(double) * vpc.size(), cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaMemcpyAsync(der.data(), c->gpDerived.p, sizeof(double) * der.size(), cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaMemcpyAsync(go.data(), c->glj_out.p, sizeof(double) * go.size(), cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  const double* sigma = vpc.data() + D * K;
+  const double* lambda = sigma + K;
+  const double* w = lambda + D;
+  const double* eta = w + K;
+  const double* delta = eta + K + K + D;  // after lnsigma[K], lnlambda[D]
+  const double* ell = der.data();
+  const double* lnc = ell + S * D;
+  const double* sn2eff = lnc + S + S + 2 * S * D;
+  const double EPS = 2.220446049250313e-16;
+  int n = 0, o_mu = 0, o_sig = 0, o_lam = 0, o_w = 0;
+  o_mu = n; if (gmask & 1) n += D * K;
+  o_sig = n; if (gmask & 2) n += K;
+  o_lam = n; if (gmask & 4) n += D;
+  o_w = n; if (gmask & 8) n += K;
+  std::vector<double> wsm(K);
+  {
+    double es = 0.0;
+    for (int k = 0; k < K; ++k) es += exp(eta[k]);
+    for (int k = 0; k < K; ++k) wsm[k] = exp(eta[k]) / es;
+  }
+  auto jw = [&](std::vector<double>& g) {  // softmax Jacobian
+    double dot = 0.0;
+    for (int k = 0; k < K; ++k) dot += wsm[k] * g[k];
+    for (int k = 0; k < K; ++k) g[k] = wsm[k] * (g[k] - dot);
+  };
+  std::vector<double> dv(static_cast<size_t>(n) * S, 0.0), dFs(static_cast<size_t>(n) * S, 0.0), gw(K);
+  for (int s = 0; s < S; ++s) {
+    double* dvs = dv.data() + static_cast<size_t>(s) * n;
+    double* dfs = dFs.data() + static_cast<size_t>(s) * n;
+    for (int k = 0; k < K; ++k) {
+      const double* g = vg.data() + (static_cast<size_t>(s) * K + k) * os;   // raw contractions with R\V_k
+      const double* f = go.data() + (static_cast<size_t>(s) * K + k) * os;   // [I, gsig, gmu, glam] of F(s)
+      double slt = 0.0, s_l2t2 = 0.0;
+      std::vector<double> t2(D);
+      for (int d = 0; d < D; ++d) {
+        t2[d] = 2.0 * sigma[k] * sigma[k] * lambda[d] * lambda[d] + ell[s * D + d] * ell[s * D + d] + 2.0 * delta[d] * delta[d];
+        slt += 0.5 * log(t2[d]);
+        s_l2t2 += lambda[d] * lambda[d] / t2[d];
+      }
+      const double nf_kk = exp(lnc[s] - slt);                                   // :275
+      const double w2 = w[k] * w[k], ise = 1.0 / sn2eff[s];
+      const double Jkk = J[(static_cast<size_t>(s) * K + k) * K + k];
+      for (int d = 0; d < D; ++d) {
+        if (gmask & 1) {
+          dvs[o_mu + k * D + d] = -w2 * 2.0 * g[2 + d] * ise;                   // :290
+          dfs[o_mu + k * D + d] = w[k] * f[2 + d];
+        }
+        if (gmask & 4) {
+          dvs[o_lam + d] -= 2.0 * w2 * (sigma[k] * sigma[k] * nf_kk * lambda[d] / t2[d] + g[2 + D + d] * ise);  // :298
+          dfs[o_lam + d] += w[k] * f[2 + D + d];
+        }
+      }
+      if (gmask & 2) {
+        dvs[o_sig + k] = -2.0 * w2 * (sigma[k] * nf_kk * s_l2t2 + g[1] * ise);  // :294
+        dfs[o_sig + k] = w[k] * f[1];
+        if (jacobian) { dvs[o_sig + k] *= sigma[k]; dfs[o_sig + k] *= sigma[k]; }
+      }
+      if (gmask & 8) {
+        dvs[o_w + k] = 2.0 * w[k] * fmax(EPS, Jkk);                             // :302
+        dfs[o_w + k] = f[0];
+      }
+    }
+    if ((gmask & 4) && jacobian)
+      for (int d = 0; d < D; ++d) { dvs[o_lam + d] *= lambda[d]; dfs[o_lam + d] *= lambda[d]; }
+    if ((gmask & 8) && jacobian) {
+      for (int k = 0; k < K; ++k) gw[k] = dvs[o_w + k];
+      jw(gw);
+      for (int k = 0; k < K; ++k) dvs[o_w + k] = gw[k];
+      for (int k = 0; k < K; ++k) gw[k] = dfs[o_w + k];
+      jw(gw);
+      for (int k = 0; k < K; ++k) dfs[o_w + k] = gw[k];
+    }
+  }
+  dvarF->assign(n, 0.0);
+  if (S > 1) {  // dvv = 2*sum(F.*dF,2)/(Ns-1) - 2*Fbar.*sum(dF,2)/(Ns-1);  dvarF = sum(dvarF,2)/Ns + dvv  (:407-410)
+    double Fbar = 0.0;
+    for (int s = 0; s < S; ++s) Fbar += Fs[s];
+    Fbar /= S;
+    for (int i = 0; i < n; ++i) {
+      double sv = 0.0, sfd = 0.0, sd = 0.0;
+      for (int s = 0; s < S; ++s) {
+        sv += dv[static_cast<size_t>(s) * n + i];
+        sfd += Fs[s] * dFs[static_cast<size_t>(s) * n + i];
+        sd += dFs[static_cast<size_t>(s) * n + i];
+      }
+      (*dvarF)[i] = sv / S + 2.0 * sfd / (S - 1) - 2.0 * Fbar * sd / (S - 1);
+    }
+  } else {
+    for (int i = 0; i < n; ++i) (*dvarF)[i] = dv[i];
+  }
+  (void)vF;
+  return VBMC_B200_OK;
+}
+
 int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
   double beta;
   int Ns, gmask;
@@ -562,12 +666,18 @@ int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
   scatter_negelcbo(c, a, nth);
   if (a->compute_var) {
     // varG (and J_sjk) from the factors; F = F + beta*sqrt(varF)   (negelcbo_vbmc.m:119-130)
-    std::vector<double> vF, J;
-    VB_TRY(run_variance(c, a->compute_var, &vF, (a->separate_K && a->J_sjk) ? &J : nullptr));
+    std::vector<double> vF, J, vg;
+    const bool need_vgrad = a->compute_grad && beta != 0.0;  // then compute_var == 2 (validated above)
+    VB_TRY(run_variance(c, a->compute_var, &vF, ((a->separate_K && a->J_sjk) || need_vgrad) ? &J : nullptr, need_vgrad ? &vg : nullptr));
     OutLayout ol;
     ol.init(nth, c->gp.S, c->K);
     double varG, varGss;
     combine_variance(c->out_pinned + ol.oFs, vF, c->gp.S, &varG, &varGss);
+    if (need_vgrad && a->dF) {  // dF = dF + 0.5*beta*dvarG/sqrt(varF)   (negelcbo_vbmc.m:128-130)
+      std::vector<double> dvar;
+      VB_TRY(assemble_vargrad(c, gmask, 1, vF, J, vg, c->out_pinned + ol.oFs, &dvar));
+      for (int i = 0; i < nth; ++i) a->dF[i] += 0.5 * beta * dvar[i] / sqrt(varG);
+    }
     if (a->varG) *a->varG = varG;
     if (a->varGss) *a->varGss = varGss;
     if (a->varH) *a->varH = 0.0;
@@ -639,8 +749,6 @@ int vbmc_b200_gplogjoint(vbmc_b200_ctx* c, const int grad_flags[4], int avg_flag
     VB_FAIL(VBMC_B200_EREFERENCE,
             "gplogjoint:FullVarianceGradient: Computation of gradient of log joint variance is currently available only "
             "for diagonal approximation of the variance.");
-  if (dvarF)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: gradient of the log-joint variance (gplogjoint.m:289-303) is not built yet");
   if (compute_var != 0 && compute_var != 1 && compute_var != 2) VB_FAIL(VBMC_B200_EINVAL, "gplogjoint: compute_var must be 0, 1 or 2");
   if (!avg_flag && c->gp.S > 1)
     VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:OutOfScope: avg_flag=0 with several hyper-parameter samples");
@@ -664,10 +772,16 @@ int vbmc_b200_gplogjoint(vbmc_b200_ctx* c, const int grad_flags[4], int avg_flag
       for (int k = 0; k < K; ++k) I_sk[s + static_cast<size_t>(k) * S] = o[ol.oIsk + s * K + k];
   }
   if (compute_var) {
-    std::vector<double> vF, J;
-    VB_TRY(run_variance(c, compute_var, &vF, J_sjk ? &J : nullptr));
+    std::vector<double> vF, J, vg;
+    const bool need_vgrad = dvarF != nullptr && gmask != 0;
+    VB_TRY(run_variance(c, compute_var, &vF, (J_sjk || need_vgrad) ? &J : nullptr, need_vgrad ? &vg : nullptr));
     double vG, vss;
     combine_variance(c->out_pinned + ol.oFs, vF, c->gp.S, &vG, &vss);
+    if (need_vgrad) {
+      std::vector<double> dvar;
+      VB_TRY(assemble_vargrad(c, gmask, jacobian_flag, vF, J, vg, c->out_pinned + ol.oFs, &dvar));
+      memcpy(dvarF, dvar.data(), sizeof(double) * nth);
+    }
     if (varF) *varF = vG;
     if (varss) *varss = vss;
     if (J_sjk) scatter_J(J, c->gp.S, c->K, J_sjk);

@@ -227,11 +227,12 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st);
 int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st);
 int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st);
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
+int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
 int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
-int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J);
+int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad = nullptr);
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);

@@ -22,6 +22,8 @@ struct GljArgs {
   GpDev gp;
   VpDev vp;
   double* out;  // [S][K][ostride] (only rows s_begin..s_begin+s_count-1 written)
+  const double* wvec;  // optional [S][K][N] weight vectors replacing alpha_s (variance gradient: K^-1 z_k)
+  int raw;             // 1: epilogue without the mean-function terms (derivative contractions only)
 };
 
 constexpr int GLJ_THREADS = 128;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
 #pragma unroll
   for (int d = 0; d < DP; ++d) B[d] = C[d] = 0.0;
   const double* __restrict__ X = a.gp.X;
-  const double* __restrict__ alpha = a.gp.alpha + static_cast<size_t>(s) * N;
+  const double* __restrict__ alpha = a.wvec ? a.wvec + (static_cast<size_t>(s) * a.K + k) * N : a.gp.alpha + static_cast<size_t>(s) * N;
   for (int n = tid; n < N; n += GLJ_THREADS) {
     double dl[DP];
     double ss = 0.0;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
   __syncthreads();
   // ---- per-(s,k) epilogue ----
   double* o = a.out + (static_cast<size_t>(s) * a.K + k) * a.ostride;
-  const bool quad = a.meanfun == 4;
+  const bool quad = a.meanfun == 4 && !a.raw;
   if (tid < D) {
     const int d = tid;
     const double lam = a.vp.lambda[d];
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
     o[2 + D + d] = glam;
   }
   if (tid == 32) {
-    double I = red[0] + (a.meanfun > 0 ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
+    double I = red[0] + ((a.meanfun > 0 && !a.raw) ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
     double gs = 0.0;
     for (int d = 0; d < D; ++d) {
       const double lam = a.vp.lambda[d], it = s_itau[d], dl = a.vp.delta[d];
@@ -212,9 +214,37 @@ int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
   a.ostride = 2 + 2 * a.D;
   a.gp = c->gp;
   a.vp = c->vp;
+  a.wvec = nullptr;
+  a.raw = 0;
   VB_TRY(c->glj_out.reserve(sizeof(double) * static_cast<size_t>(a.S) * a.K * a.ostride));
   a.out = c->glj_out.d();
   if (a.s_count <= 0) return VBMC_B200_OK;
+  switch (pick_dp(a.D)) {
+    case 2: return launch_glj<2>(c, a, st);
+    case 4: return launch_glj<4>(c, a, st);
+    case 6: return launch_glj<6>(c, a, st);
+    case 8: return launch_glj<8>(c, a, st);
+    case 10: return launch_glj<10>(c, a, st);
+    case 12: return launch_glj<12>(c, a, st);
+    case 16: return launch_glj<16>(c, a, st);
+    case 20: return launch_glj<20>(c, a, st);
+    case 24: return launch_glj<24>(c, a, st);
+  }
+  VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:gplogjoint: D=%d > 24 is not supported by this build", a.D);
+}
+
+// same contraction with per-(s,k) weight vectors w_sk (N each) and the raw epilogue; all S samples, out [S][K][2+2D]
+int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st) {
+  GljArgs a;
+  a.N = c->gp.N; a.D = c->D; a.K = c->K; a.S = c->gp.S;
+  a.s_begin = 0; a.s_count = a.S;
+  a.meanfun = c->gp.meanfun;
+  a.ostride = 2 + 2 * a.D;
+  a.gp = c->gp;
+  a.vp = c->vp;
+  a.wvec = wvec;
+  a.raw = 1;
+  a.out = out;
   switch (pick_dp(a.D)) {
     case 2: return launch_glj<2>(c, a, st);
     case 4: return launch_glj<4>(c, a, st);

@@ -136,6 +136,67 @@ __global__ void __launch_bounds__(256) var_fwd_kernel(const VarArgs a) {
   for (int i = tid; i < nrhs * N; i += 256) Zs[i] = v[i];
 }
 
+// W = R \ V (backward substitution, upper factor) for up to 8 right-hand sides per CTA, in place in Z.
+// After W: K^-1 z_k = W_k / sn2_eff (gplogjoint.m:276-277).  grid (ceil(K/8), S), 256 threads.
+__global__ void __launch_bounds__(256) var_bwd_kernel(const VarArgs a) {
+  extern __shared__ __align__(16) double vsm[];
+  const int N = a.N, ld = a.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.y, k0 = blockIdx.x * VR;
+  const int nrhs = (a.K - k0) < VR ? (a.K - k0) : VR;
+  double* v = vsm;             // [VR][N]
+  double* Rb = vsm + VR * N;   // [64][65]
+  const double* R = a.L + static_cast<size_t>(s) * a.Lstride;
+  double* Zs = a.Z + (static_cast<size_t>(s) * a.K + k0) * N;
+  for (int i = tid; i < nrhs * N; i += 256) v[i] = Zs[i];
+  for (int i = nrhs * N + tid; i < VR * N; i += 256) v[i] = 0.0;
+  __syncthreads();
+  const int nb = (N + 63) / 64;
+  for (int b = nb - 1; b >= 0; --b) {
+    const int b0 = b * 64;
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int c = i >> 6, r = i & 63;
+      Rb[c * 65 + r] = (b0 + c < N && b0 + r < N && r <= c) ? R[static_cast<size_t>(b0 + c) * ld + b0 + r] : (c == r ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (warp < nrhs) {  // upper back substitution inside the block; lane owns rows lane, lane+32
+      double* vc = v + warp * N;
+      double x0 = (b0 + lane < N) ? vc[b0 + lane] : 0.0;
+      double x1 = (b0 + lane + 32 < N) ? vc[b0 + lane + 32] : 0.0;
+      for (int p = 63; p >= 0; --p) {
+        double xp = (p >= 32 ? x1 : x0) / Rb[p * 65 + p];
+        xp = __shfl_sync(0xffffffffu, xp, p & 31);
+        if (p >= 32) {
+          if (lane == (p & 31)) x1 = xp;
+          if (lane + 32 < p) x1 = fma(-Rb[p * 65 + lane + 32], xp, x1);   // R(lane+32, p)
+          x0 = fma(-Rb[p * 65 + lane], xp, x0);
+        } else {
+          if (lane == p) x0 = xp;
+          if (lane < p) x0 = fma(-Rb[p * 65 + lane], xp, x0);
+        }
+      }
+      if (b0 + lane < N) vc[b0 + lane] = x0;
+      if (b0 + lane + 32 < N) vc[b0 + lane + 32] = x1;
+    }
+    __syncthreads();
+    // v_i -= sum_{j in block} R(i, b0+j) w_j  for i < b0   (coalesced over i)
+    for (int i = tid; i < b0; i += 256) {
+      double acc[VR];
+#pragma unroll
+      for (int c = 0; c < VR; ++c) acc[c] = 0.0;
+      const int jn = (N - b0) < 64 ? (N - b0) : 64;
+      for (int j = 0; j < jn; ++j) {
+        const double r = R[static_cast<size_t>(b0 + j) * ld + i];
+#pragma unroll
+        for (int c = 0; c < VR; ++c) acc[c] = fma(r, v[c * N + b0 + j], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < VR; ++c) v[c * N + i] -= acc[c];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < nrhs * N; i += 256) Zs[i] = v[i];
+}
+
 // G[s][j][k] = V_j . V_k  (k <= j, mirrored); grid (K, S): CTA (j, s) loops over k <= j
 __global__ void __launch_bounds__(256) var_gram_kernel(const VarArgs a) {
   extern __shared__ __align__(16) double gsm[];  // V_j [N]
@@ -207,7 +268,7 @@ __global__ void __launch_bounds__(256) var_final_kernel(const VarArgs a) {
 }
 
 // Runs the variance pipeline for all S samples; results to host: varFs[S], J[S][K][K] (optional).
-int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J) {
+int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad) {
   if (!c->gpHasL)
     VB_FAIL(VBMC_B200_ESTATE, "gplogjoint variance needs the factors gp.post(s).L on the device (gp_attach with L, or gp_post)");
   const int N = c->gp.N, K = c->K, S = c->gp.S;
@@ -222,7 +283,8 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
   a.full = compute_var == 1 ? 1 : 0;
   a.unit_rhs = 0;
   const size_t nz = static_cast<size_t>(S) * K * N, ng = static_cast<size_t>(S) * K * K;
-  VB_TRY(c->varWork.reserve(sizeof(double) * (nz + 2 * ng + S)));
+  const size_t nvg = vgrad ? static_cast<size_t>(S) * K * (2 + 2 * c->D) : 0;
+  VB_TRY(c->varWork.reserve(sizeof(double) * (nz + 2 * ng + S + nvg)));
   a.Z = c->varWork.d(); a.G = a.Z + nz; a.J = a.G + ng; a.varFs = a.J + ng;
   cudaStream_t st = c->stream;
   {
