@@ -319,6 +319,21 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
     J->assign(ng, 0.0);
     VB_CUDA(cudaMemcpyAsync(J->data(), a.J, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
   }
+  if (vgrad) {
+    // K^-1 z_k = R \ V_k / sn2_eff, then the derivative contractions dz_d(.) * K^-1 z_k  (gplogjoint.m:289-299)
+    const size_t smem_b = sizeof(double) * (static_cast<size_t>(VR) * N + 64 * 65);
+    VB_CUDA(cudaFuncSetAttribute(var_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_b)));
+    dim3 grid_b((K + VR - 1) / VR, S);
+    {
+      KernelScope ks(c, "var_trsm", st);
+      var_bwd_kernel<<<grid_b, 256, smem_b, st>>>(a);
+    }
+    VB_CUDA(cudaGetLastError());
+    double* vg = a.varFs + S;
+    VB_TRY(launch_gplogjoint_weighted(c, a.Z, vg, st));
+    vgrad->assign(nvg, 0.0);
+    VB_CUDA(cudaMemcpyAsync(vgrad->data(), vg, sizeof(double) * nvg, cudaMemcpyDeviceToHost, st));
+  }
   VB_CUDA(cudaStreamSynchronize(st));
   return VBMC_B200_OK;
 }
