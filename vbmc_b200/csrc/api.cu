@@ -107,6 +107,7 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreate(&c->ev_t0));
   VB_CUDA(cudaEventCreate(&c->ev_t1));
+  if (const char* g = getenv("VBMC_B200_GRAPHS")) c->graphs_enabled = strcmp(g, "0") != 0;
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
     if (!strcmp(f, "separable")) c->entmc_form = 0;
     if (!strcmp(f, "direct")) c->entmc_form = 1;
@@ -121,6 +122,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   vb::comm_destroy(c);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
                         &c->ent_partial, &c->glj_out, &c->flush, &c->varWork};
@@ -435,7 +437,8 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   if (doH) {
     if (c->philox_pending) {
       c->philox_pending = false;
-      VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream));
+      VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream,
+                           c->philox_dyn ? reinterpret_cast<const uint64_t*>(c->theta_dev.d() + c->ntheta) : nullptr));
     }
     int need = 0;
     if (gmask & 1) need |= NEED_MU;
@@ -542,6 +545,96 @@ static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
     for (int s = 0; s < S; ++s)
       for (int k = 0; k < K; ++k) a->I_sk[s + static_cast<size_t>(k) * S] = o[ol.oIsk + s * K + k];
   }
+}
+
+// One negelcbo evaluation on the device: H2D {theta, seed, stream}, the kernels, D2H of the output block.
+// Single rank, no profiling: the whole sequence is captured once into a CUDA graph and replayed while the step
+// signature (shapes, flags, buffer addresses) is unchanged — 10 launches + 2 copies become one graph launch.
+static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int Ns, int gmask, int nth, bool sync = true) {
+  const size_t nstage = static_cast<size_t>(c->ntheta) + 2;
+  VB_TRY(c->theta_dev.reserve(sizeof(double) * nstage));
+  VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * nstage));
+  memcpy(c->theta_pinned, a->theta, sizeof(double) * c->ntheta);
+  uint64_t dyn[2] = {a->seed, a->stream};
+  memcpy(c->theta_pinned + c->ntheta, dyn, sizeof(dyn));
+  OutLayout ol;
+  ol.init(nth, c->gp.S, c->K);
+  VB_TRY(ensure_pinned(&c->out_pinned, &c->out_pinned_cap, sizeof(double) * ol.total));
+  const bool philox = a->eps_mode == VBMC_B200_EPS_PHILOX;
+  auto body = [&]() -> int {
+    VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * nstage, cudaMemcpyHostToDevice, c->stream));
+    c->philox_dyn = philox;
+    if (philox) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, a->seed, a->stream));
+    const int rc = enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true);
+    c->philox_dyn = false;
+    VB_TRY(rc);
+    VB_CUDA(cudaMemcpyAsync(c->out_pinned, c->out_dev.p, sizeof(double) * ol.total, cudaMemcpyDeviceToHost, c->stream));
+    return VBMC_B200_OK;
+  };
+  if (!philox) VB_TRY(prepare_eps(c, Ns, a->eps_mode, a->eps, a->seed, a->stream));  // host / resident draws: outside the graph
+  const bool use_graph = c->graphs_enabled && !c->profiling && c->nranks == 1;
+  if (!use_graph) {
+    VB_TRY(body());
+    VB_CUDA(cudaStreamSynchronize(c->stream));
+    return VBMC_B200_OK;
+  }
+  std::vector<long long> key = {Ns, gmask, a->use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form,
+                                c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
+                                reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
+                                reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
+                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p),
+                                reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
+                                reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),
+                                reinterpret_cast<long long>(c->gpDerived.p), reinterpret_cast<long long>(c->bnd.p),
+                                reinterpret_cast<long long>(c->theta_pinned), reinterpret_cast<long long>(c->out_pinned)};
+  {
+    long long bits[3];
+    memcpy(&bits[0], &c->TolCon, 8); memcpy(&bits[1], &c->WeightThreshold, 8); memcpy(&bits[2], &c->WeightPenalty, 8);
+    key.insert(key.end(), bits, bits + 3);
+  }
+  if (c->graph_exec && key == c->graph_key) {
+    VB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+    c->launches += c->graph_launches;
+  } else if (key == c->warm_key) {
+    // second call with this signature: every buffer is allocated, capture the sequence
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    const long long l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    VB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != VBMC_B200_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      c->graphs_enabled = false;  // fall back to direct launches for the rest of the session
+      VB_TRY(body());
+      VB_CUDA(cudaStreamSynchronize(c->stream));
+      return VBMC_B200_OK;
+    }
+    c->graph_launches = c->launches - l0;
+    ce = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      c->graph_exec = nullptr;
+      c->graphs_enabled = false;
+      cudaGetLastError();
+      VB_TRY(body());
+      VB_CUDA(cudaStreamSynchronize(c->stream));
+      return VBMC_B200_OK;
+    }
+    c->graph_key = key;
+    VB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+  } else {
+    VB_TRY(body());   // first call with this signature: allocations happen here
+    // the key must describe the buffers AFTER this call (they may have been allocated by it)
+    std::vector<long long> k2 = key;
+    k2[13] = reinterpret_cast<long long>(c->theta_dev.p); k2[14] = reinterpret_cast<long long>(c->out_dev.p);
+    k2[15] = reinterpret_cast<long long>(c->R_dev.p); k2[16] = reinterpret_cast<long long>(c->eps.p);
+    k2[17] = reinterpret_cast<long long>(c->ent_partial.p); k2[18] = reinterpret_cast<long long>(c->glj_out.p);
+    c->warm_key = k2;
+  }
+  if (sync) VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBMC_B200_OK;
 }
 
 // Gradient of the (diagonal) log-joint variance, averaged over hyper-parameter samples
@@ -655,14 +748,8 @@ int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
   int Ns, gmask;
   VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
   VB_CUDA(cudaSetDevice(c->device));
-  VB_TRY(c->theta_dev.reserve(sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
-  VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
-  memcpy(c->theta_pinned, a->theta, sizeof(double) * c->ntheta);
-  VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * c->ntheta, cudaMemcpyHostToDevice, c->stream));
-  VB_TRY(prepare_eps(c, Ns, a->eps_mode, a->eps, a->seed, a->stream));
-  VB_TRY(enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true));
   const int nth = grad_mask_len(c, gmask);
-  VB_TRY(fetch_out(c, nth, c->gp.S));
+  VB_TRY(step_with_graph(c, a, Ns, gmask, nth));
   scatter_negelcbo(c, a, nth);
   if (a->compute_var) {
     // varG (and J_sjk) from the factors; F = F + beta*sqrt(varF)   (negelcbo_vbmc.m:119-130)
@@ -693,26 +780,24 @@ int vbmc_b200_negelcbo_resident_loop(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_
   int Ns, gmask;
   VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
   if (steps <= 0 || !ms_total) VB_FAIL(VBMC_B200_EINVAL, "resident_loop: steps > 0 and ms_total required");
+  if (a->compute_var) VB_FAIL(VBMC_B200_EINVAL, "resident_loop: compute_var must be 0");
   VB_CUDA(cudaSetDevice(c->device));
-  VB_TRY(c->theta_dev.reserve(sizeof(double) * (c->ntheta > 0 ? c->ntheta : 1)));
-  VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, a->theta, sizeof(double) * c->ntheta, cudaMemcpyHostToDevice, c->stream));
-  if (a->eps_mode == VBMC_B200_EPS_HOST) {
+  vbmc_b200_negelcbo_args b = *a;
+  if (a->eps_mode == VBMC_B200_EPS_HOST) {  // upload once, then reuse the resident draws
     VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_HOST, a->eps, 0, 0));
+    b.eps_mode = VBMC_B200_EPS_RESIDENT;
   }
+  const int nth = grad_mask_len(c, gmask);
   VB_CUDA(cudaStreamSynchronize(c->stream));
   VB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
   for (int i = 0; i < steps; ++i) {
-    if (a->eps_mode == VBMC_B200_EPS_PHILOX)
-      VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, a->seed, a->stream + i));
-    else
-      VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_RESIDENT, nullptr, 0, 0));
-    VB_TRY(enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true));
+    b.stream = a->stream + i;
+    VB_TRY(step_with_graph(c, &b, Ns, gmask, nth, /*sync=*/i + 1 < steps));
   }
   VB_CUDA(cudaEventRecord(c->ev_t1, c->stream));
   VB_CUDA(cudaEventSynchronize(c->ev_t1));
   VB_CUDA(cudaEventElapsedTime(ms_total, c->ev_t0, c->ev_t1));
-  const int nth = grad_mask_len(c, gmask);
-  VB_TRY(fetch_out(c, nth, c->gp.S));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
   scatter_negelcbo(c, a, nth);
   return VBMC_B200_OK;
 }

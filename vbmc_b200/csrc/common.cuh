@@ -189,6 +189,7 @@ struct vbmc_b200_ctx {
   int epsD = 0, epsK = 0, epsNs = 0;
   bool eps_ready = false;
   bool philox_pending = false;
+  bool philox_dyn = false;  // read {seed, stream} from theta_dev[ntheta..] (set while building / replaying a step graph)
   uint64_t philox_seed = 0, philox_stream = 0;
 
   // step buffers
@@ -198,6 +199,12 @@ struct vbmc_b200_ctx {
   size_t theta_pinned_cap = 0, out_pinned_cap = 0;
   vb::DevBuf flush;  // L2 flush scratch
   vb::DevBuf varWork;  // variance path: Z/V, Gram, J, varF(s)
+
+  // CUDA graph of one negelcbo step (single rank): replayed while the step signature is unchanged
+  bool graphs_enabled = true;
+  std::vector<long long> graph_key, warm_key;
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0;
 
   // profiling
   bool profiling = false;
@@ -229,7 +236,8 @@ int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st);
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
 int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
 int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
-int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st);
+int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
+                  const uint64_t* dyn = nullptr);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad = nullptr);

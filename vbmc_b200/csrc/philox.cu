@@ -28,6 +28,7 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 struct PhiloxArgs {
   int D, K, half, pair_begin, pair_end;
   uint64_t seed, stream;
+  const uint64_t* dyn;  // optional device pointer to {seed, stream} (graph replay: values change, the node does not)
   double* eps;  // [K][half][D]
 };
 
@@ -37,11 +38,12 @@ __global__ void philox_normal_kernel(const PhiloxArgs a) {
   const long long e_begin = (static_cast<long long>(j) * a.half + a.pair_begin) * a.D;
   const long long e_end = (static_cast<long long>(j) * a.half + a.pair_end) * a.D;
   const long long c_begin = e_begin >> 1, c_end = (e_end + 1) >> 1;
+  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = a.dyn ? a.dyn[1] : a.stream;
   for (long long c = c_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; c < c_end;
        c += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 ctr = make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
-                                 static_cast<uint32_t>(a.stream), static_cast<uint32_t>(a.stream >> 32));
-    const uint2 key = make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+                                 static_cast<uint32_t>(strm), static_cast<uint32_t>(strm >> 32));
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const uint4 r = philox4x32_10(ctr, key);
     const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
     const double rad = sqrt(-2.0 * log(u1));
@@ -59,11 +61,12 @@ __global__ void philox_raw_kernel(uint4 ctr, uint2 key, uint32_t* out) {
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
-int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st) {
+int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st, const uint64_t* dyn) {
   PhiloxArgs a;
   a.D = D; a.K = K; a.half = Ns / 2;
   shard_range(a.half, c->nranks, c->rank, &a.pair_begin, &a.pair_end);
   a.seed = seed; a.stream = stream_id;
+  a.dyn = dyn;
   a.eps = c->eps.d();
   if (a.pair_end <= a.pair_begin) return VBMC_B200_OK;
   const long long per_comp = (static_cast<long long>(a.pair_end - a.pair_begin) * D + 2) / 2;
