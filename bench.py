@@ -225,7 +225,7 @@ def main():
         else scipy_gp_post
     try:
         w = workloads.build(cfg, gp_fn, with_eps=False)
-        gp_source = "vbmc_b200.gplite_post (GPU)"
+        gp_source = "vbmc_b200.gplite_post (GPU)" if gp_fn is not scipy_gp_post else "scipy LAPACK (set-up only)"
     except vbmc_b200.VbmcB200Error as e:
         if "NotYet" not in str(e):
             raise

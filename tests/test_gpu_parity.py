@@ -31,8 +31,8 @@ SHAPES = [
     dict(D=9, N=64, K=33, S=2, Ns=130),         # K > 32: second round of the column sums
     dict(D=10, N=300, K=50, S=4, Ns=512, target="lumpy"),   # c3 shape, reduced N/Ns/S
     dict(D=20, N=128, K=12, S=2, Ns=96, target="lumpy"),    # c5 dimension
-    dict(D=20, N=96, K=100, S=2, Ns=128, target="lumpy"),   # c5 dimension and component count (K=100)
-    dict(D=7, N=50, K=128, S=1, Ns=66),                     # largest supported K
+    dict(D=20, N=160, K=100, S=2, Ns=128, target="lumpy"),  # c5 dimension and component count (K=100)
+    dict(D=7, N=140, K=128, S=1, Ns=66),                    # largest supported K
 ]
 
 
