@@ -123,6 +123,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   cudaDeviceSynchronize();
   vb::comm_destroy(c);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->refit_graph) cudaGraphExecDestroy(c->refit_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
                         &c->ent_partial, &c->glj_out, &c->flush, &c->varWork};

@@ -205,6 +205,9 @@ struct vbmc_b200_ctx {
   std::vector<long long> graph_key, warm_key;
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;
+  std::vector<long long> refit_key;   // same for the batched Cholesky of gp_post / gp_nlz
+  cudaGraphExec_t refit_graph = nullptr;
+  long long refit_launches = 0;
 
   // profiling
   bool profiling = false;

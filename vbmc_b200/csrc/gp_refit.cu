@@ -424,6 +424,60 @@ __global__ void __launch_bounds__(256) gp_bsolve_update_kernel(const GpBatch g, 
   z[i] -= acc0 + acc1;
 }
 
+// Whole back substitution of one sample in ONE CTA of 1024 threads (replaces the 2-kernels-per-block chain):
+// per 64-block: warp 0 solves the diagonal block (lane owns rows lane, lane+32; pivot broadcast by shuffle) while
+// the block was staged by all threads; then every thread updates rows i < k0 (coalesced over i).
+__global__ void __launch_bounds__(1024) gp_bsolve_kernel(const GpBatch g, const double* ascale, double* alpha) {
+  __shared__ double Rk[TB][TB + 1];
+  __shared__ double xk[TB];
+  const int s = blockIdx.x;
+  const int Np = g.Np, N = g.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* z = Ms + static_cast<size_t>(N) * Np;
+  for (int kb = (N + TB - 1) / TB - 1; kb >= 0; --kb) {
+    const int k0 = kb * TB;
+    for (int i = tid; i < TB * TB; i += 1024) {
+      const int c = i >> 6, r = i & 63;
+      Rk[c][r] = (k0 + c < N && k0 + r < N && r <= c) ? Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] : (c == r ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = (k0 + lane < N) ? z[k0 + lane] : 0.0;
+      double x1 = (k0 + lane + 32 < N) ? z[k0 + lane + 32] : 0.0;
+      for (int p = TB - 1; p >= 0; --p) {
+        double xp = (p >= 32 ? x1 : x0) / Rk[p][p];
+        xp = __shfl_sync(0xffffffffu, xp, p & 31);
+        if (p >= 32) {
+          if (lane == (p & 31)) x1 = xp;
+          if (lane + 32 < p) x1 = fma(-Rk[p][lane + 32], xp, x1);
+          x0 = fma(-Rk[p][lane], xp, x0);
+        } else {
+          if (lane == p) x0 = xp;
+          if (lane < p) x0 = fma(-Rk[p][lane], xp, x0);
+        }
+      }
+      xk[lane] = x0;
+      xk[lane + 32] = x1;
+      if (k0 + lane < N) z[k0 + lane] = x0;
+      if (k0 + lane + 32 < N) z[k0 + lane + 32] = x1;
+    }
+    __syncthreads();
+    for (int i = tid; i < k0; i += 1024) {
+      double a0 = 0.0, a1 = 0.0;
+      const double* col = Ms + static_cast<size_t>(k0) * Np + i;
+#pragma unroll 8
+      for (int j = 0; j < TB; j += 2) {
+        a0 = fma(col[static_cast<size_t>(j) * Np], xk[j], a0);
+        a1 = fma(col[static_cast<size_t>(j + 1) * Np], xk[j + 1], a1);
+      }
+      z[i] -= a0 + a1;
+    }
+    __syncthreads();
+  }
+  const double sc = ascale[s];
+  for (int i = tid; i < N; i += 1024) alpha[static_cast<size_t>(s) * N + i] = z[i] * sc;
+}
+
 __global__ void gp_alpha_kernel(const GpBatch g, const double* ascale, double* alpha) {
   const int s = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -657,29 +711,64 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
     VB_CUDA(cudaMemcpyAsync(d_ascale, h_ascale.data(), sizeof(double) * S, cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemcpyAsync(d_active, active.data(), sizeof(int) * nact, cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int) * S, st));
-    {
-      dim3 grid(nb * (nb + 1) / 2, nact);
-      KernelScope ks(c, "gram", st);
-      gp_gram_kernel<<<grid, 256, sizeof(double) * 2 * D * TB, st>>>(g);
-    }
-    for (int kb = 0; kb < nb; ++kb) {
-      const int nr = nb - kb - 1;
+    auto factor_body = [&]() -> int {
       {
-        KernelScope ks(c, "potrf_panel", st);
-        gp_potf2_kernel<<<nact, 256, 0, st>>>(g, kb);
+        dim3 grid(nb * (nb + 1) / 2, nact);
+        KernelScope ks(c, "gram", st);
+        gp_gram_kernel<<<grid, 256, sizeof(double) * 2 * D * TB, st>>>(g);
       }
-      if (nr > 0) {
-        dim3 grid(nr, nact);
-        KernelScope ks(c, "potrf_panel", st);
-        gp_trsm_kernel<<<grid, 256, 0, st>>>(g, kb);
+      for (int kb = 0; kb < nb; ++kb) {
+        const int nr = nb - kb - 1;
+        {
+          KernelScope ks(c, "potrf_panel", st);
+          gp_potf2_kernel<<<nact, 256, 0, st>>>(g, kb);
+        }
+        if (nr > 0) {
+          dim3 grid(nr, nact);
+          KernelScope ks(c, "potrf_panel", st);
+          gp_trsm_kernel<<<grid, 256, 0, st>>>(g, kb);
+        }
+        if (nr > 0) {
+          int nwork = 0;
+          for (int ii = 0; ii < nr; ++ii) nwork += (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
+          dim3 grid(nwork, nact);
+          KernelScope ks(c, "potrf_update", st);
+          gp_update_kernel<<<grid, 256, UPDATE_SMEM, st>>>(g, kb);
+        }
       }
-      if (nr > 0) {
-        int nwork = 0;
-        for (int ii = 0; ii < nr; ++ii) nwork += (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
-        dim3 grid(nwork, nact);
-        KernelScope ks(c, "potrf_update", st);
-        gp_update_kernel<<<grid, 256, UPDATE_SMEM, st>>>(g, kb);
+      return VBMC_B200_OK;
+    };
+    // ~100 dependent launches: replay them as one CUDA graph while shapes and buffers are unchanged
+    std::vector<long long> key = {N, D, Np, S, nact, gd->Nhyp, gd->meanfun, reinterpret_cast<long long>(c->gpL.p),
+                                  reinterpret_cast<long long>(c->gpWork.p), reinterpret_cast<long long>(c->gpX.p),
+                                  reinterpret_cast<long long>(c->gpY.p), reinterpret_cast<long long>(c->gpHyp.p),
+                                  reinterpret_cast<long long>(c->gpS2.p), gd->noisefun[0], gd->noisefun[1], gd->noisefun[2]};
+    if (c->graphs_enabled && !c->profiling) {
+      if (!(c->refit_graph && key == c->refit_key)) {
+        if (c->refit_graph) { cudaGraphExecDestroy(c->refit_graph); c->refit_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const long long l0 = c->launches;
+        VB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = factor_body();
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc == VBMC_B200_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&c->refit_graph, graph, 0) == cudaSuccess) {
+          c->refit_key = key;
+          c->refit_launches = c->launches - l0;
+          c->launches = l0;
+        } else {
+          c->refit_graph = nullptr;
+          cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
       }
+      if (c->refit_graph) {
+        VB_CUDA(cudaGraphLaunch(c->refit_graph, st));
+        c->launches += c->refit_launches;
+      } else {
+        VB_TRY(factor_body());
+      }
+    } else {
+      VB_TRY(factor_body());
     }
     VB_CUDA(cudaGetLastError());
     VB_CUDA(cudaMemcpyAsync(h_info.data(), d_info, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
@@ -700,21 +789,9 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
     KernelScope ks(c, "trsv", st);
     gp_nlzparts_kernel<<<S, 256, 0, st>>>(g, d_logdet, d_zz);
   }
-  for (int kb = (N + TB - 1) / TB - 1; kb >= 0; --kb) {
-    {
-      KernelScope ks(c, "trsv", st);
-      gp_bsolve_diag_kernel<<<S, 32, 0, st>>>(g, kb);
-    }
-    if (kb > 0) {
-      dim3 grid((kb * TB + 255) / 256, S);
-      KernelScope ks(c, "trsv", st);
-      gp_bsolve_update_kernel<<<grid, 256, 0, st>>>(g, kb);
-    }
-  }
   {
-    dim3 grid((N + 255) / 256, S);
     KernelScope ks(c, "trsv", st);
-    gp_alpha_kernel<<<grid, 256, 0, st>>>(g, d_ascale, c->gpAlpha.d());
+    gp_bsolve_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
   }
   VB_CUDA(cudaGetLastError());
   rr->logdet.assign(S, 0.0);
