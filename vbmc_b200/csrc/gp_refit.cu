@@ -38,6 +38,7 @@ struct GpBatch {
   const double* scale;    // [S] 1/(sn2div*mult)   (Lchol) or 1 (low noise)
   const double* dscale;   // [S] 1/sn2div          (Lchol) or mult (low noise)
   int* info;              // [S] 0 ok, >0 first failing pivot (1-based)
+  double* dscratch;       // [S][64*64] factor of the current diagonal block (written in place one step later)
 };
 
 // ---- per-point noise variance and mean (gplite_noisefun.m:176-210, gplite_meanfun.m cases 0,1,4) ----
@@ -225,6 +226,101 @@ __global__ void __launch_bounds__(256) gp_trsm_kernel(const GpBatch g, int kb) {
     for (int i = 0; i < 16; ++i) {
       const int r = q + 4 * i;
       if (r > p) x[i] = fma(-R[r][p], xp, x[i]);   // b_r -= R(p, r) x_p
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) col[q + 4 * i] = x[i];
+}
+
+// ---- fused panel step: every CTA factors the diagonal block itself (same code as gp_potf2_kernel, ~64 barriers)
+// and then solves its own column block, so a step needs one launch and never runs on only S CTAs.
+// grid (max(1, nb-kb-1), nact); CTA x == 0 writes the factor of the diagonal block back.
+__global__ void __launch_bounds__(256) gp_panel_kernel(const GpBatch g, int kb) {
+  __shared__ double A[TB][TB + 1];
+  __shared__ double lrow[TB];
+  __shared__ double ird[TB];
+  __shared__ int bad;
+  const int s = g.active[blockIdx.y];
+  const int Np = g.Np, N = g.N, tid = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  const int k0 = kb * TB;
+  const int nr = Np / TB - kb - 1;
+  if (tid == 0) bad = 0;
+  for (int i = tid; i < TB * TB; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    A[c][r] = Ms[static_cast<size_t>(k0 + c) * Np + k0 + r];
+  }
+  // The factor of the previous diagonal block is still in the scratch buffer (it could not be written in place
+  // while the other CTAs of that step were still loading the unfactored block): put it in place now.
+  if (blockIdx.x == 0 && kb > 0) {
+    const double* sc = g.dscratch + static_cast<size_t>(s) * TB * TB;
+    for (int i = tid; i < TB * TB; i += 256) {
+      const int cc = i >> 6, r = i & 63;
+      if (r <= cc) Ms[static_cast<size_t>(k0 - TB + cc) * Np + (k0 - TB) + r] = sc[i];
+    }
+  }
+  // prefetch this CTA's right-hand block into registers (thread (c, q) owns rows q, q+4, ... of column c)
+  const int c = tid >> 2, q = tid & 3;
+  const bool have_rhs = static_cast<int>(blockIdx.x) < nr;
+  const int jb = kb + 1 + blockIdx.x;
+  double* col = Ms + static_cast<size_t>(jb * TB + c) * Np + k0;
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = have_rhs ? col[q + 4 * i] : 0.0;
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int p = 0; p < TB; ++p) {
+    const bool unit = (k0 + p) >= N;
+    const double d = A[p][p];
+    if (tid == 0 && !unit && !(d > 0.0) && bad == 0) bad = k0 + p + 1;
+    const double isq = unit ? 0.0 : rsqrt(d);
+    if (tid < TB) {
+      const int j = tid;
+      double v = 0.0;
+      if (j >= p) v = unit ? (j == p ? 1.0 : 0.0) : A[j][p] * isq;
+      lrow[j] = v;
+    }
+    __syncthreads();
+    if (tid < TB) A[tid][p] = lrow[tid];
+    if (!unit) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int j = tx + 16 * a;
+        const double lj = lrow[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = ty + 16 * b;
+          if (i > p && i <= j) A[j][i] = fma(-lrow[i], lj, A[j][i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && bad != 0) atomicCAS(&g.info[s], 0, bad);
+  if (tid < TB) ird[tid] = 1.0 / A[tid][tid];
+  if (blockIdx.x == 0) {
+    if (nr == 0) {  // last block: this is the only CTA of the sample, write in place
+      for (int i = tid; i < TB * TB; i += 256) {
+        const int cc = i >> 6, r = i & 63;
+        if (r <= cc) Ms[static_cast<size_t>(k0 + cc) * Np + k0 + r] = A[cc][r];
+      }
+    } else {
+      double* sc = g.dscratch + static_cast<size_t>(s) * TB * TB;
+      for (int i = tid; i < TB * TB; i += 256) sc[i] = A[i >> 6][i & 63];
+    }
+  }
+  __syncthreads();
+  if (!have_rhs) return;
+  const unsigned lane = tid & 31;
+#pragma unroll
+  for (int p = 0; p < TB; ++p) {
+    double xp = x[p >> 2] * ird[p];
+    xp = __shfl_sync(0xffffffffu, xp, (lane & ~3u) | (p & 3));
+    if (q == (p & 3)) x[p >> 2] = xp;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int r = q + 4 * i;
+      if (r > p) x[i] = fma(-A[r][p], xp, x[i]);   // b_r -= R(p, r) x_p,  R(p, r) = A[r][p]
     }
   }
 #pragma unroll
@@ -641,7 +737,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   VB_TRY(c->gpAlpha.reserve(sizeof(double) * static_cast<size_t>(S) * N));
   VB_TRY(c->gpL.reserve(sizeof(double) * static_cast<size_t>(S) * Np * Np));
   // work: sn2[S][N] mvec[S][N] scale[S] dscale[S] ascale[S] minsn2[S] logdet[S] zz[S] | info[S] active[S]
-  const size_t nwork = 2 * static_cast<size_t>(S) * N + 6 * S;
+  const size_t nwork = 2 * static_cast<size_t>(S) * N + 6 * S + static_cast<size_t>(S) * TB * TB;
   VB_TRY(c->gpWork.reserve(sizeof(double) * nwork + sizeof(int) * 2 * S + 64));
   VB_CUDA(cudaMemcpyAsync(c->gpX.p, gd->X, sizeof(double) * N * D, cudaMemcpyHostToDevice, st));
   VB_CUDA(cudaMemcpyAsync(c->gpY.p, gd->y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
@@ -663,8 +759,10 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   double* d_minsn2 = d_ascale + S;
   double* d_logdet = d_minsn2 + S;
   double* d_zz = d_logdet + S;
-  int* d_info = reinterpret_cast<int*>(d_zz + S);
+  double* d_dscratch = d_zz + S;
+  int* d_info = reinterpret_cast<int*>(d_dscratch + static_cast<size_t>(S) * TB * TB);
   int* d_active = d_info + S;
+  g.dscratch = d_dscratch;
   g.M = c->gpL.d(); g.scale = d_scale; g.dscale = d_dscale; g.info = d_info; g.active = d_active;
   {
     dim3 grid((N + 255) / 256, S);
@@ -720,13 +818,9 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
       for (int kb = 0; kb < nb; ++kb) {
         const int nr = nb - kb - 1;
         {
+          dim3 grid(nr > 0 ? nr : 1, nact);
           KernelScope ks(c, "potrf_panel", st);
-          gp_potf2_kernel<<<nact, 256, 0, st>>>(g, kb);
-        }
-        if (nr > 0) {
-          dim3 grid(nr, nact);
-          KernelScope ks(c, "potrf_panel", st);
-          gp_trsm_kernel<<<grid, 256, 0, st>>>(g, kb);
+          gp_panel_kernel<<<grid, 256, 0, st>>>(g, kb);
         }
         if (nr > 0) {
           int nwork = 0;
