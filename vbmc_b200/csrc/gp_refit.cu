@@ -349,49 +349,57 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
 
-// copy a 64(k) x 64(cols) block (column-major, leading dim Np) into dst[c*TLD + k]
+// copy a KD(k) x 64(cols) block (column-major, leading dim Np) into dst[c*(KD+4) + k]
+template <int KD>
 __device__ __forceinline__ void load_pblock_async(double* dst, const double* src, int Np, int tid) {
+  constexpr int CH = KD / 2;  // 16-byte chunks per column
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = tid + it * 256;       // 2048 chunks of 16 B
-    const int c = idx >> 5, ch = idx & 31;
-    cp_async16(dst + c * TLD + ch * 2, src + static_cast<size_t>(c) * Np + ch * 2);
+  for (int it = 0; it < 64 * CH / 256; ++it) {
+    const int idx = tid + it * 256;
+    const int c = idx / CH, ch = idx - c * CH;
+    cp_async16(dst + c * (KD + 4) + ch * 2, src + static_cast<size_t>(c) * Np + ch * 2);
   }
 }
 
-__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kb) {
+// Trailing update with a panel of depth KD rows starting at row krow0:  C_IJ -= P_I' P_J for the block rows
+// I = Ifirst .. Ifirst+Icount-1 and J >= I.  KD = 64: strip update inside a 128-wide panel; KD = 128: the big
+// trailing update — one read-modify-write of C per 128 panel rows doubles the flop/byte (8 instead of 4), which
+// is what lifts the kernel off the HBM roof (B200: DMMA peak 37 TFLOP/s needs > 5.7 flop/B).
+template <int KD>
+__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int krow0, int Ifirst, int Icount) {
   extern __shared__ __align__(16) double usm[];
-  double* PI = usm;                 // PI[m*TLD + k] = P_I(k, m)
-  double* PJ0 = usm + TB * TLD;     // two stages
-  double* PJ1 = usm + 2 * TB * TLD;
+  constexpr int LD = KD + 4;
+  double* PI = usm;              // PI[m*LD + k] = P_I(k, m)
+  double* PJ0 = usm + TB * LD;   // two stages
+  double* PJ1 = usm + 2 * TB * LD;
   const int s = g.active[blockIdx.y];
   const int Np = g.Np, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nr = Np / TB - kb - 1;  // blocks to the right of kb
-  // decode work item -> (ii, chunk): row ii has ceil((nr-ii)/UPD_CHUNK) chunks
+  const int nb = Np / TB;
+  // decode work item -> (ii, chunk): row I = Ifirst+ii has ceil((nb-I)/UPD_CHUNK) chunks
   int t = blockIdx.x, ii = 0;
   for (;;) {
-    const int nch = (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
+    const int nch = (nb - (Ifirst + ii) + UPD_CHUNK - 1) / UPD_CHUNK;
     if (t < nch) break;
     t -= nch;
     ++ii;
   }
-  const int I = kb + 1 + ii;
+  (void)Icount;
+  const int I = Ifirst + ii;
   const int J0 = I + t * UPD_CHUNK;
-  int len = kb + 1 + nr - J0;
+  int len = nb - J0;
   len = len > UPD_CHUNK ? UPD_CHUNK : len;
   double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
-  const double* prow = Ms + static_cast<size_t>(kb) * TB;  // row offset of the panel
-  load_pblock_async(PI, prow + static_cast<size_t>(I * TB) * Np, Np, tid);
-  load_pblock_async(PJ0, prow + static_cast<size_t>(J0 * TB) * Np, Np, tid);
+  const double* prow = Ms + krow0;  // row offset of the panel
+  load_pblock_async<KD>(PI, prow + static_cast<size_t>(I * TB) * Np, Np, tid);
+  load_pblock_async<KD>(PJ0, prow + static_cast<size_t>(J0 * TB) * Np, Np, tid);
   cp_async_commit();
   const int wm = warp >> 1, wn = warp & 1;
   const int g4 = lane >> 2, t4 = lane & 3;
   for (int jj = 0; jj < len; ++jj) {
     const int J = J0 + jj;
     double* PJ = (jj & 1) ? PJ1 : PJ0;
-    if (jj + 1 < len) load_pblock_async((jj & 1) ? PJ0 : PJ1, prow + static_cast<size_t>((J + 1) * TB) * Np, Np, tid);
+    if (jj + 1 < len) load_pblock_async<KD>((jj & 1) ? PJ0 : PJ1, prow + static_cast<size_t>((J + 1) * TB) * Np, Np, tid);
     cp_async_commit();
-    // prefetch the C tile
     double cold[2][4][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -411,12 +419,12 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kb)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 #pragma unroll 4
-    for (int k = 0; k < TB; k += 4) {
+    for (int k = 0; k < KD; k += 4) {
       double af[2], bf[4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) af[a] = PI[(wm * 16 + a * 8 + g4) * TLD + k + t4];
+      for (int a = 0; a < 2; ++a) af[a] = PI[(wm * 16 + a * 8 + g4) * LD + k + t4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bf[b] = PJ[(wn * 32 + b * 8 + g4) * TLD + k + t4];
+      for (int b = 0; b < 4; ++b) bf[b] = PJ[(wn * 32 + b * 8 + g4) * LD + k + t4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -434,6 +442,13 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kb)
       }
     __syncthreads();  // all warps done with PJ before the ring slot is refilled
   }
+}
+
+// number of CTAs (work items) of gp_update_kernel for block rows Ifirst .. Ifirst+Icount-1
+static int update_work_items(int nb, int Ifirst, int Icount) {
+  int n = 0;
+  for (int ii = 0; ii < Icount; ++ii) n += (nb - (Ifirst + ii) + UPD_CHUNK - 1) / UPD_CHUNK;
+  return n;
 }
 
 // ---- back substitution R x = z (z = column N of the factored buffer), blocked like the factorisation ----
@@ -788,8 +803,9 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   std::vector<double> h_scale(S), h_dscale(S), h_ascale(S);
   std::vector<int> h_info(S);
   const int nb = Np / TB;
-  const int UPDATE_SMEM = 3 * TB * TLD * sizeof(double);
-  VB_CUDA(cudaFuncSetAttribute(gp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM));
+  const int UPDATE_SMEM64 = 3 * TB * (64 + 4) * sizeof(double), UPDATE_SMEM128 = 3 * TB * (128 + 4) * sizeof(double);
+  VB_CUDA(cudaFuncSetAttribute(gp_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM64));
+  VB_CUDA(cudaFuncSetAttribute(gp_update_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM128));
   for (int attempt = 0; attempt < 10 && !active.empty(); ++attempt) {
     for (int s : active) {
       if (rr->Lchol[s]) {
@@ -815,23 +831,29 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
         KernelScope ks(c, "gram", st);
         gp_gram_kernel<<<grid, 256, sizeof(double) * 2 * D * TB, st>>>(g);
       }
-      for (int kb = 0; kb < nb; ++kb) {
-        const int nr = nb - kb - 1;
-        {  // (a fused potf2+trsm kernel, gp_panel_kernel, was measured slower: 2.6 vs 2.2 ms at c3)
-          KernelScope ks(c, "potrf_panel", st);
-          gp_potf2_kernel<<<nact, 256, 0, st>>>(g, kb);
-        }
-        if (nr > 0) {
-          dim3 grid(nr, nact);
-          KernelScope ks(c, "potrf_panel", st);
-          gp_trsm_kernel<<<grid, 256, 0, st>>>(g, kb);
-        }
-        if (nr > 0) {
-          int nwork = 0;
-          for (int ii = 0; ii < nr; ++ii) nwork += (nr - ii + UPD_CHUNK - 1) / UPD_CHUNK;
-          dim3 grid(nwork, nact);
-          KernelScope ks(c, "potrf_update", st);
-          gp_update_kernel<<<grid, 256, UPDATE_SMEM, st>>>(g, kb);
+      // 128-wide panels: two 64-steps share one big trailing update of depth 128
+      for (int kb = 0; kb < nb; kb += 2) {
+        for (int h = 0; h < 2 && kb + h < nb; ++h) {
+          const int k = kb + h, nr = nb - k - 1;
+          {  // (a fused potf2+trsm kernel, gp_panel_kernel, was measured slower: 2.6 vs 2.2 ms at c3)
+            KernelScope ks(c, "potrf_panel", st);
+            gp_potf2_kernel<<<nact, 256, 0, st>>>(g, k);
+          }
+          if (nr > 0) {
+            dim3 grid(nr, nact);
+            KernelScope ks(c, "potrf_panel", st);
+            gp_trsm_kernel<<<grid, 256, 0, st>>>(g, k);
+          }
+          if (h == 0 && nr > 0) {  // update block row kb+1 only (needed by the second half of the panel)
+            dim3 grid(update_work_items(nb, kb + 1, 1), nact);
+            KernelScope ks(c, "potrf_update", st);
+            gp_update_kernel<64><<<grid, 256, UPDATE_SMEM64, st>>>(g, kb * TB, kb + 1, 1);
+          }
+          if (h == 1 && nr > 0) {  // trailing update with both panel rows (depth 128)
+            dim3 grid(update_work_items(nb, kb + 2, nb - kb - 2), nact);
+            KernelScope ks(c, "potrf_update", st);
+            gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, st>>>(g, kb * TB, kb + 2, nb - kb - 2);
+          }
         }
       }
       return VBMC_B200_OK;
