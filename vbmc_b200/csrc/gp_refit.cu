@@ -366,7 +366,7 @@ __device__ __forceinline__ void load_pblock_async(double* dst, const double* src
 // trailing update — one read-modify-write of C per 128 panel rows doubles the flop/byte (8 instead of 4), which
 // is what lifts the kernel off the HBM roof (B200: DMMA peak 37 TFLOP/s needs > 5.7 flop/B).
 template <int KD>
-__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int krow0, int Ifirst, int Icount) {
+__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int krow0, int Ifirst, int Icount, int chunk) {
   extern __shared__ __align__(16) double usm[];
   constexpr int LD = KD + 4;
   double* PI = usm;              // PI[m*LD + k] = P_I(k, m)
@@ -378,16 +378,16 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kro
   // decode work item -> (ii, chunk): row I = Ifirst+ii has ceil((nb-I)/UPD_CHUNK) chunks
   int t = blockIdx.x, ii = 0;
   for (;;) {
-    const int nch = (nb - (Ifirst + ii) + UPD_CHUNK - 1) / UPD_CHUNK;
+    const int nch = (nb - (Ifirst + ii) + chunk - 1) / chunk;
     if (t < nch) break;
     t -= nch;
     ++ii;
   }
   (void)Icount;
   const int I = Ifirst + ii;
-  const int J0 = I + t * UPD_CHUNK;
+  const int J0 = I + t * chunk;
   int len = nb - J0;
-  len = len > UPD_CHUNK ? UPD_CHUNK : len;
+  len = len > chunk ? chunk : len;
   double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
   const double* prow = Ms + krow0;  // row offset of the panel
   load_pblock_async<KD>(PI, prow + static_cast<size_t>(I * TB) * Np, Np, tid);
@@ -445,10 +445,18 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kro
 }
 
 // number of CTAs (work items) of gp_update_kernel for block rows Ifirst .. Ifirst+Icount-1
-static int update_work_items(int nb, int Ifirst, int Icount) {
+static int update_work_items(int nb, int Ifirst, int Icount, int chunk) {
   int n = 0;
-  for (int ii = 0; ii < Icount; ++ii) n += (nb - (Ifirst + ii) + UPD_CHUNK - 1) / UPD_CHUNK;
+  for (int ii = 0; ii < Icount; ++ii) n += (nb - (Ifirst + ii) + chunk - 1) / chunk;
   return n;
+}
+// tiles per CTA: as long as possible (P_I reuse, pipelined P_J) while keeping >= 2 CTAs per SM in flight
+static int update_chunk(int nb, int Ifirst, int Icount, int nact, int num_sms) {
+  long long tiles = 0;
+  for (int ii = 0; ii < Icount; ++ii) tiles += nb - (Ifirst + ii);
+  tiles *= nact;
+  long long ch = tiles / (2LL * num_sms);
+  return ch < 1 ? 1 : (ch > UPD_CHUNK ? UPD_CHUNK : static_cast<int>(ch));
 }
 
 // ---- back substitution R x = z (z = column N of the factored buffer), blocked like the factorisation ----
@@ -845,14 +853,16 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
             gp_trsm_kernel<<<grid, 256, 0, st>>>(g, k);
           }
           if (h == 0 && nr > 0) {  // update block row kb+1 only (needed by the second half of the panel)
-            dim3 grid(update_work_items(nb, kb + 1, 1), nact);
+            const int ch = update_chunk(nb, kb + 1, 1, nact, c->num_sms);
+            dim3 grid(update_work_items(nb, kb + 1, 1, ch), nact);
             KernelScope ks(c, "potrf_update", st);
-            gp_update_kernel<64><<<grid, 256, UPDATE_SMEM64, st>>>(g, kb * TB, kb + 1, 1);
+            gp_update_kernel<64><<<grid, 256, UPDATE_SMEM64, st>>>(g, kb * TB, kb + 1, 1, ch);
           }
           if (h == 1 && nr > 0) {  // trailing update with both panel rows (depth 128)
-            dim3 grid(update_work_items(nb, kb + 2, nb - kb - 2), nact);
+            const int ch = update_chunk(nb, kb + 2, nb - kb - 2, nact, c->num_sms);
+            dim3 grid(update_work_items(nb, kb + 2, nb - kb - 2, ch), nact);
             KernelScope ks(c, "potrf_update", st);
-            gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, st>>>(g, kb * TB, kb + 2, nb - kb - 2);
+            gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, st>>>(g, kb * TB, kb + 2, nb - kb - 2, ch);
           }
         }
       }
