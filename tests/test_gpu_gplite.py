@@ -194,3 +194,16 @@ def test_gplite_post_low_noise_branch(gpu_ctx):
         assert np.max(np.abs(a["L"] @ Amat + np.eye(N))) < 100 * cond * np.finfo(float).eps
         assert rel(a["alpha"], b["alpha"]) < 100 * cond * np.finfo(float).eps
         assert rel(a["sW"], b["sW"]) < 1e-14
+
+
+def test_gplite_nlZ_gradient_c5_points(gpu_ctx):
+    """N = 4000 (BASELINE config 5): the triangular inverse keeps 4 columns per CTA instead of 8."""
+    import vbmc_b200
+    N, D = 4000, 2
+    X, y, s2, hyp = problem(N, D, 1, meanfun=4, noisy=False)
+    hyp[D + 1, 0] = math.log(0.3)   # keeps K/sn2 + I comfortably conditioned at this N
+    gp = orc.gplite_post(hyp, X, y, 1, 4, [1, 0, 0], None)
+    nlZ, dnlZ = vbmc_b200.gplite_nlZ(hyp[:, 0], gp, None, nargout=2)
+    ref = orc.gplite_nlZ(hyp[:, 0], gp, None, nargout=2)
+    assert rel(nlZ, ref[0]) < 1e-10
+    assert rel(dnlZ, ref[1]) < 1e-6   # inv(A) entries carry cond(A)*eps; cond(A) ~ 1e8 for 4000 clustered points

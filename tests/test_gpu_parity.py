@@ -317,3 +317,49 @@ def test_variance_gradient_elcbo(gpu_ctx, S):
     with pytest.raises(vbmc_b200.VbmcB200Error) as ei:
         vbmc_b200.gplogjoint(v, gp, True, True, True, 1, nargout=4)
     assert ei.value.identifier == "gplogjoint:FullVarianceGradient"
+
+
+def _low_noise_problem(K=5, S=3, N=70, D=3):
+    """GP whose noise variance is below 1e-6: gplite_core takes the branch post.L = -inv(K + diag), Lchol = 0
+    (gplite_core.m:86-100).  Short length scales keep K + diag well conditioned so J_sjk is not round-off noise."""
+    w = _var_problem(K=K, S=S, N=N, D=D)
+    hyp = w["hyp"].copy()
+    hyp[:D] -= 1.5
+    hyp[D + 1] = 0.5 * math.log(2e-7)
+    gp = orc.gplite_post(hyp, w["X"], w["y"], 1, 4, [1, 0, 0], None)
+    assert not any(p["Lchol"] for p in gp["post"])
+    return w, hyp, gp
+
+
+@pytest.mark.parametrize("compute_var", [1, 2])
+@pytest.mark.parametrize("source", ["attach", "refit"])
+def test_gplogjoint_variance_low_noise_posterior(gpu_ctx, compute_var, source):
+    """Lchol == 0: K^-1 z_k = -L z_k with L = -inv (gplogjoint.m:279, 325).  'attach' multiplies by the matrix the
+    host hands over; 'refit' keeps the Cholesky factor of K + sn2_mult*diag(sn2) resident and solves with it."""
+    import vbmc_b200
+    w, hyp, gp_ref = _low_noise_problem()
+    gp = gp_ref if source == "attach" else vbmc_b200.gplite_post(hyp, w["X"], w["y"], 1, 4, [1, 0, 0], None)
+    got = vbmc_b200.gplogjoint(w["vp"], gp, False, True, True, compute_var, nargout=7)
+    ref = orc.gplogjoint(w["vp"], gp_ref, False, True, True, compute_var, nargout=7)
+    assert rel(got[0], ref[0]) < 1e-9
+    assert rel(got[6], ref[6]) < 1e-8
+    assert rel(got[2], ref[2]) < 1e-8 and rel(got[4], ref[4]) < 1e-8
+
+
+def test_variance_gradient_low_noise_posterior(gpu_ctx):
+    import vbmc_b200
+    w, hyp, gp = _low_noise_problem(K=4, S=2, N=60)
+    g = vbmc_b200.gplogjoint(w["vp"], gp, True, True, True, 2, nargout=5)
+    r = orc.gplogjoint(w["vp"], gp, True, True, True, 2, nargout=5)
+    assert rel(g[1], r[1]) < 1e-9 and rel(g[2], r[2]) < 1e-8 and rel(g[3], r[3]) < 1e-7
+
+
+def test_variance_more_points_than_eight_columns_fit(gpu_ctx):
+    """N = 3600: only 4 solution columns of V = R'\\Z fit in shared memory (the kernel is instantiated for 8/4/2/1)."""
+    import vbmc_b200
+    w = mk(D=2, N=3600, K=3, S=1, Ns=8, log_sn=math.log(0.3))
+    got = vbmc_b200.gplogjoint(w["vp"], w["gp"], True, True, True, 2, nargout=7)
+    ref = orc.gplogjoint(w["vp"], w["gp"], True, True, True, 2, nargout=7)
+    # J = prior term (O(1)) - z K^-1 z cancels four digits here, on top of the conditioning of a 3600-point Gram matrix
+    assert rel(got[0], ref[0]) < 1e-9 and rel(got[2], ref[2]) < 1e-5 and rel(got[6], ref[6]) < 1e-5
+    assert rel(got[3], ref[3]) < 1e-4

@@ -188,7 +188,7 @@ static int gp_check_desc(const vbmc_b200_gp_desc* g, int* Ncov, int* Nnoise, int
 }  // extern "C"
 namespace vb {
 // derived per-sample constants used by gplogjoint (gplogjoint.m:99-122)
-int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1) {
+int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1, const int* Lchol) {
   const int D = g->D, S = g->S;
   std::vector<double> h(static_cast<size_t>(S) * (3 * D + 3));
   double* ell = h.data();
@@ -216,7 +216,8 @@ int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, in
         iom2[s * D + d] = 0.0;
       }
     }
-    sn2eff[s] = sW1 ? 1.0 / (sW1[s] * sW1[s]) : 1.0;
+    // low-noise posterior (Lchol == 0): K^-1 is used unscaled (gplogjoint.m:279), i.e. sn2_eff plays no role
+    sn2eff[s] = (sW1 && !(Lchol && !Lchol[s])) ? 1.0 / (sW1[s] * sW1[s]) : 1.0;
   }
   VB_TRY(c->gpDerived.reserve(h.size() * sizeof(double)));
   VB_CUDA(cudaMemcpyAsync(c->gpDerived.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -258,12 +259,13 @@ int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const doub
   c->gpLchol.assign(S, 1);
   if (Lchol)
     for (size_t s = 0; s < S; ++s) c->gpLchol[s] = Lchol[s];
+  c->gpLfactor = c->gpLchol;
   c->gp.N = g->N; c->gp.D = g->D; c->gp.S = g->S; c->gp.Nhyp = g->Nhyp;
   c->gp.Ncov = Ncov; c->gp.Nnoise = Nnoise; c->gp.Nmean = Nmean; c->gp.meanfun = g->meanfun;
   c->gp.X = c->gpX.d();
   c->gp.hyp = c->gpHyp.d();
   c->gp.alpha = c->gpAlpha.d();
-  VB_TRY(gp_upload_derived(c, g, Ncov, Nnoise, sW1));
+  VB_TRY(gp_upload_derived(c, g, Ncov, Nnoise, sW1, Lchol));
   c->gp_ready = true;
   return VBMC_B200_OK;
 }

@@ -163,6 +163,7 @@ struct vbmc_b200_ctx {
   vb::GpDev gp{};
   vb::DevBuf gpX, gpHyp, gpAlpha, gpDerived, gpL, gpY, gpS2, gpWork;
   std::vector<int> gpLchol;
+  std::vector<int> gpLfactor;  // per sample: device L is a Cholesky factor (1) or -inv(K + diag) handed over by the host (0)
   std::vector<double> gpSn2mult;
   bool gpHasL = false;
   int gpLd = 0;  // leading dimension of the factors in gpL (N when attached from the host, Np after gp_post)
@@ -229,7 +230,7 @@ struct KernelScope {
   ~KernelScope();
 };
 int profile_collect(vbmc_b200_ctx* c);
-int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1);  // sync + fold pending event pairs into c->prof
+int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, int Nnoise, const double* sW1, const int* Lchol);  // sync + fold pending event pairs into c->prof
 
 // ---- step pieces (each defined in its own .cu) ----
 int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);

@@ -1033,13 +1033,14 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
   if (Lchol) memcpy(Lchol, rr.Lchol.data(), sizeof(int) * S);
   // the refit posterior becomes the attached GP
   c->gpLchol = rr.Lchol;
+  c->gpLfactor.assign(S, 1);  // the device keeps R with R'R = K + sn2_mult*diag(sn2) for the low-noise samples too
   c->gpSn2mult = rr.mult;
   c->gpHasL = true;
   c->gpLd = Np;
   c->gp.N = N; c->gp.D = gd->D; c->gp.S = S; c->gp.Nhyp = gd->Nhyp;
   c->gp.Ncov = Ncov; c->gp.Nnoise = Nnoise; c->gp.Nmean = Nmean; c->gp.meanfun = gd->meanfun;
   c->gp.X = c->gpX.d(); c->gp.hyp = c->gpHyp.d(); c->gp.alpha = c->gpAlpha.d();
-  VB_TRY(vb::gp_upload_derived(c, gd, Ncov, Nnoise, h_sw.data()));
+  VB_TRY(vb::gp_upload_derived(c, gd, Ncov, Nnoise, h_sw.data(), rr.Lchol.data()));
   c->gp_ready = true;
   return VBMC_B200_OK;
 }

@@ -25,6 +25,8 @@ struct VarArgs {
   double* varFs;      // [S]
   int full;           // 1: full matrix, 0: diagonal only
   int unit_rhs;       // 1: right-hand sides are the identity columns k0.. (inverse of the factor), Z is output only
+  const int* isfac;   // [S] or null: 1 = L is the Cholesky factor (Lchol), 0 = L is -inv(K + diag) (gplite_core.m:96-99)
+  double* W;          // [S][K][N]  K^-1 z_k of the samples with isfac == 0
 };
 
 // z_k(n) = exp(lnnf_k - 0.5*sum_d ((mu_kd - X_nd)/tau_kd)^2)   (gplogjoint.m:164-167); grid (K, S)
@@ -55,13 +57,14 @@ __global__ void __launch_bounds__(256) glj_z_kernel(const VarArgs a) {
   }
 }
 
-// V = R' \ Z for up to 8 right-hand sides per CTA (kept in shared memory), blocked by 64 rows.
-// grid (ceil(K/8), S), 256 threads = 8 warps.
-constexpr int VR = 8;
+// V = R' \ Z for up to VR right-hand sides per CTA (kept in shared memory), blocked by 64 rows.
+// grid (ceil(K/VR), S), 256 threads = 8 warps.  VR = 8 unless N is too large for 8 resident columns.
+template <int VR>
 __global__ void __launch_bounds__(256) var_fwd_kernel(const VarArgs a) {
   extern __shared__ __align__(16) double vsm[];
   const int N = a.N, ld = a.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.y, k0 = blockIdx.x * VR;
+  if (a.isfac && !a.isfac[s]) return;
   const int nrhs = (a.K - k0) < VR ? (a.K - k0) : VR;
   double* v = vsm;                 // [VR][N]
   double* Rb = vsm + VR * N;       // [64][65]  Rb[c][r] = R(b0+r, b0+c)
@@ -136,12 +139,14 @@ __global__ void __launch_bounds__(256) var_fwd_kernel(const VarArgs a) {
   for (int i = tid; i < nrhs * N; i += 256) Zs[i] = v[i];
 }
 
-// W = R \ V (backward substitution, upper factor) for up to 8 right-hand sides per CTA, in place in Z.
-// After W: K^-1 z_k = W_k / sn2_eff (gplogjoint.m:276-277).  grid (ceil(K/8), S), 256 threads.
+// W = R \ V (backward substitution, upper factor) for up to VR right-hand sides per CTA, in place in Z.
+// After W: K^-1 z_k = W_k / sn2_eff (gplogjoint.m:276-277).  grid (ceil(K/VR), S), 256 threads.
+template <int VR>
 __global__ void __launch_bounds__(256) var_bwd_kernel(const VarArgs a) {
   extern __shared__ __align__(16) double vsm[];
   const int N = a.N, ld = a.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.y, k0 = blockIdx.x * VR;
+  if (a.isfac && !a.isfac[s]) return;
   const int nrhs = (a.K - k0) < VR ? (a.K - k0) : VR;
   double* v = vsm;             // [VR][N]
   double* Rb = vsm + VR * N;   // [64][65]
@@ -197,18 +202,57 @@ __global__ void __launch_bounds__(256) var_bwd_kernel(const VarArgs a) {
   for (int i = tid; i < nrhs * N; i += 256) Zs[i] = v[i];
 }
 
-// G[s][j][k] = V_j . V_k  (k <= j, mirrored); grid (K, S): CTA (j, s) loops over k <= j
+// Low-noise posterior handed over by gp_attach: post.L = -inv(K + diag) (gplite_core.m:96-99), so
+// K^-1 z_k = -L z_k (gplogjoint.m:279, 325).  W_k(i) = -sum_j L(j,i) z_k(j): column i of the symmetric L is
+// contiguous over j.  grid (ceil(K/VR), S); samples with a Cholesky factor are skipped.
+template <int VR>
+__global__ void __launch_bounds__(256) var_symv_kernel(const VarArgs a) {
+  extern __shared__ __align__(16) double vsm[];
+  const int N = a.N, ld = a.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.y, k0 = blockIdx.x * VR;
+  if (!a.isfac || a.isfac[s]) return;
+  const int nrhs = (a.K - k0) < VR ? (a.K - k0) : VR;
+  double* v = vsm;  // [VR][N]
+  const double* Lm = a.L + static_cast<size_t>(s) * a.Lstride;
+  const double* Zs = a.Z + (static_cast<size_t>(s) * a.K + k0) * N;
+  double* Ws = a.W + (static_cast<size_t>(s) * a.K + k0) * N;
+  for (int i = tid; i < nrhs * N; i += 256) v[i] = Zs[i];
+  for (int i = nrhs * N + tid; i < VR * N; i += 256) v[i] = 0.0;
+  __syncthreads();
+  for (int i = warp; i < N; i += 8) {
+    double acc[VR];
+#pragma unroll
+    for (int c = 0; c < VR; ++c) acc[c] = 0.0;
+    const double* col = Lm + static_cast<size_t>(i) * ld;
+    for (int j = lane; j < N; j += 32) {
+      const double r = col[j];
+#pragma unroll
+      for (int c = 0; c < VR; ++c) acc[c] = fma(r, v[c * N + j], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < VR; ++c) {
+      double x = acc[c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+      if (lane == 0 && c < nrhs) Ws[static_cast<size_t>(c) * N + i] = -x;
+    }
+  }
+}
+
+// G[s][j][k] = V_j . V_k  (k <= j, mirrored); grid (K, S): CTA (j, s) loops over k <= j.
+// Samples without a factor: G[s][j][k] = z_j . W_k = z_j K^-1 z_k directly.
 __global__ void __launch_bounds__(256) var_gram_kernel(const VarArgs a) {
   extern __shared__ __align__(16) double gsm[];  // V_j [N]
   __shared__ double part[8];
   const int j = blockIdx.x, s = blockIdx.y, N = a.N, K = a.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* Vs = a.Z + static_cast<size_t>(s) * K * N;
+  const double* Bs = (a.isfac && !a.isfac[s]) ? a.W + static_cast<size_t>(s) * K * N : Vs;
   for (int i = tid; i < N; i += 256) gsm[i] = Vs[static_cast<size_t>(j) * N + i];
   __syncthreads();
   const int kbeg = a.full ? 0 : j;
   for (int k = kbeg; k <= j; ++k) {
     double acc = 0.0;
-    const double* vk = Vs + static_cast<size_t>(k) * N;
+    const double* vk = Bs + static_cast<size_t>(k) * N;
     for (int i = tid; i < N; i += 256) acc = fma(gsm[i], vk[i], acc);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -267,14 +311,53 @@ __global__ void __launch_bounds__(256) var_final_kernel(const VarArgs a) {
   if (tid == 0) a.varFs[s] = fmax(part[0], EPS);  // varF = max(varF,eps) (:350)
 }
 
+enum { VK_FWD = 0, VK_BWD = 1, VK_SYMV = 2 };
+
+template <int VR>
+static int launch_vk(int which, const VarArgs& a, int ncols, int S, size_t smem, cudaStream_t st) {
+  dim3 grid((ncols + VR - 1) / VR, S);
+  switch (which) {
+    case VK_FWD:
+      VB_CUDA(cudaFuncSetAttribute(var_fwd_kernel<VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      var_fwd_kernel<VR><<<grid, 256, smem, st>>>(a);
+      break;
+    case VK_BWD:
+      VB_CUDA(cudaFuncSetAttribute(var_bwd_kernel<VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      var_bwd_kernel<VR><<<grid, 256, smem, st>>>(a);
+      break;
+    default:
+      VB_CUDA(cudaFuncSetAttribute(var_symv_kernel<VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      var_symv_kernel<VR><<<grid, 256, smem, st>>>(a);
+      break;
+  }
+  VB_CUDA(cudaGetLastError());
+  return VBMC_B200_OK;
+}
+
+// one of the column-block kernels with the widest block that fits; `extra` = doubles of shared memory besides the columns
+static int launch_var_kernel(vbmc_b200_ctx* c, int which, const VarArgs& a, int ncols, int S, size_t extra_fixed, size_t extra_per_col,
+                             cudaStream_t st, const char* what) {
+  int vr = 0;
+  for (int t = 8; t >= 1; t >>= 1)
+    if (sizeof(double) * (static_cast<size_t>(t) * a.N + extra_fixed + extra_per_col * t) <= c->smem_optin) { vr = t; break; }
+  if (!vr)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:%s: N=%d does not fit one solution column in shared memory (%zu B)", what, a.N, c->smem_optin);
+  const size_t smem = sizeof(double) * (static_cast<size_t>(vr) * a.N + extra_fixed + extra_per_col * vr);
+  switch (vr) {
+    case 8: return launch_vk<8>(which, a, ncols, S, smem, st);
+    case 4: return launch_vk<4>(which, a, ncols, S, smem, st);
+    case 2: return launch_vk<2>(which, a, ncols, S, smem, st);
+    default: return launch_vk<1>(which, a, ncols, S, smem, st);
+  }
+}
+
 // Runs the variance pipeline for all S samples; results to host: varFs[S], J[S][K][K] (optional).
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad) {
   if (!c->gpHasL)
     VB_FAIL(VBMC_B200_ESTATE, "gplogjoint variance needs the factors gp.post(s).L on the device (gp_attach with L, or gp_post)");
   const int N = c->gp.N, K = c->K, S = c->gp.S;
-  for (int s = 0; s < S; ++s)
-    if (!c->gpLchol[s])
-      VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:NotYet: variance with the low-noise posterior (Lchol == 0, gplogjoint.m:279,325)");
+  bool any_inv = false;
+  for (int s = 0; s < S; ++s) any_inv = any_inv || !c->gpLfactor[s];
   VarArgs a;
   a.N = N; a.D = c->D; a.K = K; a.S = S; a.ld = c->gpLd;
   a.Lstride = static_cast<size_t>(c->gpLd) * c->gpLd;
@@ -284,22 +367,30 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
   a.unit_rhs = 0;
   const size_t nz = static_cast<size_t>(S) * K * N, ng = static_cast<size_t>(S) * K * K;
   const size_t nvg = vgrad ? static_cast<size_t>(S) * K * (2 + 2 * c->D) : 0;
-  VB_TRY(c->varWork.reserve(sizeof(double) * (nz + 2 * ng + S + nvg)));
+  const size_t nw = any_inv ? nz : 0, nflag = any_inv ? (static_cast<size_t>(S) + 1) / 2 : 0;  // ints packed behind the doubles
+  VB_TRY(c->varWork.reserve(sizeof(double) * (nz + 2 * ng + S + nvg + nw + nflag)));
   a.Z = c->varWork.d(); a.G = a.Z + nz; a.J = a.G + ng; a.varFs = a.J + ng;
+  double* vg = a.varFs + S;
+  a.W = any_inv ? vg + nvg : nullptr;
+  a.isfac = nullptr;
   cudaStream_t st = c->stream;
+  if (any_inv) {
+    int* flags = reinterpret_cast<int*>(a.W + nw);
+    VB_CUDA(cudaMemcpyAsync(flags, c->gpLfactor.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+    a.isfac = flags;
+  }
   {
     dim3 grid(K, S);
     KernelScope ks(c, "var_z", st);
     glj_z_kernel<<<grid, 256, 0, st>>>(a);
   }
   {
-    const size_t smem = sizeof(double) * (static_cast<size_t>(VR) * N + 64 * 65 + 64 * VR);
-    if (smem > c->smem_optin)
-      VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:variance: N=%d needs %zu B shared memory for the solve (> %zu)", N, smem, c->smem_optin);
-    VB_CUDA(cudaFuncSetAttribute(var_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    dim3 grid((K + VR - 1) / VR, S);
     KernelScope ks(c, "var_trsm", st);
-    var_fwd_kernel<<<grid, 256, smem, st>>>(a);
+    VB_TRY(launch_var_kernel(c, VK_FWD, a, K, S, 64 * 65, 64, st, "variance"));
+  }
+  if (any_inv) {
+    KernelScope ks(c, "var_symv", st);
+    VB_TRY(launch_var_kernel(c, VK_SYMV, a, K, S, 0, 0, st, "variance"));
   }
   {
     const size_t smem = sizeof(double) * N;
@@ -320,16 +411,16 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
     VB_CUDA(cudaMemcpyAsync(J->data(), a.J, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
   }
   if (vgrad) {
-    // K^-1 z_k = R \ V_k / sn2_eff, then the derivative contractions dz_d(.) * K^-1 z_k  (gplogjoint.m:289-299)
-    const size_t smem_b = sizeof(double) * (static_cast<size_t>(VR) * N + 64 * 65);
-    VB_CUDA(cudaFuncSetAttribute(var_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_b)));
-    dim3 grid_b((K + VR - 1) / VR, S);
+    // K^-1 z_k = R \ V_k / sn2_eff (or W_k for an inverse-form posterior), then the derivative contractions
+    // dz_d(.) * K^-1 z_k  (gplogjoint.m:289-299)
     {
       KernelScope ks(c, "var_trsm", st);
-      var_bwd_kernel<<<grid_b, 256, smem_b, st>>>(a);
+      VB_TRY(launch_var_kernel(c, VK_BWD, a, K, S, 64 * 65, 0, st, "variance"));
     }
-    VB_CUDA(cudaGetLastError());
-    double* vg = a.varFs + S;
+    for (int s = 0; any_inv && s < S; ++s)
+      if (!c->gpLfactor[s])
+        VB_CUDA(cudaMemcpyAsync(a.Z + static_cast<size_t>(s) * K * N, a.W + static_cast<size_t>(s) * K * N, sizeof(double) * K * N,
+                                cudaMemcpyDeviceToDevice, st));
     VB_TRY(launch_gplogjoint_weighted(c, a.Z, vg, st));
     vgrad->assign(nvg, 0.0);
     VB_CUDA(cudaMemcpyAsync(vgrad->data(), vg, sizeof(double) * nvg, cudaMemcpyDeviceToHost, st));
@@ -348,14 +439,8 @@ int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double*
   a.L = R;
   a.Z = out;
   a.unit_rhs = 1;
-  const size_t smem = sizeof(double) * (static_cast<size_t>(VR) * N + 64 * 65 + 64 * VR);
-  if (smem > c->smem_optin)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:inverse: N=%d needs %zu B shared memory for the solve (> %zu)", N, smem, c->smem_optin);
-  VB_CUDA(cudaFuncSetAttribute(var_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid((N + VR - 1) / VR, 1);
   KernelScope ks(c, "trtri", c->stream);
-  var_fwd_kernel<<<grid, 256, smem, c->stream>>>(a);
-  VB_CUDA(cudaGetLastError());
+  VB_TRY(launch_var_kernel(c, VK_FWD, a, N, 1, 64 * 65, 64, c->stream, "inverse"));
   return VBMC_B200_OK;
 }
 
