@@ -159,7 +159,7 @@ def run_reference(args, cfg_name):
     print(json.dumps(line))
 
 
-def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local):
+def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=64):
     """Device-resident steps/s of another configuration (same protocol as the headline `value`)."""
     import ctypes as C
     from vbmc_b200 import _lib, workloads
@@ -175,18 +175,22 @@ def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local):
     a.eps_mode, a.seed, a.stream = _lib.EPS_PHILOX, 20260925, 0
     a.F, a.dF = C.pointer(F), _lib.dptr(dF)
     tot = 0.0
-    for i in range(warmup + steps):
-        ctx.flush_l2()
-        a.stream = 50_000 + i
-        _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
-        if i >= warmup:
-            tot += ms.value
+    ctx.set_precision(precision)
+    try:
+        for i in range(warmup + steps):
+            ctx.flush_l2()
+            a.stream = 50_000 + i
+            _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
+            if i >= warmup:
+                tot += ms.value
+    finally:
+        ctx.set_precision(64)
     if dist is not None:
         import torch
         t = torch.tensor([tot], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot = float(t.item())
-    return {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")}, "steps": steps,
+    return {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")}, "steps": steps, "entropy_sweep_bits": precision,
             "ms_per_step": tot / steps, "value": 1e3 * steps / tot, "unit": "steps/s"}
 
 
@@ -351,6 +355,14 @@ def main():
     c4 = None
     if args.config is None:
         c4 = quick_value(ctx, vbmc_b200, "c4", max(10, args.steps // 5), 3, dist, local)
+    # ---- c5 (D=20, N=4000, K=100, Ns=262144, S=40): BASELINE.json's FP32 configuration, FP32 and FP64 sweeps ----
+    c5 = None
+    if args.config is None and os.environ.get("VBMC_B200_BENCH_C5", "1") != "0":
+        try:
+            c5 = {"fp32": quick_value(ctx, vbmc_b200, "c5", 5, 2, dist, local, precision=32),
+                  "fp64": quick_value(ctx, vbmc_b200, "c5", 3, 1, dist, local, precision=64)}
+        except Exception as e:   # a sub-measurement must never cost the headline line (every rank fails alike: no collective is left hanging)
+            c5 = {"error": str(e)[:300]}
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if dist is not None:
@@ -400,6 +412,7 @@ def main():
         "roofline": roofline,
         "refit": refit,
         "c4": c4,
+        "c5": c5,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

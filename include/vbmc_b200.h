@@ -54,6 +54,11 @@ int vbmc_b200_destroy(vbmc_b200_ctx* ctx);
 int vbmc_b200_sync(vbmc_b200_ctx* ctx);
 /* number of kernels this library launched on the context since creation (bench: gpu_launches) */
 int vbmc_b200_launch_count(vbmc_b200_ctx* ctx, long long* count);
+/* Arithmetic of the Monte-Carlo entropy sweep (ent/entmc_vbmc.m:49-104): bits = 64 (default; 1e-10 rel against
+ * the reference) or 32 (BASELINE config 5; 1e-4 rel).  With 32 the per-draw scoring of the K components runs
+ * in FP32 with hardware exp2; every sum over draws, the expected log-joint, Jacobians and penalties stay FP64.
+ * The reference has no such switch (MATLAB doubles throughout): a caller that never calls this gets FP64. */
+int vbmc_b200_set_precision(vbmc_b200_ctx* ctx, int bits);
 
 /* ---------------------------------------------------------------------------------------
  * multi-GPU: one context per rank, one NCCL all-reduce per negelcbo step.

@@ -71,7 +71,7 @@ class NegelcboArgs(C.Structure):
 # every symbol include/vbmc_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "vbmc_b200_version", "vbmc_b200_last_error", "vbmc_b200_create", "vbmc_b200_destroy", "vbmc_b200_sync",
-    "vbmc_b200_launch_count", "vbmc_b200_comm_unique_id", "vbmc_b200_comm_init", "vbmc_b200_comm_info",
+    "vbmc_b200_launch_count", "vbmc_b200_set_precision", "vbmc_b200_comm_unique_id", "vbmc_b200_comm_init", "vbmc_b200_comm_info",
     "vbmc_b200_gp_attach", "vbmc_b200_gp_post", "vbmc_b200_gp_nlz", "vbmc_b200_vp_set", "vbmc_b200_thetabnd_set",
     "vbmc_b200_eps_upload", "vbmc_b200_eps_philox", "vbmc_b200_negelcbo", "vbmc_b200_entmc", "vbmc_b200_gplogjoint",
     "vbmc_b200_negelcbo_resident_loop", "vbmc_b200_profile_enable", "vbmc_b200_profile_get",
@@ -99,6 +99,7 @@ def load():
     lib.vbmc_b200_destroy.argtypes = [vp]
     lib.vbmc_b200_sync.argtypes = [vp]
     lib.vbmc_b200_launch_count.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.vbmc_b200_set_precision.argtypes = [vp, C.c_int]
     lib.vbmc_b200_comm_unique_id.argtypes = [C.c_void_p]
     lib.vbmc_b200_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
     lib.vbmc_b200_comm_info.argtypes = [vp, c_int_p, c_int_p]

@@ -69,6 +69,10 @@ class Context:
     def sync(self):
         _lib.check(self.lib.vbmc_b200_sync(self._h))
 
+    def set_precision(self, bits: int):
+        """64 (default) or 32: arithmetic of the entropy sweep (vbmc_b200_set_precision in include/vbmc_b200.h)."""
+        _lib.check(self.lib.vbmc_b200_set_precision(self._h, int(bits)))
+
     def launch_count(self) -> int:
         n = C.c_longlong()
         _lib.check(self.lib.vbmc_b200_launch_count(self._h, C.byref(n)))

@@ -149,6 +149,13 @@ int vbmc_b200_sync(vbmc_b200_ctx* c) {
   return VBMC_B200_OK;
 }
 
+int vbmc_b200_set_precision(vbmc_b200_ctx* c, int bits) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  if (bits != 32 && bits != 64) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_set_precision: bits must be 32 or 64 (got %d)", bits);
+  c->precision = bits;
+  return VBMC_B200_OK;
+}
+
 int vbmc_b200_launch_count(vbmc_b200_ctx* c, long long* count) {
   if (!c || !count) VB_FAIL(VBMC_B200_EINVAL, "null argument");
   *count = c->launches;
@@ -373,6 +380,7 @@ int vbmc_b200_eps_upload(vbmc_b200_ctx* c, int D, int K, int Ns, const double* e
                           c->stream));
   VB_CUDA(cudaStreamSynchronize(c->stream));
   c->eps_ready = true;
+  c->eps_f32 = false;
   return VBMC_B200_OK;
 }
 
@@ -384,10 +392,15 @@ int vbmc_b200_eps_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, 
   if (c->nranks > 1 && eps_out)  // a read-back must see every element, not only this rank's shard
     VB_CUDA(cudaMemsetAsync(c->eps.p, 0, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2), c->stream));
   VB_TRY(launch_philox(c, D, K, Ns, seed, stream, c->stream));
-  if (eps_out)
-    VB_CUDA(cudaMemcpyAsync(eps_out, c->eps.p, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2),
-                            cudaMemcpyDeviceToHost, c->stream));
+  const size_t n = static_cast<size_t>(D) * K * (Ns / 2);
+  if (eps_out && !c->eps_f32)
+    VB_CUDA(cudaMemcpyAsync(eps_out, c->eps.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   VB_CUDA(cudaStreamSynchronize(c->stream));
+  if (eps_out && c->eps_f32) {  // FP32 mode: the draws are floats on the device; hand them out widened (exactly)
+    std::vector<float> tmp(n);
+    VB_CUDA(cudaMemcpy(tmp.data(), c->eps.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) eps_out[i] = static_cast<double>(tmp[i]);
+  }
   c->eps_ready = true;
   return VBMC_B200_OK;
 }
@@ -404,6 +417,7 @@ static int prepare_eps(vbmc_b200_ctx* c, int Ns, int mode, const double* eps, ui
       VB_TRY(eps_reserve(c, D, K, Ns));
       VB_CUDA(cudaMemcpyAsync(c->eps.p, eps, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
       c->eps_ready = true;
+      c->eps_f32 = false;
       return VBMC_B200_OK;
     case VBMC_B200_EPS_RESIDENT:
       if (!c->eps_ready || c->epsD != D || c->epsK != K || c->epsNs != Ns)
@@ -581,11 +595,13 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
     VB_CUDA(cudaStreamSynchronize(c->stream));
     return VBMC_B200_OK;
   }
-  std::vector<long long> key = {Ns, gmask, a->use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form,
+  auto make_key = [&]() {
+  std::vector<long long> key = {Ns, gmask, a->use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form, c->precision,
                                 c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
                                 reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
                                 reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
                                 reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p),
+                                reinterpret_cast<long long>(c->ent_tables.p),
                                 reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
                                 reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),
                                 reinterpret_cast<long long>(c->gpDerived.p), reinterpret_cast<long long>(c->bnd.p),
@@ -595,6 +611,9 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
     memcpy(&bits[0], &c->TolCon, 8); memcpy(&bits[1], &c->WeightThreshold, 8); memcpy(&bits[2], &c->WeightPenalty, 8);
     key.insert(key.end(), bits, bits + 3);
   }
+  return key;
+  };
+  const std::vector<long long> key = make_key();
   if (c->graph_exec && key == c->graph_key) {
     VB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
     c->launches += c->graph_launches;
@@ -630,12 +649,9 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
   } else {
     VB_TRY(body());   // first call with this signature: allocations happen here
     // the key must describe the buffers AFTER this call (they may have been allocated by it)
-    std::vector<long long> k2 = key;
-    k2[13] = reinterpret_cast<long long>(c->theta_dev.p); k2[14] = reinterpret_cast<long long>(c->out_dev.p);
-    k2[15] = reinterpret_cast<long long>(c->R_dev.p); k2[16] = reinterpret_cast<long long>(c->eps.p);
-    k2[17] = reinterpret_cast<long long>(c->ent_partial.p); k2[18] = reinterpret_cast<long long>(c->glj_out.p);
-    c->warm_key = k2;
+    c->warm_key = make_key();
   }
+  if (philox) c->eps_f32 = c->precision == 32;  // a replayed graph does not pass through launch_philox
   if (sync) VB_CUDA(cudaStreamSynchronize(c->stream));
   return VBMC_B200_OK;
 }

@@ -152,6 +152,7 @@ struct vbmc_b200_ctx {
   cudaStream_t stream2 = nullptr;  // gplogjoint branch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   long long launches = 0;
+  int precision = 64;  // 64: everything FP64; 32: the entropy sweep in FP32 (vbmc_b200_set_precision)
   int entmc_form = -1;  // -1 auto (device guard), 0 force expanded, 1 force direct (VBMC_B200_ENTMC_FORM)
 
   // multi-GPU
@@ -189,12 +190,14 @@ struct vbmc_b200_ctx {
   vb::DevBuf eps;
   int epsD = 0, epsK = 0, epsNs = 0;
   bool eps_ready = false;
+  bool eps_f32 = false;  // the resident draws are floats (generated by the device generator in FP32 mode)
   bool philox_pending = false;
   bool philox_dyn = false;  // read {seed, stream} from theta_dev[ntheta..] (set while building / replaying a step graph)
   uint64_t philox_seed = 0, philox_stream = 0;
 
   // step buffers
   vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out;
+  vb::DevBuf ent_tables;  // FP32 sweep: per-step tables (entmc_f32.cu)
   double* theta_pinned = nullptr;
   double* out_pinned = nullptr;
   size_t theta_pinned_cap = 0, out_pinned_cap = 0;

@@ -21,76 +21,9 @@
 // that the w-gradient column sums W_jl = sum_s e_l(x_s)/q_s (:100) can be formed once q_s is known.
 // eps tiles are staged global->shared with TMA bulk copies (cp.async.bulk + mbarrier), one tile
 // ahead.  All reductions run in a fixed order => results are bit-reproducible run to run.
-#include "common.cuh"
+#include "entmc_shared.cuh"
 
 namespace vb {
-
-struct EntmcArgs {
-  int D, K, half;            // half = Ns/2 pairs per component
-  int pair_begin, pair_end;  // this rank's shard of the pair axis (same range for every component)
-  int tiles_per_comp, pairs_per_tile, ntiles;
-  int need;                  // NEED_* mask
-  int pstride;               // 1 + 2*D + K doubles per tile partial
-  int iq_in_smem;            // 1: 1/q broadcast through shared memory, 0: through shuffles
-  const int* form_flag;      // device flag: 2 -> expanded form (default), 1 -> direct, 0 -> separable (experimental)
-  int c_mu, c_ck, c_akis, c_ilam;  // offsets (doubles) inside the __constant__ blob c_ent
-  const double* eps;         // [K][half][D]
-  const double* mu;          // [K][D]
-  const double* sigma;       // [K]
-  const double* lambda;      // [D]
-  const double* ck;          // [K]  w_k*nf/sigma_k^D
-  const double* ak;          // [K]  ck_k/sigma_k
-  double* partial;           // [ntiles][pstride]
-  // shared-memory carve-up (byte offsets, computed on the host)
-  int off_u, off_s, off_t16, off_bar, off_warp, warp_bytes;
-  int woff_eps, woff_iq, woff_stage;  // offsets inside a warp region
-};
-
-// ---- PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk => SASS UBLKCP) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// Stage the eps chunk of one warp (npairs*D doubles, contiguous in global memory) into shared
-// memory.  TMA bulk copy when 16-byte aligned, plain coalesced loads otherwise (odd D tails).
-// Returns true when the chunk was issued through TMA (consumer must wait on the mbarrier).
-__device__ __forceinline__ bool eps_stage(double* dst, const double* src, int ndbl, uint64_t* bar, int lane) {
-  const uint32_t bytes = static_cast<uint32_t>(ndbl) * 8u;
-  const bool tma_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15u) == 0) && bytes > 0;
-  if (tma_ok) {
-    if (lane == 0) {
-      mbar_expect_tx(bar, bytes);
-      tma_bulk_g2s(dst, src, bytes, bar);
-    }
-  } else {
-    for (int i = lane; i < ndbl; i += 32) dst[i] = __ldg(src + i);
-  }
-  return tma_ok;
-}
 
 // exp(x) for x <= ~0: 2^(m + j/16) * p(r), 16-entry table in shared memory + degree-6 polynomial
 // (|r| <= ln2/32, truncation 4e-16).  Arguments below -708 return 0 (denormals flushed; q always
@@ -694,11 +627,6 @@ static int pick_dp(int D) {
 
 int entmc_pick_dp(int D) { return pick_dp(D); }
 
-struct EntmcPlan {
-  int DP, maxw, nw, pairs_per_tile, tiles_per_comp, ntiles, npairs_local, pair_begin, pair_end;
-  size_t smem;
-  EntmcArgs a;
-};
 
 static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   const int D = c->D, K = c->K;
@@ -726,12 +654,13 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   off = round_up(off, 16);
   a.off_warp = off;
   // per-warp region; the stage planes double as [wres | red] scratch after the column sums
-  const int stage_bytes = K2 * 32 * 16;
+  const bool f32 = c->precision == 32;
+  const int stage_bytes = K2 * 32 * (f32 ? 8 : 16);  // {e+, e-} per (component, pair)
   const int scratch_bytes = (round_up(a.pstride, 2) + (1 + 2 * D) * 33) * 8;
   const int stage_alloc = round_up(stage_bytes > scratch_bytes ? stage_bytes : scratch_bytes, 16);
   const size_t avail = c->smem_optin;
   int best_nw = 0, best_iq = 0;
-  for (int iq = 1; iq >= 0; --iq) {
+  for (int iq = 1; iq >= (f32 ? 1 : 0); --iq) {
     const int wb = round_up(32 * D * 8, 16) + (iq ? 32 * 16 : 0) + stage_alloc;
     int nw_fit = static_cast<int>((avail - a.off_warp) / wb);
     if (nw_fit > pl->maxw) nw_fit = pl->maxw;
@@ -755,7 +684,16 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   const long long total_pairs = static_cast<long long>(pl->npairs_local) * K;
   while (nw > 1 && total_pairs / (nw * 32) < 2LL * c->num_sms) nw = (nw > 4) ? nw - 4 : nw - 1;
   pl->nw = nw;
-  pl->pairs_per_tile = nw * 32;
+  // FP32 sweep: several groups per tile amortise the table load and the block reduction, while keeping
+  // >= ~10 tiles per SM so that the persistent CTAs stay balanced
+  int G = 1;
+  if (f32) {
+    const long long groups = static_cast<long long>(K) * ((pl->npairs_local + nw * 32 - 1) / (nw * 32));
+    const long long g = groups / (10LL * c->num_sms);
+    G = g < 1 ? 1 : (g > 8 ? 8 : static_cast<int>(g));
+  }
+  a.groups_per_tile = G;
+  pl->pairs_per_tile = nw * 32 * G;
   pl->tiles_per_comp = (pl->npairs_local + pl->pairs_per_tile - 1) / pl->pairs_per_tile;
   pl->ntiles = pl->tiles_per_comp * K;
   pl->smem = a.off_warp + static_cast<size_t>(nw) * a.warp_bytes;
@@ -826,6 +764,10 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   a.ck = c->vp.ck;
   a.ak = c->vp.ak;
   a.partial = c->ent_partial.d();
+  a.eps_f32 = c->eps_f32 ? 1 : 0;
+  if (c->precision == 32) return launch_entmc_f32(c, pl, st);
+  if (c->eps_f32)
+    VB_FAIL(VBMC_B200_ESTATE, "entmc: the resident draws were generated in FP32 mode; upload or regenerate them for the FP64 sweep");
   switch (pl.DP) {
     case 2: return launch_one<2>(c, pl, st);
     case 4: return launch_one<4>(c, pl, st);

@@ -29,7 +29,7 @@ struct PhiloxArgs {
   int D, K, half, pair_begin, pair_end;
   uint64_t seed, stream;
   const uint64_t* dyn;  // optional device pointer to {seed, stream} (graph replay: values change, the node does not)
-  double* eps;  // [K][half][D]
+  double* eps;  // [K][half][D]  (floats in FP32 mode)
 };
 
 // one thread per Philox counter = two consecutive elements (2c, 2c+1) of the flat eps array
@@ -55,6 +55,40 @@ __global__ void philox_normal_kernel(const PhiloxArgs a) {
   }
 }
 
+// FP32 mode: one Philox counter = FOUR consecutive elements (4c .. 4c+3); each 32-bit word gives one uniform
+// u = (x + 0.5) * 2^-32 and two words one Box-Muller pair in single precision (|z| <= 6.7).  Stored as float.
+__global__ void philox_normal_f32_kernel(const PhiloxArgs a) {
+  const int j = blockIdx.y;
+  float* out = reinterpret_cast<float*>(a.eps);
+  const long long e_begin = (static_cast<long long>(j) * a.half + a.pair_begin) * a.D;
+  const long long e_end = (static_cast<long long>(j) * a.half + a.pair_end) * a.D;
+  const long long c_begin = e_begin >> 2, c_end = (e_end + 3) >> 2;
+  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = a.dyn ? a.dyn[1] : a.stream;
+  for (long long c = c_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; c < c_end;
+       c += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 ctr = make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
+                                 static_cast<uint32_t>(strm) ^ 0x32323232u, static_cast<uint32_t>(strm >> 32));
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const uint4 r = philox4x32_10(ctr, key);
+    const float S = 2.3283064365386963e-10f, H = 1.1641532182693481e-10f;  // 2^-32, 2^-33
+    const float u1 = fmaf(static_cast<float>(r.x), S, H), u2 = fmaf(static_cast<float>(r.y), S, H);
+    const float u3 = fmaf(static_cast<float>(r.z), S, H), u4 = fmaf(static_cast<float>(r.w), S, H);
+    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    float sa, ca, sb, cb;
+    sincospif(2.0f * u2, &sa, &ca);
+    sincospif(2.0f * u4, &sb, &cb);
+    const float z[4] = {ra * ca, ra * sa, rb * cb, rb * sb};
+    const long long e0 = 4 * c;
+    if (e0 >= e_begin && e0 + 3 < e_end) {
+      *reinterpret_cast<float4*>(out + e0) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (e0 + i >= e_begin && e0 + i < e_end) out[e0 + i] = z[i];
+    }
+  }
+}
+
 // raw generator output for the known-answer test (tests/test_philox.py)
 __global__ void philox_raw_kernel(uint4 ctr, uint2 key, uint32_t* out) {
   const uint4 r = philox4x32_10(ctr, key);
@@ -69,13 +103,19 @@ int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_
   a.dyn = dyn;
   a.eps = c->eps.d();
   if (a.pair_end <= a.pair_begin) return VBMC_B200_OK;
-  const long long per_comp = (static_cast<long long>(a.pair_end - a.pair_begin) * D + 2) / 2;
+  const bool f32 = c->precision == 32;
+  c->eps_f32 = f32;
+  const int per_ctr = f32 ? 4 : 2;
+  const long long per_comp = (static_cast<long long>(a.pair_end - a.pair_begin) * D + per_ctr) / per_ctr;
   int bx = static_cast<int>((per_comp + 255) / 256);
   const int cap = (c->num_sms * 8 + K - 1) / K;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, K);
   KernelScope ks(c, "philox", st);
-  philox_normal_kernel<<<grid, 256, 0, st>>>(a);
+  if (f32)
+    philox_normal_f32_kernel<<<grid, 256, 0, st>>>(a);
+  else
+    philox_normal_kernel<<<grid, 256, 0, st>>>(a);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
