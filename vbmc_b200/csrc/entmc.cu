@@ -175,7 +175,19 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     double e[DP];
     const bool valid = lane < np;
 #pragma unroll
-    for (int d = 0; d < DP; ++d) e[d] = (valid && d < D) ? eps_s[lane * D + d] : 0.0;
+    for (int d = 0; d < DP; ++d) e[d] = 0.0;
+    if (valid) {
+      if ((D & 1) == 0) {  // 16-byte loads: the 32 row reads (stride D doubles) stay free of bank conflicts
+        const double2* row = reinterpret_cast<const double2*>(eps_s + lane * D);
+#pragma unroll
+        for (int d = 0; d < DP; d += 2)
+          if (d < D) { const double2 v = row[d >> 1]; e[d] = v.x; e[d + 1] = v.y; }
+      } else {
+#pragma unroll
+        for (int d = 0; d < DP; ++d)
+          if (d < D) e[d] = eps_s[lane * D + d];
+      }
+    }
     __syncwarp();  // all lanes have consumed eps_s -> safe to refill it for the next tile
     tma_pending = issue_eps(tile + gridDim.x);
     __syncthreads();  // tables ready
@@ -650,21 +662,24 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   off = round_up(off, 32);
   a.off_s = off; off += K2 * 32;
   a.off_t16 = off; off += 16 * 8;
-  a.off_bar = off; off += 8 * 8;
+  a.off_bar = off; off += 16 * 8;   // one mbarrier per warp (up to 16 warps)
   off = round_up(off, 16);
   a.off_warp = off;
   // per-warp region; the stage planes double as [wres | red] scratch after the column sums
   const bool f32 = c->precision == 32;
-  const int stage_bytes = K2 * 32 * (f32 ? 8 : 16);  // {e+, e-} per (component, pair)
+  const int ppw = 32;                                  // pairs per warp and group
+  const int stage_bytes = K2 * 32 * (f32 ? 8 : 16);    // {e+, e-} per (component, pair)
+  const int iq_bytes = f32 ? 32 * 8 : 32 * 16;
+  const int eps_bytes = round_up(ppw * D * 8, 16);
   const int scratch_bytes = (round_up(a.pstride, 2) + (1 + 2 * D) * 33) * 8;
   const int stage_alloc = round_up(stage_bytes > scratch_bytes ? stage_bytes : scratch_bytes, 16);
   const size_t avail = c->smem_optin;
   int best_nw = 0, best_iq = 0;
   for (int iq = 1; iq >= (f32 ? 1 : 0); --iq) {
-    const int wb = round_up(32 * D * 8, 16) + (iq ? 32 * 16 : 0) + stage_alloc;
+    const int wb = eps_bytes + (iq ? iq_bytes : 0) + stage_alloc;
     int nw_fit = static_cast<int>((avail - a.off_warp) / wb);
     if (nw_fit > pl->maxw) nw_fit = pl->maxw;
-    if (nw_fit >= 4) nw_fit = nw_fit / 4 * 4;  // equal load on the 4 SM sub-partitions
+    if (nw_fit >= 4) nw_fit = nw_fit / 4 * 4;  // equal load on the 4 SM sub-partitions (5-7 warps measured no faster than 4)
     if (nw_fit > best_nw) {
       best_nw = nw_fit;
       best_iq = iq;
@@ -675,25 +690,26 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
             K, D, avail - a.off_warp);
   a.iq_in_smem = best_iq;
   int w = 0;
-  a.woff_eps = w; w += round_up(32 * D * 8, 16);
-  a.woff_iq = w; w += best_iq ? 32 * 16 : 0;
+  a.woff_eps = w; w += eps_bytes;
+  a.woff_iq = w; w += best_iq ? iq_bytes : 0;
+  w = round_up(w, 16);
   a.woff_stage = w; w += stage_alloc;
   a.warp_bytes = w;
   int nw = best_nw;
   // small problems: prefer more, smaller tiles so that every SM gets work
   const long long total_pairs = static_cast<long long>(pl->npairs_local) * K;
-  while (nw > 1 && total_pairs / (nw * 32) < 2LL * c->num_sms) nw = (nw > 4) ? nw - 4 : nw - 1;
+  while (nw > 1 && total_pairs / (nw * ppw) < 2LL * c->num_sms) nw = (nw > 4) ? nw - 4 : nw - 1;
   pl->nw = nw;
   // FP32 sweep: several groups per tile amortise the table load and the block reduction, while keeping
   // >= ~10 tiles per SM so that the persistent CTAs stay balanced
   int G = 1;
   if (f32) {
-    const long long groups = static_cast<long long>(K) * ((pl->npairs_local + nw * 32 - 1) / (nw * 32));
+    const long long groups = static_cast<long long>(K) * ((pl->npairs_local + nw * ppw - 1) / (nw * ppw));
     const long long g = groups / (10LL * c->num_sms);
     G = g < 1 ? 1 : (g > 8 ? 8 : static_cast<int>(g));
   }
   a.groups_per_tile = G;
-  pl->pairs_per_tile = nw * 32 * G;
+  pl->pairs_per_tile = nw * ppw * G;
   pl->tiles_per_comp = (pl->npairs_local + pl->pairs_per_tile - 1) / pl->pairs_per_tile;
   pl->ntiles = pl->tiles_per_comp * K;
   pl->smem = a.off_warp + static_cast<size_t>(nw) * a.warp_bytes;

@@ -10,6 +10,10 @@
 //     only if no target k can both matter (x > -30 for some 6-sigma draw) and carry intermediates larger than
 //     F32_EXPANDED_MAX; otherwise the subtraction-then-square form of the reference (:55,:62) whose FP32
 //     error is proportional to |u_d||z_d| instead of ||u||^2.
+// Tried and dropped (round 1, c5 on B200): one SAMPLE per lane (16 pairs per warp, half the staging, 12 warps
+// per SM instead of 4).  Issue slots went from 44% to 72% busy, but the kernel executes 37% more instructions
+// (the dot product is no longer shared by the antithetic pair, table loads are amortised over half as many
+// pairs): 8.1 ms vs 7.8 ms for this kernel.
 // The expected log-joint (gplogjoint) is NOT run in FP32: z*alpha cancels 4-5 digits at VBMC's noise levels
 // (|alpha| ~ 1e4), which would break the 1e-4 bound; it is <5% of a step.
 #include <type_traits>
@@ -40,7 +44,8 @@ struct F32Tables {
   double* misc;    // [3]
 };
 
-__global__ void __launch_bounds__(128) entmc_f32_tables_kernel(const EntmcArgs a, const int DP, const F32Tables t) {
+__global__ void __launch_bounds__(256) entmc_f32_tables_kernel(const EntmcArgs a, const int DP, const F32Tables t) {
+  __shared__ double s_u[128 * 24];  // u_jkd in FP64 (K <= 128, DP <= 24) for the row norms
   __shared__ double s_ic;
   __shared__ int s_direct;
   const int D = a.D, K = a.K, K2 = (K + 1) & ~1, j = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -60,25 +65,26 @@ __global__ void __launch_bounds__(128) entmc_f32_tables_kernel(const EntmcArgs a
       }
     }
   }
+  float* U = t.U + static_cast<size_t>(j) * K2 * DP;
+  for (int i = tid; i < K2 * DP; i += 256) {
+    const int k = i / DP, d = i - k * DP;
+    double u = 0.0;
+    if (d < D && k < K) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
+    s_u[i] = u;
+    U[i] = static_cast<float>(u);
+  }
   __syncthreads();
   const double icmax = s_ic, sj = a.sigma[j];
   // 6-sigma bound on ||eps||: decides which formulation is accurate enough, never correctness
   const double em2 = D + 6.0 * sqrt(2.0 * D), em = sqrt(em2);
-  float* U = t.U + static_cast<size_t>(j) * K2 * DP;
   float4* S = t.S + static_cast<size_t>(j) * 2 * K2;
   int want_direct = 0;
-  for (int k = tid; k < K2; k += 128) {
+  for (int k = tid; k < K2; k += 256) {
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-    double uu = 0.0;
-    const double isk = k < K ? 1.0 / a.sigma[k] : 0.0;
-    for (int d = 0; d < DP; ++d) {
-      double u = 0.0;
-      if (d < D && k < K) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
-      uu = fma(u, u, uu);
-      U[k * DP + d] = static_cast<float>(u);
-    }
     if (k < K) {
-      const double r = sj * isk;
+      double uu = 0.0;
+      for (int d = 0; d < D; ++d) uu = fma(s_u[k * DP + d], s_u[k * DP + d], uu);
+      const double r = sj / a.sigma[k];
       s0 = make_float4(static_cast<float>(r), static_cast<float>(-0.5 * 1.4426950408889634 * uu),
                        static_cast<float>(-0.5 * 1.4426950408889634 * r * r), static_cast<float>(1.4426950408889634 * r));
       s1 = make_float4(static_cast<float>(a.ck[k] * icmax), static_cast<float>(a.ak[k] * icmax), 0.f, 0.f);
@@ -192,8 +198,36 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
       float e[DP];
       const bool valid = lane < np;
 #pragma unroll
-      for (int d = 0; d < DP; ++d)
-        e[d] = (valid && d < D) ? (a.eps_f32 ? eps_sf[lane * D + d] : static_cast<float>(eps_s[lane * D + d])) : 0.f;
+      for (int d = 0; d < DP; ++d) e[d] = 0.f;
+      if (valid) {
+        // rows of D values per pair: vector loads keep the 32 row reads (stride D) free of bank conflicts
+        if (a.eps_f32) {
+          if (DP % 4 == 0 && (D & 3) == 0) {
+            const float4* row = reinterpret_cast<const float4*>(eps_sf + lane * D);
+#pragma unroll
+            for (int d = 0; d < DP; d += 4)
+              if (d < D) { const float4 v = row[d >> 2]; e[d] = v.x; e[d + 1] = v.y; e[d + 2] = v.z; e[d + 3] = v.w; }
+          } else if ((D & 1) == 0) {
+            const float2* row = reinterpret_cast<const float2*>(eps_sf + lane * D);
+#pragma unroll
+            for (int d = 0; d < DP; d += 2)
+              if (d < D) { const float2 v = row[d >> 1]; e[d] = v.x; e[d + 1] = v.y; }
+          } else {
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+              if (d < D) e[d] = eps_sf[lane * D + d];
+          }
+        } else if ((D & 1) == 0) {
+          const double2* row = reinterpret_cast<const double2*>(eps_s + lane * D);
+#pragma unroll
+          for (int d = 0; d < DP; d += 2)
+            if (d < D) { const double2 v = row[d >> 1]; e[d] = static_cast<float>(v.x); e[d + 1] = static_cast<float>(v.y); }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DP; ++d)
+            if (d < D) e[d] = static_cast<float>(eps_s[lane * D + d]);
+        }
+      }
       __syncwarp();  // all lanes have consumed eps_s -> safe to refill it
       tma_pending = issue_eps(tile, g + 1);
 
@@ -212,12 +246,22 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
         for (int k = 0; k < K2; k += 2) {
           const float4 sa0 = tab_s[2 * k], sa1 = tab_s[2 * k + 1], sb0 = tab_s[2 * k + 2], sb1 = tab_s[2 * k + 3];
           float ua[DP], ub[DP];
+          if (DP % 4 == 0) {
 #pragma unroll
-          for (int d = 0; d < DP; d += 2) {
-            const float2 a2 = *reinterpret_cast<const float2*>(tab_u + k * DP + d);
-            const float2 b2 = *reinterpret_cast<const float2*>(tab_u + (k + 1) * DP + d);
-            ua[d] = a2.x; ua[d + 1] = a2.y;
-            ub[d] = b2.x; ub[d + 1] = b2.y;
+            for (int d = 0; d < DP; d += 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(tab_u + k * DP + d);
+              const float4 b4 = *reinterpret_cast<const float4*>(tab_u + (k + 1) * DP + d);
+              ua[d] = a4.x; ua[d + 1] = a4.y; ua[d + 2] = a4.z; ua[d + 3] = a4.w;
+              ub[d] = b4.x; ub[d + 1] = b4.y; ub[d + 2] = b4.z; ub[d + 3] = b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < DP; d += 2) {
+              const float2 a2 = *reinterpret_cast<const float2*>(tab_u + k * DP + d);
+              const float2 b2 = *reinterpret_cast<const float2*>(tab_u + (k + 1) * DP + d);
+              ua[d] = a2.x; ua[d + 1] = a2.y;
+              ub[d] = b2.x; ub[d + 1] = b2.y;
+            }
           }
           float x0, x1, x2, x3;
           if (EXPANDED) {
@@ -375,7 +419,7 @@ static int launch_f32(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
   t.direct = reinterpret_cast<int*>(base + nU + nS + 32);
   {
     KernelScope ks(c, "entmc_f32_tables", st);
-    entmc_f32_tables_kernel<<<K, 128, 0, st>>>(pl.a, DP, t);
+    entmc_f32_tables_kernel<<<K, 256, 0, st>>>(pl.a, DP, t);
     VB_CUDA(cudaGetLastError());
   }
   KernelScope ks(c, "entmc_f32", st);
