@@ -185,6 +185,43 @@ typedef struct vbmc_b200_negelcbo_args {
 
 int vbmc_b200_negelcbo(vbmc_b200_ctx* ctx, const vbmc_b200_negelcbo_args* args);
 
+/* ---------------------------------------------------------------------------------------
+ * [x,f,xtab,ftab,iter] = fminadam(fun,x0,LB,UB,TolFun,MaxIter,master_stepsize) — utils/fminadam.m:1-102,
+ * with fun = @(theta_) negelcbo_vbmc(theta_,beta,vp0,gp,Ns,1,compute_var,altent,thetabnd,entropy_alpha), the closure
+ * misc/vpoptimize_vbmc.m:71 builds and passes at :127.  The iterate, the Adam moments and
+ * the histories stay on the device: one call = one whole stochastic optimisation, no per-iteration host copies;
+ * the host only reads the termination flag every 20 iterations (:65-83).
+ * vp / gp / thetabnd are the ones last set on the context.  beta must be 0 (VBMC's default ELCBOWeight = 0; the
+ * variance gradient needs a host assembly): otherwise EUNSUPPORTED and the caller keeps the per-step path.
+ * ------------------------------------------------------------------------------------- */
+typedef struct vbmc_b200_fminadam_args {
+  /* inputs */
+  const double* x0;       /* nvars (= numel(theta0), vpoptimize_vbmc.m:58-63)                          */
+  int nvars;
+  const double* LB;       /* nvars or NULL (= -Inf, fminadam.m:35)                                     */
+  const double* UB;       /* nvars or NULL (= +Inf, fminadam.m:36)                                     */
+  double TolFun;          /* <= 0 or NaN => 0.001 (fminadam.m:6)                                       */
+  int MaxIter;            /* <= 0 => 10000 (fminadam.m:7); must be >= 20 (the reference indexes iter-19) */
+  double stepsize_max, stepsize_min, stepsize_decay; /* <= 0 or NaN => 0.1, 0.001, 200 (fminadam.m:11-18) */
+  double beta;            /* objective arguments, as vbmc_b200_negelcbo_args                            */
+  int Ns;
+  int compute_var;        /* accepted; has no effect on F, dF when beta == 0                            */
+  int use_thetabnd;
+  int eps_mode;           /* EPS_HOST / EPS_RESIDENT: the same draws every iteration (parity mode);
+                             EPS_PHILOX: iteration i (0-based) draws from Philox stream `stream + i`     */
+  const double* eps;
+  uint64_t seed, stream;
+  /* outputs (host; NULL = not wanted) */
+  double* x;              /* nvars: mean of the last 20 iterates (fminadam.m:95)                        */
+  double* f;              /* mean of the last 20 objective values (fminadam.m:96)                       */
+  double* xtab;           /* nvars x MaxIter column-major; the first *iter columns are written (:63,98) */
+  double* ftab;           /* MaxIter; the first *iter entries are written (:48,99)                      */
+  int* iter;              /* iterations executed                                                       */
+  double* stats;          /* optional [5]: stop flag, dx, slope, slope_err, slope_err_max of the last test */
+} vbmc_b200_fminadam_args;
+
+int vbmc_b200_fminadam(vbmc_b200_ctx* ctx, const vbmc_b200_fminadam_args* args);
+
 /* [H,dH] = entmc_vbmc(vp,Ns,grad_flags,jacobian_flag) — ent/entmc_vbmc.m:1-125.
  * Uses the vp last set (no theta unpacking).  grad_flags[4]; dH length = D*K*gf0 + K*gf1 + D*gf2 + K*gf3. */
 int vbmc_b200_entmc(vbmc_b200_ctx* ctx, int Ns, const int grad_flags[4], int jacobian_flag, int eps_mode,

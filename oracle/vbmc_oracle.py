@@ -974,3 +974,64 @@ class AdamState:
         vhat = self.v / (1 - self.beta2**it)
         stepsize = self.step_min + (self.step_max - self.step_min) * math.exp(-it / self.decay)
         return x - stepsize * mhat / (np.sqrt(vhat) + self.fudge)
+
+
+def fminadam(fun, x0, LB=None, UB=None, TolFun=None, MaxIter=None, master_stepsize=None):
+    """[x,f,xtab,ftab,iter] = fminadam(fun,x0,LB,UB,TolFun,MaxIter,master_stepsize), utils/fminadam.m:1-102.
+
+    ``fun(x) -> (f, grad)``.  Returns x (mean of the last 20 iterates, :95), f (mean of the last 20 values, :96),
+    xtab (nvars, iter), ftab (iter,), iter.  The slope test follows polyfit's own algebra (QR of the Vandermonde
+    matrix, S.R / S.df / S.normr, :69-73).
+    """
+    TolFun = 0.001 if TolFun is None else TolFun            # :6
+    MaxIter = 10000 if MaxIter is None else int(MaxIter)    # :7
+    ms = {"max": 0.1, "min": 0.001, "decay": 200.0}         # :11-18
+    for k, v in (master_stepsize or {}).items():
+        if v is not None:
+            ms[k] = v
+    fudge = math.sqrt(EPS)                                  # :21
+    beta1, beta2, batchsize = 0.9, 0.999, 20                # :22-24
+    TolX, TolX_max, TolFun_max = 0.001, 0.1, TolFun * 100   # :25-27
+    MinIter = batchsize * 2                                 # :29
+    x = np.asarray(x0, dtype=np.float64).ravel().copy()
+    nvars = x.size
+    LB = np.full(nvars, -np.inf) if LB is None else np.asarray(LB, dtype=np.float64).ravel()
+    UB = np.full(nvars, np.inf) if UB is None else np.asarray(UB, dtype=np.float64).ravel()
+    m = np.zeros(nvars)
+    v = np.zeros(nvars)
+    xtab = np.zeros((nvars, MaxIter))
+    ftab = np.full(MaxIter, np.nan)
+    it = 0
+    for it in range(1, MaxIter + 1):
+        f, grad = fun(x)                                    # :48
+        ftab[it - 1] = f
+        grad = np.asarray(grad, dtype=np.float64).ravel()
+        m = beta1 * m + (1 - beta1) * grad                  # :51
+        v = beta2 * v + (1 - beta2) * grad**2               # :52
+        mhat = m / (1 - beta1**it)
+        vhat = v / (1 - beta2**it)
+        stepsize = ms["min"] + (ms["max"] - ms["min"]) * math.exp(-it / ms["decay"])   # :56-57
+        x = x - stepsize * mhat / (np.sqrt(vhat) + fudge)   # :59
+        x = np.minimum(np.maximum(x, LB), UB)               # :60
+        xtab[:, it - 1] = x                                 # :63
+        if it % batchsize == 0 and it >= MinIter:           # :65
+            xxp = np.linspace(-(batchsize - 1) / 2, (batchsize - 1) / 2, batchsize)
+            y = ftab[it - batchsize:it]
+            V = np.stack([xxp, np.ones(batchsize)], axis=1)  # polyfit(x,y,1): Vandermonde, QR, p = R\(Q'y)
+            Q, R = np.linalg.qr(V)
+            p = np.linalg.solve(R, Q.T @ y)
+            normr = np.linalg.norm(y - V @ p)
+            df = batchsize - 2
+            Rinv = np.linalg.inv(R)
+            A = (Rinv @ Rinv.T) * normr**2 / df             # :71
+            slope = p[0]
+            slope_err = math.sqrt(A[0, 0] + TolFun**2)      # :72
+            slope_err_max = math.sqrt(A[0, 0] + TolFun_max**2)
+            cur = xtab[:, it - batchsize:it].mean(axis=1)
+            prev = xtab[:, it - 2 * batchsize:it - batchsize].mean(axis=1)
+            dx = math.sqrt(np.sum((cur - prev) ** 2 / batchsize))   # :77
+            if (dx < TolX and abs(slope) < slope_err_max) or (abs(slope) < slope_err and dx < TolX_max):   # :80
+                break
+    x = xtab[:, it - batchsize:it].mean(axis=1)             # :95
+    f = float(np.mean(ftab[it - batchsize:it]))             # :96
+    return x, f, xtab[:, :it].copy(), ftab[:it].copy(), it

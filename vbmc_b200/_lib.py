@@ -68,6 +68,18 @@ class NegelcboArgs(C.Structure):
     ]
 
 
+class FminadamArgs(C.Structure):
+    _fields_ = [
+        ("x0", c_double_p), ("nvars", C.c_int), ("LB", c_double_p), ("UB", c_double_p),
+        ("TolFun", C.c_double), ("MaxIter", C.c_int),
+        ("stepsize_max", C.c_double), ("stepsize_min", C.c_double), ("stepsize_decay", C.c_double),
+        ("beta", C.c_double), ("Ns", C.c_int), ("compute_var", C.c_int), ("use_thetabnd", C.c_int),
+        ("eps_mode", C.c_int), ("eps", c_double_p), ("seed", C.c_uint64), ("stream", C.c_uint64),
+        ("x", c_double_p), ("f", c_double_p), ("xtab", c_double_p), ("ftab", c_double_p), ("iter", c_int_p),
+        ("stats", c_double_p),
+    ]
+
+
 # every symbol include/vbmc_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "vbmc_b200_version", "vbmc_b200_last_error", "vbmc_b200_create", "vbmc_b200_destroy", "vbmc_b200_sync",
@@ -76,7 +88,7 @@ EXPORTS = [
     "vbmc_b200_eps_upload", "vbmc_b200_eps_philox", "vbmc_b200_negelcbo", "vbmc_b200_entmc", "vbmc_b200_gplogjoint",
     "vbmc_b200_negelcbo_resident_loop", "vbmc_b200_profile_enable", "vbmc_b200_profile_get",
     "vbmc_b200_profile_reset", "vbmc_b200_measure_fp64_peak", "vbmc_b200_measure_hbm_copy", "vbmc_b200_flush_l2",
-    "vbmc_b200_philox_raw", "vbmc_b200_shard_range",
+    "vbmc_b200_philox_raw", "vbmc_b200_shard_range", "vbmc_b200_fminadam",
 ]
 
 _lib = None
@@ -113,6 +125,7 @@ def load():
     lib.vbmc_b200_eps_philox.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, c_double_p]
     lib.vbmc_b200_negelcbo.argtypes = [vp, C.POINTER(NegelcboArgs)]
     lib.vbmc_b200_negelcbo_resident_loop.argtypes = [vp, C.POINTER(NegelcboArgs), C.c_int, C.POINTER(C.c_float)]
+    lib.vbmc_b200_fminadam.argtypes = [vp, C.POINTER(FminadamArgs)]
     lib.vbmc_b200_entmc.argtypes = [vp, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p, C.c_uint64, C.c_uint64,
                                     c_double_p, c_double_p]
     lib.vbmc_b200_gplogjoint.argtypes = [vp, c_int_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,

@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import VbmcB200Error, dptr, f64
 
 __all__ = [
-    "Context", "default_context", "negelcbo_vbmc", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ",
+    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ",
     "vpbounds", "rescale_params", "get_vptheta", "VbmcB200Error",
 ]
 
@@ -367,6 +367,51 @@ def negelcbo_vbmc(theta, beta, vp, gp, Ns=0, compute_grad=None, compute_var=None
     _lib.check(ctx.lib.vbmc_b200_negelcbo(ctx.handle, C.byref(a)))
     out = (float(sc[0]), dF, float(sc[1]), float(sc[2]), float(sc[3]), dH, float(sc[4]), float(sc[5]), float(sc[6]),
            None if Isk is None else Isk.T.copy(), None if Jsjk is None else Jsjk.transpose(2, 1, 0).copy())
+    return out[:max(1, nargout)]
+
+
+def fminadam_negelcbo(x0, beta, vp, gp, Ns, compute_var=0, thetabnd=None, LB=None, UB=None, TolFun=None, MaxIter=None,
+                      master_stepsize=None, *, epsilon=None, rng=None, nargout=5, ctx=None):
+    """[x,f,xtab,ftab,iter] = fminadam(@(t) negelcbo_vbmc(t,beta,vp,gp,Ns,1,compute_var,0,thetabnd,0), x0, LB, UB,
+    TolFun, MaxIter, master_stepsize) — utils/fminadam.m:1-102 driven by the closure of misc/vpoptimize_vbmc.m:71,127,
+    with the whole loop on the device (vbmc_b200_fminadam).
+
+    ``master_stepsize``: dict with any of max/min/decay (missing or None -> fminadam.m:11-18 defaults).  ``xtab`` is
+    returned as (iter, nvars) — what the reference hands back for a row-vector x0 (fminadam.m:101), the shape
+    vpoptimize_vbmc.m:131 indexes (``theta_lst(idx_mid,:)``).  Draws: ``epsilon`` (same draws every iteration, parity
+    mode) or ``rng=(seed, stream)`` (iteration i uses Philox stream ``stream+i``: fresh draws per call like ``randn``).
+    """
+    ctx = ctx or default_context()
+    x0 = f64(x0).ravel()
+    ctx.vp_set(vp)
+    ctx.gp_attach(gp, want_L=False)
+    ctx.thetabnd_set(thetabnd)
+    a = _lib.FminadamArgs()
+    a.x0, a.nvars = dptr(x0), x0.size
+    lb = None if LB is None or np.size(LB) == 0 else f64(LB).ravel() * np.ones(x0.size)
+    ub = None if UB is None or np.size(UB) == 0 else f64(UB).ravel() * np.ones(x0.size)
+    a.LB, a.UB = dptr(lb), dptr(ub)
+    a.TolFun = float("nan") if TolFun is None or np.size(TolFun) == 0 else float(TolFun)
+    a.MaxIter = 0 if MaxIter is None or np.size(MaxIter) == 0 else int(MaxIter)
+    ms = master_stepsize or {}
+    get = lambda k: float("nan") if ms.get(k) is None or np.size(ms.get(k)) == 0 else float(ms[k])
+    a.stepsize_max, a.stepsize_min, a.stepsize_decay = get("max"), get("min"), get("decay")
+    a.beta = 0.0 if beta is None or not np.isfinite(beta) else float(beta)
+    a.Ns, a.compute_var, a.use_thetabnd = int(Ns), int(compute_var or 0), int(thetabnd is not None)
+    mode, e, seed, stream = _eps_args(vp, Ns, epsilon, rng)
+    a.eps_mode, a.eps, a.seed, a.stream = mode, dptr(e), seed, stream
+    maxit = a.MaxIter if a.MaxIter > 0 else 10000
+    x = np.zeros(x0.size)
+    fval = C.c_double()
+    it = C.c_int()
+    xtab = np.zeros((maxit, x0.size)) if nargout > 2 else None   # C order (iter, nvars) == column-major nvars x iter
+    ftab = np.zeros(maxit) if nargout > 3 else None
+    stats = np.zeros(5)
+    a.x, a.f, a.xtab, a.ftab, a.iter, a.stats = dptr(x), C.pointer(fval), dptr(xtab), dptr(ftab), C.pointer(it), dptr(stats)
+    _lib.check(ctx.lib.vbmc_b200_fminadam(ctx.handle, C.byref(a)))
+    n = it.value
+    out = (x, fval.value, None if xtab is None else xtab[:n].copy(), None if ftab is None else ftab[:n].copy(), n)
+    fminadam_negelcbo.last_stats = dict(zip(("stop", "dx", "slope", "slope_err", "slope_err_max"), stats))
     return out[:max(1, nargout)]
 
 

@@ -124,9 +124,10 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   vb::comm_destroy(c);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->refit_graph) cudaGraphExecDestroy(c->refit_graph);
+  if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -564,6 +565,25 @@ static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
   }
 }
 
+// Everything a captured step depends on: shapes, flags and the addresses of every buffer a kernel node reads or
+// writes.  A graph is replayed only while this signature is unchanged.
+static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask, int use_thetabnd, bool philox) {
+  std::vector<long long> key = {Ns, gmask, use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form, c->precision,
+                                c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
+                                reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
+                                reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
+                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p),
+                                reinterpret_cast<long long>(c->ent_tables.p),
+                                reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
+                                reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),
+                                reinterpret_cast<long long>(c->gpDerived.p), reinterpret_cast<long long>(c->bnd.p),
+                                reinterpret_cast<long long>(c->theta_pinned), reinterpret_cast<long long>(c->out_pinned)};
+  long long bits[3];
+  memcpy(&bits[0], &c->TolCon, 8); memcpy(&bits[1], &c->WeightThreshold, 8); memcpy(&bits[2], &c->WeightPenalty, 8);
+  key.insert(key.end(), bits, bits + 3);
+  return key;
+}
+
 // One negelcbo evaluation on the device: H2D {theta, seed, stream}, the kernels, D2H of the output block.
 // Single rank, no profiling: the whole sequence is captured once into a CUDA graph and replayed while the step
 // signature (shapes, flags, buffer addresses) is unchanged — 10 launches + 2 copies become one graph launch.
@@ -595,24 +615,7 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
     VB_CUDA(cudaStreamSynchronize(c->stream));
     return VBMC_B200_OK;
   }
-  auto make_key = [&]() {
-  std::vector<long long> key = {Ns, gmask, a->use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form, c->precision,
-                                c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
-                                reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
-                                reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
-                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p),
-                                reinterpret_cast<long long>(c->ent_tables.p),
-                                reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
-                                reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),
-                                reinterpret_cast<long long>(c->gpDerived.p), reinterpret_cast<long long>(c->bnd.p),
-                                reinterpret_cast<long long>(c->theta_pinned), reinterpret_cast<long long>(c->out_pinned)};
-  {
-    long long bits[3];
-    memcpy(&bits[0], &c->TolCon, 8); memcpy(&bits[1], &c->WeightThreshold, 8); memcpy(&bits[2], &c->WeightPenalty, 8);
-    key.insert(key.end(), bits, bits + 3);
-  }
-  return key;
-  };
+  auto make_key = [&]() { return step_signature(c, Ns, gmask, a->use_thetabnd, philox); };
   const std::vector<long long> key = make_key();
   if (c->graph_exec && key == c->graph_key) {
     VB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
@@ -818,6 +821,164 @@ int vbmc_b200_negelcbo_resident_loop(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_
   VB_CUDA(cudaEventElapsedTime(ms_total, c->ev_t0, c->ev_t1));
   VB_CUDA(cudaStreamSynchronize(c->stream));
   scatter_negelcbo(c, a, nth);
+  return VBMC_B200_OK;
+}
+
+// fminadam(@(theta_) negelcbo_vbmc(theta_, ...), x0, LB, UB, TolFun, MaxIter, master_stepsize) with the loop on the
+// device (utils/fminadam.m:20-102; kernels in adam.cu).  Iteration 1 runs as direct launches (buffers get allocated),
+// iteration 2 is captured into a CUDA graph, every later iteration is one graph launch; the host syncs only at the
+// mini-batch ends where the reference tests for termination.
+int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
+  if (!c || !f) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  if (!f->x0) VB_FAIL(VBMC_B200_EINVAL, "fminadam: x0 is required");
+  vbmc_b200_negelcbo_args na;
+  memset(&na, 0, sizeof(na));
+  na.theta = f->x0; na.ntheta = f->nvars; na.beta = f->beta; na.Ns = f->Ns;
+  na.compute_grad = 1; na.compute_var = 0; na.separate_K = 0; na.use_thetabnd = f->use_thetabnd;
+  na.eps_mode = f->eps_mode; na.eps = f->eps; na.seed = f->seed; na.stream = f->stream;
+  double beta;
+  int Ns, gmask;
+  VB_TRY(negelcbo_validate(c, &na, &beta, &Ns, &gmask));
+  if (beta != 0.0)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED,
+            "vbmc_b200:OutOfScope: the device-resident fminadam loop supports beta == 0 only (ELCBOWeight default); "
+            "use negelcbo_vbmc per step for the variance-penalised objective");
+  const double TolFun = (f->TolFun > 0.0) ? f->TolFun : 0.001;        // fminadam.m:6 (NaN compares false)
+  const int MaxIter = f->MaxIter > 0 ? f->MaxIter : 10000;            // :7
+  const int B = 20;                                                   // batchsize (:24)
+  if (MaxIter < B) VB_FAIL(VBMC_B200_EINVAL, "fminadam: MaxIter=%d < 20 (the reference indexes xtab(:,iter-19:iter))", MaxIter);
+  VB_CUDA(cudaSetDevice(c->device));
+  const int n = c->ntheta;
+  const int nth = grad_mask_len(c, gmask);  // == n: every optimised block has a gradient
+  const size_t nstage = static_cast<size_t>(n) + 2;
+  VB_TRY(c->theta_dev.reserve(sizeof(double) * nstage));
+  VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * nstage));
+  OutLayout ol;
+  ol.init(nth, c->gp.S, c->K);
+  VB_TRY(c->out_dev.reserve(sizeof(double) * ol.total));
+  VB_TRY(ensure_pinned(&c->out_pinned, &c->out_pinned_cap, sizeof(double) * (ol.total > 16 ? ol.total : 16)));
+  // state: m | v | lb | ub | xout | stats[8] | it (8 bytes) | ftab[MaxIter]
+  const size_t nstate = 5 * static_cast<size_t>(n) + 8 + 1 + MaxIter;
+  VB_TRY(c->adamState.reserve(sizeof(double) * nstate));
+  VB_TRY(c->adamXtab.reserve(sizeof(double) * static_cast<size_t>(n) * MaxIter));
+  double* sb = c->adamState.d();
+  AdamArgs aa;
+  aa.n = n;
+  aa.step_max = (f->stepsize_max > 0.0) ? f->stepsize_max : 0.1;      // :11-18
+  aa.step_min = (f->stepsize_min > 0.0) ? f->stepsize_min : 0.001;
+  aa.decay = (f->stepsize_decay > 0.0) ? f->stepsize_decay : 200.0;
+  aa.x = c->theta_dev.d();
+  aa.grad = c->out_dev.d() + ol.oDF;
+  aa.fval = c->out_dev.d() + ol.oF;
+  aa.m = sb; aa.v = sb + n;
+  double* lb = sb + 2 * static_cast<size_t>(n);
+  double* ub = sb + 3 * static_cast<size_t>(n);
+  aa.lb = lb; aa.ub = ub;
+  aa.xout = sb + 4 * static_cast<size_t>(n);
+  aa.stats = sb + 5 * static_cast<size_t>(n);
+  aa.it = reinterpret_cast<int*>(aa.stats + 8);
+  aa.ftab = aa.stats + 9;
+  aa.xtab = c->adamXtab.d();
+  const bool philox = f->eps_mode == VBMC_B200_EPS_PHILOX;
+  aa.dyn = philox ? reinterpret_cast<unsigned long long*>(c->theta_dev.d() + n) : nullptr;
+
+  // ---- initial state ----
+  memcpy(c->theta_pinned, f->x0, sizeof(double) * n);
+  uint64_t dyn[2] = {f->seed, f->stream};
+  memcpy(c->theta_pinned + n, dyn, sizeof(dyn));
+  VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * nstage, cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaMemsetAsync(sb, 0, sizeof(double) * (2 * static_cast<size_t>(n)), c->stream));          // m = v = 0 (:38)
+  VB_CUDA(cudaMemsetAsync(aa.stats, 0, sizeof(double) * 9, c->stream));                               // stats, it = 0
+  {
+    std::vector<double> bnd(2 * static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) {
+      bnd[i] = f->LB ? f->LB[i] : -INFINITY;                                                          // :35-36
+      bnd[n + i] = f->UB ? f->UB[i] : INFINITY;
+    }
+    VB_CUDA(cudaMemcpyAsync(lb, bnd.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    VB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  int eps_mode = f->eps_mode;
+  if (eps_mode == VBMC_B200_EPS_HOST) {  // parity mode: the same draws every iteration, uploaded once
+    VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_HOST, f->eps, 0, 0));
+    eps_mode = VBMC_B200_EPS_RESIDENT;
+  }
+  if (!philox) VB_TRY(prepare_eps(c, Ns, eps_mode, nullptr, 0, 0));
+
+  auto body = [&]() -> int {
+    c->philox_dyn = philox;
+    if (philox) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, f->seed, f->stream));
+    const int rc = enqueue_step(c, Ns, gmask, f->use_thetabnd, 1, FIN_NEGELCBO, true);
+    c->philox_dyn = false;
+    VB_TRY(rc);
+    VB_TRY(launch_adam_step(c, aa, c->stream));
+    return VBMC_B200_OK;
+  };
+  auto make_key = [&]() {
+    std::vector<long long> key = step_signature(c, Ns, gmask, f->use_thetabnd, philox);
+    long long bits[3];
+    memcpy(&bits[0], &aa.step_max, 8); memcpy(&bits[1], &aa.step_min, 8); memcpy(&bits[2], &aa.decay, 8);
+    key.insert(key.end(), bits, bits + 3);
+    key.push_back(reinterpret_cast<long long>(c->adamState.p));
+    key.push_back(reinterpret_cast<long long>(c->adamXtab.p));
+    key.push_back(MaxIter);
+    return key;
+  };
+  bool use_graph = c->graphs_enabled && !c->profiling && c->nranks == 1;
+  double* stats_h = c->out_pinned;  // the pinned output mirror doubles as the read-back slot of the termination test
+  int it = 0;
+  while (it < MaxIter) {
+    ++it;
+    if (!use_graph || it == 1) {
+      VB_TRY(body());
+    } else {
+      if (it == 2) {
+        const std::vector<long long> key = make_key();
+        if (!(c->adam_graph && key == c->adam_key)) {
+          if (c->adam_graph) { cudaGraphExecDestroy(c->adam_graph); c->adam_graph = nullptr; }
+          const long long l0 = c->launches;
+          cudaGraph_t graph = nullptr;
+          VB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+          const int rc = body();
+          cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+          if (rc == VBMC_B200_OK && ce == cudaSuccess && graph) {
+            c->adam_graph_launches = c->launches - l0;
+            c->launches = l0;
+            ce = cudaGraphInstantiate(&c->adam_graph, graph, 0);
+            if (ce != cudaSuccess) c->adam_graph = nullptr;
+          }
+          if (graph) cudaGraphDestroy(graph);
+          if (!c->adam_graph) {  // capture unavailable: direct launches for the rest of this call
+            cudaGetLastError();
+            use_graph = false;
+            VB_TRY(body());
+            continue;
+          }
+          c->adam_key = key;
+        }
+      }
+      VB_CUDA(cudaGraphLaunch(c->adam_graph, c->stream));
+      c->launches += c->adam_graph_launches;
+    }
+    if (it % B == 0 && it >= 2 * B) {  // isMinibatchEnd && iter >= MinIter (:65)
+      VB_TRY(launch_adam_check(c, aa, it, TolFun, c->stream));
+      VB_CUDA(cudaMemcpyAsync(stats_h, aa.stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+      VB_CUDA(cudaStreamSynchronize(c->stream));
+      if (stats_h[0] != 0.0) break;    // :80-82
+    }
+  }
+  VB_TRY(launch_adam_final(c, aa, it, c->stream));
+  VB_CUDA(cudaMemcpyAsync(stats_h, aa.stats, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (f->x) VB_CUDA(cudaMemcpyAsync(f->x, aa.xout, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (f->ftab) VB_CUDA(cudaMemcpyAsync(f->ftab, aa.ftab, sizeof(double) * it, cudaMemcpyDeviceToHost, c->stream));
+  if (f->xtab)
+    VB_CUDA(cudaMemcpyAsync(f->xtab, aa.xtab, sizeof(double) * static_cast<size_t>(n) * it, cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  if (f->f) *f->f = stats_h[5];
+  if (f->iter) *f->iter = it;
+  if (f->stats)
+    for (int i = 0; i < 5; ++i) f->stats[i] = stats_h[i];
+  if (philox) c->eps_f32 = c->precision == 32;
   return VBMC_B200_OK;
 }
 

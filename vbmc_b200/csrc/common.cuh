@@ -133,6 +133,23 @@ struct OutLayout {
   }
 };
 
+// device-resident fminadam state (adam.cu; utils/fminadam.m:20-102)
+struct AdamArgs {
+  int n;               // nvars
+  double step_max, step_min, decay;
+  double* x;           // [n] current iterate == the theta staging buffer the step kernels read
+  const double* grad;  // [n] dF of the step that just ran (output block)
+  const double* fval;  // F of that step
+  double *m, *v;       // [n] Adam moments
+  const double *lb, *ub;  // [n]
+  double* xtab;        // [MaxIter][n] iterate history (MATLAB xtab(:,iter))
+  double* ftab;        // [MaxIter]
+  double* xout;        // [n] mean of the last 20 iterates
+  double* stats;       // [8] stop flag, dx, slope, slope_err, slope_err_max, f
+  int* it;             // iterations done so far
+  unsigned long long* dyn;  // {seed, stream} of the device draw generator (stream advanced every iteration) or NULL
+};
+
 struct Prof {
   double ms = 0;
   long long n = 0;
@@ -209,6 +226,10 @@ struct vbmc_b200_ctx {
   std::vector<long long> graph_key, warm_key;
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;
+  std::vector<long long> adam_key;    // one fminadam iteration (step kernels + Adam update, no host copies)
+  cudaGraphExec_t adam_graph = nullptr;
+  long long adam_graph_launches = 0;
+  vb::DevBuf adamState, adamXtab;
   std::vector<long long> refit_key;   // same for the batched Cholesky of gp_post / gp_nlz
   cudaGraphExec_t refit_graph = nullptr;
   long long refit_launches = 0;
@@ -246,6 +267,9 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
                   const uint64_t* dyn = nullptr);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
+int launch_adam_step(vbmc_b200_ctx* c, const AdamArgs& a, cudaStream_t st);
+int launch_adam_check(vbmc_b200_ctx* c, const AdamArgs& a, int iter, double TolFun, cudaStream_t st);
+int launch_adam_final(vbmc_b200_ctx* c, const AdamArgs& a, int iter, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad = nullptr);
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
