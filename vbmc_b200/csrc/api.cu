@@ -834,7 +834,7 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   vbmc_b200_negelcbo_args na;
   memset(&na, 0, sizeof(na));
   na.theta = f->x0; na.ntheta = f->nvars; na.beta = f->beta; na.Ns = f->Ns;
-  na.compute_grad = 1; na.compute_var = 0; na.separate_K = 0; na.use_thetabnd = f->use_thetabnd;
+  na.compute_grad = 1; na.compute_var = f->compute_var; na.separate_K = 0; na.use_thetabnd = f->use_thetabnd;
   na.eps_mode = f->eps_mode; na.eps = f->eps; na.seed = f->seed; na.stream = f->stream;
   double beta;
   int Ns, gmask;
