@@ -351,6 +351,29 @@ def main():
         heps = workloads.make_epsilon(cfg)
         e2e_host_eps = 1.0 / e2e_loop(max(3, args.steps // 4), 2, host_eps=heps)
 
+    # ---- whole-optimisation call: fminadam with the loop on the device, host x0 in, x/f/xtab/ftab out ----
+    fmin = None
+    try:
+        nit = max(40, args.steps)
+        vbmc_b200.fminadam_negelcbo(theta0, 0.0, vp, gp, Ns, 0, tb, None, None, 1e-9, 40, None, rng=(778, 0), ctx=ctx)  # warm (graph capture)
+        barrier()
+        t0 = time.perf_counter()
+        _, _, xtab_, ftab_, it_ = vbmc_b200.fminadam_negelcbo(theta0, 0.0, vp, gp, Ns, 0, tb, None, None, 1e-9, nit, None,
+                                                            rng=(778, 1000), ctx=ctx)
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        fmin = {"value": it_ / dt, "unit": "steps/s", "iterations": it_, "wall_s": dt, "h2d_bytes_per_call": theta0.size * 8 * 3,
+                "d2h_bytes_per_call": int(xtab_.nbytes + ftab_.nbytes + theta0.size * 8 + 64),
+                "what": "one vbmc_b200.fminadam_negelcbo call = utils/fminadam.m with negelcbo_vbmc as objective; Adam state, xtab, "
+                        "ftab on the device, host reads the termination flag every 20 iterations"}
+    except Exception as e:   # reporting only
+        fmin = {"error": str(e)[:300]}
+
     # ---- c4 (Ns=131072): the MC-shard configuration BASELINE.json names for 2/4/8 GPUs, same protocol ----
     c4 = None
     if args.config is None:
@@ -406,6 +429,7 @@ def main():
                 "includes": "host theta H2D, F/dF D2H, host Adam update (fminadam.m:51-60); draws from the device generator",
                 "host_eps_variant_steps_per_s": e2e_host_eps,
                 "host_eps_variant_h2d_bytes_per_step": counts["entmc_bytes"] if e2e_host_eps else None},
+        "fminadam_device_loop": fmin,
         "gpu_launches": launches,
         "wall_s_timed_region": t_wall,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in prof.items()},

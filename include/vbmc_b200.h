@@ -60,6 +60,14 @@ int vbmc_b200_launch_count(vbmc_b200_ctx* ctx, long long* count);
  * The reference has no such switch (MATLAB doubles throughout): a caller that never calls this gets FP64. */
 int vbmc_b200_set_precision(vbmc_b200_ctx* ctx, int bits);
 
+/* Entropy sweep: a mixture component whose term is below exp(-log_threshold) of q(x) for ALL 32 draws a warp scores
+ * (bound from ||u_jk||, sigma_j/sigma_k and the warp's largest ||eps||; see csrc/entmc.cu) is skipped for that warp.
+ * Default 50 (2e-22 of q: below FP64 round-off; the reference's exp() underflows to exactly 0 for most such terms);
+ * 0 scores every component like the reference loop (ent/entmc_vbmc.m:60-65).  Also VBMC_B200_ENTMC_PRUNE in the environment. */
+int vbmc_b200_entmc_prune(vbmc_b200_ctx* ctx, double log_threshold);
+/* counters of (warp, component) blocks scored / candidate since the last call; enable != 0 keeps counting (bench) */
+int vbmc_b200_entmc_prune_stats(vbmc_b200_ctx* ctx, int enable, unsigned long long* kept, unsigned long long* total);
+
 /* ---------------------------------------------------------------------------------------
  * multi-GPU: one context per rank, one NCCL all-reduce per negelcbo step.
  * The MC pair axis of entmc_vbmc and the hyper-parameter-sample axis of gplogjoint are

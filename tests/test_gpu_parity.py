@@ -363,3 +363,47 @@ def test_variance_more_points_than_eight_columns_fit(gpu_ctx):
     # J = prior term (O(1)) - z K^-1 z cancels four digits here, on top of the conditioning of a 3600-point Gram matrix
     assert rel(got[0], ref[0]) < 1e-9 and rel(got[2], ref[2]) < 1e-5 and rel(got[6], ref[6]) < 1e-5
     assert rel(got[3], ref[3]) < 1e-4
+
+
+def test_entmc_pruning_is_invisible(gpu_ctx):
+    """Components that a whole warp of draws cannot see (below exp(-50) of q) are skipped; the result must equal the
+    un-pruned sweep to round-off and the oracle to the parity bar, and the counters must show that pruning happened."""
+    import vbmc_b200
+    w = mk(D=10, N=120, K=50, S=2, Ns=1024, target="lumpy")
+    vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
+    vp = dict(vp)
+    vp["sigma"] = vp["sigma"] * 0.5          # well separated components: most cross terms underflow
+    theta = workloads.theta_of(vp)
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    ref = orc.negelcbo_vbmc(theta, 0.0, vp, gp, 1024, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+    try:
+        gpu_ctx.entmc_prune(0.0)
+        gpu_ctx.entmc_prune_stats(True)
+        full = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 1024, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+        kept0, tot0 = gpu_ctx.entmc_prune_stats(True)
+        gpu_ctx.entmc_prune(50.0)
+        pruned = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 1024, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+        kept1, tot1 = gpu_ctx.entmc_prune_stats(False)
+    finally:
+        gpu_ctx.entmc_prune(50.0)
+        gpu_ctx.entmc_prune_stats(False)
+    assert kept0 == tot0 and tot1 == tot0 and kept1 < 0.9 * tot1
+    for i in (0, 1, 3, 5):   # F, dF, H, dH
+        assert rel(pruned[i], full[i]) < 1e-14
+        assert rel(pruned[i], ref[i]) < TOL
+
+
+def test_entmc_pruning_overlapping_components_keeps_everything(gpu_ctx):
+    """Heavily overlapping components: nothing may be skipped."""
+    import vbmc_b200
+    w = mk(D=3, N=40, K=9, S=2, Ns=256)
+    vp = dict(w["vp"])
+    vp["mu"] = 0.05 * vp["mu"]
+    try:
+        gpu_ctx.entmc_prune_stats(True)
+        H, dH = vbmc_b200.entmc_vbmc(vp, 256, epsilon=w["epsilon"])
+        kept, tot = gpu_ctx.entmc_prune_stats(False)
+    finally:
+        gpu_ctx.entmc_prune_stats(False)
+    Ho, dHo = orc.entmc_vbmc(vp, 256, epsilon=w["epsilon"])
+    assert kept == tot and rel(H, Ho) < TOL and rel(dH, dHo) < TOL

@@ -73,6 +73,16 @@ class Context:
         """64 (default) or 32: arithmetic of the entropy sweep (vbmc_b200_set_precision in include/vbmc_b200.h)."""
         _lib.check(self.lib.vbmc_b200_set_precision(self._h, int(bits)))
 
+    def entmc_prune(self, log_threshold: float):
+        """Skip mixture components below exp(-log_threshold) of q for a whole warp of draws (0: score everything)."""
+        _lib.check(self.lib.vbmc_b200_entmc_prune(self._h, float(log_threshold)))
+
+    def entmc_prune_stats(self, enable=True):
+        """(kept, total) (warp, component) blocks since the last call; ``enable`` keeps the counters running."""
+        k, t = C.c_ulonglong(), C.c_ulonglong()
+        _lib.check(self.lib.vbmc_b200_entmc_prune_stats(self._h, int(bool(enable)), C.byref(k), C.byref(t)))
+        return k.value, t.value
+
     def launch_count(self) -> int:
         n = C.c_longlong()
         _lib.check(self.lib.vbmc_b200_launch_count(self._h, C.byref(n)))

@@ -103,11 +103,15 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   VB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  VB_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork0, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_philox, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreate(&c->ev_t0));
   VB_CUDA(cudaEventCreate(&c->ev_t1));
   if (const char* g = getenv("VBMC_B200_GRAPHS")) c->graphs_enabled = strcmp(g, "0") != 0;
+  if (const char* pc = getenv("VBMC_B200_ENTMC_PRUNE")) c->entmc_prune_c = atof(pc);
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
     if (!strcmp(f, "separable")) c->entmc_form = 0;
     if (!strcmp(f, "direct")) c->entmc_form = 1;
@@ -127,7 +131,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -138,6 +142,9 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   cudaEventDestroy(c->ev_t1);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->stream2);
+  cudaStreamDestroy(c->stream3);
+  cudaEventDestroy(c->ev_fork0);
+  cudaEventDestroy(c->ev_philox);
   delete c;
   return VBMC_B200_OK;
 }
@@ -145,6 +152,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
 int vbmc_b200_sync(vbmc_b200_ctx* c) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
   VB_CUDA(cudaSetDevice(c->device));
+  VB_CUDA(cudaStreamSynchronize(c->stream3));
   VB_CUDA(cudaStreamSynchronize(c->stream2));
   VB_CUDA(cudaStreamSynchronize(c->stream));
   return VBMC_B200_OK;
@@ -154,6 +162,27 @@ int vbmc_b200_set_precision(vbmc_b200_ctx* c, int bits) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
   if (bits != 32 && bits != 64) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_set_precision: bits must be 32 or 64 (got %d)", bits);
   c->precision = bits;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_entmc_prune(vbmc_b200_ctx* c, double log_threshold) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  if (!(log_threshold >= 0.0)) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_entmc_prune: threshold must be >= 0 (0 disables pruning)");
+  c->entmc_prune_c = log_threshold;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_entmc_prune_stats(vbmc_b200_ctx* c, int enable, unsigned long long* kept, unsigned long long* total) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  unsigned long long h[2] = {0ull, 0ull};
+  if (c->entmc_prune_stats.p) VB_CUDA(cudaMemcpy(h, c->entmc_prune_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+  if (kept) *kept = h[0];
+  if (total) *total = h[1];
+  VB_TRY(c->entmc_prune_stats.reserve(sizeof(h)));
+  VB_CUDA(cudaMemset(c->entmc_prune_stats.p, 0, sizeof(h)));
+  c->entmc_prune_stats_on = enable != 0;
   return VBMC_B200_OK;
 }
 
@@ -444,6 +473,16 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   if (what == FIN_ENTMC) rl.init(c->D, c->K, 0);
   VB_TRY(c->R_dev.reserve(sizeof(double) * rl.total));
   VB_CUDA(cudaMemsetAsync(c->R_dev.p, 0, sizeof(double) * rl.total, c->stream));
+  // the draws do not depend on theta: generate them on a third stream while vp_unpack (and then gplogjoint) run
+  const bool philox_now = doH && c->philox_pending;
+  if (philox_now) {
+    c->philox_pending = false;
+    VB_CUDA(cudaEventRecord(c->ev_fork0, c->stream));
+    VB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork0, 0));
+    VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream3,
+                         c->philox_dyn ? reinterpret_cast<const uint64_t*>(c->theta_dev.d() + c->ntheta) : nullptr));
+    VB_CUDA(cudaEventRecord(c->ev_philox, c->stream3));
+  }
   VB_TRY(launch_vp_unpack(c, have_theta));
   if (doG) {
     VB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
@@ -453,11 +492,7 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
   }
   if (doH) {
-    if (c->philox_pending) {
-      c->philox_pending = false;
-      VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream,
-                           c->philox_dyn ? reinterpret_cast<const uint64_t*>(c->theta_dev.d() + c->ntheta) : nullptr));
-    }
+    if (philox_now) VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_philox, 0));
     int need = 0;
     if (gmask & 1) need |= NEED_MU;
     if (gmask & (2 | 4)) need |= NEED_E;
@@ -572,15 +607,17 @@ static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask
                                 c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
                                 reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
                                 reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
-                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p),
+                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p), reinterpret_cast<long long>(c->glj_part.p),
                                 reinterpret_cast<long long>(c->ent_tables.p),
                                 reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
                                 reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),
                                 reinterpret_cast<long long>(c->gpDerived.p), reinterpret_cast<long long>(c->bnd.p),
                                 reinterpret_cast<long long>(c->theta_pinned), reinterpret_cast<long long>(c->out_pinned)};
-  long long bits[3];
+  long long bits[4];
   memcpy(&bits[0], &c->TolCon, 8); memcpy(&bits[1], &c->WeightThreshold, 8); memcpy(&bits[2], &c->WeightPenalty, 8);
-  key.insert(key.end(), bits, bits + 3);
+  memcpy(&bits[3], &c->entmc_prune_c, 8);
+  key.insert(key.end(), bits, bits + 4);
+  key.push_back(c->entmc_prune_stats_on ? reinterpret_cast<long long>(c->entmc_prune_stats.p) : 0);
   return key;
 }
 

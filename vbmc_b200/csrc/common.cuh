@@ -167,9 +167,14 @@ struct vbmc_b200_ctx {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // gplogjoint branch
+  cudaStream_t stream3 = nullptr;  // draw generation (independent of theta)
+  cudaEvent_t ev_fork0 = nullptr, ev_philox = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   long long launches = 0;
   int precision = 64;  // 64: everything FP64; 32: the entropy sweep in FP32 (vbmc_b200_set_precision)
+  double entmc_prune_c = 50.0;  // entmc: skip components that contribute < exp(-c) of q to a whole warp (VBMC_B200_ENTMC_PRUNE, 0 = off)
+  bool entmc_prune_stats_on = false;
+  vb::DevBuf entmc_prune_stats;  // {kept, total} counters (bench)
   int entmc_form = -1;  // -1 auto (device guard), 0 force expanded, 1 force direct (VBMC_B200_ENTMC_FORM)
 
   // multi-GPU
@@ -213,7 +218,7 @@ struct vbmc_b200_ctx {
   uint64_t philox_seed = 0, philox_stream = 0;
 
   // step buffers
-  vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out;
+  vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out, glj_part;
   vb::DevBuf ent_tables;  // FP32 sweep: per-step tables (entmc_f32.cu)
   double* theta_pinned = nullptr;
   double* out_pinned = nullptr;

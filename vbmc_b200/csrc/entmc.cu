@@ -111,9 +111,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
   double* tab_u = reinterpret_cast<double*>(smem + a.off_u);      // [K][DP]
   double4* tab_s = reinterpret_cast<double4*>(smem + a.off_s);    // [K] {r, -0.5||u||^2, ck, ak}
   double* t16 = reinterpret_cast<double*>(smem + a.off_t16);      // [16] 2^(j/16)
+  float2* tab_m = reinterpret_cast<float2*>(smem + a.off_m);      // [K] {||u_jk|| (rounded down), prune_c + log(ck_k/ck_j) (rounded up)}
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + warp;
   unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
   double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);      // [32*D]
+  unsigned char* klist = wbase + a.woff_klist;                        // [K2+2] indices of the components this warp scores
   double2* iq_s = reinterpret_cast<double2*>(wbase + a.woff_iq);      // [32] {1/q+, 1/q-} (optional)
   double2* stage = reinterpret_cast<double2*>(wbase + a.woff_stage);  // [K][32] {e+, e-}, swizzled
   double* wres = reinterpret_cast<double*>(wbase + a.woff_stage);     // [pstride]   (aliases stage)
@@ -152,17 +154,20 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
     __syncthreads();  // previous tile: tables and the wres/stage regions are free again
     {
       const double sj = a.sigma[j];
-      for (int i = tid; i < K2 * DP; i += blockDim.x) {
+      for (int i = tid; i < (K2 + 1) * DP; i += blockDim.x) {  // row K2 (and K when K is odd): dummy component
         const int k = i / DP, d = i - k * DP;
         double u = 0.0;
         if (d < D && k < K) u = (a.mu[j * D + d] - a.mu[k * D + d]) / (a.sigma[k] * a.lambda[d]);
         tab_u[i] = u;
       }
       __syncthreads();
-      for (int k = tid; k < K2; k += blockDim.x) {
+      for (int k = tid; k < K2 + 1; k += blockDim.x) {
         double uu = 0.0;
         for (int d = 0; d < D; ++d) uu = fma(tab_u[k * DP + d], tab_u[k * DP + d], uu);
         tab_s[k] = k < K ? make_double4(sj / a.sigma[k], -0.5 * uu, a.ck[k], a.ak[k]) : make_double4(0.0, 0.0, 0.0, 0.0);
+        // pruning test operands in FP32, rounded so that the test can only err towards keeping a component
+        if (k < K)
+          tab_m[k] = make_float2(__double2float_rd(sqrt(uu) * 0.999999), __double2float_ru(a.prune_c + log(a.ck[k]) - log(a.ck[j]) + 0.5));
       }
     }
     // ---- this thread's draw ----
@@ -198,20 +203,54 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
 #pragma unroll
       for (int d = 0; d < DP; ++d) Ap[d] = Am[d] = 0.0;
       double mhee = 0.0;  // -0.5*||eps||^2
-      if (EXPANDED) {
 #pragma unroll
-        for (int d = 0; d < DP; ++d) mhee = fma(e[d], e[d], mhee);
-        mhee *= -0.5;
+      for (int d = 0; d < DP; ++d) mhee = fma(e[d], e[d], mhee);
+      mhee *= -0.5;
+      // ---- components that can matter for this warp's 32 pairs ----
+      // For every pair of the warp ||eps|| <= emax, so both signs satisfy  -0.5||u_jk +- r eps||^2 <= -0.5 max(0,||u_jk|| - r emax)^2 =: b_k,
+      // while q >= ck_j exp(-0.5 emax^2) (the source component's own term).  A component with
+      //     log ck_k + b_k < log ck_j - 0.5 emax^2 - PRUNE_C
+      // contributes less than exp(-PRUNE_C) = 2e-22 of q (and of T, W) for every pair of the warp: below FP64 round-off.  It is
+      // left out (warp-uniform decision => no divergence); the reference's own exp() underflows to 0 for most of them.
+      int nact = 0;
+      {
+        double mx = -2.0 * mhee;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const float emax = __double2float_ru(sqrt(mx) * 1.000001);
+        const float he2 = 0.5f * emax * emax;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int k = lane + 32 * rr;
+          bool keep = false;
+          if (32 * rr < K && k < K) {
+            const float2 m = tab_m[k];
+            const float t = m.x - __double2float_ru(tab_s[k].x) * emax;
+            const float b = t > 0.0f ? -0.5f * t * t : 0.0f;
+            keep = !(b + he2 + m.y < 0.0f) || a.prune_c <= 0.0;   // NaN keeps
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) klist[nact + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned char>(k);  // compacted, ascending
+          nact += __popc(bal);
+        }
+        if (lane == 0) klist[nact] = static_cast<unsigned char>(K2);  // dummy partner when the count is odd (ck = ak = 0)
+        __syncwarp();
+        if (a.prune_stats && lane == 0) {
+          atomicAdd(a.prune_stats, static_cast<unsigned long long>(nact));
+          atomicAdd(a.prune_stats + 1, static_cast<unsigned long long>(K));
+        }
       }
-      // two components per iteration => four independent exp chains (k, k+1) x (+, -) per thread
+      // two components per iteration => four independent exp chains (ka, kb) x (+, -) per thread
 #pragma unroll 1
-      for (int k = 0; k < K2; k += 2) {
-        const double4 sa = tab_s[k], sb = tab_s[k + 1];  // {r, -0.5||u||^2, ck, ak}
+      for (int ia = 0; ia < nact; ia += 2) {
+        const unsigned kk = *reinterpret_cast<const unsigned short*>(klist + ia);  // two byte indices, one broadcast load
+        const int k = kk & 0xff, kb = kk >> 8;
+        const double4 sa = tab_s[k], sb = tab_s[kb];  // {r, -0.5||u||^2, ck, ak}
         double ua[DP], ub[DP];
 #pragma unroll
         for (int d = 0; d < DP; d += 2) {
           const double2 a2 = *reinterpret_cast<const double2*>(tab_u + k * DP + d);
-          const double2 b2 = *reinterpret_cast<const double2*>(tab_u + (k + 1) * DP + d);
+          const double2 b2 = *reinterpret_cast<const double2*>(tab_u + kb * DP + d);
           ua[d] = a2.x; ua[d + 1] = a2.y;
           ub[d] = b2.x; ub[d + 1] = b2.y;
         }
@@ -248,7 +287,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
         exp_neg4(x, ex, t16);
         if (needW) {
           stage[k * 32 + (lane ^ (k & 7))] = make_double2(ex[0], ex[1]);
-          stage[(k + 1) * 32 + (lane ^ ((k + 1) & 7))] = make_double2(ex[2], ex[3]);
+          if (kb < K2) stage[kb * 32 + (lane ^ (kb & 7))] = make_double2(ex[2], ex[3]);
         }
         qp = fma(sa.z, ex[0], qp);
         qm = fma(sa.z, ex[1], qm);
@@ -285,39 +324,51 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
           Am[d] = e[d] * (tp - tm);
         }
       }
-      // ---- column sums W_l = sum_p e+_l/q+ + e-_l/q-  (lanes over l, p serial) ----
+      // ---- column sums W_l = sum_p e+_l/q+ + e-_l/q-  over the components this warp scored ----
+      // lane i owns the rows klist[i + 32*rr]; rows rr and rr+1 share the 1/q broadcast of each pair; two partial sums per
+      // row (even / odd pairs) keep two DFMA chains in flight
       double wacc[4] = {0.0, 0.0, 0.0, 0.0};
+      int wrow[4] = {-1, -1, -1, -1};
       if (needW) {
         if (a.iq_in_smem) iq_s[lane] = make_double2(iqp, iqm);
         __syncwarp();
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int l = lane + 32 * rr;
-          const bool act = l < K;
-          const double2* row = stage + (act ? l : 0) * 32;
-          const int x = l & 7;
-          double acc = 0.0;
-          if (32 * rr < K) {  // warp-uniform
-            if (a.iq_in_smem) {
-              if (act) {
-#pragma unroll 8
-                for (int p = 0; p < 32; ++p) {
-                  const double2 ee = row[p ^ x];
-                  const double2 iq = iq_s[p];
-                  acc = fma(ee.x, iq.x, acc);
-                  acc = fma(ee.y, iq.y, acc);
-                }
+        for (int r2 = 0; r2 < 4; r2 += 2) {
+          if (32 * r2 < nact) {  // warp-uniform
+            const int ia = lane + 32 * r2, ib = ia + 32;
+            const bool acta = ia < nact, actb = ib < nact;
+            const int la = acta ? klist[ia] : 0, lb = actb ? klist[ib] : 0;
+            const double2* rowa = stage + la * 32;
+            const double2* rowb = stage + lb * 32;
+            const int xa = la & 7, xb = lb & 7;
+            const bool two = 32 * (r2 + 1) < nact;  // warp-uniform
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < 32; p += 2) {
+              double2 q0, q1;
+              if (a.iq_in_smem) {
+                q0 = iq_s[p];
+                q1 = iq_s[p + 1];
+              } else {
+                q0 = make_double2(__shfl_sync(0xffffffffu, iqp, p), __shfl_sync(0xffffffffu, iqm, p));
+                q1 = make_double2(__shfl_sync(0xffffffffu, iqp, p + 1), __shfl_sync(0xffffffffu, iqm, p + 1));
               }
-            } else {
-#pragma unroll 8
-              for (int p = 0; p < 32; ++p) {
-                const double2 ee = row[p ^ x];
-                acc = fma(ee.x, __shfl_sync(0xffffffffu, iqp, p), acc);
-                acc = fma(ee.y, __shfl_sync(0xffffffffu, iqm, p), acc);
+              const double2 ea0 = rowa[p ^ xa], ea1 = rowa[(p + 1) ^ xa];
+              a0 = fma(ea0.x, q0.x, a0);
+              a1 = fma(ea1.x, q1.x, a1);
+              a0 = fma(ea0.y, q0.y, a0);
+              a1 = fma(ea1.y, q1.y, a1);
+              if (two) {
+                const double2 eb0 = rowb[p ^ xb], eb1 = rowb[(p + 1) ^ xb];
+                b0 = fma(eb0.x, q0.x, b0);
+                b1 = fma(eb1.x, q1.x, b1);
+                b0 = fma(eb0.y, q0.y, b0);
+                b1 = fma(eb1.y, q1.y, b1);
               }
             }
+            if (acta) { wacc[r2] = a0 + a1; wrow[r2] = la; }
+            if (actb) { wacc[r2 + 1] = b0 + b1; wrow[r2 + 1] = lb; }
           }
-          wacc[rr] = act ? acc : 0.0;
         }
         __syncwarp();  // stage is free: reuse it as reduction scratch
       }
@@ -343,11 +394,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
       }
       if (!needT)
         for (int i = 1 + lane; i < 1 + 2 * D; i += 32) wres[i] = 0.0;
+      for (int l = lane; l < K; l += 32) wres[1 + 2 * D + l] = 0.0;  // components this warp skipped
+      __syncwarp();
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int l = lane + 32 * rr;
-        if (l < K) wres[1 + 2 * D + l] = wacc[rr];
-      }
+      for (int rr = 0; rr < 4; ++rr)
+        if (wrow[rr] >= 0) wres[1 + 2 * D + wrow[rr]] = wacc[rr];
     } else {
       for (int i = lane; i < a.pstride; i += 32) wres[i] = 0.0;
     }
@@ -358,247 +409,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
       for (int w = 0; w < nw; ++w)
         s += reinterpret_cast<const double*>(smem + a.off_warp + static_cast<size_t>(w) * a.warp_bytes + a.woff_stage)[i];
       a.partial[static_cast<size_t>(tile) * a.pstride + i] = s;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// SEPARABLE form (experimental, VBMC_B200_ENTMC_FORM=separable).  u_jkd = (mu_jd - mu_kd)/(sigma_k lambda_d) factorises, so with et_d = eps_d/lambda_d
-//   eps.u_jk = (et.mu_j - et.mu_k)/sigma_k,        A(+-)_d = (mu_jd S(+-) - Q(+-)_d)/lambda_d,   B(+-) = sigma_j S(+-),
-//   S(+-) = sum_k s_k,  Q(+-)_d = sum_k s_k mu_kd,  s_k = ak_k e(+-)_k / sigma_k.
-// All D-vectors the inner loop needs (mu_k, centred) are now independent of the source component j: they live in
-// the constant bank (c_ent) and reach the FP64 pipe through LDC, not through the shared-memory -> register path that
-// bounded the table-in-shared-memory version (broadcast LDS.128 cost as many SM cycles as the DFMAs they fed).
-// Only three scalars per (j,k) stay in shared memory: -0.5||u_jk||^2, r_jk^2 and sigma_j/sigma_k^2.
-__constant__ double c_ent[4096];
-
-template <int DP, int MAXW>
-__global__ void __launch_bounds__(MAXW * 32, 1) entmc_sep_kernel(const EntmcArgs a) {
-  if (*a.form_flag != 0) return;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int D = a.D, K = a.K;
-  const int K2 = (K + 1) & ~1;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nw = blockDim.x >> 5;
-  double2* tab_a = reinterpret_cast<double2*>(smem + a.off_u);   // [K2] {-0.5||u_jk||^2, r_jk^2}
-  double* tab_b = reinterpret_cast<double*>(smem + a.off_s);     // [K2] sigma_j / sigma_k^2
-  double* t16 = reinterpret_cast<double*>(smem + a.off_t16);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + warp;
-  unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
-  double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);
-  double2* iq_s = reinterpret_cast<double2*>(wbase + a.woff_iq);
-  double2* stage = reinterpret_cast<double2*>(wbase + a.woff_stage);
-  double* wres = reinterpret_cast<double*>(wbase + a.woff_stage);
-  double* red = wres + ((a.pstride + 1) & ~1);
-  const double* cmu = c_ent + a.c_mu;      // [K2][DP] centred means
-  const double* cck = c_ent + a.c_ck;      // [K2]
-  const double* cak = c_ent + a.c_akis;    // [K2] ak_k / sigma_k
-  const double* cil = c_ent + a.c_ilam;    // [DP] 1 / lambda_d
-
-  const bool needT = (a.need & (NEED_MU | NEED_E)) != 0;
-  const bool needW = (a.need & NEED_W) != 0;
-  if (lane == 0) mbar_init(bar, 1);
-  if (tid < 16) t16[tid] = c_t16[tid];
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-
-  uint32_t phase = 0;
-  int tile = blockIdx.x;
-  bool tma_pending = false;
-  auto issue_eps = [&](int t) -> bool {
-    if (t >= a.ntiles) return false;
-    const int j = t / a.tiles_per_comp, tt = t - j * a.tiles_per_comp;
-    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
-    int np = a.pair_end - p0;
-    np = np < 0 ? 0 : (np > 32 ? 32 : np);
-    if (np == 0) return false;
-    const double* src = a.eps + (static_cast<size_t>(j) * a.half + p0) * D;
-    return eps_stage(eps_s, src, np * D, bar, lane);
-  };
-  tma_pending = issue_eps(tile);
-
-  for (; tile < a.ntiles; tile += gridDim.x) {
-    const int j = tile / a.tiles_per_comp, tt = tile - j * a.tiles_per_comp;
-    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
-    int np = a.pair_end - p0;
-    np = np < 0 ? 0 : (np > 32 ? 32 : np);
-    const double sj = a.sigma[j];
-    __syncthreads();  // previous tile: tables and the wres/stage regions are free again
-    for (int k = tid; k < K2; k += blockDim.x) {
-      double2 ta = make_double2(0.0, 0.0);
-      double tb = 0.0;
-      if (k < K) {
-        const double isg = 1.0 / a.sigma[k];
-        double uu = 0.0;
-        for (int d = 0; d < D; ++d) {
-          const double df = (cmu[j * DP + d] - cmu[k * DP + d]) * cil[d];
-          uu = fma(df, df, uu);
-        }
-        ta = make_double2(-0.5 * uu * isg * isg, sj * sj * isg * isg);
-        tb = sj * isg * isg;
-      }
-      tab_a[k] = ta;
-      tab_b[k] = tb;
-    }
-    if (tma_pending) {
-      mbar_wait(bar, phase);
-      phase ^= 1;
-    } else {
-      __syncwarp();
-    }
-    double et[DP];  // eps_d / lambda_d
-    const bool valid = lane < np;
-    double mhee = 0.0, cj = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const double e = (valid && d < D) ? eps_s[lane * D + d] : 0.0;
-      mhee = fma(e, e, mhee);
-      et[d] = e * cil[d];
-      cj = fma(et[d], cmu[j * DP + d], cj);
-    }
-    mhee *= -0.5;
-    __syncwarp();
-    tma_pending = issue_eps(tile + gridDim.x);
-    __syncthreads();  // tables ready
-
-    if (np > 0) {
-      double qp = 0.0, qm = 0.0, Sp = 0.0, Sm = 0.0;
-      double Qp[DP], Qm[DP];
-#pragma unroll
-      for (int d = 0; d < DP; ++d) Qp[d] = Qm[d] = 0.0;
-#pragma unroll 1
-      for (int k = 0; k < K2; k += 2) {
-        const double* mua = cmu + k * DP;
-        const double* mub = mua + DP;
-        double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
-#pragma unroll
-        for (int d = 0; d < DP; d += 2) {
-          da0 = fma(et[d], mua[d], da0);
-          db0 = fma(et[d], mub[d], db0);
-          da1 = fma(et[d + 1], mua[d + 1], da1);
-          db1 = fma(et[d + 1], mub[d + 1], db1);
-        }
-        const double2 ta = tab_a[k], tb = tab_a[k + 1];
-        const double rta = tab_b[k] * (cj - (da0 + da1));      // r_jk * (eps.u_jk)
-        const double rtb = tab_b[k + 1] * (cj - (db0 + db1));
-        const double xba = fma(ta.y, mhee, ta.x), xbb = fma(tb.y, mhee, tb.x);
-        double x[4], ex[4];
-        x[0] = xba - rta; x[1] = xba + rta;
-        x[2] = xbb - rtb; x[3] = xbb + rtb;
-        exp_neg4(x, ex, t16);
-        if (needW) {
-          stage[k * 32 + (lane ^ (k & 7))] = make_double2(ex[0], ex[1]);
-          stage[(k + 1) * 32 + (lane ^ ((k + 1) & 7))] = make_double2(ex[2], ex[3]);
-        }
-        const double cka = cck[k], ckb = cck[k + 1];
-        qp = fma(cka, ex[0], qp);
-        qm = fma(cka, ex[1], qm);
-        qp = fma(ckb, ex[2], qp);
-        qm = fma(ckb, ex[3], qm);
-        if (needT) {
-          const double aka = cak[k], akb = cak[k + 1];
-          const double spa = aka * ex[0], sma = aka * ex[1], spb = akb * ex[2], smb = akb * ex[3];
-          Sp += spa + spb;
-          Sm += sma + smb;
-#pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            Qp[d] = fma(spa, mua[d], Qp[d]);
-            Qm[d] = fma(sma, mua[d], Qm[d]);
-          }
-#pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            Qp[d] = fma(spb, mub[d], Qp[d]);
-            Qm[d] = fma(smb, mub[d], Qm[d]);
-          }
-        }
-      }
-      const double iqp = valid ? 1.0 / qp : 0.0;
-      const double iqm = valid ? 1.0 / qm : 0.0;
-      const double Hs = valid ? log(qp) + log(qm) : 0.0;
-      if (needT) {
-        // T+ = (A+ + eps B+)/q+, T- = (A- - eps B-)/q-;  A = (mu_j S - Q)/lambda, B = sigma_j S, eps = et*lambda
-        const double Bp = sj * Sp, Bm = sj * Sm;
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          const double il = cil[d];
-          const double e = (d < D) ? et[d] / il : 0.0;
-          const double mj = cmu[j * DP + d];
-          const double tp = fma(e, Bp, (mj * Sp - Qp[d]) * il) * iqp;
-          const double tm = fma(-e, Bm, (mj * Sm - Qm[d]) * il) * iqm;
-          Qp[d] = tp + tm;
-          Qm[d] = e * (tp - tm);
-        }
-      }
-      double wacc[4] = {0.0, 0.0, 0.0, 0.0};
-      if (needW) {
-        if (a.iq_in_smem) iq_s[lane] = make_double2(iqp, iqm);
-        __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int l = lane + 32 * rr;
-          const bool act = l < K;
-          const double2* row = stage + (act ? l : 0) * 32;
-          const int x = l & 7;
-          double acc = 0.0;
-          if (32 * rr < K) {
-            if (a.iq_in_smem) {
-              if (act) {
-#pragma unroll 8
-                for (int p = 0; p < 32; ++p) {
-                  const double2 ee = row[p ^ x];
-                  const double2 iq = iq_s[p];
-                  acc = fma(ee.x, iq.x, acc);
-                  acc = fma(ee.y, iq.y, acc);
-                }
-              }
-            } else {
-#pragma unroll 8
-              for (int p = 0; p < 32; ++p) {
-                const double2 ee = row[p ^ x];
-                acc = fma(ee.x, __shfl_sync(0xffffffffu, iqp, p), acc);
-                acc = fma(ee.y, __shfl_sync(0xffffffffu, iqm, p), acc);
-              }
-            }
-          }
-          wacc[rr] = act ? acc : 0.0;
-        }
-        __syncwarp();
-      }
-      red[0 * 33 + lane] = Hs;
-      if (needT) {
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          if (d < D) {
-            red[(1 + d) * 33 + lane] = Qp[d];
-            red[(1 + D + d) * 33 + lane] = Qm[d];
-          }
-        }
-      }
-      __syncwarp();
-      const int nval = needT ? 1 + 2 * D : 1;
-      for (int i = lane; i < nval; i += 32) {
-        const double* rr = red + i * 33;
-        double sacc = 0.0;
-#pragma unroll 8
-        for (int p = 0; p < 32; ++p) sacc += rr[p];
-        wres[i] = sacc;
-      }
-      if (!needT)
-        for (int i = 1 + lane; i < 1 + 2 * D; i += 32) wres[i] = 0.0;
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int l = lane + 32 * rr;
-        if (l < K) wres[1 + 2 * D + l] = wacc[rr];
-      }
-    } else {
-      for (int i = lane; i < a.pstride; i += 32) wres[i] = 0.0;
-    }
-    __syncthreads();
-    for (int i = tid; i < a.pstride; i += blockDim.x) {
-      double sacc = 0.0;
-      for (int w = 0; w < nw; ++w)
-        sacc += reinterpret_cast<const double*>(smem + a.off_warp + static_cast<size_t>(w) * a.warp_bytes + a.woff_stage)[i];
-      a.partial[static_cast<size_t>(tile) * a.pstride + i] = sacc;
     }
   }
 }
@@ -658,10 +468,11 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   // CTA-shared region
   int off = 0;
   const int K2 = (K + 1) & ~1;
-  a.off_u = off; off += K2 * DP * 8;
+  a.off_u = off; off += (K2 + 1) * DP * 8;   // + one dummy row (pads an odd number of active components)
   off = round_up(off, 32);
-  a.off_s = off; off += K2 * 32;
+  a.off_s = off; off += (K2 + 1) * 32;
   a.off_t16 = off; off += 16 * 8;
+  a.off_m = off; off += round_up((K2 + 1) * 8, 16);
   a.off_bar = off; off += 16 * 8;   // one mbarrier per warp (up to 16 warps)
   off = round_up(off, 16);
   a.off_warp = off;
@@ -671,12 +482,13 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   const int stage_bytes = K2 * 32 * (f32 ? 8 : 16);    // {e+, e-} per (component, pair)
   const int iq_bytes = f32 ? 32 * 8 : 32 * 16;
   const int eps_bytes = round_up(ppw * D * 8, 16);
+  const int klist_bytes = round_up(K2 + 2, 16);
   const int scratch_bytes = (round_up(a.pstride, 2) + (1 + 2 * D) * 33) * 8;
   const int stage_alloc = round_up(stage_bytes > scratch_bytes ? stage_bytes : scratch_bytes, 16);
   const size_t avail = c->smem_optin;
   int best_nw = 0, best_iq = 0;
   for (int iq = 1; iq >= (f32 ? 1 : 0); --iq) {
-    const int wb = eps_bytes + (iq ? iq_bytes : 0) + stage_alloc;
+    const int wb = eps_bytes + klist_bytes + (iq ? iq_bytes : 0) + stage_alloc;
     int nw_fit = static_cast<int>((avail - a.off_warp) / wb);
     if (nw_fit > pl->maxw) nw_fit = pl->maxw;
     if (nw_fit >= 4) nw_fit = nw_fit / 4 * 4;  // equal load on the 4 SM sub-partitions (5-7 warps measured no faster than 4)
@@ -691,6 +503,7 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   a.iq_in_smem = best_iq;
   int w = 0;
   a.woff_eps = w; w += eps_bytes;
+  a.woff_klist = w; w += klist_bytes;
   a.woff_iq = w; w += best_iq ? iq_bytes : 0;
   w = round_up(w, 16);
   a.woff_stage = w; w += stage_alloc;
@@ -731,10 +544,8 @@ int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_pe
 
 template <int DP>
 static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
-  auto ksep = entmc_sep_kernel<DP, 8>;
   auto kdir = entmc_kernel<DP, 8, false>;
   auto kexp = entmc_kernel<DP, 8, true>;
-  VB_CUDA(cudaFuncSetAttribute(ksep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   const int grid = pl.ntiles < c->num_sms ? pl.ntiles : c->num_sms;
   VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
@@ -748,14 +559,6 @@ static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
     kdir<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
     VB_CUDA(cudaGetLastError());
   }
-  if (c->entmc_form == 0) {
-    // experimental separable form with constant-bank tables (VBMC_B200_ENTMC_FORM=separable): measured slower
-    // on B200 (0.56 ms vs 0.35 ms at c3) — LDC latency is exposed with two warps per sub-partition.
-    VB_CUDA(cudaMemcpyToSymbolAsync(c_ent, c->vp.cblob, sizeof(double) * c->vp_cblob_len, 0, cudaMemcpyDeviceToDevice, st));
-    KernelScope ks(c, "entmc_separable", st);
-    ksep<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
-    VB_CUDA(cudaGetLastError());
-  }
   return VBMC_B200_OK;
 }
 
@@ -767,12 +570,6 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   EntmcArgs& a = pl.a;
   a.need = need_mask;
   a.form_flag = c->vp.form_flag;
-  {
-    const int K2 = (c->K + 1) & ~1;
-    a.c_mu = 0; a.c_ck = K2 * pl.DP; a.c_akis = a.c_ck + K2; a.c_ilam = a.c_akis + K2;
-    if (a.c_ilam + pl.DP > 4096) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: K=%d, D=%d exceed the constant-bank table", c->K, c->D);
-    if (c->vp_cblob_dp != pl.DP) VB_FAIL(VBMC_B200_ESTATE, "entmc: constant tables were built for another padded dimension");
-  }
   a.eps = c->eps.d();
   a.mu = c->vp.mu;
   a.sigma = c->vp.sigma;
@@ -781,6 +578,9 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   a.ak = c->vp.ak;
   a.partial = c->ent_partial.d();
   a.eps_f32 = c->eps_f32 ? 1 : 0;
+  a.stagger = 0;
+  a.prune_c = c->entmc_prune_c;
+  a.prune_stats = c->entmc_prune_stats_on ? reinterpret_cast<unsigned long long*>(c->entmc_prune_stats.p) : nullptr;
   if (c->precision == 32) return launch_entmc_f32(c, pl, st);
   if (c->eps_f32)
     VB_FAIL(VBMC_B200_ESTATE, "entmc: the resident draws were generated in FP32 mode; upload or regenerate them for the FP64 sweep");

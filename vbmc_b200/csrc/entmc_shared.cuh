@@ -14,6 +14,9 @@ struct EntmcArgs {
   int pstride;               // 1 + 2*D + K doubles per tile partial
   int iq_in_smem;            // 1: 1/q broadcast through shared memory, 0: through shuffles
   int eps_f32;               // 1: eps holds floats (FP32 mode, device generator), 0: doubles
+  int stagger;               // unused (kept for layout stability of experiments)
+  double prune_c;            // components below exp(-prune_c) of q for a whole warp are skipped (<= 0: keep all)
+  unsigned long long* prune_stats;  // optional {kept, total} (warp, component) counters
   const int* form_flag;      // device flag: 2 -> expanded form (default), 1 -> direct, 0 -> separable (experimental)
   int c_mu, c_ck, c_akis, c_ilam;  // offsets (doubles) inside the __constant__ blob c_ent
   const double* eps;         // [K][half][D]
@@ -24,8 +27,8 @@ struct EntmcArgs {
   const double* ak;          // [K]  ck_k/sigma_k
   double* partial;           // [ntiles][pstride]
   // shared-memory carve-up (byte offsets, computed on the host)
-  int off_u, off_s, off_t16, off_bar, off_warp, warp_bytes;
-  int woff_eps, woff_iq, woff_stage;  // offsets inside a warp region
+  int off_u, off_s, off_t16, off_m, off_bar, off_warp, warp_bytes;
+  int woff_eps, woff_iq, woff_stage, woff_klist;  // offsets inside a warp region
 };
 
 // ---- PTX helpers: mbarrier + TMA bulk copy (cp.async.bulk => SASS UBLKCP) ----

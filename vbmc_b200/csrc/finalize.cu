@@ -10,7 +10,7 @@
 namespace vb {
 
 struct UnpackArgs {
-  int D, K, ntheta, have_theta, force_form, DPc;
+  int D, K, ntheta, have_theta, force_form, DPc, want_cblob;
   int opt[4];
   const double* theta;
   const double *base_mu, *base_sigma, *base_lambda, *base_w, *base_eta;
@@ -19,8 +19,17 @@ struct UnpackArgs {
   double* scratch;  // [K*D]
 };
 
-__global__ void vp_unpack_kernel(const UnpackArgs a) {
+// One CTA.  Everything the later phases re-read (mu, sigma, lambda, 1/(sigma lambda)^2) is kept in shared memory, so the
+// kernel's critical path is three block-wide phases instead of a chain of dependent global round trips.
+__global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
+  extern __shared__ double usm[];
   const int D = a.D, K = a.K, tid = threadIdx.x, nt = blockDim.x;
+  double* s_mu = usm;                  // [K*D]
+  double* s_isl2 = s_mu + K * D;       // [K*D]  1/(sigma_k lambda_d)^2
+  double* s_sigma = s_isl2 + K * D;    // [K]
+  double* s_eta = s_sigma + K;         // [K]
+  double* s_lambda = s_eta + K;        // [D]
+  __shared__ double part[256];
   __shared__ double s_es, s_nf;
   const bool ht = a.have_theta != 0;
   int idx = 0;
@@ -30,78 +39,84 @@ __global__ void vp_unpack_kernel(const UnpackArgs a) {
   if (ht && a.opt[1]) idx += K;
   const int o_lam = idx;
   const int o_eta = a.ntheta - K;
-  for (int i = tid; i < D * K; i += nt) a.vp.mu[i] = (ht && a.opt[0]) ? a.theta[o_mu + i] : a.base_mu[i];
+  for (int i = tid; i < D * K; i += nt) {
+    const double m = (ht && a.opt[0]) ? a.theta[o_mu + i] : a.base_mu[i];
+    s_mu[i] = m;
+    a.vp.mu[i] = m;
+  }
+  double es = 0.0;
   for (int k = tid; k < K; k += nt) {
+    double sg, ls;
     if (ht && a.opt[1]) {
-      const double ls = a.theta[o_sig + k];
-      a.vp.lnsigma[k] = ls;
-      a.vp.sigma[k] = exp(ls);  // vp.sigma(1,:) = exp(theta(idx_start+(1:K)))  (:39-42)
+      ls = a.theta[o_sig + k];
+      sg = exp(ls);  // vp.sigma(1,:) = exp(theta(idx_start+(1:K)))  (:39-42)
     } else {
-      a.vp.sigma[k] = a.base_sigma[k];
-      a.vp.lnsigma[k] = log(a.base_sigma[k]);
+      sg = a.base_sigma[k];
+      ls = log(sg);
     }
-    a.vp.eta[k] = (ht && a.opt[3]) ? a.theta[o_eta + k] : a.base_eta[k];
+    a.vp.lnsigma[k] = ls;
+    a.vp.sigma[k] = sg;
+    s_sigma[k] = sg;
+    const double et = (ht && a.opt[3]) ? a.theta[o_eta + k] : a.base_eta[k];
+    a.vp.eta[k] = et;
+    s_eta[k] = et;
+    es += exp(et);  // (:46-47) no max-shift, like the reference
   }
   for (int d = tid; d < D; d += nt) {
+    double lm, ll;
     if (ht && a.opt[2]) {
-      const double ll = a.theta[o_lam + d];
-      a.vp.lnlambda[d] = ll;
-      a.vp.lambda[d] = exp(ll);  // (:43)
+      ll = a.theta[o_lam + d];
+      lm = exp(ll);  // (:43)
     } else {
-      a.vp.lambda[d] = a.base_lambda[d];
-      a.vp.lnlambda[d] = log(a.base_lambda[d]);
+      lm = a.base_lambda[d];
+      ll = log(lm);
     }
+    a.vp.lnlambda[d] = ll;
+    a.vp.lambda[d] = lm;
+    s_lambda[d] = lm;
   }
+  part[tid] = es;
   __syncthreads();
-  {
-    __shared__ double part[256];
-    double es = 0.0;
-    for (int k = tid; k < K; k += nt) es += exp(a.vp.eta[k]);  // (:46-47) no max-shift, like the reference
-    part[tid] = es;
+  for (int off = 128; off > 0; off >>= 1) {
+    if (tid < off) part[tid] += part[tid + off];
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-      if (tid < off) part[tid] += part[tid + off];
-      __syncthreads();
-    }
-    if (tid == 0) s_es = part[0];
   }
   if (tid == 0) {
+    s_es = part[0];
     double pl = 1.0;
-    for (int d = 0; d < D; ++d) pl *= a.vp.lambda[d];
+    for (int d = 0; d < D; ++d) pl *= s_lambda[d];
     s_nf = 1.0 / pow(2.0 * 3.14159265358979323846, 0.5 * D) / pl;  // nf (entmc_vbmc.m:40)
     a.cn[K] = s_nf;
+  }
+  for (int i = tid; i < K * D; i += nt) {
+    const double sl = s_sigma[i / D] * s_lambda[i % D];
+    s_isl2[i] = 1.0 / (sl * sl);
   }
   __syncthreads();
   // ---- choose the entmc formulation for this step (see entmc.cu) ----
   // expanded form error ~ eps_mach * (||u_jk||^2 + r_jk^2 ||eps||^2); keep it below ~1e-10 absolute in d^2.
-  // ||u_jk||^2 = sum_d (mu_jd - mu_kd)^2 * isl2_kd with isl2_kd = 1/(sigma_k lambda_d)^2 (a.scratch, [K][D])
+  // ||u_jk||^2 = sum_d (mu_jd - mu_kd)^2 * isl2_kd with isl2_kd = 1/(sigma_k lambda_d)^2
   {
-    __shared__ double pmax[256];
-    for (int i = tid; i < K * D; i += nt) {
-      const double sl = a.vp.sigma[i / D] * a.vp.lambda[i % D];
-      a.scratch[i] = 1.0 / (sl * sl);
-    }
-    __syncthreads();
     const double eemax = D + 12.0 * sqrt(2.0 * D) + 72.0;  // > 12 sigma bound on ||eps||^2
     double m = 0.0;
     for (int i = tid; i < K * K; i += nt) {
       const int j = i / K, k = i - j * K;
       double uu = 0.0;
       for (int d = 0; d < D; ++d) {
-        const double dm = a.vp.mu[j * D + d] - a.vp.mu[k * D + d];
-        uu = fma(dm * dm, a.scratch[k * D + d], uu);
+        const double dm = s_mu[j * D + d] - s_mu[k * D + d];
+        uu = fma(dm * dm, s_isl2[k * D + d], uu);
       }
-      const double r2 = a.vp.sigma[j] * a.vp.sigma[j] * a.scratch[k * D] * a.vp.lambda[0] * a.vp.lambda[0];
+      const double r2 = s_sigma[j] * s_sigma[j] * s_isl2[k * D] * s_lambda[0] * s_lambda[0];
       const double v = fma(r2, eemax, uu);
       m = (v > m || !(v == v)) ? v : m;
     }
-    pmax[tid] = m;
+    part[tid] = m;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
-      if (tid < off) pmax[tid] = (pmax[tid + off] > pmax[tid] || !(pmax[tid + off] == pmax[tid + off])) ? pmax[tid + off] : pmax[tid];
+      if (tid < off) part[tid] = (part[tid + off] > part[tid] || !(part[tid + off] == part[tid + off])) ? part[tid + off] : part[tid];
       __syncthreads();
     }
-    if (tid == 0) *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((pmax[0] <= 2.0e5) ? 2 : 1);
+    if (tid == 0) *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((part[0] <= 2.0e5) ? 2 : 1);
   }
   const int K2 = (K + 1) & ~1, DPc = a.DPc;
   double* b_mu = a.vp.cblob;              // [K2][DPc] means centred on their average (only differences matter)
@@ -111,9 +126,9 @@ __global__ void vp_unpack_kernel(const UnpackArgs a) {
   for (int k = tid; k < K2; k += nt) {
     double ck = 0.0, aks = 0.0;
     if (k < K) {
-      const double w = (ht && a.opt[3]) ? exp(a.vp.eta[k]) / s_es : a.base_w[k];
+      const double w = (ht && a.opt[3]) ? exp(s_eta[k]) / s_es : a.base_w[k];
       a.vp.w[k] = w;
-      const double sg = a.vp.sigma[k];
+      const double sg = s_sigma[k];
       const double cn = s_nf / pow(sg, static_cast<double>(D));  // nf/sigma(k)^D  (:63)
       a.cn[k] = cn;
       ck = w * cn;
@@ -124,14 +139,16 @@ __global__ void vp_unpack_kernel(const UnpackArgs a) {
     b_ck[k] = ck;
     b_ak[k] = aks;
   }
-  for (int d = tid; d < DPc; d += nt) {
-    double mean = 0.0;
-    if (d < D) {
-      for (int k = 0; k < K; ++k) mean += a.vp.mu[k * D + d];
-      mean /= K;
+  if (a.want_cblob) {  // only the experimental separable entmc form reads the centred means
+    for (int d = tid; d < DPc; d += nt) {
+      double mean = 0.0;
+      if (d < D) {
+        for (int k = 0; k < K; ++k) mean += s_mu[k * D + d];
+        mean /= K;
+      }
+      b_il[d] = d < D ? 1.0 / s_lambda[d] : 0.0;
+      for (int k = 0; k < K2; ++k) b_mu[k * DPc + d] = (d < D && k < K) ? s_mu[k * D + d] - mean : 0.0;
     }
-    b_il[d] = d < D ? 1.0 / a.vp.lambda[d] : 0.0;
-    for (int k = 0; k < K2; ++k) b_mu[k * DPc + d] = (d < D && k < K) ? a.vp.mu[k * D + d] - mean : 0.0;
   }
 }
 
@@ -141,6 +158,7 @@ struct FinArgs {
   int jacobian;    // jacobian_flag
   int what;        // FIN_*
   int use_bnd, nbnd, opt[4];
+  int stage_R;     // R fits in shared memory next to the work arrays
   double TolCon, WThresh, WPen;
   const double* R;
   const double* lb;
@@ -188,7 +206,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   rl.init(D, K, S);
   OutLayout ol;
   ol.init(a.ntheta_out, S, K);
-  const double* R = a.R;
   double* out = a.out;
   double* wsm = sm;            // [K]   softmax(eta)
   double* gHw = wsm + K;       // [K]   entropy w-grad (before J_w)
@@ -197,6 +214,33 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   double* dls = gPw + K;       // [D*K] d(penalty)/d(lnscale)
   double* part = dls + D * K;  // [256]
   double* sc = part + 256;     // scalars: 0 es, 1 H, 2 G, 3 L, 4 Lw, 5 dotH, 6 dotG, 7 dotP
+  // the step's inputs are staged in shared memory once (coalesced, all loads in flight together): the serial sums
+  // below then run at shared-memory latency instead of one L2 round trip per term
+  double* v_mu = sc + 16;          // [K*D]
+  double* v_sigma = v_mu + K * D;  // [K]
+  double* v_w = v_sigma + K;       // [K]
+  double* v_eta = v_w + K;         // [K]
+  double* v_lnsigma = v_eta + K;   // [K]
+  double* v_cn = v_lnsigma + K;    // [K+1]
+  double* v_lambda = v_cn + K + 1; // [D]
+  double* v_lnlambda = v_lambda + D;  // [D]
+  double* sR = v_lnlambda + D;     // [rl.total] when a.stage_R
+  for (int i = tid; i < K * D; i += nt) v_mu[i] = a.vp.mu[i];
+  for (int k = tid; k < K; k += nt) {
+    v_sigma[k] = a.vp.sigma[k];
+    v_w[k] = a.vp.w[k];
+    v_eta[k] = a.vp.eta[k];
+    v_lnsigma[k] = a.vp.lnsigma[k];
+  }
+  for (int k = tid; k < K + 1; k += nt) v_cn[k] = a.cn[k];
+  for (int d = tid; d < D; d += nt) {
+    v_lambda[d] = a.vp.lambda[d];
+    v_lnlambda[d] = a.vp.lnlambda[d];
+  }
+  if (a.stage_R)
+    for (int i = tid; i < rl.total; i += nt) sR[i] = a.R[i];
+  const double* R = a.stage_R ? sR : a.R;
+  __syncthreads();
   const bool doH = a.what != FIN_GPLOGJOINT, doG = a.what != FIN_ENTMC;
   const double invNs = 1.0 / static_cast<double>(a.Ns > 0 ? a.Ns : 1);
   const double invS = 1.0 / static_cast<double>(S > 0 ? S : 1);
@@ -210,7 +254,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
 
   {
     double es = 0.0;
-    for (int k = tid; k < K; k += nt) es += exp(a.vp.eta[k]);
+    for (int k = tid; k < K; k += nt) es += exp(v_eta[k]);
     es = block_sum256(es, part);
     if (tid == 0) {
       sc[0] = es;
@@ -220,7 +264,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   for (int i = tid; i < 8; i += nt) out[i] = 0.0;
   __syncthreads();
   for (int k = tid; k < K; k += nt) {
-    wsm[k] = exp(a.vp.eta[k]) / sc[0];
+    wsm[k] = exp(v_eta[k]) / sc[0];
     gPw[k] = 0.0;
   }
   for (int i = tid; i < 3 * a.ntheta_out; i += nt) out[ol.oDF + i] = 0.0;
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   if (doH) {
     {
       double H = 0.0;
-      for (int j = tid; j < K; j += nt) H -= a.vp.w[j] * R[rl.oHs + j] * invNs;  // :67
+      for (int j = tid; j < K; j += nt) H -= v_w[j] * R[rl.oHs + j] * invNs;  // :67
       H = block_sum256(H, part);
       if (tid == 0) {
         sc[1] = H;
@@ -240,36 +284,36 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     if (a.gf[0])
       for (int i = tid; i < D * K; i += nt) {
         const int j = i / D, d = i - j * D;
-        out[ol.oDH + o_mu + i] = a.vp.w[j] * R[rl.oM + i] * invNs / a.vp.lambda[d];  // :82
+        out[ol.oDH + o_mu + i] = v_w[j] * R[rl.oM + i] * invNs / v_lambda[d];  // :82
       }
     if (a.gf[1])
       for (int j = tid; j < K; j += nt) {
         double acc = 0.0;
         for (int d = 0; d < D; ++d) acc += R[rl.oE + j * D + d];  // :87-88
-        double g = a.vp.w[j] * acc * invNs;
-        if (a.jacobian) g *= a.vp.sigma[j];  // :112-114
+        double g = v_w[j] * acc * invNs;
+        if (a.jacobian) g *= v_sigma[j];  // :112-114
         out[ol.oDH + o_sig + j] = g;
       }
     if (a.gf[2])
       for (int d = tid; d < D; d += nt) {
         double acc = 0.0;
-        for (int j = 0; j < K; ++j) acc += a.vp.w[j] * a.vp.sigma[j] * R[rl.oE + j * D + d];  // :93, :106-108
+        for (int j = 0; j < K; ++j) acc += v_w[j] * v_sigma[j] * R[rl.oE + j * D + d];  // :93, :106-108
         double g = acc * invNs;
-        if (!a.jacobian) g /= a.vp.lambda[d];  // :116-118
+        if (!a.jacobian) g /= v_lambda[d];  // :116-118
         out[ol.oDH + o_lam + d] = g;
       }
     if (a.gf[3])
       for (int l = tid; l < K; l += nt) {
         double acc = 0.0;
-        for (int j = 0; j < K; ++j) acc += a.vp.w[j] * R[rl.oWc + j * K + l];
-        gHw[l] = -R[rl.oHs + l] * invNs - a.cn[l] * acc * invNs;  // :97, :100
+        for (int j = 0; j < K; ++j) acc += v_w[j] * R[rl.oWc + j * K + l];
+        gHw[l] = -R[rl.oHs + l] * invNs - v_cn[l] * acc * invNs;  // :97, :100
       }
   }
   // ------------------------------------------------------------------ expected log joint
   if (doG) {
     {
       double G = 0.0;
-      for (int i = tid; i < S * K; i += nt) G += a.vp.w[i % K] * R[rl.oI + i];  // F(s) += w(k)*I_k  (:203)
+      for (int i = tid; i < S * K; i += nt) G += v_w[i % K] * R[rl.oI + i];  // F(s) += w(k)*I_k  (:203)
       G = block_sum256(G, part) * invS;                                          // mean over s (:398-399)
       if (tid == 0) {
         sc[2] = G;
@@ -279,21 +323,21 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     for (int i = tid; i < S * K; i += nt) out[ol.oIsk + i] = R[rl.oI + i];
     for (int s = tid; s < S; s += nt) {
       double Fs = 0.0;
-      for (int k = 0; k < K; ++k) Fs += a.vp.w[k] * R[rl.oI + s * K + k];
+      for (int k = 0; k < K; ++k) Fs += v_w[k] * R[rl.oI + s * K + k];
       out[ol.oFs + s] = Fs;
     }
     if (a.gf[0])
-      for (int i = tid; i < D * K; i += nt) out[ol.oDG + o_mu + i] = a.vp.w[i / D] * R[rl.oGmu + i] * invS;
+      for (int i = tid; i < D * K; i += nt) out[ol.oDG + o_mu + i] = v_w[i / D] * R[rl.oGmu + i] * invS;
     if (a.gf[1])
       for (int k = tid; k < K; k += nt) {
-        double g = a.vp.w[k] * R[rl.oGsig + k] * invS;
-        if (a.jacobian) g *= a.vp.sigma[k];  // :357-359
+        double g = v_w[k] * R[rl.oGsig + k] * invS;
+        if (a.jacobian) g *= v_sigma[k];  // :357-359
         out[ol.oDG + o_sig + k] = g;
       }
     if (a.gf[2])
       for (int d = tid; d < D; d += nt) {
         double g = R[rl.oGlam + d] * invS;
-        if (a.jacobian) g *= a.vp.lambda[d];  // :361-363
+        if (a.jacobian) g *= v_lambda[d];  // :361-363
         out[ol.oDG + o_lam + d] = g;
       }
     if (a.gf[3])
@@ -315,27 +359,27 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     if (a.opt[0])
       for (int i = tid; i < D * K; i += nt) {
         double dy;
-        lacc += soft_pen(a.vp.mu[i], a.lb[b_mu + i], a.ub[b_mu + i], a.TolCon, &dy);
+        lacc += soft_pen(v_mu[i], a.lb[b_mu + i], a.ub[b_mu + i], a.TolCon, &dy);
         if (a.gf[0]) out[ol.oDF + o_mu + i] = dy;
       }
     if (a.opt[1] || a.opt[2])
       for (int i = tid; i < D * K; i += nt) {
         const int k = i / D, d = i - k * D;
         double dy;
-        lacc += soft_pen(a.vp.lnsigma[k] + a.vp.lnlambda[d], a.lb[b_ls + i], a.ub[b_ls + i], a.TolCon, &dy);
+        lacc += soft_pen(v_lnsigma[k] + v_lnlambda[d], a.lb[b_ls + i], a.ub[b_ls + i], a.TolCon, &dy);
         dls[i] = dy;
       }
     if (a.opt[3])
       for (int k = tid; k < K; k += nt) {
         double dy;
-        lacc += soft_pen(a.vp.eta[k], a.lb[b_eta + k], a.ub[b_eta + k], a.TolCon, &dy);
+        lacc += soft_pen(v_eta[k], a.lb[b_eta + k], a.ub[b_eta + k], a.TolCon, &dy);
         if (a.gf[3]) out[ol.oDF + o_w + k] = dy;
       }
     {
       const double L = block_sum256(lacc, part);
       double Lw = 0.0;
       if (a.opt[3])  // negelcbo_vbmc.m:146-151
-        for (int k = tid; k < K; k += nt) Lw += (a.vp.w[k] < a.WThresh) ? a.vp.w[k] : a.WThresh;
+        for (int k = tid; k < K; k += nt) Lw += (v_w[k] < a.WThresh) ? v_w[k] : a.WThresh;
       Lw = block_sum256(Lw, part);
       if (tid == 0) {
         sc[3] = L;
@@ -355,7 +399,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
         out[ol.oDF + o_lam + d] = acc;
       }
     if (a.opt[3] && a.gf[3])
-      for (int k = tid; k < K; k += nt) gPw[k] = a.WPen * ((a.vp.w[k] < a.WThresh) ? 1.0 : 0.0);  // :155
+      for (int k = tid; k < K; k += nt) gPw[k] = a.WPen * ((v_w[k] < a.WThresh) ? 1.0 : 0.0);  // :155
   }
   __syncthreads();
   // ------------------------------------------------------------------ softmax Jacobian J_w * g
@@ -406,8 +450,12 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   a.vp = c->vp;
   a.cn = c->vp.cn;
   a.scratch = c->vp.scratch;
+  a.want_cblob = c->entmc_form == 0 ? 1 : 0;
+  const size_t smem = sizeof(double) * (2 * static_cast<size_t>(c->D) * c->K + 2 * c->K + c->D);
+  if (smem > 48 * 1024)
+    VB_CUDA(cudaFuncSetAttribute(vp_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   KernelScope ks(c, "vp_unpack", c->stream);
-  vp_unpack_kernel<<<1, 256, 0, c->stream>>>(a);
+  vp_unpack_kernel<<<1, 256, smem, c->stream>>>(a);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
@@ -439,7 +487,12 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
   ol.init(n, a.S, c->K);
   VB_TRY(c->out_dev.reserve(sizeof(double) * ol.total));
   a.out = c->out_dev.d();
-  const size_t smem = sizeof(double) * (4 * c->K + static_cast<size_t>(c->D) * c->K + 256 + 16);
+  RLayout rl;
+  rl.init(c->D, c->K, a.S);
+  size_t smem = sizeof(double) * (4 * c->K + static_cast<size_t>(c->D) * c->K + 256 + 16 +
+                                  static_cast<size_t>(c->D) * c->K + 5 * c->K + 1 + 2 * c->D);
+  a.stage_R = smem + sizeof(double) * rl.total <= c->smem_optin ? 1 : 0;
+  if (a.stage_R) smem += sizeof(double) * rl.total;
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   KernelScope ks(c, "finalize", st);

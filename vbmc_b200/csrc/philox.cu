@@ -2,6 +2,8 @@
 // + Box-Muller.  Replaces MATLAB's global randn stream (ent/entmc_vbmc.m:53), which cannot be
 // reproduced outside MATLAB; draws depend only on (seed, stream, element index), never on the
 // number of GPUs or on the sharding, so any rank can regenerate any slice.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -108,7 +110,9 @@ int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_
   const int per_ctr = f32 ? 4 : 2;
   const long long per_comp = (static_cast<long long>(a.pair_end - a.pair_begin) * D + per_ctr) / per_ctr;
   int bx = static_cast<int>((per_comp + 255) / 256);
-  const int cap = (c->num_sms * 8 + K - 1) / K;
+  // resident blocks per SM are capped so that the gplogjoint branch (own stream) can co-run instead of queueing behind the generator
+  static const int per_sm = getenv("VBMC_B200_PHILOX_BLOCKS_PER_SM") ? atoi(getenv("VBMC_B200_PHILOX_BLOCKS_PER_SM")) : 4;
+  const int cap = (c->num_sms * per_sm + K - 1) / K;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, K);
   KernelScope ks(c, "philox", st);
