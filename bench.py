@@ -324,6 +324,12 @@ def main():
         t_ms, n = ctx.profile_get(name)
         prof[name] = {"ms_per_step": t_ms / nprof, "launches_per_step": n / nprof}
 
+    # ---- how much of the K x K component sweep the entropy kernel actually scores (warp-uniform pruning, csrc/entmc.cu) ----
+    ctx.entmc_prune_stats(True)
+    resident_step(20_000)
+    kept, total = ctx.entmc_prune_stats(False)
+    kept_frac = kept / max(1, total)
+
     # ---- e2e through the public host API: host theta -> F, dF on the host + host Adam ----
     def e2e_loop(nsteps, warm, host_eps=None):
         x = theta0.copy()
@@ -405,6 +411,10 @@ def main():
                         "peak_source": peak_src + " MEASURED_PEAKS.json"},
                 "algorithmic": {"flops_per_launch": counts["entmc_flops"] * shard, "bytes_per_launch": counts["entmc_bytes"] * shard,
                                 "ms_per_launch": ent_ms},
+                "executed": {"kept_fraction": kept_frac, "tflops": ent_tflops * kept_frac if ent_tflops else None,
+                             "frac": ent_tflops * kept_frac / fp64_peak if ent_tflops else None,
+                             "what": "components whose term is < exp(-50) of q for a whole warp of draws are skipped (below FP64 round-off; "
+                                     "parity-tested); `achieved` counts the ALGORITHMIC K^2 Ns (5D+12) flops, `executed` only the scored ones"},
                 "note": "entmc at K=50 has ~78 flop/B: FP64-pipe bound, not HBM bound (SURVEY.md 8d); both fractions reported"}
     cpu = None
     if not args.no_cpu_baseline:

@@ -113,7 +113,7 @@ struct RLayout {
     oGmu = oI + S * K;
     oGsig = oGmu + K * D;
     oGlam = oGsig + K;
-    total = oGlam + D;
+    total = oGlam + K * D;  // GlamK[k][d]: the sum over k is taken in finalize
   }
 };
 

@@ -132,23 +132,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
   uint32_t phase = 0;
   int tile = blockIdx.x;
   bool tma_pending = false;
-  auto issue_eps = [&](int t) -> bool {
+  const int G = a.groups_per_tile, gpairs = nw * 32;  // a tile = G groups of (nw x 32) pairs of one component
+  auto issue_eps = [&](int t, int g) -> bool {
     if (t >= a.ntiles) return false;
     const int j = t / a.tiles_per_comp, tt = t - j * a.tiles_per_comp;
-    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
+    const int p0 = a.pair_begin + tt * a.pairs_per_tile + g * gpairs + warp * 32;
     int np = a.pair_end - p0;
     np = np < 0 ? 0 : (np > 32 ? 32 : np);
     if (np == 0) return false;
     const double* src = a.eps + (static_cast<size_t>(j) * a.half + p0) * D;
     return eps_stage(eps_s, src, np * D, bar, lane);
   };
-  tma_pending = issue_eps(tile);
+  tma_pending = issue_eps(tile, 0);
 
   for (; tile < a.ntiles; tile += gridDim.x) {
     const int j = tile / a.tiles_per_comp, tt = tile - j * a.tiles_per_comp;
-    const int p0 = a.pair_begin + tt * a.pairs_per_tile + warp * 32;
-    int np = a.pair_end - p0;
-    np = np < 0 ? 0 : (np > 32 ? 32 : np);
 
     // ---- per-component tables (shared by all warps of the CTA) ----
     __syncthreads();  // previous tile: tables and the wres/stage regions are free again
@@ -170,6 +168,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
           tab_m[k] = make_float2(__double2float_rd(sqrt(uu) * 0.999999), __double2float_ru(a.prune_c + log(a.ck[k]) - log(a.ck[j]) + 0.5));
       }
     }
+    __syncthreads();  // tables ready
+    // per-lane running sums of this warp's tile result: lane i holds entries i, i+32, ... of [Hs | M[D] | E[D] | W[K]]
+    double racc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+    const int p0 = a.pair_begin + tt * a.pairs_per_tile + g * gpairs + warp * 32;
+    int np = a.pair_end - p0;
+    np = np < 0 ? 0 : (np > 32 ? 32 : np);
     // ---- this thread's draw ----
     if (tma_pending) {
       mbar_wait(bar, phase);
@@ -193,9 +199,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
           if (d < D) e[d] = eps_s[lane * D + d];
       }
     }
-    __syncwarp();  // all lanes have consumed eps_s -> safe to refill it for the next tile
-    tma_pending = issue_eps(tile + gridDim.x);
-    __syncthreads();  // tables ready
+    __syncwarp();  // all lanes have consumed eps_s -> safe to refill it for the next group
+    tma_pending = (g + 1 < G) ? issue_eps(tile, g + 1) : issue_eps(tile + gridDim.x, 0);
 
     if (np > 0) {
       double qp = 0.0, qm = 0.0, Bp = 0.0, Bm = 0.0;
@@ -399,9 +404,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
         if (wrow[rr] >= 0) wres[1 + 2 * D + wrow[rr]] = wacc[rr];
-    } else {
-      for (int i = lane; i < a.pstride; i += 32) wres[i] = 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 6; ++t)
+        if (lane + 32 * t < a.pstride) racc[t] += wres[lane + 32 * t];
+      __syncwarp();  // wres/red alias the stage planes the next group writes
     }
+    }  // groups
+#pragma unroll
+    for (int t = 0; t < 6; ++t)
+      if (lane + 32 * t < a.pstride) wres[lane + 32 * t] = racc[t];
     __syncthreads();  // every warp's wres is complete
     // ---- cross-warp sum (fixed order) -> tile partial ----
     for (int i = tid; i < a.pstride; i += blockDim.x) {
@@ -515,11 +527,14 @@ static int make_plan(vbmc_b200_ctx* c, int Ns, EntmcPlan* pl) {
   pl->nw = nw;
   // FP32 sweep: several groups per tile amortise the table load and the block reduction, while keeping
   // >= ~10 tiles per SM so that the persistent CTAs stay balanced
+  // several groups per tile amortise the table build, the barriers and the block reduction, while keeping >= ~10 tiles
+  // per SM so that the persistent CTAs stay balanced
   int G = 1;
-  if (f32) {
+  {
     const long long groups = static_cast<long long>(K) * ((pl->npairs_local + nw * ppw - 1) / (nw * ppw));
     const long long g = groups / (10LL * c->num_sms);
     G = g < 1 ? 1 : (g > 8 ? 8 : static_cast<int>(g));
+    if (const char* ge = getenv("VBMC_B200_ENTMC_GROUPS")) G = atoi(ge) > 0 ? atoi(ge) : G;
   }
   a.groups_per_tile = G;
   pl->pairs_per_tile = nw * ppw * G;

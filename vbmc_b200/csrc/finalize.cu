@@ -39,12 +39,14 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   if (ht && a.opt[1]) idx += K;
   const int o_lam = idx;
   const int o_eta = a.ntheta - K;
+#pragma unroll 1
   for (int i = tid; i < D * K; i += nt) {
     const double m = (ht && a.opt[0]) ? a.theta[o_mu + i] : a.base_mu[i];
     s_mu[i] = m;
     a.vp.mu[i] = m;
   }
   double es = 0.0;
+#pragma unroll 1
   for (int k = tid; k < K; k += nt) {
     double sg, ls;
     if (ht && a.opt[1]) {
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
     s_eta[k] = et;
     es += exp(et);  // (:46-47) no max-shift, like the reference
   }
+#pragma unroll 1
   for (int d = tid; d < D; d += nt) {
     double lm, ll;
     if (ht && a.opt[2]) {
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   }
   part[tid] = es;
   __syncthreads();
+#pragma unroll 1
   for (int off = 128; off > 0; off >>= 1) {
     if (tid < off) part[tid] += part[tid + off];
     __syncthreads();
@@ -84,10 +88,12 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   if (tid == 0) {
     s_es = part[0];
     double pl = 1.0;
+#pragma unroll 1
     for (int d = 0; d < D; ++d) pl *= s_lambda[d];
     s_nf = 1.0 / pow(2.0 * 3.14159265358979323846, 0.5 * D) / pl;  // nf (entmc_vbmc.m:40)
     a.cn[K] = s_nf;
   }
+#pragma unroll 1
   for (int i = tid; i < K * D; i += nt) {
     const double sl = s_sigma[i / D] * s_lambda[i % D];
     s_isl2[i] = 1.0 / (sl * sl);
@@ -99,9 +105,11 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   {
     const double eemax = D + 12.0 * sqrt(2.0 * D) + 72.0;  // > 12 sigma bound on ||eps||^2
     double m = 0.0;
+#pragma unroll 1
     for (int i = tid; i < K * K; i += nt) {
       const int j = i / K, k = i - j * K;
       double uu = 0.0;
+#pragma unroll 1
       for (int d = 0; d < D; ++d) {
         const double dm = s_mu[j * D + d] - s_mu[k * D + d];
         uu = fma(dm * dm, s_isl2[k * D + d], uu);
@@ -112,6 +120,7 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
     }
     part[tid] = m;
     __syncthreads();
+#pragma unroll 1
     for (int off = 128; off > 0; off >>= 1) {
       if (tid < off) part[tid] = (part[tid + off] > part[tid] || !(part[tid + off] == part[tid + off])) ? part[tid + off] : part[tid];
       __syncthreads();
@@ -123,6 +132,7 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   double* b_ck = b_mu + K2 * DPc;         // [K2]
   double* b_ak = b_ck + K2;               // [K2] ak_k / sigma_k
   double* b_il = b_ak + K2;               // [DPc] 1/lambda_d
+#pragma unroll 1
   for (int k = tid; k < K2; k += nt) {
     double ck = 0.0, aks = 0.0;
     if (k < K) {
@@ -140,13 +150,16 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
     b_ak[k] = aks;
   }
   if (a.want_cblob) {  // only the experimental separable entmc form reads the centred means
+#pragma unroll 1
     for (int d = tid; d < DPc; d += nt) {
       double mean = 0.0;
       if (d < D) {
+#pragma unroll 1
         for (int k = 0; k < K; ++k) mean += s_mu[k * D + d];
         mean /= K;
       }
       b_il[d] = d < D ? 1.0 / s_lambda[d] : 0.0;
+#pragma unroll 1
       for (int k = 0; k < K2; ++k) b_mu[k * DPc + d] = (d < D && k < K) ? s_mu[k * D + d] - mean : 0.0;
     }
   }
@@ -168,7 +181,7 @@ struct FinArgs {
   double* out;
 };
 
-__device__ __forceinline__ double soft_pen(double x, double lb, double ub, double tol, double* dy) {
+__device__ __noinline__ double soft_pen(double x, double lb, double ub, double tol, double* dy) {
   // utils/softbndloss.m:12-27
   const double ell = (ub - lb) * tol;
   double y = 0.0;
@@ -185,18 +198,19 @@ __device__ __forceinline__ double soft_pen(double x, double lb, double ub, doubl
   return y;
 }
 
-// deterministic block-wide sum (fixed tree) of one value per thread; blockDim.x == 256
-__device__ __forceinline__ double block_sum256(double v, double* part) {
+// deterministic block-wide sum (fixed order) of one value per thread; blockDim.x == 256.  Out of line and shuffle based:
+// these one-CTA kernels run once per step with a cold instruction cache, so code size is what they pay for.
+__device__ __noinline__ double block_sum256(double v, double* part) {
   const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   __syncthreads();
-  part[tid] = v;
+  if ((tid & 31) == 0) part[tid >> 5] = v;
   __syncthreads();
-#pragma unroll
-  for (int off = 128; off > 0; off >>= 1) {
-    if (tid < off) part[tid] += part[tid + off];
-    __syncthreads();
-  }
-  return part[0];
+  double t = part[0];
+#pragma unroll 1
+  for (int i = 1; i < 8; ++i) t += part[i];
+  return t;
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
@@ -225,19 +239,24 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   double* v_lambda = v_cn + K + 1; // [D]
   double* v_lnlambda = v_lambda + D;  // [D]
   double* sR = v_lnlambda + D;     // [rl.total] when a.stage_R
+#pragma unroll 1
   for (int i = tid; i < K * D; i += nt) v_mu[i] = a.vp.mu[i];
+#pragma unroll 1
   for (int k = tid; k < K; k += nt) {
     v_sigma[k] = a.vp.sigma[k];
     v_w[k] = a.vp.w[k];
     v_eta[k] = a.vp.eta[k];
     v_lnsigma[k] = a.vp.lnsigma[k];
   }
+#pragma unroll 1
   for (int k = tid; k < K + 1; k += nt) v_cn[k] = a.cn[k];
+#pragma unroll 1
   for (int d = tid; d < D; d += nt) {
     v_lambda[d] = a.vp.lambda[d];
     v_lnlambda[d] = a.vp.lnlambda[d];
   }
   if (a.stage_R)
+#pragma unroll 1
     for (int i = tid; i < rl.total; i += nt) sR[i] = a.R[i];
   const double* R = a.stage_R ? sR : a.R;
   __syncthreads();
@@ -254,6 +273,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
 
   {
     double es = 0.0;
+#pragma unroll 1
     for (int k = tid; k < K; k += nt) es += exp(v_eta[k]);
     es = block_sum256(es, part);
     if (tid == 0) {
@@ -261,12 +281,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       sc[1] = sc[2] = sc[3] = sc[4] = 0.0;
     }
   }
+#pragma unroll 1
   for (int i = tid; i < 8; i += nt) out[i] = 0.0;
   __syncthreads();
+#pragma unroll 1
   for (int k = tid; k < K; k += nt) {
     wsm[k] = exp(v_eta[k]) / sc[0];
     gPw[k] = 0.0;
   }
+#pragma unroll 1
   for (int i = tid; i < 3 * a.ntheta_out; i += nt) out[ol.oDF + i] = 0.0;
   __syncthreads();
 
@@ -274,6 +297,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   if (doH) {
     {
       double H = 0.0;
+#pragma unroll 1
       for (int j = tid; j < K; j += nt) H -= v_w[j] * R[rl.oHs + j] * invNs;  // :67
       H = block_sum256(H, part);
       if (tid == 0) {
@@ -282,29 +306,36 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       }
     }
     if (a.gf[0])
+#pragma unroll 1
       for (int i = tid; i < D * K; i += nt) {
         const int j = i / D, d = i - j * D;
         out[ol.oDH + o_mu + i] = v_w[j] * R[rl.oM + i] * invNs / v_lambda[d];  // :82
       }
     if (a.gf[1])
+#pragma unroll 1
       for (int j = tid; j < K; j += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int d = 0; d < D; ++d) acc += R[rl.oE + j * D + d];  // :87-88
         double g = v_w[j] * acc * invNs;
         if (a.jacobian) g *= v_sigma[j];  // :112-114
         out[ol.oDH + o_sig + j] = g;
       }
     if (a.gf[2])
+#pragma unroll 1
       for (int d = tid; d < D; d += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int j = 0; j < K; ++j) acc += v_w[j] * v_sigma[j] * R[rl.oE + j * D + d];  // :93, :106-108
         double g = acc * invNs;
         if (!a.jacobian) g /= v_lambda[d];  // :116-118
         out[ol.oDH + o_lam + d] = g;
       }
     if (a.gf[3])
+#pragma unroll 1
       for (int l = tid; l < K; l += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int j = 0; j < K; ++j) acc += v_w[j] * R[rl.oWc + j * K + l];
         gHw[l] = -R[rl.oHs + l] * invNs - v_cn[l] * acc * invNs;  // :97, :100
       }
@@ -313,6 +344,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   if (doG) {
     {
       double G = 0.0;
+#pragma unroll 1
       for (int i = tid; i < S * K; i += nt) G += v_w[i % K] * R[rl.oI + i];  // F(s) += w(k)*I_k  (:203)
       G = block_sum256(G, part) * invS;                                          // mean over s (:398-399)
       if (tid == 0) {
@@ -320,29 +352,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
         out[ol.oG] = G;
       }
     }
+#pragma unroll 1
     for (int i = tid; i < S * K; i += nt) out[ol.oIsk + i] = R[rl.oI + i];
+#pragma unroll 1
     for (int s = tid; s < S; s += nt) {
       double Fs = 0.0;
+#pragma unroll 1
       for (int k = 0; k < K; ++k) Fs += v_w[k] * R[rl.oI + s * K + k];
       out[ol.oFs + s] = Fs;
     }
     if (a.gf[0])
+#pragma unroll 1
       for (int i = tid; i < D * K; i += nt) out[ol.oDG + o_mu + i] = v_w[i / D] * R[rl.oGmu + i] * invS;
     if (a.gf[1])
+#pragma unroll 1
       for (int k = tid; k < K; k += nt) {
         double g = v_w[k] * R[rl.oGsig + k] * invS;
         if (a.jacobian) g *= v_sigma[k];  // :357-359
         out[ol.oDG + o_sig + k] = g;
       }
     if (a.gf[2])
+#pragma unroll 1
       for (int d = tid; d < D; d += nt) {
-        double g = R[rl.oGlam + d] * invS;
+        double g = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) g += R[rl.oGlam + k * D + d];  // sum_k w_k (...)  (gplogjoint.m:248-252)
+        g *= invS;
         if (a.jacobian) g *= v_lambda[d];  // :361-363
         out[ol.oDG + o_lam + d] = g;
       }
     if (a.gf[3])
+#pragma unroll 1
       for (int k = tid; k < K; k += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int s = 0; s < S; ++s) acc += R[rl.oI + s * K + k];
         gGw[k] = acc * invS;  // w_grad(k,s) = I_k  (:269-271), mean over s
       }
@@ -357,12 +400,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     b_eta = nb; if (a.opt[3]) nb += K;
     double lacc = 0.0;
     if (a.opt[0])
+#pragma unroll 1
       for (int i = tid; i < D * K; i += nt) {
         double dy;
         lacc += soft_pen(v_mu[i], a.lb[b_mu + i], a.ub[b_mu + i], a.TolCon, &dy);
         if (a.gf[0]) out[ol.oDF + o_mu + i] = dy;
       }
     if (a.opt[1] || a.opt[2])
+#pragma unroll 1
       for (int i = tid; i < D * K; i += nt) {
         const int k = i / D, d = i - k * D;
         double dy;
@@ -370,6 +415,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
         dls[i] = dy;
       }
     if (a.opt[3])
+#pragma unroll 1
       for (int k = tid; k < K; k += nt) {
         double dy;
         lacc += soft_pen(v_eta[k], a.lb[b_eta + k], a.ub[b_eta + k], a.TolCon, &dy);
@@ -379,6 +425,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       const double L = block_sum256(lacc, part);
       double Lw = 0.0;
       if (a.opt[3])  // negelcbo_vbmc.m:146-151
+#pragma unroll 1
         for (int k = tid; k < K; k += nt) Lw += (v_w[k] < a.WThresh) ? v_w[k] : a.WThresh;
       Lw = block_sum256(Lw, part);
       if (tid == 0) {
@@ -387,18 +434,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       }
     }
     if (a.opt[1] && a.gf[1])
+#pragma unroll 1
       for (int k = tid; k < K; k += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int d = 0; d < D; ++d) acc += dls[k * D + d];  // dsigma = sum(dlnscale,1)  (:52)
         out[ol.oDF + o_sig + k] = acc;
       }
     if (a.opt[2] && a.gf[2])
+#pragma unroll 1
       for (int d = tid; d < D; d += nt) {
         double acc = 0.0;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) acc += dls[k * D + d];  // dlambda = sum(dlnscale,2)  (:57)
         out[ol.oDF + o_lam + d] = acc;
       }
     if (a.opt[3] && a.gf[3])
+#pragma unroll 1
       for (int k = tid; k < K; k += nt) gPw[k] = a.WPen * ((v_w[k] < a.WThresh) ? 1.0 : 0.0);  // :155
   }
   __syncthreads();
@@ -406,6 +458,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   // J_w = diag(e/es) - e e'/es^2  =>  (J_w g)_i = wsm_i (g_i - sum_l wsm_l g_l)   (gplogjoint.m:366-368)
   if (a.gf[3]) {
     double dh = 0.0, dg = 0.0, dp = 0.0;
+#pragma unroll 1
     for (int l = tid; l < K; l += nt) {
       if (doH) dh += wsm[l] * gHw[l];
       if (doG) dg += wsm[l] * gGw[l];
@@ -418,6 +471,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       sc[5] = dh; sc[6] = dg; sc[7] = dp;
     }
     __syncthreads();
+#pragma unroll 1
     for (int k = tid; k < K; k += nt) {
       if (doH) out[ol.oDH + o_w + k] = a.jacobian ? wsm[k] * (gHw[k] - sc[5]) : gHw[k];
       if (doG) out[ol.oDG + o_w + k] = a.jacobian ? wsm[k] * (gGw[k] - sc[6]) : gGw[k];
@@ -427,6 +481,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   __syncthreads();
   // ------------------------------------------------------------------ F, dF
   if (a.what == FIN_NEGELCBO) {
+#pragma unroll 1
     for (int i = tid; i < a.ntheta_out; i += nt)
       out[ol.oDF + i] = -out[ol.oDG + i] - out[ol.oDH + i] + out[ol.oDF + i];  // dF = -dG - dH (+ dL)
     if (tid == 0) out[ol.oF] = -sc[2] - sc[1] + sc[3] + sc[4];               // F = -G - H (+ L)

@@ -149,41 +149,38 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
   }
 }
 
-// R.I[s][k] (all S rows: zero outside the local shard), R.Gmu[k][d], R.Gsig[k], R.Glam[d]
-__global__ void __launch_bounds__(256) glj_reduce_kernel(const double* __restrict__ out, int ostride, int D, int K, int S,
+// R.I[s][k] (all S rows: zero outside the local shard), R.Gmu[k][d], R.Gsig[k], R.GlamK[k][d] = w_k * sum_s glam[s][k][d]
+// (finalize adds the K rows of GlamK).  One thread per output, the <= S loads of a thread are independent.
+__global__ void __launch_bounds__(128) glj_reduce_kernel(const double* __restrict__ out, int ostride, int D, int K, int S,
                                                          int s_begin, int s_count, const double* __restrict__ w,
                                                          double* __restrict__ RI, double* __restrict__ Gmu,
-                                                         double* __restrict__ Gsig, double* __restrict__ Glam) {
-  extern __shared__ double tmp[];  // [K*D]  w_k * sum_s glam[s][k][d]
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < S * K; i += nt) {
+                                                         double* __restrict__ Gsig, double* __restrict__ GlamK) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nI = S * K, nM = K * D;
+  if (i < nI) {
     const int s = i / K;
     RI[i] = (s >= s_begin && s < s_begin + s_count) ? out[static_cast<size_t>(i) * ostride] : 0.0;
+    return;
   }
-  for (int i = tid; i < K * D; i += nt) {
-    const int k = i / D, d = i - k * D;
-    double gm = 0.0, gl = 0.0;
-#pragma unroll 4
-    for (int s = s_begin; s < s_begin + s_count; ++s) {
-      const double* o = out + (static_cast<size_t>(s) * K + k) * ostride;
-      gm += o[2 + d];
-      gl += o[2 + D + d];
-    }
-    Gmu[i] = gm;
-    tmp[i] = w[k] * gl;
+  int r = i - nI, off, k;
+  double scale = 1.0;
+  double* dst;
+  if (r < nM) {
+    k = r / D; off = 2 + (r - k * D); dst = Gmu + r;
+  } else if (r < nM + K) {
+    k = r - nM; off = 1; dst = Gsig + k;
+  } else if (r < 2 * nM + K) {
+    r -= nM + K;
+    k = r / D; off = 2 + D + (r - k * D); dst = GlamK + r; scale = w[k];
+  } else {
+    return;
   }
-  for (int k = tid; k < K; k += nt) {
-    double acc = 0.0;
-#pragma unroll 4
-    for (int s = s_begin; s < s_begin + s_count; ++s) acc += out[(static_cast<size_t>(s) * K + k) * ostride + 1];
-    Gsig[k] = acc;
-  }
-  __syncthreads();
-  for (int d = tid; d < D; d += nt) {
-    double acc = 0.0;
-    for (int k = 0; k < K; ++k) acc += tmp[k * D + d];
-    Glam[d] = acc;
-  }
+  const double* o = out + (static_cast<size_t>(s_begin) * K + k) * ostride + off;
+  const size_t step = static_cast<size_t>(K) * ostride;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int s = 0; s < s_count; ++s) acc += o[s * step];
+  *dst = scale * acc;
 }
 
 static int pick_dp(int D) {
@@ -457,8 +454,9 @@ int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st) {
   shard_range(c->gp.S, c->nranks, c->rank, &sb, &se);
   double* R = c->R_dev.d();
   KernelScope ks(c, "reduce", st);
-  glj_reduce_kernel<<<1, 256, sizeof(double) * c->K * c->D, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w,
-                                       R + rl.oI, R + rl.oGmu, R + rl.oGsig, R + rl.oGlam);
+  const int nout = c->gp.S * c->K + 2 * c->K * c->D + c->K;
+  glj_reduce_kernel<<<(nout + 127) / 128, 128, 0, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w,
+                                                       R + rl.oI, R + rl.oGmu, R + rl.oGsig, R + rl.oGlam);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
