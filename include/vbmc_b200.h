@@ -109,6 +109,17 @@ int vbmc_b200_gp_attach(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const d
 int vbmc_b200_gp_post(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, double* alpha, double* L,
                       double* sW1, double* sn2_mult, int* Lchol);
 
+/* [ymu,ys2,fmu,fs2,lp] = gplite_pred(gp,Xstar,ystar,s2star,ssflag) — gplite/gplite_pred.m:1-163 for the attached posterior
+ * (SE-ARD covfun, meanfun 0/1/4, no integrated mean, no output warping: the VBMC defaults).
+ * Xstar: Nstar x D column-major; ystar, s2star: Nstar or NULL.  want_var == 0 is nargout == 1 (means only).
+ * Outputs (any may be NULL): Nstar x S column-major when ssflag != 0 or S == 1, else Nstar (averaged over the
+ * samples, :153-163); lp is always Nstar x S (the reference never averages it) and needs ystar and want_var. */
+int vbmc_b200_gp_pred(vbmc_b200_ctx* ctx, int Nstar, const double* Xstar, const double* ystar, const double* s2star,
+                      int ssflag, int want_var, double* ymu, double* ys2, double* fmu, double* fs2, double* lp);
+/* gp.post(s).sn2_mult of an attached posterior (S values; 1 after vbmc_b200_gp_attach, set by vbmc_b200_gp_post):
+ * gplite_pred.m:119 scales the test-point noise with it. */
+int vbmc_b200_gp_set_sn2_mult(vbmc_b200_ctx* ctx, const double* sn2_mult);
+
 /* Hyper-prior of gplite_nlZ (gplite/gplite_hypprior.m:18-58); arrays of length Nhyp. */
 typedef struct vbmc_b200_hprior {
   const double* mu;

@@ -1035,3 +1035,63 @@ def fminadam(fun, x0, LB=None, UB=None, TolFun=None, MaxIter=None, master_stepsi
     x = xtab[:, it - batchsize:it].mean(axis=1)             # :95
     f = float(np.mean(ftab[it - batchsize:it]))             # :96
     return x, f, xtab[:, :it].copy(), ftab[:it].copy(), it
+
+
+def gplite_pred(gp, Xstar, ystar=None, s2star=None, ssflag=False, nowarpflag=False, nargout=2):
+    """[ymu,ys2,fmu,fs2,lp] = gplite_pred(gp,Xstar,ystar,s2star,ssflag,nowarpflag), gplite/gplite_pred.m:1-163
+    (SE-ARD covfun, no integrated mean function, no output warping)."""
+    X = gp["X"]
+    N, D = X.shape
+    Ns = len(gp["post"])
+    Xstar = np.atleast_2d(np.asarray(Xstar, dtype=np.float64))
+    Nstar = Xstar.shape[0]
+    if ystar is not None and np.size(ystar) != Nstar:
+        raise OracleError("gplite_pred:ydimmismatch", "YSTAR should be empty or a column vector of NSTAR observations.")
+    if s2star is not None and np.size(s2star) != Nstar:
+        raise OracleError("gplite_pred:s2dimmismatch", "S2STAR should be empty or a column vector of NSTAR estimated variances.")
+    fmu = np.zeros((Nstar, Ns))
+    ymu = np.zeros((Nstar, Ns))
+    fs2 = np.zeros((Nstar, Ns))
+    ys2 = np.zeros((Nstar, Ns))
+    lp = np.zeros((Nstar, Ns)) if (ystar is not None and nargout > 4) else None
+    Ncov, Nnoise, Nmean = gp["Ncov"], gp["Nnoise"], gp["Nmean"]
+    for s, post in enumerate(gp["post"]):
+        hyp = np.asarray(post["hyp"], dtype=np.float64).ravel()
+        alpha, L, Lchol = post["alpha"], post["L"], post["Lchol"]
+        sW = np.asarray(post["sW"], dtype=np.float64).ravel()
+        sn2_mult = post.get("sn2_mult", 1.0)
+        sn2_star = gplite_noisefun(hyp[Ncov:Ncov + Nnoise], Xstar, gp["noisefun"], ystar, s2star)   # :60-61
+        if isinstance(sn2_star, tuple):
+            sn2_star = sn2_star[0]
+        mstar = gplite_meanfun(hyp[Ncov + Nnoise:Ncov + Nnoise + Nmean], Xstar, gp["meanfun"])      # :64-65
+        if isinstance(mstar, tuple):
+            mstar = mstar[0]
+        ell = np.exp(hyp[:D])
+        sf2 = math.exp(2 * hyp[D])
+        Ks = sf2 * np.exp(-sq_dist(X.T / ell[:, None], Xstar.T / ell[:, None]) / 2)                 # :68-71
+        kss = sf2 * np.ones(Nstar)                                                                    # :72
+        fmu[:, s] = mstar + Ks.T @ alpha                                                              # :80
+        ymu[:, s] = fmu[:, s]                                                                         # :92
+        if nargout > 1:
+            if Lchol:
+                V = sla.solve_triangular(L, sW[:, None] * Ks, trans="T", lower=False)                 # :97
+                fs2[:, s] = kss - np.sum(V * V, axis=0)                                               # :98
+            else:
+                fs2[:, s] = kss + np.sum(Ks * (L @ Ks), axis=0)                                       # :100-101
+            fs2[:, s] = np.maximum(fs2[:, s], 0)                                                      # :118
+            ys2[:, s] = fs2[:, s] + sn2_star * sn2_mult                                               # :119
+            if lp is not None:
+                lp[:, s] = -0.5 * (np.ravel(ystar) - ymu[:, s]) ** 2 / ys2[:, s] - 0.5 * np.log(2 * math.pi * ys2[:, s])   # :124
+    if Ns > 1 and not ssflag:                                                                         # :153-163
+        fbar = fmu.sum(axis=1) / Ns
+        ybar = ymu.sum(axis=1) / Ns
+        if nargout > 1:
+            vf = ((fmu - fbar[:, None]) ** 2).sum(axis=1) / (Ns - 1)
+            fs2 = fs2.sum(axis=1) / Ns + vf
+            vy = ((ymu - ybar[:, None]) ** 2).sum(axis=1) / (Ns - 1)
+            ys2 = ys2.sum(axis=1) / Ns + vy
+        fmu, ymu = fbar, ybar
+    elif Ns == 1:
+        pass
+    out = (ymu, ys2 if nargout > 1 else None, fmu, fs2 if nargout > 1 else None, lp)
+    return out[:max(1, nargout)]

@@ -1,0 +1,128 @@
+"""gplite_pred (gplite/gplite_pred.m:1-163): oracle identities (CPU) and CUDA-vs-oracle parity through the C ABI (GPU)."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import vbmc_oracle as orc
+from vbmc_b200 import workloads
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def _mk(D, N, S, seed=0, target="rosenbrock", noisy=False, **kw):
+    cfg = dict(D=D, N=N, K=2, S=S, Ns=4, target=target, noisy=noisy, **kw)
+    return workloads.build(cfg, orc.gplite_post, seeds=(seed + 1, seed + 2, seed + 3, seed + 4), with_eps=False)
+
+
+# ---------------------------------------------------------------------------------------------- oracle (CPU)
+def test_oracle_pred_matches_dense_gaussian_conditioning():
+    """fmu, fs2 against the textbook formulas with an explicit (K + Sigma)^-1 (independent of the factor algebra)."""
+    w = _mk(3, 35, 2)
+    gp = w["gp"]
+    X, y = gp["X"], gp["y"]
+    Xs = np.random.default_rng(5).standard_normal((6, 3))
+    ymu, ys2, fmu, fs2 = orc.gplite_pred(gp, Xs, ssflag=True, nargout=4)
+    for s, post in enumerate(gp["post"]):
+        h = post["hyp"]
+        ell, sf2, sn2 = np.exp(h[:3]), math.exp(2 * h[3]), math.exp(2 * h[4])
+        k = lambda A, B: sf2 * np.exp(-0.5 * (((A[:, None, :] - B[None, :, :]) / ell) ** 2).sum(-1))
+        m = lambda A: h[5] - 0.5 * (((A - h[6:9]) / np.exp(h[9:12])) ** 2).sum(-1)
+        Kn = k(X, X) + sn2 * post["sn2_mult"] * np.eye(len(y))
+        Ks = k(X, Xs)
+        assert rel(fmu[:, s], m(Xs) + Ks.T @ np.linalg.solve(Kn, y - m(X))) < 1e-8
+        assert rel(fs2[:, s], sf2 - np.sum(Ks * np.linalg.solve(Kn, Ks), axis=0)) < 1e-6
+        assert rel(ys2[:, s], fs2[:, s] + sn2 * post["sn2_mult"]) < 1e-12
+
+
+def test_oracle_pred_sample_average_and_lp():
+    w = _mk(2, 30, 5)
+    gp = w["gp"]
+    Xs = np.random.default_rng(6).standard_normal((4, 2))
+    ys = np.random.default_rng(7).standard_normal(4)
+    ymu_s, ys2_s, fmu_s, fs2_s, lp = orc.gplite_pred(gp, Xs, ys, None, True, nargout=5)
+    ymu, ys2, fmu, fs2 = orc.gplite_pred(gp, Xs, nargout=4)
+    assert rel(fmu, fmu_s.mean(1)) < 1e-14
+    assert rel(fs2, fs2_s.mean(1) + fmu_s.var(1, ddof=1)) < 1e-13           # :157-158
+    assert rel(ys2, ys2_s.mean(1) + ymu_s.var(1, ddof=1)) < 1e-13
+    assert rel(lp, -0.5 * (ys[:, None] - ymu_s) ** 2 / ys2_s - 0.5 * np.log(2 * math.pi * ys2_s)) < 1e-14
+    with pytest.raises(orc.OracleError):
+        orc.gplite_pred(gp, Xs, ystar=np.zeros(3))
+
+
+# ---------------------------------------------------------------------------------------------- CUDA (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [dict(D=2, N=50, S=8), dict(D=1, N=20, S=1), dict(D=5, N=130, S=3), dict(D=10, N=300, S=4, target="lumpy")],
+                         ids=lambda s: "D{D}N{N}S{S}".format(**s))
+@pytest.mark.parametrize("Nstar", [1, 37])
+def test_pred_matches_oracle(gpu_ctx, shape, Nstar):
+    import vbmc_b200
+    w = _mk(**shape)
+    gp = w["gp"]
+    D = shape["D"]
+    r = np.random.default_rng(11)
+    Xs = np.concatenate([gp["X"][:Nstar // 2] + 0.05 * r.standard_normal((Nstar // 2, D)), 1.5 * r.standard_normal((Nstar - Nstar // 2, D))])
+    ys = r.standard_normal(Nstar)
+    for ssflag in (False, True):
+        got = vbmc_b200.gplite_pred(gp, Xs, ys, None, ssflag, nargout=5)
+        ref = orc.gplite_pred(gp, Xs, ys, None, ssflag, nargout=5)
+        for g, o, name in zip(got, ref, ("ymu", "ys2", "fmu", "fs2", "lp")):
+            assert g.shape == o.shape, name
+            # fs2 = kss - sum(V.^2) cancels: compare on the scale of kss (the reference has the same cancellation)
+            scale = np.max(np.abs(o)) if name not in ("fs2", "ys2") else max(np.max(np.abs(o)), math.exp(2 * gp["post"][0]["hyp"][D]))
+            # lp divides by ys2 = fs2 + sn2 with sn2 ~ 1e-5: the round-off of the cancellation in fs2 (~1e-16 kss, in the
+            # reference as well) is amplified by kss/ys2 ~ 1e5..1e7
+            assert np.max(np.abs(g - o)) / scale < (1e-6 if name == "lp" else TOL), name
+    (ymu,) = vbmc_b200.gplite_pred(gp, Xs, nargout=1)
+    assert rel(ymu, orc.gplite_pred(gp, Xs, nargout=1)[0]) < TOL
+
+
+@pytest.mark.gpu
+def test_pred_after_device_refit_and_noisy_gp(gpu_ctx):
+    """Posterior computed by vbmc_b200.gplite_post (factors stay on the device, leading dimension Np) + user noise s2star."""
+    import vbmc_b200
+    w = _mk(4, 90, 3, noisy=True)
+    X, y, s2, hyp = w["X"], w["y"], w["s2"], w["hyp"]
+    gp_dev = vbmc_b200.gplite_post(hyp, X, y, 1, 4, [1, 1, 0], s2, want_L=False)
+    gp_ref = orc.gplite_post(hyp, X, y, 1, 4, [1, 1, 0], s2)
+    r = np.random.default_rng(3)
+    Xs, s2s = r.standard_normal((25, 4)), 0.5 + r.random(25)
+    got = vbmc_b200.gplite_pred(gp_dev, Xs, None, s2s, True, nargout=4)
+    ref = orc.gplite_pred(gp_ref, Xs, None, s2s, True, nargout=4)
+    for g, o in zip(got, ref):
+        assert rel(g, o) < 1e-9
+
+
+@pytest.mark.gpu
+def test_pred_low_noise_inverse_form_posterior(gpu_ctx):
+    """Lchol == 0: post.L = -inv(K+Sigma) handed over by the host (gplite_pred.m:100-102)."""
+    import vbmc_b200
+    w = _mk(2, 40, 2, log_sn=0.5 * math.log(1e-7))
+    gp = w["gp"]
+    assert not any(p["Lchol"] for p in gp["post"])
+    Xs = np.random.default_rng(4).standard_normal((9, 2))
+    got = vbmc_b200.gplite_pred(gp, Xs, None, None, True, nargout=4)
+    ref = orc.gplite_pred(gp, Xs, None, None, True, nargout=4)
+    assert rel(got[2], ref[2]) < 1e-8
+    sf2 = math.exp(2 * gp["post"][0]["hyp"][2])
+    # sn2 = 1e-7 makes K + Sigma numerically singular (cond ~ 1e10): kss + sum(Ks.*(L*Ks)) with an explicit inverse carries
+    # round-off of order cond * eps * kss in the reference too (half of its values clamp to 0)
+    assert np.max(np.abs(got[3] - ref[3])) / sf2 < 1e-5
+
+
+@pytest.mark.gpu
+def test_pred_errors(gpu_ctx):
+    import vbmc_b200
+    w = _mk(2, 30, 2)
+    with pytest.raises(vbmc_b200.VbmcB200Error) as e:
+        vbmc_b200.gplite_pred(w["gp"], np.zeros((3, 2)), ystar=np.zeros(4))
+    assert e.value.identifier == "gplite_pred:ydimmismatch"
+    with pytest.raises(vbmc_b200.VbmcB200Error) as e:
+        vbmc_b200.gplite_pred(w["gp"], np.zeros((3, 2)), s2star=np.zeros(2))
+    assert e.value.identifier == "gplite_pred:s2dimmismatch"

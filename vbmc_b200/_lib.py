@@ -88,7 +88,7 @@ EXPORTS = [
     "vbmc_b200_eps_upload", "vbmc_b200_eps_philox", "vbmc_b200_negelcbo", "vbmc_b200_entmc", "vbmc_b200_gplogjoint",
     "vbmc_b200_negelcbo_resident_loop", "vbmc_b200_profile_enable", "vbmc_b200_profile_get",
     "vbmc_b200_profile_reset", "vbmc_b200_measure_fp64_peak", "vbmc_b200_measure_hbm_copy", "vbmc_b200_flush_l2",
-    "vbmc_b200_philox_raw", "vbmc_b200_shard_range", "vbmc_b200_fminadam", "vbmc_b200_entmc_prune", "vbmc_b200_entmc_prune_stats",
+    "vbmc_b200_philox_raw", "vbmc_b200_shard_range", "vbmc_b200_fminadam", "vbmc_b200_entmc_prune", "vbmc_b200_entmc_prune_stats", "vbmc_b200_gp_pred", "vbmc_b200_gp_set_sn2_mult",
 ]
 
 _lib = None
@@ -127,6 +127,9 @@ def load():
     lib.vbmc_b200_negelcbo_resident_loop.argtypes = [vp, C.POINTER(NegelcboArgs), C.c_int, C.POINTER(C.c_float)]
     lib.vbmc_b200_entmc_prune.argtypes = [vp, C.c_double]
     lib.vbmc_b200_entmc_prune_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.vbmc_b200_gp_pred.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p,
+                                      c_double_p, c_double_p, c_double_p]
+    lib.vbmc_b200_gp_set_sn2_mult.argtypes = [vp, c_double_p]
     lib.vbmc_b200_fminadam.argtypes = [vp, C.POINTER(FminadamArgs)]
     lib.vbmc_b200_entmc.argtypes = [vp, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p, C.c_uint64, C.c_uint64,
                                     c_double_p, c_double_p]

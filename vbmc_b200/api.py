@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import VbmcB200Error, dptr, f64
 
 __all__ = [
-    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ",
+    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ", "gplite_pred",
     "vpbounds", "rescale_params", "get_vptheta", "VbmcB200Error",
 ]
 
@@ -146,6 +146,8 @@ class Context:
             L = np.ascontiguousarray(np.stack([f64(p["L"]).T for p in post]))  # each column-major
         _lib.check(self.lib.vbmc_b200_gp_attach(self._h, C.byref(d), dptr(alpha), dptr(sW1),
                                                 Lchol.ctypes.data_as(_lib.c_int_p), dptr(L)))
+        mult = f64([float(p.get("sn2_mult", 1.0) or 1.0) for p in post])
+        _lib.check(self.lib.vbmc_b200_gp_set_sn2_mult(self._h, dptr(mult)))
         self._gp_key = key
 
     # -- VP ---------------------------------------------------------------------------------
@@ -524,6 +526,42 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     ctx._gp_key = (id(gp), gp["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
                    float(hyp[-1, -1]), True)   # the factors stay on the device whether or not they were copied out
     return gp
+
+
+def gplite_pred(gp, Xstar, ystar=None, s2star=None, ssflag=False, nowarpflag=False, *, nargout=2, ctx=None):
+    """[ymu,ys2,fmu,fs2,lp] = gplite_pred(gp,Xstar,ystar,s2star,ssflag,nowarpflag), gplite/gplite_pred.m:1-163.
+
+    Arrays come back as (Nstar, S) when ``ssflag`` (or one sample), else (Nstar,); ``lp`` is (Nstar, S) or None.
+    """
+    ctx = ctx or default_context()
+    Xs = f64(Xstar)
+    if Xs.ndim == 1:
+        Xs = Xs[None, :]
+    Nstar = Xs.shape[0]
+    ystar = None if ystar is None or np.size(ystar) == 0 else f64(ystar).ravel()
+    s2star = None if s2star is None or np.size(s2star) == 0 else f64(s2star).ravel()
+    if ystar is not None and ystar.size != Nstar:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_pred:ydimmismatch: YSTAR should be empty or a column vector of NSTAR observations.")
+    if s2star is not None and s2star.size != Nstar:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_pred:s2dimmismatch: S2STAR should be empty or a column vector of NSTAR estimated variances.")
+    if gp.get("intmeanfun") or gp.get("outwarpfun"):
+        raise VbmcB200Error(_lib.EUNSUPPORTED, "vbmc_b200:OutOfScope: integrated mean functions / output warping (not VBMC defaults)")
+    want_var = nargout > 1
+    ctx.gp_attach(gp, want_L=want_var)
+    S = len(gp["post"])
+    sep = bool(ssflag) or S == 1
+    ncol = S if sep else 1
+    Xc = np.ascontiguousarray(Xs.T)   # column-major Nstar x D
+    mk = lambda n: np.zeros((n, Nstar))
+    ymu, fmu = mk(ncol), mk(ncol)
+    ys2 = mk(ncol) if want_var else None
+    fs2 = mk(ncol) if want_var else None
+    lp = mk(S) if (ystar is not None and nargout > 4) else None
+    _lib.check(ctx.lib.vbmc_b200_gp_pred(ctx.handle, Nstar, dptr(Xc), dptr(ystar), dptr(s2star), int(bool(ssflag)), int(want_var),
+                                         dptr(ymu), dptr(ys2), dptr(fmu), dptr(fs2), dptr(lp)))
+    shape = (lambda a: None if a is None else (a.T.copy() if sep else a[0].copy()))
+    out = (shape(ymu), shape(ys2), shape(fmu), shape(fs2), None if lp is None else lp.T.copy())
+    return out[:max(1, nargout)]
 
 
 def gplite_nlZ(hyp, gp, hprior=None, *, nargout=1, ctx=None):

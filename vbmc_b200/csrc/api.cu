@@ -131,7 +131,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->predWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -297,6 +297,9 @@ int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const doub
   if (Lchol)
     for (size_t s = 0; s < S; ++s) c->gpLchol[s] = Lchol[s];
   c->gpLfactor = c->gpLchol;
+  c->gpSn2mult.assign(S, 1.0);
+  c->gpHypHost.assign(g->hyp, g->hyp + S * g->Nhyp);
+  for (int i = 0; i < 3; ++i) c->gp_noisefun[i] = g->noisefun[i];
   c->gp.N = g->N; c->gp.D = g->D; c->gp.S = g->S; c->gp.Nhyp = g->Nhyp;
   c->gp.Ncov = Ncov; c->gp.Nnoise = Nnoise; c->gp.Nmean = Nmean; c->gp.meanfun = g->meanfun;
   c->gp.X = c->gpX.d();

@@ -1035,6 +1035,8 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
   c->gpLchol = rr.Lchol;
   c->gpLfactor.assign(S, 1);  // the device keeps R with R'R = K + sn2_mult*diag(sn2) for the low-noise samples too
   c->gpSn2mult = rr.mult;
+  c->gpHypHost.assign(gd->hyp, gd->hyp + static_cast<size_t>(S) * gd->Nhyp);
+  for (int i = 0; i < 3; ++i) c->gp_noisefun[i] = gd->noisefun[i];
   c->gpHasL = true;
   c->gpLd = Np;
   c->gp.N = N; c->gp.D = gd->D; c->gp.S = S; c->gp.Nhyp = gd->Nhyp;

@@ -430,6 +430,30 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
 }
 
 
+// V = R' \ Z in place for `ncols` right-hand sides per sample (Z: [S][ncols][N]) against the resident factors; samples whose
+// resident matrix is -inv(K+Sigma) instead of a factor get W = K^-1 Z (gplite_pred.m:96-102).
+int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* isfac_dev, cudaStream_t st) {
+  const int S = c->gp.S;
+  bool any_inv = false;
+  for (int s = 0; s < S; ++s) any_inv = any_inv || !c->gpLfactor[s];
+  VarArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = c->gp.N; a.D = c->gp.D; a.K = ncols; a.S = S; a.ld = c->gpLd;
+  a.Lstride = static_cast<size_t>(c->gpLd) * c->gpLd;
+  a.L = c->gpL.d();
+  a.gp = c->gp; a.vp = c->vp;
+  a.Z = Z; a.W = W; a.isfac = isfac_dev; a.unit_rhs = 0;
+  {
+    KernelScope ks(c, "pred_trsm", st);
+    VB_TRY(launch_var_kernel(c, VK_FWD, a, ncols, S, 64 * 65, 64, st, "gplite_pred"));
+  }
+  if (any_inv) {
+    KernelScope ks(c, "pred_symv", st);
+    VB_TRY(launch_var_kernel(c, VK_SYMV, a, ncols, S, 0, 0, st, "gplite_pred"));
+  }
+  return VBMC_B200_OK;
+}
+
 // X = R^-T (lower triangular) of sample `s`, written column-major with leading dimension N into `out`.
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out) {
   VarArgs a;
