@@ -133,6 +133,10 @@ typedef struct vbmc_b200_hprior {
 int vbmc_b200_gp_nlz(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const vbmc_b200_hprior* hprior,
                      double* nlZ, double* dnlZ);
 
+/* nlZ[s] = gplite_nlZ(hyp(:,s),gp,hprior), s = 1..gp->S, value only, as ONE batched Gram + Cholesky:
+ * what gplite_train.m evaluates one call at a time for the fminfill design (:200-204) and the slice sampler (:318-330). */
+int vbmc_b200_gp_nlz_batch(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const vbmc_b200_hprior* hprior, double* nlZ);
+
 /* ---------------------------------------------------------------------------------------
  * VP struct (reference type: misc/setupvars_vbmc.m:78-99)
  * ------------------------------------------------------------------------------------- */

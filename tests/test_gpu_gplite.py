@@ -207,3 +207,24 @@ def test_gplite_nlZ_gradient_c5_points(gpu_ctx):
     ref = orc.gplite_nlZ(hyp[:, 0], gp, None, nargout=2)
     assert rel(nlZ, ref[0]) < 1e-10
     assert rel(dnlZ, ref[1]) < 1e-6   # inv(A) entries carry cond(A)*eps; cond(A) ~ 1e8 for 4000 clustered points
+
+
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_gplite_nlZ_batch_matches_single_calls(gpu_ctx, with_prior):
+    """S hyper-parameter vectors in one batched factorisation == S reference calls of gplite_nlZ (gplite_train.m:200-204)."""
+    import vbmc_b200
+    N, D, S = 150, 4, 7
+    X, y, s2, hyp = problem(N, D, S)
+    hyp = hyp.copy()
+    hyp[:D, 3] += 0.7          # spread the design
+    hyp[D + 1, 5] = math.log(0.5)
+    ref_gp = orc.gplite_post(hyp[:, :1], X, y, 1, 4, [1, 0, 0], None)
+    hp = None
+    if with_prior:
+        Nh = hyp.shape[0]
+        hp = dict(mu=np.zeros(Nh), sigma=2.0 * np.ones(Nh), df=np.array([0, 3, 7, np.inf] * Nh)[:Nh].astype(float))
+    got = vbmc_b200.gplite_nlZ_batch(hyp, ref_gp, hp)
+    ref = np.array([orc.gplite_nlZ(hyp[:, s], ref_gp, hp, nargout=1)[0] for s in range(S)])
+    assert got.shape == (S,) and rel(got, ref) < TOL
+    (got2,) = vbmc_b200.gplite_nlZ(hyp, ref_gp, hp, nargout=1)
+    assert np.array_equal(got, got2)

@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import VbmcB200Error, dptr, f64
 
 __all__ = [
-    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ", "gplite_pred",
+    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ", "gplite_nlZ_batch", "gplite_pred",
     "vpbounds", "rescale_params", "get_vptheta", "VbmcB200Error",
 ]
 
@@ -528,6 +528,34 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     return gp
 
 
+def gplite_nlZ_batch(hyp, gp, hprior=None, *, ctx=None):
+    """nlZ[s] = gplite_nlZ(hyp[:, s], gp, hprior) for all columns of ``hyp`` in one batched factorisation (value only):
+    the evaluations gplite_train.m makes one at a time (fminfill design :200-204, slice sampler :318-330)."""
+    ctx = ctx or default_context()
+    hyp = f64(hyp)
+    if hyp.ndim == 1:
+        hyp = hyp[:, None]
+    Nhyp, Ns = hyp.shape
+    D = gp["X"].shape[1]
+    Ncov, Nnoise, Nmean = D + 1, _noise_count(gp["noisefun"]), _mean_count(D, gp["meanfun"])
+    if Nmean is None or Nhyp != Ncov + Nnoise + Nmean:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_nlZ:dimmismatch: Number of hyperparameters mismatched with dimension of training inputs.")
+    keep = []
+    d, _ = ctx._gp_desc(gp, np.ascontiguousarray(hyp.T), keep)
+    hp = None
+    if hprior is not None:
+        hp = _lib.HPrior()
+        mu, sg = f64(hprior["mu"]).ravel(), f64(hprior["sigma"]).ravel()
+        df = hprior.get("df")
+        df = None if df is None or np.size(df) == 0 else f64(df).ravel()
+        hp.mu, hp.sigma, hp.df = dptr(mu), dptr(sg), dptr(df)
+        keep += [mu, sg, df]
+    out = np.zeros(Ns)
+    _lib.check(ctx.lib.vbmc_b200_gp_nlz_batch(ctx.handle, C.byref(d), None if hp is None else C.byref(hp), dptr(out)))
+    ctx._gp_key = None  # the GP work buffers were reused
+    return out
+
+
 def gplite_pred(gp, Xstar, ystar=None, s2star=None, ssflag=False, nowarpflag=False, *, nargout=2, ctx=None):
     """[ymu,ys2,fmu,fs2,lp] = gplite_pred(gp,Xstar,ystar,s2star,ssflag,nowarpflag), gplite/gplite_pred.m:1-163.
 
@@ -577,6 +605,8 @@ def gplite_nlZ(hyp, gp, hprior=None, *, nargout=1, ctx=None):
         raise VbmcB200Error(_lib.EREFERENCE, "gplite_nlZ:dimmismatch: Number of hyperparameters mismatched with dimension of training inputs.")
     if nargout > 1 and Ns > 1:
         raise VbmcB200Error(_lib.EREFERENCE, "gplite_nlZ:NoSampling: Computation of the log marginal likelihood is available only for one-sample hyperparameter inputs.")
+    if Ns > 1:
+        return (gplite_nlZ_batch(hyp, gp, hprior, ctx=ctx),)
     keep = []
     d, _ = ctx._gp_desc(gp, np.ascontiguousarray(hyp[:, :1].T), keep)
     hp = None

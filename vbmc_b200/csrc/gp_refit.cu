@@ -1047,6 +1047,31 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
   return VBMC_B200_OK;
 }
 
+// nlZ of sample s from the factorisation results, minus the log hyper-prior (gplite_core.m:193, gplite_nlZ.m:57-66,
+// gplite_hypprior.m:24-58; O(Nhyp) on the host)
+static double nlz_value(const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hprior, const RefitResult& rr, int s) {
+  const int N = gd->N;
+  // nlZ = (y-m)'*alpha/2 + sum(log(diag(L))) + N*log(2*pi*sl)/2   (:193);  (y-m)'alpha = z'z/sl
+  double v = 0.5 * rr.zz[s] / rr.sl[s] + rr.logdet[s] + 0.5 * N * log(2.0 * 3.14159265358979323846 * rr.sl[s]);
+  if (hprior && hprior->mu && hprior->sigma) {
+    const double* hyp = gd->hyp + static_cast<size_t>(s) * gd->Nhyp;
+    double lp = 0.0;
+    for (int i = 0; i < gd->Nhyp; ++i) {
+      const double mu = hprior->mu[i], sg = fabs(hprior->sigma[i]);
+      const double df = hprior->df ? hprior->df[i] : 7.0;
+      if (!isfinite(mu) || !isfinite(sg)) continue;  // uniform
+      const double z2 = ((hyp[i] - mu) / sg) * ((hyp[i] - mu) / sg);
+      if (df == 0.0 || !isfinite(df))
+        lp -= 0.5 * (log(2.0 * 3.14159265358979323846 * sg * sg) + z2);
+      else if (df > 0.0)
+        lp += lgamma(0.5 * (df + 1.0)) - lgamma(0.5 * df) - 0.5 * log(3.14159265358979323846 * df) - log(sg) -
+              0.5 * (df + 1.0) * log1p(z2 / df);
+    }
+    v -= lp;
+  }
+  return v;
+}
+
 int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hprior, double* nlZ,
                      double* dnlZ) {
   if (!c || !nlZ) VB_FAIL(VBMC_B200_EINVAL, "null argument");
@@ -1064,23 +1089,7 @@ int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b
   RefitResult rr;
   VB_TRY(refit_core(c, gd, Ncov, Nnoise, Nmean, &rr));
   const int N = gd->N, D = gd->D;
-  // nlZ = (y-m)'*alpha/2 + sum(log(diag(L))) + N*log(2*pi*sl)/2   (:193);  (y-m)'alpha = z'z/sl
-  double v = 0.5 * rr.zz[0] / rr.sl[0] + rr.logdet[0] + 0.5 * N * log(2.0 * 3.14159265358979323846 * rr.sl[0]);
-  if (hprior && hprior->mu && hprior->sigma) {  // gplite_hypprior.m:24-58 (host: O(Nhyp))
-    double lp = 0.0;
-    for (int i = 0; i < gd->Nhyp; ++i) {
-      const double mu = hprior->mu[i], sg = fabs(hprior->sigma[i]);
-      const double df = hprior->df ? hprior->df[i] : 7.0;
-      if (!isfinite(mu) || !isfinite(sg)) continue;  // uniform
-      const double z2 = ((gd->hyp[i] - mu) / sg) * ((gd->hyp[i] - mu) / sg);
-      if (df == 0.0 || !isfinite(df))
-        lp -= 0.5 * (log(2.0 * 3.14159265358979323846 * sg * sg) + z2);
-      else if (df > 0.0)
-        lp += lgamma(0.5 * (df + 1.0)) - lgamma(0.5 * df) - 0.5 * log(3.14159265358979323846 * df) - log(sg) -
-              0.5 * (df + 1.0) * log1p(z2 / df);
-    }
-    v -= lp;
-  }
+  const double v = nlz_value(gd, hprior, rr, 0);
   *nlZ = v;
   if (!dnlZ) return VBMC_B200_OK;
   // ---- gradient (gplite_core.m:226-261) ----
@@ -1156,6 +1165,24 @@ int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b
       dnlZ[i] -= dlp;
     }
   }
+  return VBMC_B200_OK;
+}
+
+// nlZ(s) = gplite_nlZ(hyp(:,s), gp, hprior) for S hyper-parameter vectors in ONE batched factorisation (value only).
+// The reference evaluates them one call at a time: the space-filling design of gplite_train.m:200-204 (fminfill ->
+// gpoptimize_fun -> gplite_nlZ, Ninit vectors) and every slice-sampler step (gplite_train.m:318-330).
+int vbmc_b200_gp_nlz_batch(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hprior, double* nlZ) {
+  if (!c || !nlZ) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  int Ncov, Nnoise, Nmean;
+  VB_TRY(check_desc(gd, &Ncov, &Nnoise, &Nmean, "gp_nlz_batch"));
+  if (gd->Nhyp != Ncov + Nnoise + Nmean)
+    VB_FAIL(VBMC_B200_EREFERENCE,
+            "gplite_nlZ:dimmismatch: Number of hyperparameters mismatched with dimension of training inputs.");
+  VB_CUDA(cudaSetDevice(c->device));
+  c->gp_ready = false;  // the GP buffers are reused
+  RefitResult rr;
+  VB_TRY(refit_core(c, gd, Ncov, Nnoise, Nmean, &rr));
+  for (int s = 0; s < gd->S; ++s) nlZ[s] = nlz_value(gd, hprior, rr, s);
   return VBMC_B200_OK;
 }
 
