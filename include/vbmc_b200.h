@@ -120,6 +120,13 @@ int vbmc_b200_gp_pred(vbmc_b200_ctx* ctx, int Nstar, const double* Xstar, const 
  * gplite_pred.m:119 scales the test-point noise with it. */
 int vbmc_b200_gp_set_sn2_mult(vbmc_b200_ctx* ctx, const double* sn2_mult);
 
+/* gp = gplite_post(gp,xstar,ystar,[],[],[],[],1) — the rank-one update of gplite/gplite_post.m:50-92,173-251 applied to the
+ * resident posterior (Cholesky branch; constant or output-dependent noise, no s2: with s2 the reference itself refits).
+ * xstar: D values.  Optional outputs: alpha (N+1) x S, the new factor column (N+1) x S (L_new = [L c; 0 d]), sW_new S.
+ * The context's GP then has N+1 training points (private/activesample_vbmc.m:483 calls this once per acquired point). */
+int vbmc_b200_gp_post_update1(vbmc_b200_ctx* ctx, const double* xstar, double ystar, double* alpha, double* Lcol,
+                              double* sW_new);
+
 /* Hyper-prior of gplite_nlZ (gplite/gplite_hypprior.m:18-58); arrays of length Nhyp. */
 typedef struct vbmc_b200_hprior {
   const double* mu;

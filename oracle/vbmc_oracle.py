@@ -1095,3 +1095,60 @@ def gplite_pred(gp, Xstar, ystar=None, s2star=None, ssflag=False, nowarpflag=Fal
         pass
     out = (ymu, ys2 if nargout > 1 else None, fmu, fs2 if nargout > 1 else None, lp)
     return out[:max(1, nargout)]
+
+
+def gplite_post_update1(gp, xstar, ystar, s2star=None):
+    """gp = gplite_post(gp,xstar,ystar,[],[],[],s2star,1): rank-one update, gplite/gplite_post.m:50-92,173-251.
+    With s2star the reference falls back to the standard update with the enlarged training set (:78-91)."""
+    xstar = np.atleast_2d(np.asarray(xstar, dtype=np.float64))
+    if xstar.shape[0] > 1:
+        raise OracleError("gplite_post:NotRankOne", "GPLITE_POST with this input format only supports rank-one updates.")
+    if gp is None:
+        raise OracleError("gplite_post:NoGP", "GPLITE_POST can perform rank-one update only with an existing GP struct.")
+    ystar = float(np.ravel(ystar)[0])
+    D = gp["X"].shape[1]
+    if s2star is not None or gp.get("intmeanfun", 0):
+        hyp = np.stack([p["hyp"] for p in gp["post"]], axis=1)
+        s2 = None if s2star is None else np.append(np.ravel(gp["s2"]), np.ravel(s2star))
+        return gplite_post(hyp, np.vstack([gp["X"], xstar]), np.append(gp["y"], ystar), gp["covfun"], gp["meanfun"], gp["noisefun"], s2)
+    Ncov, Nnoise = gp["Ncov"], gp["Nnoise"]
+    mstar, vstar = gplite_pred(gp, xstar, np.array([ystar]), None, True, True, nargout=2)     # :191
+    new = dict(gp)
+    new["post"] = []
+    for s, post in enumerate(gp["post"]):
+        hyp = np.asarray(post["hyp"], dtype=np.float64).ravel()
+        sn2 = gplite_noisefun(hyp[Ncov:Ncov + Nnoise], xstar, gp["noisefun"], np.array([ystar]), None)   # :207-208
+        if isinstance(sn2, tuple):
+            sn2 = sn2[0]
+        sn2 = float(np.ravel(sn2)[0])
+        sn2_eff = sn2 * post["sn2_mult"]                                                      # :209
+        ell = np.exp(hyp[:D])
+        sf2 = math.exp(2 * hyp[D])
+        K = sf2
+        Ks = sf2 * np.exp(-sq_dist(gp["X"].T / ell[:, None], xstar.T / ell[:, None]) / 2)   # :215-217 (N x 1)
+        L, Lchol = post["L"], post["Lchol"]
+        if Lchol:                                                                             # :227-233
+            c = sla.solve_triangular(L, Ks, trans="T", lower=False) / sn2_eff
+            alpha_update = sla.solve_triangular(L, sla.solve_triangular(L, Ks, trans="T", lower=False), lower=False) / sn2_eff
+            n = L.shape[0]
+            Lnew = np.zeros((n + 1, n + 1))
+            Lnew[:n, :n] = L
+            Lnew[:n, n] = c[:, 0]
+            Lnew[n, n] = math.sqrt(1 + K / sn2_eff - float(c[:, 0] @ c[:, 0]))
+        else:                                                                                 # :234-238
+            alpha_update = -L @ Ks
+            v = -alpha_update / vstar[0, s]
+            n = L.shape[0]
+            Lnew = np.zeros((n + 1, n + 1))
+            Lnew[:n, :n] = L + v @ alpha_update.T
+            Lnew[:n, n] = -v[:, 0]
+            Lnew[n, :n] = -v[:, 0]
+            Lnew[n, n] = -1 / vstar[0, s]
+        p = dict(post)
+        p["L"] = Lnew
+        p["sW"] = np.append(np.ravel(post["sW"]), 1 / math.sqrt(sn2_eff))                     # :242
+        p["alpha"] = np.append(post["alpha"], 0.0) + (mstar[0, s] - ystar) / vstar[0, s] * np.append(alpha_update[:, 0], -1.0)   # :245-247
+        new["post"].append(p)
+    new["X"] = np.vstack([gp["X"], xstar])                                                    # :251-253
+    new["y"] = np.append(gp["y"], ystar)
+    return new

@@ -126,3 +126,62 @@ def test_pred_errors(gpu_ctx):
     with pytest.raises(vbmc_b200.VbmcB200Error) as e:
         vbmc_b200.gplite_pred(w["gp"], np.zeros((3, 2)), s2star=np.zeros(2))
     assert e.value.identifier == "gplite_pred:s2dimmismatch"
+
+
+# ---------------------------------------------------------------------------------------------- rank-one update
+def test_oracle_rank1_equals_full_refit():
+    """gplite_test.m:87-105: a sequence of rank-one updates reproduces the posterior of the full refit."""
+    w = _mk(3, 40, 2, log_sn=math.log(0.05))
+    X, y, hyp = w["X"], w["y"], w["hyp"]
+    full = orc.gplite_post(hyp, X, y, 1, 4, [1, 0, 0], None)
+    gp1 = orc.gplite_post(hyp, X[:32], y[:32], 1, 4, [1, 0, 0], None)
+    for i in range(32, 40):
+        gp1 = orc.gplite_post_update1(gp1, X[i], y[i])
+    for s in range(2):
+        assert rel(gp1["post"][s]["alpha"], full["post"][s]["alpha"]) < 1e-7
+        assert rel(gp1["post"][s]["L"], full["post"][s]["L"]) < 1e-9
+        assert rel(gp1["post"][s]["sW"], full["post"][s]["sW"]) < 1e-13
+    with pytest.raises(orc.OracleError):
+        orc.gplite_post_update1(gp1, X[:2], y[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [True, False], ids=["after_gp_post", "attached_from_host"])
+def test_rank1_update_matches_oracle(gpu_ctx, resident):
+    """Eight successive updates on the device (factor buffer grows past its leading dimension when attached from the host)."""
+    import vbmc_b200
+    w = _mk(4, 70, 3, log_sn=math.log(0.05))
+    X, y, hyp = w["X"], w["y"], w["hyp"]
+    n0 = 62   # the factor of a 62-point GP is padded to 64 columns: updates 63, 64 fit, 65 forces the buffer to grow
+    ref = orc.gplite_post(hyp, X[:n0], y[:n0], 1, 4, [1, 0, 0], None)
+    gp = vbmc_b200.gplite_post(hyp, X[:n0], y[:n0], 1, 4, [1, 0, 0], None, want_L=True) if resident else ref
+    for i in range(n0, 70):
+        gp = vbmc_b200.gplite_post_update1(gp, X[i], y[i])
+        ref = orc.gplite_post_update1(ref, X[i], y[i])
+        for s in range(3):
+            assert rel(gp["post"][s]["alpha"], ref["post"][s]["alpha"]) < 1e-8
+            assert rel(gp["post"][s]["L"], ref["post"][s]["L"]) < 1e-10
+            assert rel(gp["post"][s]["sW"], ref["post"][s]["sW"]) < 1e-13
+    assert gp["X"].shape == (70, 4) and gp["y"].shape == (70,)
+    # the updated posterior is the one resident on the device: predictions and a negelcbo step use it
+    Xs = np.random.default_rng(2).standard_normal((5, 4))
+    got = vbmc_b200.gplite_pred(gp, Xs, None, None, True, nargout=4)
+    exp = orc.gplite_pred(ref, Xs, None, None, True, nargout=4)
+    sf2 = math.exp(2 * hyp[4, 0])
+    assert rel(got[2], exp[2]) < 1e-8 and np.max(np.abs(got[3] - exp[3])) / sf2 < 1e-9
+    full = orc.gplite_post(hyp, X, y, 1, 4, [1, 0, 0], None)
+    assert rel(gp["post"][0]["alpha"], full["post"][0]["alpha"]) < 1e-6
+
+
+@pytest.mark.gpu
+def test_rank1_update_with_s2_falls_back_to_refit(gpu_ctx):
+    import vbmc_b200
+    w = _mk(3, 40, 2, noisy=True)
+    X, y, s2, hyp = w["X"], w["y"], w["s2"], w["hyp"]
+    gp = vbmc_b200.gplite_post(hyp, X[:39], y[:39], 1, 4, [1, 1, 0], s2[:39])
+    gp = vbmc_b200.gplite_post_update1(gp, X[39], y[39], s2[39])
+    ref = orc.gplite_post(hyp, X, y, 1, 4, [1, 1, 0], s2)
+    assert gp["X"].shape == (40, 3) and rel(gp["post"][1]["alpha"], ref["post"][1]["alpha"]) < 1e-8
+    with pytest.raises(vbmc_b200.VbmcB200Error) as e:
+        vbmc_b200.gplite_post_update1(gp, X[:2], y[0])
+    assert e.value.identifier == "gplite_post:NotRankOne"

@@ -28,7 +28,7 @@ from . import _lib
 from ._lib import VbmcB200Error, dptr, f64
 
 __all__ = [
-    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ", "gplite_nlZ_batch", "gplite_pred",
+    "Context", "default_context", "negelcbo_vbmc", "fminadam_negelcbo", "gplogjoint", "entmc_vbmc", "gplite_post", "gplite_nlZ", "gplite_nlZ_batch", "gplite_pred", "gplite_post_update1",
     "vpbounds", "rescale_params", "get_vptheta", "VbmcB200Error",
 ]
 
@@ -526,6 +526,56 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     ctx._gp_key = (id(gp), gp["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
                    float(hyp[-1, -1]), True)   # the factors stay on the device whether or not they were copied out
     return gp
+
+
+def gplite_post_update1(gp, xstar, ystar, s2star=None, *, ctx=None):
+    """gp = gplite_post(gp,xstar,ystar,[],[],[],s2star,1) — rank-one update (gplite/gplite_post.m:50-92,173-251) of the
+    posterior resident on the GPU.  With ``s2star`` (heteroskedastic noise) the reference itself performs the standard
+    update with the enlarged training set (:78-91): so does this mirror (full GPU refit)."""
+    ctx = ctx or default_context()
+    xs = f64(xstar)
+    if xs.ndim > 1 and xs.shape[0] > 1:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_post:NotRankOne: GPLITE_POST with this input format only supports rank-one updates.")
+    if gp is None:
+        raise VbmcB200Error(_lib.EREFERENCE, "gplite_post:NoGP: GPLITE_POST can perform rank-one update only with an existing GP struct.")
+    xs = xs.ravel()
+    ystar = float(np.ravel(ystar)[0])
+    X, y = f64(gp["X"]), f64(gp["y"]).ravel()
+    N, D = X.shape
+    post = gp["post"]
+    S = len(post)
+    if s2star is not None and np.size(s2star) > 0 or gp.get("intmeanfun", 0):
+        hyp = np.stack([f64(p["hyp"]).ravel() for p in post], axis=1)
+        s2 = None if s2star is None else np.append(f64(gp["s2"]).ravel(), f64(s2star).ravel())
+        return gplite_post(hyp, np.vstack([X, xs[None, :]]), np.append(y, ystar), gp["covfun"], gp["meanfun"], gp["noisefun"], s2,
+                           ctx=ctx, want_L=any(p.get("L") is not None for p in post))
+    have_L = all(p.get("L") is not None for p in post)
+    resident = ctx._gp_key is not None and ctx._gp_key[0] == id(gp) and ctx._gp_key[-1]
+    if not resident:
+        ctx.gp_attach(gp, want_L=True)   # raises vbmc_b200:noL when the factors are neither resident nor in the struct
+    alpha = np.zeros((S, N + 1))
+    Lcol = np.zeros((S, N + 1))
+    sWn = np.zeros(S)
+    _lib.check(ctx.lib.vbmc_b200_gp_post_update1(ctx.handle, dptr(xs), ystar, dptr(alpha), dptr(Lcol), dptr(sWn)))
+    new = dict(gp)
+    new["X"] = np.vstack([X, xs[None, :]])
+    new["y"] = np.append(y, ystar)
+    new["post"] = []
+    for s, p in enumerate(post):
+        q = dict(p)
+        q["alpha"] = alpha[s].copy()
+        q["sW"] = np.append(np.ravel(p["sW"]), sWn[s])
+        if have_L:
+            Ln = np.zeros((N + 1, N + 1))
+            Ln[:N, :N] = p["L"]
+            Ln[:, N] = Lcol[s]
+            q["L"] = Ln
+        else:
+            q["L"] = None
+        new["post"].append(q)
+    h0, h1 = np.asarray(new["post"][0]["hyp"]), np.asarray(new["post"][-1]["hyp"])
+    ctx._gp_key = (id(new), new["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(h0.flat[0]), float(h1.flat[-1]), True)
+    return new
 
 
 def gplite_nlZ_batch(hyp, gp, hprior=None, *, ctx=None):

@@ -256,6 +256,7 @@ int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, in
     // low-noise posterior (Lchol == 0): K^-1 is used unscaled (gplogjoint.m:279), i.e. sn2_eff plays no role
     sn2eff[s] = (sW1 && !(Lchol && !Lchol[s])) ? 1.0 / (sW1[s] * sW1[s]) : 1.0;
   }
+  c->gpSn2effHost.assign(sn2eff, sn2eff + S);
   VB_TRY(c->gpDerived.reserve(h.size() * sizeof(double)));
   VB_CUDA(cudaMemcpyAsync(c->gpDerived.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   VB_CUDA(cudaStreamSynchronize(c->stream));

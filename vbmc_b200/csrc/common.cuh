@@ -188,6 +188,7 @@ struct vbmc_b200_ctx {
   std::vector<int> gpLchol;
   std::vector<int> gpLfactor;  // per sample: device L is a Cholesky factor (1) or -inv(K + diag) handed over by the host (0)
   std::vector<double> gpSn2mult;
+  std::vector<double> gpSn2effHost;  // 1/sW(1)^2 per sample (host copy of gp.sn2eff)
   std::vector<double> gpHypHost;  // host copy of gp.post(s).hyp ([S][Nhyp]) for O(S) host epilogues
   int gp_noisefun[3] = {1, 0, 0};
   vb::DevBuf predWork;  // gplite_pred: test points, cross-kernel columns, results
@@ -282,6 +283,7 @@ void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad = nullptr);
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
 int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* isfac_dev, cudaStream_t st);
+int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);
 int entmc_pick_dp(int D);

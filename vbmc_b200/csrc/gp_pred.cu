@@ -102,6 +102,40 @@ __global__ void __launch_bounds__(256) pred_var_kernel(const PredArgs a) {
   }
 }
 
+
+// ---- rank-one update of the posterior (gplite_post.m:173-251, Cholesky branch) ----
+// par[s] = {gamma = (mstar - ystar)/vstar, colscale = sqrt(sn2_eff_old)/sn2_eff_new, diagadd = 1 + K/sn2_eff_new}
+// new_L_column = (L'\Ks)/sn2_eff (:229-230) is the forward-substitution result V = L'\(sW.*Ks) rescaled;
+// L(N+1,N+1) = sqrt(1 + K/sn2_eff - c'c) (:231-233).  grid (S), 256 threads.
+__global__ void __launch_bounds__(256) rank1_column_kernel(int N, int ld, double* L, double* Z, const double* par) {
+  __shared__ double part[8];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  double* z = Z + static_cast<size_t>(s) * N;
+  double* col = L + static_cast<size_t>(s) * ld * ld + static_cast<size_t>(N) * ld;
+  const double cs = par[3 * s + 1];
+  double acc = 0.0;
+  for (int n = tid; n < N; n += 256) {
+    const double cv = z[n] * cs;
+    z[n] = cv;      // right-hand side of the backward solve: alpha_update = L\c  (== (L\(L'\Ks))/sn2_eff, :228)
+    col[n] = cv;
+    acc = fma(cv, cv, acc);
+  }
+  acc = block_sum_256(acc, part);
+  if (tid == 0) col[N] = sqrt(par[3 * s + 2] - acc);
+}
+
+// alpha = [alpha; 0] + (mstar - ystar)/vstar * [alpha_update; -1]   (:245-247); grid (S)
+__global__ void __launch_bounds__(256) rank1_alpha_kernel(int N, const double* alpha_old, const double* W, const double* par,
+                                                          double* alpha_new) {
+  const int s = blockIdx.x;
+  const double g = par[3 * s];
+  const double* ao = alpha_old + static_cast<size_t>(s) * N;
+  const double* w = W + static_cast<size_t>(s) * N;
+  double* an = alpha_new + static_cast<size_t>(s) * (N + 1);
+  for (int n = threadIdx.x; n < N; n += 256) an[n] = fma(g, w[n], ao[n]);
+  if (threadIdx.x == 0) an[N] = -g;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -229,5 +263,121 @@ extern "C" int vbmc_b200_gp_set_sn2_mult(vbmc_b200_ctx* c, const double* sn2_mul
   if (!c || !sn2_mult) VB_FAIL(VBMC_B200_EINVAL, "null argument");
   if (!c->gp_ready) VB_FAIL(VBMC_B200_ESTATE, "gp_set_sn2_mult: no GP attached");
   c->gpSn2mult.assign(sn2_mult, sn2_mult + c->gp.S);
+  return VBMC_B200_OK;
+}
+
+// gp = gplite_post(gp,xstar,ystar,[],[],[],[],1) — rank-one update, gplite/gplite_post.m:50-92,173-251.
+// One new training point is folded into the resident posterior: prediction at xstar (one cross-kernel column + forward
+// substitution per sample), the new factor column, a backward substitution for alpha_update, O(N) updates.  N^2 work
+// per sample instead of the N^3/3 refit.  Outputs (optional): alpha (N+1) x S, the new factor column (N+1) x S, the new sW entry.
+extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, double ystar, double* alpha_out,
+                                         double* Lcol_out, double* sW_out) {
+  if (!c || !xstar) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  if (!c->gp_ready)
+    VB_FAIL(VBMC_B200_EREFERENCE, "gplite_post:NoGP: GPLITE_POST can perform rank-one update only with an existing GP struct.");
+  if (!c->gpHasL) VB_FAIL(VBMC_B200_ESTATE, "gplite_post (rank-one): the factors gp.post(s).L must be resident (gp_attach with L, or gp_post)");
+  if (c->gp_noisefun[1] != 0)
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:FullUpdate: rank-one updates are not defined for heteroskedastic noise (gplite_post.m:78-81): refit with gplite_post");
+  const int N = c->gp.N, D = c->gp.D, S = c->gp.S;
+  for (int s = 0; s < S; ++s)
+    if (!c->gpLchol[s] || !c->gpLfactor[s])
+      VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:OutOfScope: rank-one update of a low-noise (Lchol == 0) posterior; refit with gplite_post");
+  VB_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  // ---- [mstar,vstar] = gplite_pred(gp,xstar,y,s2,1,1)  (:191) ----
+  const size_t nhead = static_cast<size_t>(D) + 2 * S + (static_cast<size_t>(S) + 1) / 2 + 3 * static_cast<size_t>(S);
+  VB_TRY(c->predWork.reserve(sizeof(double) * (nhead + static_cast<size_t>(S) * N)));
+  double* d_xs = c->predWork.d();
+  double* d_fmu = d_xs + D;
+  double* d_fs2 = d_fmu + S;
+  int* d_isfac = reinterpret_cast<int*>(d_fs2 + S);
+  double* d_par = d_fs2 + S + (static_cast<size_t>(S) + 1) / 2;
+  double* d_Z = d_par + 3 * static_cast<size_t>(S);
+  VB_CUDA(cudaMemcpyAsync(d_isfac, c->gpLfactor.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
+  VB_CUDA(cudaMemcpyAsync(d_xs, xstar, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+  PredArgs a;
+  a.N = N; a.D = D; a.S = S; a.T = 1;
+  a.meanfun = c->gp.meanfun; a.Ncov = c->gp.Ncov; a.Nnoise = c->gp.Nnoise; a.Nhyp = c->gp.Nhyp;
+  a.X = c->gp.X; a.Xs = d_xs; a.hyp = c->gp.hyp; a.alpha = c->gp.alpha; a.sn2eff = c->gp.sn2eff;
+  a.isfac = d_isfac; a.Z = d_Z; a.W = nullptr; a.fmu = d_fmu; a.fs2 = d_fs2;
+  {
+    KernelScope ks(c, "pred_cross", st);
+    pred_cross_kernel<<<dim3(1, S), 256, 0, st>>>(a);
+    VB_CUDA(cudaGetLastError());
+  }
+  VB_TRY(run_rhs_solve(c, 1, d_Z, nullptr, d_isfac, st));
+  {
+    KernelScope ks(c, "pred_var", st);
+    pred_var_kernel<<<dim3(1, S), 256, 0, st>>>(a);
+    VB_CUDA(cudaGetLastError());
+  }
+  std::vector<double> hf(S), hv(S), par(3 * static_cast<size_t>(S)), sw(S);
+  VB_CUDA(cudaMemcpyAsync(hf.data(), d_fmu, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaMemcpyAsync(hv.data(), d_fs2, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < S; ++s) {
+    const double* h = c->gpHypHost.data() + static_cast<size_t>(s) * c->gp.Nhyp;
+    const double* hn = h + c->gp.Ncov;
+    int idx = 0;
+    double sn2 = 2.220446049250313e-16;                       // gplite_noisefun.m:177-184
+    if (c->gp_noisefun[0] == 1) sn2 = exp(2.0 * hn[idx++]);
+    if (c->gp_noisefun[2] == 1) {                             // :196-209
+      const double zz = fmax(0.0, hn[idx] - ystar);
+      sn2 += exp(2.0 * hn[idx + 1]) * zz * zz;
+    }
+    const double sn2_eff = sn2 * c->gpSn2mult[s];             // gplite_post.m:209
+    const double vstar = hv[s] + sn2 * c->gpSn2mult[s];       // ys2 of gplite_pred (:119)
+    par[3 * s] = (hf[s] - ystar) / vstar;                     // :247
+    par[3 * s + 1] = sqrt(c->gpSn2effHost[s]) / sn2_eff;      // V = (L'\Ks)/sqrt(sn2_eff_old)  ->  (L'\Ks)/sn2_eff
+    par[3 * s + 2] = 1.0 + exp(2.0 * h[D]) / sn2_eff;         // :233
+    sw[s] = 1.0 / sqrt(sn2_eff);                              // :242
+  }
+  VB_CUDA(cudaMemcpyAsync(d_par, par.data(), sizeof(double) * par.size(), cudaMemcpyHostToDevice, st));
+  // ---- grow the resident arrays by one point ----
+  const int N1 = N + 1;
+  int ld = c->gpLd;
+  if (N1 > ld) {
+    const int ld2 = (N1 + 63) / 64 * 64;
+    DevBuf nb;
+    VB_TRY(nb.reserve(sizeof(double) * static_cast<size_t>(S) * ld2 * ld2));
+    VB_CUDA(cudaMemsetAsync(nb.p, 0, sizeof(double) * static_cast<size_t>(S) * ld2 * ld2, st));
+    for (int s = 0; s < S; ++s)
+      VB_CUDA(cudaMemcpy2DAsync(nb.d() + static_cast<size_t>(s) * ld2 * ld2, sizeof(double) * ld2,
+                                c->gpL.d() + static_cast<size_t>(s) * ld * ld, sizeof(double) * ld, sizeof(double) * N, N,
+                                cudaMemcpyDeviceToDevice, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    c->gpL.release();
+    c->gpL = nb;
+    c->gpLd = ld = ld2;
+  }
+  {
+    KernelScope ks(c, "rank1", st);
+    rank1_column_kernel<<<S, 256, 0, st>>>(N, ld, c->gpL.d(), d_Z, d_par);
+    VB_CUDA(cudaGetLastError());
+  }
+  VB_TRY(run_rhs_backsolve(c, 1, d_Z, st));                   // alpha_update (old N x N factor)
+  DevBuf na, nx;
+  VB_TRY(na.reserve(sizeof(double) * static_cast<size_t>(S) * N1));
+  VB_TRY(nx.reserve(sizeof(double) * static_cast<size_t>(D) * N1));
+  {
+    KernelScope ks(c, "rank1", st);
+    rank1_alpha_kernel<<<S, 256, 0, st>>>(N, c->gp.alpha, d_Z, d_par, na.d());
+    VB_CUDA(cudaGetLastError());
+  }
+  VB_CUDA(cudaMemcpy2DAsync(nx.p, sizeof(double) * N1, c->gpX.p, sizeof(double) * N, sizeof(double) * N, D, cudaMemcpyDeviceToDevice, st));
+  VB_CUDA(cudaMemcpy2DAsync(nx.d() + N, sizeof(double) * N1, d_xs, sizeof(double), sizeof(double), D, cudaMemcpyDeviceToDevice, st));
+  if (alpha_out) VB_CUDA(cudaMemcpyAsync(alpha_out, na.p, sizeof(double) * static_cast<size_t>(S) * N1, cudaMemcpyDeviceToHost, st));
+  if (Lcol_out)
+    VB_CUDA(cudaMemcpy2DAsync(Lcol_out, sizeof(double) * N1, c->gpL.d() + static_cast<size_t>(N) * ld, sizeof(double) * ld * ld,
+                              sizeof(double) * N1, S, cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaStreamSynchronize(st));
+  if (sW_out) memcpy(sW_out, sw.data(), sizeof(double) * S);
+  c->gpAlpha.release();
+  c->gpAlpha = na;
+  c->gpX.release();
+  c->gpX = nx;
+  c->gp.N = N1;
+  c->gp.X = c->gpX.d();
+  c->gp.alpha = c->gpAlpha.d();
   return VBMC_B200_OK;
 }

@@ -454,6 +454,19 @@ int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* 
   return VBMC_B200_OK;
 }
 
+// W = R \ Z in place (backward substitution with the resident upper factors), `ncols` right-hand sides per sample
+int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st) {
+  VarArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = c->gp.N; a.D = c->gp.D; a.K = ncols; a.S = c->gp.S; a.ld = c->gpLd;
+  a.Lstride = static_cast<size_t>(c->gpLd) * c->gpLd;
+  a.L = c->gpL.d();
+  a.gp = c->gp; a.vp = c->vp;
+  a.Z = Z;
+  KernelScope ks(c, "pred_trsm", st);
+  return launch_var_kernel(c, VK_BWD, a, ncols, c->gp.S, 64 * 65, 0, st, "gplite_post");
+}
+
 // X = R^-T (lower triangular) of sample `s`, written column-major with leading dimension N into `out`.
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out) {
   VarArgs a;
