@@ -139,7 +139,7 @@ def adam_update(state, x, grad):
     return x - step * mhat / (np.sqrt(vhat) + math.sqrt(np.finfo(float).eps))
 
 
-def run_reference(args, cfg_name):
+def run_reference(args, cfg_name, emit):
     """Reference arm: the reference's CPU algorithm (oracle C/OpenMP port) on the host cores."""
     from vbmc_b200 import workloads
     from oracle import cport
@@ -156,7 +156,7 @@ def run_reference(args, cfg_name):
             "cpu_baseline": {"value": res["steps_per_s"], "unit": "steps/s", "cores": res["threads"], "kind": "port",
                              "sample": res["sample"]},
             "e2e": {"value": res["steps_per_s"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=64):
@@ -195,13 +195,24 @@ def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=
 
 
 def main():
+    # stdout carries exactly ONE JSON line: library banners (e.g. NCCL's version line at NCCL_DEBUG=WARN/VERSION) go to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name = args.config or "c3"   # the configuration BASELINE.json quotes the metric on, at every N (strong scaling)
     if args.impl == "reference":
-        run_reference(args, cfg_name)
+        run_reference(args, cfg_name, emit)
         return
 
     import vbmc_b200
@@ -380,6 +391,41 @@ def main():
     except Exception as e:   # reporting only
         fmin = {"error": str(e)[:300]}
 
+    # ---- the callers either side of the path, each timed through the host API (wall clock, synced) ----
+    nxt = None
+    if rank == 0 and gp_source.startswith("vbmc_b200") and os.environ.get("VBMC_B200_BENCH_NEXT", "1") != "0":
+        try:
+            nxt = {}
+            noisefun = [1, 1, 0] if w["s2"] is not None else [1, 0, 0]
+            gpd = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
+            rs = np.random.default_rng(5)
+            Xs = w["X"][rs.integers(0, cfg["N"], 1024)] + 0.3 * rs.standard_normal((1024, cfg["D"]))
+            vbmc_b200.gplite_pred(gpd, Xs[:64], nargout=2, ctx=ctx)
+            ctx.sync(); t0 = time.perf_counter()
+            vbmc_b200.gplite_pred(gpd, Xs, nargout=2, ctx=ctx)
+            ctx.sync(); dt = time.perf_counter() - t0
+            nxt["gplite_pred"] = {"Nstar": 1024, "S": cfg["S"], "N": cfg["N"], "ms": dt * 1e3,
+                                  "trsm_flops": float(cfg["S"]) * cfg["N"] ** 2 * 1024,
+                                  "tflops": float(cfg["S"]) * cfg["N"] ** 2 * 1024 / dt / 1e12}
+            if w["s2"] is None:
+                xnew = w["X"][0] + 0.1
+                ctx.sync(); t0 = time.perf_counter()
+                gpu1 = vbmc_b200.gplite_post_update1(gpd, xnew, float(w["y"][0]), ctx=ctx)
+                ctx.sync(); dt = time.perf_counter() - t0
+                nxt["gplite_post_rank1"] = {"ms": dt * 1e3, "full_refit_ms": refit["gplite_post_wall_ms"] if refit else None,
+                                            "N_after": int(gpu1["X"].shape[0])}
+            hyps = np.repeat(w["hyp"], 2, axis=1)[:, :32] + 0.05 * rs.standard_normal((w["hyp"].shape[0], min(32, 2 * cfg["S"])))
+            vbmc_b200.gplite_nlZ_batch(hyps, gpd, None, ctx=ctx)
+            ctx.sync(); t0 = time.perf_counter()
+            vbmc_b200.gplite_nlZ_batch(hyps, gpd, None, ctx=ctx)
+            ctx.sync(); dt = time.perf_counter() - t0
+            nxt["gplite_nlZ_batch"] = {"vectors": int(hyps.shape[1]), "ms": dt * 1e3, "ms_per_vector": dt * 1e3 / hyps.shape[1]}
+            # make the step's GP resident again for the measurements below
+            gp = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
+            ctx.vp_set(vp); ctx.gp_attach(gp); ctx.thetabnd_set(tb)
+        except Exception as e:   # reporting only
+            nxt = {"error": str(e)[:300]}
+
     # ---- c4 (Ns=131072): the MC-shard configuration BASELINE.json names for 2/4/8 GPUs, same protocol ----
     c4 = None
     if args.config is None:
@@ -440,6 +486,7 @@ def main():
                 "host_eps_variant_steps_per_s": e2e_host_eps,
                 "host_eps_variant_h2d_bytes_per_step": counts["entmc_bytes"] if e2e_host_eps else None},
         "fminadam_device_loop": fmin,
+        "next_rows": nxt,
         "gpu_launches": launches,
         "wall_s_timed_region": t_wall,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in prof.items()},
@@ -449,7 +496,7 @@ def main():
         "c5": c5,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

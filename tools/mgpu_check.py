@@ -54,6 +54,18 @@ def main():
             errs = (rel(F, Fo), rel(dF, dFo), rel(G, Go), rel(H, Ho))
             worst = max(worst, *errs)
             print(f"[mgpu_check] world={world} {shape}: rel errors F,dF,G,H = {errs}", flush=True)
+    # device-resident fminadam loop: every rank runs the same loop on its shard; iterates must agree bit for bit
+    x, f, xtab, ftab, it = vbmc_b200.fminadam_negelcbo(theta, 0.0, vp, gp, cfg["Ns"], 0, tb, None, None, 0.001, 45, None, epsilon=eps, ctx=ctx)
+    t = torch.tensor(np.concatenate([[f, it], x, ftab]), device=f"cuda:{local}")
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(t, ref), f"rank {rank}: fminadam results differ from rank 0"
+    if rank == 0:
+        fun = lambda t_: orc.negelcbo_vbmc(t_, 0.0, vp, gp, cfg["Ns"], 1, 0, 0, tb, 0, epsilon=eps, nargout=2)[:2]
+        xo, fo, xtabo, ftabo, ito = orc.fminadam(fun, theta, None, None, 0.001, 45, None)
+        e = float(np.max(np.abs(ftab - ftabo)) / np.max(np.abs(ftabo)))
+        print(f"[mgpu_check] fminadam world={world}: iter {it} (oracle {ito}), rel err ftab {e:.2e}", flush=True)
+        assert it == ito and e < 1e-8
     if rank == 0:
         assert worst < 1e-10, worst
         print(f"[mgpu_check] OK world={world} worst={worst:.3e}", flush=True)
