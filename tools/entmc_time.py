@@ -7,6 +7,7 @@ from vbmc_b200 import workloads, _lib
 import ctypes as C
 
 def main(cfg_name="c3", reps=20):
+    reps = int(os.environ.get("VBMC_REPS", reps))
     ctx = vbmc_b200.default_context()
     cfg = dict(workloads.CONFIGS[cfg_name])
     w = workloads.build(cfg, lambda *a: vbmc_b200.gplite_post(*a, ctx=ctx, want_L=False), with_eps=False)
@@ -19,6 +20,7 @@ def main(cfg_name="c3", reps=20):
     a.compute_grad, a.compute_var, a.separate_K, a.use_thetabnd = 1, 0, 0, 1
     a.eps_mode, a.seed, a.stream = _lib.EPS_PHILOX, 1, 0
     a.F, a.dF = C.pointer(F), _lib.dptr(dF)
+    ctx.set_precision(int(os.environ.get("VBMC_PREC", "64")))
     for i in range(3):
         _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
     tot = 0.0
@@ -34,7 +36,10 @@ def main(cfg_name="c3", reps=20):
         ctx.flush_l2(); a.stream = 100 + i
         _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
     ctx.profile_enable(False)
-    out = {k: round(ctx.profile_get(k)[0] / reps, 4) for k in ("entmc", "philox", "gplogjoint", "reduce", "finalize", "vp_unpack")}
+    out = {k: round(ctx.profile_get(k)[0] / reps, 4) for k in ("entmc", "entmc_f32", "philox", "gplogjoint", "reduce", "finalize", "vp_unpack")}
+    if os.environ.get("VBMC_PREC", "64") != "64":
+        print(cfg_name, "step_ms", round(tot / reps, 4), out, "kept", round(kept / max(1, total), 4), flush=True)
+        return
     # the entropy sweep alone (no gplogjoint branch competing for the SMs), resident draws
     ctx.profile_reset(); ctx.profile_enable(True)
     for i in range(reps):

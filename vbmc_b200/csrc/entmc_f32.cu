@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(256) entmc_f32_tables_kernel(const EntmcArgs a
       const double r = sj / a.sigma[k];
       s0 = make_float4(static_cast<float>(r), static_cast<float>(-0.5 * 1.4426950408889634 * uu),
                        static_cast<float>(-0.5 * 1.4426950408889634 * r * r), static_cast<float>(1.4426950408889634 * r));
-      s1 = make_float4(static_cast<float>(a.ck[k] * icmax), static_cast<float>(a.ak[k] * icmax), 0.f, 0.f);
+      // .z/.w: operands of the warp-uniform pruning test (entmc.cu), rounded towards keeping the component
+      const double pc = a.prune_c > 32.0 ? 32.0 : a.prune_c;   // exp(-32) = 1e-14 of q: far below FP32 resolution
+      s1 = make_float4(static_cast<float>(a.ck[k] * icmax), static_cast<float>(a.ak[k] * icmax),
+                       __double2float_rd(sqrt(uu) * 0.999999), __double2float_ru(pc + log(a.ck[k]) - log(a.ck[j]) + 0.5));
       const double gap = sqrt(uu) - r * em;   // smallest ||z|| any 6-sigma draw can reach
       const bool negligible = gap > 7.75;     // exp(-gap^2/2) < 1e-13
       const bool small = (uu + r * r * em2) <= F32_EXPANDED_MAX;
@@ -115,6 +118,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
   unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
   double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);      // [32*D] draws as stored in HBM: doubles, or
   float* eps_sf = reinterpret_cast<float*>(wbase + a.woff_eps);       //        floats when the device generator made them
+  unsigned char* klist = wbase + a.woff_klist;                        // [K2+2] components this warp scores in the current group
   float2* iq_s = reinterpret_cast<float2*>(wbase + a.woff_iq);        // [32] {1/q+, 1/q-}
   float2* stage = reinterpret_cast<float2*>(wbase + a.woff_stage);    // [K2][32] {e+, e-}, swizzled
   double* wres = reinterpret_cast<double*>(wbase + a.woff_stage);     // [pstride]   (aliases stage)
@@ -171,6 +175,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
       for (int i = tid; i < K2 * DP / 4; i += blockDim.x) su[i] = __ldg(gu + i);
       const float4* gs = tabs.S + static_cast<size_t>(j) * 2 * K2;
       for (int i = tid; i < 2 * K2; i += blockDim.x) tab_s[i] = __ldg(gs + i);
+      // row K2: dummy partner of an odd number of scored components (ck = ak = 0)
+      for (int i = tid; i < DP; i += blockDim.x) tab_u[K2 * DP + i] = 0.f;
+      if (tid < 2) tab_s[2 * K2 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const int direct = tabs.direct[j];  // tile-uniform choice of the formulation
     __syncthreads();  // tables ready
@@ -238,19 +245,52 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
       float ee = 0.f;
 #pragma unroll
       for (int d = 0; d < DP; ++d) ee = fmaf(e[d], e[d], ee);
+      // components that can matter for this warp's 32 pairs (same bound as the FP64 sweep, entmc.cu)
+      unsigned long long kmask0 = 0ull, kmask1 = 0ull;
+      int nact = 0;
+      {
+        float mx = ee;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const float emax = sqrtf(mx) * 1.00001f, he2 = 0.5f * emax * emax;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int k = lane + 32 * rr;
+          bool keep = false;
+          if (32 * rr < K && k < K) {
+            const float4 m = tab_s[2 * k + 1];
+            const float t = m.z - tab_s[2 * k].x * 1.00001f * emax;
+            const float b = t > 0.f ? -0.5f * t * t : 0.f;
+            keep = !(b + he2 + m.w < 0.f) || a.prune_c <= 0.0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (rr < 2) kmask0 |= static_cast<unsigned long long>(bal) << (32 * (rr & 1));
+          else kmask1 |= static_cast<unsigned long long>(bal) << (32 * (rr & 1));
+          if (keep) klist[nact + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned char>(k);
+          nact += __popc(bal);
+        }
+        if (lane == 0) klist[nact] = static_cast<unsigned char>(K2);
+        __syncwarp();
+        if (a.prune_stats && lane == 0) {
+          atomicAdd(a.prune_stats, static_cast<unsigned long long>(nact));
+          atomicAdd(a.prune_stats + 1, static_cast<unsigned long long>(K));
+        }
+      }
 
       // two components per iteration, both signs; the formulation is tile-uniform
       auto sweep = [&](auto form_tag) {
         constexpr bool EXPANDED = decltype(form_tag)::value;
 #pragma unroll 1
-        for (int k = 0; k < K2; k += 2) {
-          const float4 sa0 = tab_s[2 * k], sa1 = tab_s[2 * k + 1], sb0 = tab_s[2 * k + 2], sb1 = tab_s[2 * k + 3];
+        for (int ia = 0; ia < nact; ia += 2) {
+          const unsigned kk = *reinterpret_cast<const unsigned short*>(klist + ia);
+          const int k = kk & 0xff, kb = kk >> 8;
+          const float4 sa0 = tab_s[2 * k], sa1 = tab_s[2 * k + 1], sb0 = tab_s[2 * kb], sb1 = tab_s[2 * kb + 1];
           float ua[DP], ub[DP];
           if (DP % 4 == 0) {
 #pragma unroll
             for (int d = 0; d < DP; d += 4) {
               const float4 a4 = *reinterpret_cast<const float4*>(tab_u + k * DP + d);
-              const float4 b4 = *reinterpret_cast<const float4*>(tab_u + (k + 1) * DP + d);
+              const float4 b4 = *reinterpret_cast<const float4*>(tab_u + kb * DP + d);
               ua[d] = a4.x; ua[d + 1] = a4.y; ua[d + 2] = a4.z; ua[d + 3] = a4.w;
               ub[d] = b4.x; ub[d + 1] = b4.y; ub[d + 2] = b4.z; ub[d + 3] = b4.w;
             }
@@ -258,7 +298,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
 #pragma unroll
             for (int d = 0; d < DP; d += 2) {
               const float2 a2 = *reinterpret_cast<const float2*>(tab_u + k * DP + d);
-              const float2 b2 = *reinterpret_cast<const float2*>(tab_u + (k + 1) * DP + d);
+              const float2 b2 = *reinterpret_cast<const float2*>(tab_u + kb * DP + d);
               ua[d] = a2.x; ua[d + 1] = a2.y;
               ub[d] = b2.x; ub[d + 1] = b2.y;
             }
@@ -292,7 +332,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
           const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
           if (needW) {
             stage[k * 32 + (lane ^ (k & 15))] = make_float2(e0, e1);
-            stage[(k + 1) * 32 + (lane ^ ((k + 1) & 15))] = make_float2(e2, e3);
+            if (kb < K2) stage[kb * 32 + (lane ^ (kb & 15))] = make_float2(e2, e3);
           }
           qp = fmaf(sa1.x, e0, qp);
           qm = fmaf(sa1.x, e1, qm);
@@ -343,7 +383,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_f32_kernel(const EntmcArgs
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
           const int l = lane + 32 * rr;
-          if (32 * rr < K && l < K) {
+          if (32 * rr < K && l < K && (((rr < 2 ? kmask0 : kmask1) >> (l & 63)) & 1ull)) {  // skipped rows hold stale values
             const float2* row = stage + l * 32;
             const int x = l & 15;
             float acc0 = 0.f, acc1 = 0.f;
