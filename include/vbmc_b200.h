@@ -69,14 +69,20 @@ int vbmc_b200_entmc_prune(vbmc_b200_ctx* ctx, double log_threshold);
 int vbmc_b200_entmc_prune_stats(vbmc_b200_ctx* ctx, int enable, unsigned long long* kept, unsigned long long* total);
 
 /* ---------------------------------------------------------------------------------------
- * multi-GPU: one context per rank, one NCCL all-reduce per negelcbo step.
+ * multi-GPU: one context per rank, one all-reduce of the partial sums per negelcbo step.
  * The MC pair axis of entmc_vbmc and the hyper-parameter-sample axis of gplogjoint are
- * sharded over ranks; results are replicated on every rank after the all-reduce.
+ * sharded over ranks; results are replicated (bit-identical) on every rank after the all-reduce.
+ * comm_init builds an NCCL communicator (rendezvous, fallback) and, over it, exchanges CUDA IPC handles so that
+ * every rank maps every other rank's exchange buffer: the per-step all-reduce then runs INSIDE the step's last
+ * kernel over NVLink peer memory (push to all inboxes, flag, wait, sum in rank order) — no NCCL call and no extra
+ * launch per step, and the whole multi-GPU step is CUDA-graph capturable.  VBMC_B200_P2P=0 keeps NCCL.
  * ------------------------------------------------------------------------------------- */
 #define VBMC_B200_UNIQUE_ID_BYTES 128
 int vbmc_b200_comm_unique_id(void* id128);                                  /* rank 0, then broadcast out of band */
 int vbmc_b200_comm_init(vbmc_b200_ctx* ctx, int nranks, int rank, const void* id128);
 int vbmc_b200_comm_info(vbmc_b200_ctx* ctx, int* nranks, int* rank);
+/* *peer_memory = 1 when the per-step all-reduce runs over mapped peer memory, 0 when it goes through NCCL */
+int vbmc_b200_comm_p2p(vbmc_b200_ctx* ctx, int* peer_memory);
 /* contiguous balanced split of `total` units (MC pairs per component, hyper-parameter samples) over ranks */
 int vbmc_b200_shard_range(int total, int nranks, int rank, int* begin, int* end);
 

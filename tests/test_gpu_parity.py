@@ -201,6 +201,38 @@ def test_device_rng_equals_parity_mode_on_dumped_draws(gpu_ctx):
     assert not np.array_equal(eps, eps2)
 
 
+def test_ahead_of_time_draws_are_invisible(gpu_ctx):
+    """Generator mode produces the next stream's draws ahead of time once the caller is seen to advance the stream by one
+    (csrc/api.cu step_with_graph): whatever the call pattern — streaming (direct launches, graph capture, graph replay),
+    a repeated stream, jumps forwards and backwards — every call must equal parity mode fed with that stream's dumped draws."""
+    import vbmc_b200
+    w = mk(D=5, N=40, K=8, S=2, Ns=256)
+    vp, gp, theta = w["vp"], w["gp"], w["theta"]
+    streams = [7, 8, 9, 10, 11, 12, 13, 13, 40, 41, 42, 43, 5, 6, 6, 7]
+    ref = {}
+    for t in sorted(set(streams)):
+        eps = gpu_ctx.eps_philox(5, 8, 256, seed=77, stream=t, readback=True)
+        ref[t] = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 256, 1, 0, epsilon=eps, nargout=2)
+    for i, t in enumerate(streams):
+        th = theta + 1e-3 * i          # the parameters move while the draws are being prefetched
+        a = vbmc_b200.negelcbo_vbmc(th, 0.0, vp, gp, 256, 1, 0, rng=(77, t), nargout=2)
+        eps = gpu_ctx.eps_philox(5, 8, 256, seed=77, stream=t, readback=True) if i % 5 == 4 else None   # also disturbs the buffer
+        b = vbmc_b200.negelcbo_vbmc(th, 0.0, vp, gp, 256, 1, 0, epsilon=eps, nargout=2) if eps is not None else None
+        if b is not None:
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]), (i, t)
+        if i == 0:
+            assert a[0] == ref[t][0] and np.array_equal(a[1], ref[t][1])
+    # same sequence, fixed theta: every call equals its parity-mode reference bit for bit
+    for t in streams:
+        a = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 256, 1, 0, rng=(77, t), nargout=2)
+        assert a[0] == ref[t][0] and np.array_equal(a[1], ref[t][1]), t
+    # a different seed with the stream the buffer was prefetched for is a miss
+    eps = gpu_ctx.eps_philox(5, 8, 256, seed=78, stream=8, readback=True)
+    a = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 256, 1, 0, rng=(78, 8), nargout=2)
+    b = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, 256, 1, 0, epsilon=eps, nargout=2)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
 def test_philox_known_answers(gpu_ctx):
     """Random123 known-answer vectors for philox4x32-10."""
     import ctypes as C

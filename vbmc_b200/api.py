@@ -99,6 +99,12 @@ class Context:
         buf = C.create_string_buffer(uid, _lib.UNIQUE_ID_BYTES) if uid is not None else None
         _lib.check(self.lib.vbmc_b200_comm_init(self._h, nranks, rank, buf))
 
+    def comm_p2p(self) -> bool:
+        """True when the per-step all-reduce runs inside finalize_kernel over NVLink peer memory (else NCCL)."""
+        v = C.c_int()
+        _lib.check(self.lib.vbmc_b200_comm_p2p(self._h, C.byref(v)))
+        return bool(v.value)
+
     # -- GP ---------------------------------------------------------------------------------
     @staticmethod
     def _gp_desc(gp, hyp, keep):

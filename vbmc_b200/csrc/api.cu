@@ -106,6 +106,11 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork0, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_philox, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_glj, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_trail_fork, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
+  if (const char* pf = getenv("VBMC_B200_PREFETCH")) c->prefetch_enabled = strcmp(pf, "0") != 0;
+  if (const char* gf = getenv("VBMC_B200_GLJ_FIRST")) c->glj_first = strcmp(gf, "0") != 0;
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreate(&c->ev_t0));
@@ -145,6 +150,9 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   cudaStreamDestroy(c->stream3);
   cudaEventDestroy(c->ev_fork0);
   cudaEventDestroy(c->ev_philox);
+  cudaEventDestroy(c->ev_glj);
+  cudaEventDestroy(c->ev_trail_fork);
+  cudaEventDestroy(c->ev_trail);
   delete c;
   return VBMC_B200_OK;
 }
@@ -347,7 +355,7 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   const int K2c = (K + 1) & ~1;
   c->vp_cblob_dp = DPc;
   c->vp_cblob_len = K2c * DPc + 2 * K2c + DPc;
-  const size_t ncur = 2 * static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K + 2 + c->vp_cblob_len;
+  const size_t ncur = 2 * static_cast<size_t>(D) * K + 6 * K + 3 * D + 1 + K + 2 + 2 + c->vp_cblob_len;
   VB_TRY(c->vpCur.reserve(ncur * sizeof(double)));
   double* q = c->vpCur.d();
   c->vp.D = D; c->vp.K = K;
@@ -363,6 +371,7 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   c->vp.ak = q; q += K;
   c->vp.cn = q; q += K + 1;
   c->vp.form_flag = reinterpret_cast<int*>(q); q += 2;
+  c->vp.dyn_snap = reinterpret_cast<unsigned long long*>(q); q += 2;
   c->vp.scratch = q; q += D * K;
   c->vp.cblob = q; q += c->vp_cblob_len;
   std::vector<double> dl(D, 0.0);
@@ -400,9 +409,23 @@ int vbmc_b200_thetabnd_set(vbmc_b200_ctx* c, int n, const double* lb, const doub
 // ---------------------------------------------------------------------------------------------
 static int eps_reserve(vbmc_b200_ctx* c, int D, int K, int Ns) {
   if (D <= 0 || K <= 0 || Ns <= 0 || (Ns & 1)) VB_FAIL(VBMC_B200_EINVAL, "eps: D, K > 0 and Ns even > 0 required");
-  VB_TRY(c->eps.reserve(sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2)));
+  const size_t bytes = sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2);
+  if (bytes > c->eps.cap || c->epsD != D || c->epsK != K || c->epsNs != Ns) c->eps_key.valid = false;  // contents are lost / reinterpreted
+  VB_TRY(c->eps.reserve(bytes));
   c->epsD = D; c->epsK = K; c->epsNs = Ns;
   return VBMC_B200_OK;
+}
+
+static void eps_key_set(vbmc_b200_ctx* c, uint64_t seed, uint64_t stream, int Ns) {
+  c->eps_key.valid = true;
+  c->eps_key.seed = seed; c->eps_key.stream = stream;
+  c->eps_key.D = c->D; c->eps_key.K = c->K; c->eps_key.Ns = Ns;
+  c->eps_key.f32 = c->precision == 32;
+}
+static bool eps_key_matches(const vbmc_b200_ctx* c, uint64_t seed, uint64_t stream, int Ns) {
+  const auto& k = c->eps_key;
+  return k.valid && c->eps_ready && k.seed == seed && k.stream == stream && k.D == c->D && k.K == c->K && k.Ns == Ns &&
+         k.f32 == (c->precision == 32) && c->epsD == c->D && c->epsK == c->K && c->epsNs == Ns;
 }
 
 int vbmc_b200_eps_upload(vbmc_b200_ctx* c, int D, int K, int Ns, const double* eps) {
@@ -415,6 +438,7 @@ int vbmc_b200_eps_upload(vbmc_b200_ctx* c, int D, int K, int Ns, const double* e
   VB_CUDA(cudaStreamSynchronize(c->stream));
   c->eps_ready = true;
   c->eps_f32 = false;
+  c->eps_key.valid = false;
   return VBMC_B200_OK;
 }
 
@@ -423,6 +447,7 @@ int vbmc_b200_eps_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, 
   VB_CUDA(cudaSetDevice(c->device));
   Ns = (Ns + 1) / 2 * 2;
   VB_TRY(eps_reserve(c, D, K, Ns));
+  c->eps_key.valid = false;  // (D, K) may differ from the resident vp: never treated as a step's draws
   if (c->nranks > 1 && eps_out)  // a read-back must see every element, not only this rank's shard
     VB_CUDA(cudaMemsetAsync(c->eps.p, 0, sizeof(double) * static_cast<size_t>(D) * K * (Ns / 2), c->stream));
   VB_TRY(launch_philox(c, D, K, Ns, seed, stream, c->stream));
@@ -452,6 +477,7 @@ static int prepare_eps(vbmc_b200_ctx* c, int Ns, int mode, const double* eps, ui
       VB_CUDA(cudaMemcpyAsync(c->eps.p, eps, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
       c->eps_ready = true;
       c->eps_f32 = false;
+      c->eps_key.valid = false;
       return VBMC_B200_OK;
     case VBMC_B200_EPS_RESIDENT:
       if (!c->eps_ready || c->epsD != D || c->epsK != K || c->epsNs != Ns)
@@ -464,9 +490,18 @@ static int prepare_eps(vbmc_b200_ctx* c, int Ns, int mode, const double* eps, ui
       c->philox_seed = seed;
       c->philox_stream = stream_id;
       c->eps_ready = true;
+      eps_key_set(c, seed, stream_id, Ns);  // what the buffer holds once the step has been enqueued
       return VBMC_B200_OK;
   }
   VB_FAIL(VBMC_B200_EINVAL, "unknown eps_mode %d", mode);
+}
+
+// multi-GPU steps whose partial sums go through NCCL (peer mapping unavailable or R larger than the exchange slots)
+static bool step_uses_nccl(const vbmc_b200_ctx* c) {
+  if (c->nranks <= 1) return false;
+  RLayout rl;
+  rl.init(c->D, c->K, c->gp_ready ? c->gp.S : 0);
+  return !(c->p2p_ready && rl.total <= c->xdev.cap);
 }
 
 // enqueue the device part of one evaluation; `what` selects negelcbo / entmc / gplogjoint
@@ -479,12 +514,14 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   VB_CUDA(cudaMemsetAsync(c->R_dev.p, 0, sizeof(double) * rl.total, c->stream));
   // the draws do not depend on theta: generate them on a third stream while vp_unpack (and then gplogjoint) run
   const bool philox_now = doH && c->philox_pending;
+  const bool trail = doH && c->philox_trail;
+  c->philox_trail = false;
+  const uint64_t* dyn_src = c->philox_dyn ? reinterpret_cast<const uint64_t*>(c->theta_dev.d() + c->ntheta) : nullptr;
   if (philox_now) {
     c->philox_pending = false;
     VB_CUDA(cudaEventRecord(c->ev_fork0, c->stream));
     VB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_fork0, 0));
-    VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream3,
-                         c->philox_dyn ? reinterpret_cast<const uint64_t*>(c->theta_dev.d() + c->ntheta) : nullptr));
+    VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream3, dyn_src));
     VB_CUDA(cudaEventRecord(c->ev_philox, c->stream3));
   }
   VB_TRY(launch_vp_unpack(c, have_theta));
@@ -492,21 +529,50 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     VB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     VB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     VB_TRY(launch_gplogjoint(c, gmask != 0, c->stream2));
+    VB_CUDA(cudaEventRecord(c->ev_glj, c->stream2));
     VB_TRY(launch_glj_reduce(c, c->stream2));
     VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
   }
   if (doH) {
     if (philox_now) VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_philox, 0));
+    // The entropy sweep's persistent CTAs take a whole SM each (registers + shared memory), so the log-joint kernel cannot
+    // co-reside with them: when both become runnable together they race for the SMs and the loser waits for the winner's
+    // last CTA.  Without a generator in front of the sweep (its draws were produced ahead of time) the order is made
+    // explicit: log-joint first on the whole GPU, then the sweep.  VBMC_B200_GLJ_FIRST=0 leaves it to the block scheduler.
+    if (doG && !philox_now && c->glj_first) {
+      VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_glj, 0));  // the kernel itself; its small reduction may trail behind
+    }
     int need = 0;
     if (gmask & 1) need |= NEED_MU;
     if (gmask & (2 | 4)) need |= NEED_E;
     if (gmask & 8) need |= NEED_W;
     VB_TRY(launch_entmc(c, Ns, need, c->stream));
+    if (trail) {
+      // the sweep has consumed this step's draws: generate the next step's (stream + 1) on stream3, in the shadow of the
+      // single-CTA tail (reduce, all-reduce, finalize, Adam update).  With a device-side key the generator reads the
+      // snapshot vp_unpack_kernel took at the start of THIS step (adam_step_kernel advances the original concurrently).
+      VB_CUDA(cudaEventRecord(c->ev_trail_fork, c->stream));
+      VB_CUDA(cudaStreamWaitEvent(c->stream3, c->ev_trail_fork, 0));
+      VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream3,
+                           dyn_src ? reinterpret_cast<const uint64_t*>(c->vp.dyn_snap) : nullptr, 1));
+      VB_CUDA(cudaEventRecord(c->ev_trail, c->stream3));
+      c->trail_join_pending = true;
+    }
     VB_TRY(launch_entmc_reduce(c, Ns, rl.S, c->stream));
   }
   if (doG) VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-  if (c->nranks > 1) VB_TRY(allreduce_R(c, rl.total, c->stream));
+  // multi-GPU: the partial sums are all-reduced inside finalize_kernel over NVLink peer memory (finalize.cu exchange_sum);
+  // NCCL only when the peer mapping is unavailable or R exceeds the exchange slots
+  if (c->nranks > 1 && !(c->p2p_ready && rl.total <= c->xdev.cap)) VB_TRY(allreduce_R(c, rl.total, c->stream));
   VB_TRY(launch_finalize(c, Ns, gmask, use_bnd, jacobian, what, c->stream));
+  return VBMC_B200_OK;
+}
+
+// make `stream` wait for a pending ahead-of-time draw generation (no-op when none)
+static int join_trail(vbmc_b200_ctx* c) {
+  if (!c->trail_join_pending) return VBMC_B200_OK;
+  c->trail_join_pending = false;
+  VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_trail, 0));
   return VBMC_B200_OK;
 }
 
@@ -606,7 +672,7 @@ static void scatter_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
 
 // Everything a captured step depends on: shapes, flags and the addresses of every buffer a kernel node reads or
 // writes.  A graph is replayed only while this signature is unchanged.
-static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask, int use_thetabnd, bool philox) {
+static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask, int use_thetabnd, int philox) {
   std::vector<long long> key = {Ns, gmask, use_thetabnd, philox, c->D, c->K, c->gp.S, c->gp.N, c->ntheta, c->nbnd, c->entmc_form, c->precision,
                                 c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
                                 reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
@@ -622,13 +688,18 @@ static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask
   memcpy(&bits[3], &c->entmc_prune_c, 8);
   key.insert(key.end(), bits, bits + 4);
   key.push_back(c->entmc_prune_stats_on ? reinterpret_cast<long long>(c->entmc_prune_stats.p) : 0);
+  key.push_back(c->nranks);
+  key.push_back(c->rank);
+  key.push_back(c->p2p_ready ? reinterpret_cast<long long>(c->xchg_peers.p) : 0);
+  key.push_back(c->glj_first);
   return key;
 }
 
 // One negelcbo evaluation on the device: H2D {theta, seed, stream}, the kernels, D2H of the output block.
 // Single rank, no profiling: the whole sequence is captured once into a CUDA graph and replayed while the step
 // signature (shapes, flags, buffer addresses) is unchanged — 10 launches + 2 copies become one graph launch.
-static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int Ns, int gmask, int nth, bool sync = true) {
+static int step_with_graph_impl(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int Ns, int gmask, int nth, bool sync, bool hit,
+                                bool trail) {
   const size_t nstage = static_cast<size_t>(c->ntheta) + 2;
   VB_TRY(c->theta_dev.reserve(sizeof(double) * nstage));
   VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * nstage));
@@ -639,24 +710,33 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
   ol.init(nth, c->gp.S, c->K);
   VB_TRY(ensure_pinned(&c->out_pinned, &c->out_pinned_cap, sizeof(double) * ol.total));
   const bool philox = a->eps_mode == VBMC_B200_EPS_PHILOX;
+  // generator mode: skip the generation when the buffer already holds this step's draws (generated ahead of time by the
+  // previous step); generate the next step's draws ahead of time once the caller has been seen to advance the stream by one
+  const bool lead = philox && !hit;
   auto body = [&]() -> int {
     VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * nstage, cudaMemcpyHostToDevice, c->stream));
     c->philox_dyn = philox;
-    if (philox) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, a->seed, a->stream));
+    if (lead) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, a->seed, a->stream));
+    c->philox_seed = a->seed;
+    c->philox_stream = a->stream;
+    c->philox_trail = trail;
     const int rc = enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO, true);
     c->philox_dyn = false;
+    c->philox_trail = false;
     VB_TRY(rc);
     VB_CUDA(cudaMemcpyAsync(c->out_pinned, c->out_dev.p, sizeof(double) * ol.total, cudaMemcpyDeviceToHost, c->stream));
+    VB_TRY(join_trail(c));  // after the read-back has been enqueued: the copy does not wait for the generator
     return VBMC_B200_OK;
   };
+
   if (!philox) VB_TRY(prepare_eps(c, Ns, a->eps_mode, a->eps, a->seed, a->stream));  // host / resident draws: outside the graph
-  const bool use_graph = c->graphs_enabled && !c->profiling && c->nranks == 1;
+  const bool use_graph = c->graphs_enabled && !c->profiling && !step_uses_nccl(c);  // no NCCL node inside a captured step
   if (!use_graph) {
     VB_TRY(body());
     VB_CUDA(cudaStreamSynchronize(c->stream));
     return VBMC_B200_OK;
   }
-  auto make_key = [&]() { return step_signature(c, Ns, gmask, a->use_thetabnd, philox); };
+  auto make_key = [&]() { return step_signature(c, Ns, gmask, a->use_thetabnd, (philox ? 1 : 0) | (lead ? 2 : 0) | (trail ? 4 : 0)); };
   const std::vector<long long> key = make_key();
   if (c->graph_exec && key == c->graph_key) {
     VB_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
@@ -697,6 +777,39 @@ static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, i
   }
   if (philox) c->eps_f32 = c->precision == 32;  // a replayed graph does not pass through launch_philox
   if (sync) VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBMC_B200_OK;
+}
+
+// a NaN objective on a multi-GPU step: tell a peer that never arrived (exchange_sum timed out) from a genuine NaN
+static int check_exchange(vbmc_b200_ctx* c) {
+  if (c->nranks <= 1 || !c->p2p_ready) return VBMC_B200_OK;
+  unsigned long long err = 0;
+  VB_CUDA(cudaMemcpy(&err, static_cast<unsigned long long*>(c->xchg.p) + XCHG_ERR, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err)
+    VB_FAIL(VBMC_B200_ENCCL, "vbmc_b200:exchange: a peer rank did not deliver its partial sums in time (peer-memory all-reduce, VBMC_B200_P2P_TIMEOUT_S); re-create the communicator");
+  return VBMC_B200_OK;
+}
+
+static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int Ns, int gmask, int nth, bool sync = true) {
+  const bool philox = a->eps_mode == VBMC_B200_EPS_PHILOX;
+  const bool hit = philox && eps_key_matches(c, a->seed, a->stream, Ns);
+  const bool trail = philox && c->prefetch_enabled &&
+                     (hit || (c->have_last_key && c->last_seed == a->seed && c->last_stream + 1 == a->stream));
+  const int rc = step_with_graph_impl(c, a, Ns, gmask, nth, sync, hit, trail);
+  if (rc != VBMC_B200_OK) {  // whatever was enqueued, the buffer is not trusted any more
+    c->eps_key.valid = false;
+    c->have_last_key = false;
+    c->philox_pending = false;
+    c->trail_join_pending = false;
+    return rc;
+  }
+  if (philox) {
+    c->have_last_key = true;
+    c->last_seed = a->seed;
+    c->last_stream = a->stream;
+    eps_key_set(c, a->seed, a->stream + (trail ? 1 : 0), Ns);   // what the buffer holds now (a replayed graph bypasses prepare_eps)
+  }
+  if (sync && c->nranks > 1 && c->out_pinned && c->out_pinned[0] != c->out_pinned[0]) VB_TRY(check_exchange(c));
   return VBMC_B200_OK;
 }
 
@@ -869,8 +982,20 @@ int vbmc_b200_negelcbo_resident_loop(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_
 // device (utils/fminadam.m:20-102; kernels in adam.cu).  Iteration 1 runs as direct launches (buffers get allocated),
 // iteration 2 is captured into a CUDA graph, every later iteration is one graph launch; the host syncs only at the
 // mini-batch ends where the reference tests for termination.
+static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f);
 int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   if (!c || !f) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  const int rc = fminadam_impl(c, f);
+  if (rc != VBMC_B200_OK) {  // the draw buffer's bookkeeping is only trusted after a completed loop
+    c->eps_key.valid = false;
+    c->have_last_key = false;
+    c->philox_pending = false;
+    c->philox_trail = false;
+    c->trail_join_pending = false;
+  }
+  return rc;
+}
+static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   if (!f->x0) VB_FAIL(VBMC_B200_EINVAL, "fminadam: x0 is required");
   vbmc_b200_negelcbo_args na;
   memset(&na, 0, sizeof(na));
@@ -946,17 +1071,29 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   }
   if (!philox) VB_TRY(prepare_eps(c, Ns, eps_mode, nullptr, 0, 0));
 
-  auto body = [&]() -> int {
+  // generator mode: iteration i + 1's draws are generated ahead of time in the tail of iteration i (the loop advances the stream
+  // by one per iteration), so only iteration 1 may have to generate its own — unless an earlier call left them behind
+  const bool hit0 = philox && eps_key_matches(c, f->seed, f->stream, Ns);
+  const bool trail = philox && c->prefetch_enabled;
+  c->eps_key.valid = false;  // set again when the loop has completed
+  c->have_last_key = false;
+  auto body = [&](bool lead) -> int {
     c->philox_dyn = philox;
-    if (philox) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, f->seed, f->stream));
+    if (lead) VB_TRY(prepare_eps(c, Ns, VBMC_B200_EPS_PHILOX, nullptr, f->seed, f->stream));
+    c->philox_seed = f->seed;
+    c->philox_stream = f->stream;
+    c->philox_trail = trail;
     const int rc = enqueue_step(c, Ns, gmask, f->use_thetabnd, 1, FIN_NEGELCBO, true);
     c->philox_dyn = false;
+    c->philox_trail = false;
     VB_TRY(rc);
     VB_TRY(launch_adam_step(c, aa, c->stream));
+    VB_TRY(join_trail(c));
     return VBMC_B200_OK;
   };
+  const bool lead_first = philox && !hit0, lead_later = philox && !trail;
   auto make_key = [&]() {
-    std::vector<long long> key = step_signature(c, Ns, gmask, f->use_thetabnd, philox);
+    std::vector<long long> key = step_signature(c, Ns, gmask, f->use_thetabnd, (philox ? 1 : 0) | (lead_later ? 2 : 0) | (trail ? 4 : 0));
     long long bits[3];
     memcpy(&bits[0], &aa.step_max, 8); memcpy(&bits[1], &aa.step_min, 8); memcpy(&bits[2], &aa.decay, 8);
     key.insert(key.end(), bits, bits + 3);
@@ -965,13 +1102,13 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
     key.push_back(MaxIter);
     return key;
   };
-  bool use_graph = c->graphs_enabled && !c->profiling && c->nranks == 1;
+  bool use_graph = c->graphs_enabled && !c->profiling && !step_uses_nccl(c);
   double* stats_h = c->out_pinned;  // the pinned output mirror doubles as the read-back slot of the termination test
   int it = 0;
   while (it < MaxIter) {
     ++it;
     if (!use_graph || it == 1) {
-      VB_TRY(body());
+      VB_TRY(body(it == 1 ? lead_first : lead_later));
     } else {
       if (it == 2) {
         const std::vector<long long> key = make_key();
@@ -980,7 +1117,7 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
           const long long l0 = c->launches;
           cudaGraph_t graph = nullptr;
           VB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-          const int rc = body();
+          const int rc = body(lead_later);
           cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
           if (rc == VBMC_B200_OK && ce == cudaSuccess && graph) {
             c->adam_graph_launches = c->launches - l0;
@@ -992,7 +1129,7 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
           if (!c->adam_graph) {  // capture unavailable: direct launches for the rest of this call
             cudaGetLastError();
             use_graph = false;
-            VB_TRY(body());
+            VB_TRY(body(lead_later));
             continue;
           }
           c->adam_key = key;
@@ -1019,7 +1156,14 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   if (f->iter) *f->iter = it;
   if (f->stats)
     for (int i = 0; i < 5; ++i) f->stats[i] = stats_h[i];
-  if (philox) c->eps_f32 = c->precision == 32;
+  if (philox) {
+    c->eps_f32 = c->precision == 32;
+    // the buffer holds the draws of stream + it (generated ahead of time) or of the last iteration, stream + it - 1
+    eps_key_set(c, f->seed, f->stream + static_cast<uint64_t>(it) - (trail ? 0 : 1), Ns);
+    c->have_last_key = true;
+    c->last_seed = f->seed;
+    c->last_stream = f->stream + static_cast<uint64_t>(it) - 1;
+  }
   return VBMC_B200_OK;
 }
 

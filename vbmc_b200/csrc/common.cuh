@@ -84,6 +84,8 @@ struct VpDev {  // unpacked variational posterior (filled by vp_unpack_kernel ea
   double* scratch;   // [K*D] work array of vp_unpack_kernel
   double* cblob;     // [K2*DP | K2 | K2 | DP] centred mu, ck, ak/sigma, 1/lambda: source of entmc's constant-bank tables
   int* form_flag;    // entmc formulation of this step: 0 expanded, 1 direct (set by vp_unpack_kernel)
+  unsigned long long* dyn_snap;  // [2] {seed, stream} of the step being evaluated (copied by vp_unpack_kernel from the theta staging
+                                 // buffer): the ahead-of-time draw generator reads it while adam_step_kernel may already advance the original
 };
 
 struct GpDev {  // attached GP posterior
@@ -150,6 +152,22 @@ struct AdamArgs {
   unsigned long long* dyn;  // {seed, stream} of the device draw generator (stream advanced every iteration) or NULL
 };
 
+// One-shot all-reduce of R over NVLink peer memory, fused into finalize_kernel (misc.cu sets it up, finalize.cu uses it).
+// Every rank owns one exchange buffer and maps every peer's through CUDA IPC:
+//   words [0, 32)   : arrival flags  [parity][rank]   (sequence number of the step whose partial sums have landed)
+//   word  32        : sequence number of the last completed exchange (same on every rank)
+//   word  33        : error flag (a peer did not arrive in time)
+//   words [64, ...) : inbox [parity][rank][cap] doubles
+// A step pushes its R into slot [seq & 1][my rank] of every rank's inbox, raises its flag there, waits for all flags in
+// its own buffer, and sums the nranks slots in rank order (=> bit-identical results on all ranks).
+enum { XCHG_MAXR = 16, XCHG_SEQ = 32, XCHG_ERR = 33, XCHG_HDR = 64 };
+struct XchgDev {
+  int nranks = 1, rank = 0;
+  int cap = 0;                         // doubles per (parity, rank) slot
+  unsigned long long* const* peer = nullptr;  // device array [nranks]: base of every rank's exchange buffer
+  long long timeout_cycles = 0;        // give up waiting for a peer after this many SM cycles
+};
+
 struct Prof {
   double ms = 0;
   long long n = 0;
@@ -169,6 +187,8 @@ struct vbmc_b200_ctx {
   cudaStream_t stream2 = nullptr;  // gplogjoint branch
   cudaStream_t stream3 = nullptr;  // draw generation (independent of theta)
   cudaEvent_t ev_fork0 = nullptr, ev_philox = nullptr;
+  cudaEvent_t ev_glj = nullptr;  // log-joint kernel done (before its reduction)
+  cudaEvent_t ev_trail_fork = nullptr, ev_trail = nullptr;  // ahead-of-time draw generation (forked after the entropy sweep)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   long long launches = 0;
   int precision = 64;  // 64: everything FP64; 32: the entropy sweep in FP32 (vbmc_b200_set_precision)
@@ -180,6 +200,11 @@ struct vbmc_b200_ctx {
   // multi-GPU
   int nranks = 1, rank = 0;
   ncclComm* comm = nullptr;
+  // peer-memory exchange (fused all-reduce): ready when every rank mapped every other rank's buffer
+  bool p2p_ready = false;
+  vb::DevBuf xchg, xchg_peers;
+  void* xchg_mapped[16] = {nullptr};   // cudaIpcOpenMemHandle results (own slot unused)
+  vb::XchgDev xdev{};
 
   // GP
   bool gp_ready = false;
@@ -220,6 +245,21 @@ struct vbmc_b200_ctx {
   bool philox_pending = false;
   bool philox_dyn = false;  // read {seed, stream} from theta_dev[ntheta..] (set while building / replaying a step graph)
   uint64_t philox_seed = 0, philox_stream = 0;
+  // Draws of the device generator are a pure function of (seed, stream, shape), so the NEXT step's draws (stream + 1) are generated
+  // right after the entropy sweep has consumed the current ones, in the shadow of the single-CTA tail of the step (reduce, finalize,
+  // Adam update).  `eps_key` says which draws the buffer holds; a step whose (seed, stream) matches skips its own generation.
+  bool prefetch_enabled = true;      // VBMC_B200_PREFETCH=0 turns the ahead-of-time generation off
+  bool glj_first = true;             // run the log-joint kernel before the entropy sweep when no generator precedes the sweep
+  bool philox_trail = false;         // request: generate (seed, stream + 1) after the sweep of the step being enqueued
+  bool trail_join_pending = false;   // stream3 carries an ahead-of-time generation that `stream` has not joined yet
+  struct EpsKey {
+    bool valid = false;
+    uint64_t seed = 0, stream = 0;
+    int D = 0, K = 0, Ns = 0;
+    bool f32 = false;
+  } eps_key;
+  bool have_last_key = false;        // (seed, stream) of the previous generator-mode step: a +1 successor switches prefetching on
+  uint64_t last_seed = 0, last_stream = 0;
 
   // step buffers
   vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out, glj_part;
@@ -274,7 +314,7 @@ int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
 int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
 int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
-                  const uint64_t* dyn = nullptr);
+                  const uint64_t* dyn = nullptr, uint64_t stream_add = 0);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 int launch_adam_step(vbmc_b200_ctx* c, const AdamArgs& a, cudaStream_t st);
 int launch_adam_check(vbmc_b200_ctx* c, const AdamArgs& a, int iter, double TolFun, cudaStream_t st);

@@ -13,6 +13,7 @@ struct UnpackArgs {
   int D, K, ntheta, have_theta, force_form, DPc, want_cblob;
   int opt[4];
   const double* theta;
+  const unsigned long long* dyn_src;  // {seed, stream} of this step's draws behind theta in the staging buffer (or NULL)
   const double *base_mu, *base_sigma, *base_lambda, *base_w, *base_eta;
   VpDev vp;
   double* cn;  // [K] nf/sigma_k^D ; cn[K] = nf
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   __shared__ double part[256];
   __shared__ double s_es, s_nf;
   const bool ht = a.have_theta != 0;
+  if (tid < 2 && a.dyn_src) a.vp.dyn_snap[tid] = a.dyn_src[tid];  // private copy for the ahead-of-time draw generator (api.cu)
   int idx = 0;
   const int o_mu = 0;
   if (ht && a.opt[0]) idx += D * K;
@@ -174,6 +176,8 @@ struct FinArgs {
   int stage_R;     // R fits in shared memory next to the work arrays
   double TolCon, WThresh, WPen;
   const double* R;
+  double* Rw;      // == R, writable: receives the all-reduced sums when they do not fit in shared memory
+  XchgDev xc;      // nranks > 1: all-reduce R across ranks over peer memory before it is used (common.cuh)
   const double* lb;
   const double* ub;
   const double* cn;  // [K+1]
@@ -211,6 +215,83 @@ __device__ __noinline__ double block_sum256(double v, double* part) {
 #pragma unroll 1
   for (int i = 1; i < 8; ++i) t += part[i];
   return t;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One-shot all-reduce of this rank's partial sums R[0..total) over NVLink peer memory (layout: XchgDev, common.cuh):
+// push R into slot [parity][my rank] of EVERY rank's inbox (plain stores to the IPC-mapped peer buffers), publish the step's
+// sequence number in every rank's flag word (release, system scope), wait until all ranks' flags show it in the local
+// buffer (acquire), then sum the nranks local slots in rank order into dst.  No kernel launch and no NCCL call between the
+// partial sums and their use; every rank adds the same numbers in the same order => identical results everywhere.
+__device__ __noinline__ void exchange_sum(const XchgDev& xc, const double* __restrict__ R, int total, double* dst) {
+  const int tid = threadIdx.x, nt = blockDim.x, nr = xc.nranks;
+  unsigned long long* me = xc.peer[xc.rank];
+  const unsigned long long seq = me[XCHG_SEQ] + 1;
+  const int par = static_cast<int>(seq & 1);
+  const size_t slot = (static_cast<size_t>(par) * nr + xc.rank) * xc.cap;
+#pragma unroll 1
+  for (int i0 = tid; i0 < total; i0 += 4 * nt) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i0 + u * nt < total) ? R[i0 + u * nt] : 0.0;
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+      double* out = reinterpret_cast<double*>(xc.peer[r] + XCHG_HDR) + slot;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * nt < total) out[i0 + u * nt] = v[u];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  bool late = false;
+  if (tid < nr) {
+    st_release_sys(xc.peer[tid] + par * XCHG_MAXR + xc.rank, seq);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(me + par * XCHG_MAXR + tid) < seq) {
+      if (clock64() - t0 > xc.timeout_cycles) {
+        late = true;
+        break;
+      }
+    }
+  }
+  late = __syncthreads_or(late) != 0;
+  const double* in0 = reinterpret_cast<const double*>(me + XCHG_HDR) + static_cast<size_t>(par) * nr * xc.cap;
+#pragma unroll 1
+  for (int i0 = tid; i0 < total; i0 += 8 * nt) {
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < nr; r += 4) {
+      double x[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          x[q][u] = (r + q < nr && i0 + u * nt < total) ? __ldcg(in0 + static_cast<size_t>(r + q) * xc.cap + i0 + u * nt) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (r + q < nr) acc[u] += x[q][u];  // rank order
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * nt < total) dst[i0 + u * nt] = late ? __longlong_as_double(0x7ff8000000000000LL) : acc[u];
+  }
+  if (tid == 0) {
+    me[XCHG_SEQ] = seq;
+    if (late) me[XCHG_ERR] = 1;
+  }
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
@@ -255,9 +336,22 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     v_lambda[d] = a.vp.lambda[d];
     v_lnlambda[d] = a.vp.lnlambda[d];
   }
-  if (a.stage_R)
+  if (a.xc.nranks > 1) {
+    exchange_sum(a.xc, a.R, rl.total, a.stage_R ? sR : a.Rw);
+  } else if (a.stage_R) {
+    // 8 independent loads in flight per thread: the staging is one L2 round trip per 2048 doubles, not one per 256
+    int i = tid;
 #pragma unroll 1
-    for (int i = tid; i < rl.total; i += nt) sR[i] = a.R[i];
+    for (; i + 7 * nt < rl.total; i += 8 * nt) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = a.R[i + u * nt];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sR[i + u * nt] = t[u];
+    }
+#pragma unroll 1
+    for (; i < rl.total; i += nt) sR[i] = a.R[i];
+  }
   const double* R = a.stage_R ? sR : a.R;
   __syncthreads();
   const bool doH = a.what != FIN_GPLOGJOINT, doG = a.what != FIN_ENTMC;
@@ -500,6 +594,7 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   a.DPc = c->vp_cblob_dp;
   for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
   a.theta = c->theta_dev.d();
+  a.dyn_src = (have_theta && c->philox_dyn) ? reinterpret_cast<const unsigned long long*>(c->theta_dev.d() + c->ntheta) : nullptr;
   a.base_mu = c->base_mu; a.base_sigma = c->base_sigma; a.base_lambda = c->base_lambda;
   a.base_w = c->base_w; a.base_eta = c->base_eta;
   a.vp = c->vp;
@@ -534,6 +629,8 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
   for (int i = 0; i < 4; ++i) a.opt[i] = c->opt[i];
   a.TolCon = c->TolCon; a.WThresh = c->WeightThreshold; a.WPen = c->WeightPenalty;
   a.R = c->R_dev.d();
+  a.Rw = c->R_dev.d();
+  a.xc = XchgDev{};
   a.lb = c->bnd.d();
   a.ub = c->bnd.d() + c->nbnd;
   a.cn = c->vp.cn;
@@ -548,6 +645,7 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
                                   static_cast<size_t>(c->D) * c->K + 5 * c->K + 1 + 2 * c->D);
   a.stage_R = smem + sizeof(double) * rl.total <= c->smem_optin ? 1 : 0;
   if (a.stage_R) smem += sizeof(double) * rl.total;
+  if (c->nranks > 1 && c->p2p_ready && rl.total <= c->xdev.cap) a.xc = c->xdev;  // else: allreduce_R (NCCL) ran before this launch
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   KernelScope ks(c, "finalize", st);

@@ -62,11 +62,103 @@ int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st) {
   return VBMC_B200_OK;
 }
 
+// ---- peer-memory exchange set-up (see XchgDev in common.cuh) ----
+static void p2p_teardown(vbmc_b200_ctx* c) {
+  for (int r = 0; r < XCHG_MAXR; ++r) {
+    if (c->xchg_mapped[r]) cudaIpcCloseMemHandle(c->xchg_mapped[r]);
+    c->xchg_mapped[r] = nullptr;
+  }
+  c->xchg.release();
+  c->xchg_peers.release();
+  c->p2p_ready = false;
+  c->xdev = XchgDev{};
+  cudaGetLastError();
+}
+
+// gather `words` int32 per rank through the communicator (sum of disjoint slots); used for the IPC handles and to agree on success
+static int gather_words(vbmc_b200_ctx* c, const int* mine, int words, std::vector<int>* all) {
+  const int n = c->nranks * words;
+  DevBuf d;
+  VB_TRY(d.reserve(sizeof(int) * n));
+  std::vector<int> h(n, 0);
+  memcpy(h.data() + c->rank * words, mine, sizeof(int) * words);
+  cudaError_t e = cudaMemcpyAsync(d.p, h.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream);
+  int rc = 0;
+  if (e == cudaSuccess) rc = g_nccl.allreduce(d.p, d.p, static_cast<size_t>(n), /*ncclInt32*/ 2, /*ncclSum*/ 0, c->comm, c->stream);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(h.data(), d.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(c->stream);
+  d.release();
+  if (rc != 0) VB_FAIL(VBMC_B200_ENCCL, "vbmc_b200:nccl: handle exchange failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+  if (e != cudaSuccess) VB_FAIL(VBMC_B200_ECUDA, "CUDA error during the handle exchange: %s", cudaGetErrorString(e));
+  *all = h;
+  return VBMC_B200_OK;
+}
+
+// Every rank allocates its exchange buffer, publishes its IPC handle and maps the others'.  Ranks agree (second gather) on
+// whether ALL mappings succeeded; if not, every rank keeps the NCCL all-reduce.  VBMC_B200_P2P=0 skips the attempt.
+static int p2p_setup(vbmc_b200_ctx* c) {
+  if (const char* e = getenv("VBMC_B200_P2P"))
+    if (!strcmp(e, "0")) return VBMC_B200_OK;
+  if (c->nranks > XCHG_MAXR) return VBMC_B200_OK;
+  const int cap = 40960;  // doubles per slot: covers R for K <= 128, D <= 24, S <= 100 (larger steps use NCCL)
+  const size_t bytes = sizeof(double) * (XCHG_HDR + 2 * static_cast<size_t>(c->nranks) * cap);
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (c->xchg.reserve(bytes) != VBMC_B200_OK) ok = 0;
+  if (ok && cudaMemset(c->xchg.p, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaDeviceSynchronize() != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, c->xchg.p) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  int words[17];
+  memcpy(words, &mine, 64);
+  words[16] = ok;
+  std::vector<int> all;
+  VB_TRY(gather_words(c, words, 17, &all));
+  std::vector<unsigned long long*> peers(c->nranks, nullptr);
+  for (int r = 0; r < c->nranks && ok; ++r) {
+    if (!all[r * 17 + 16]) { ok = 0; break; }
+    if (r == c->rank) { peers[r] = static_cast<unsigned long long*>(c->xchg.p); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, &all[r * 17], 64);
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    c->xchg_mapped[r] = ptr;
+    peers[r] = static_cast<unsigned long long*>(ptr);
+  }
+  if (ok && c->xchg_peers.reserve(sizeof(void*) * XCHG_MAXR) != VBMC_B200_OK) ok = 0;
+  if (ok && cudaMemcpy(c->xchg_peers.p, peers.data(), sizeof(void*) * c->nranks, cudaMemcpyHostToDevice) != cudaSuccess) ok = 0;
+  int okw = ok;
+  VB_TRY(gather_words(c, &okw, 1, &all));  // also a barrier: nobody pushes before every buffer is zeroed and mapped
+  for (int r = 0; r < c->nranks; ++r) ok = ok && all[r];
+  if (!ok) {
+    p2p_teardown(c);
+    return VBMC_B200_OK;
+  }
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+  c->xdev.nranks = c->nranks;
+  c->xdev.rank = c->rank;
+  c->xdev.cap = cap;
+  c->xdev.peer = reinterpret_cast<unsigned long long* const*>(c->xchg_peers.p);
+  // How long a rank waits inside finalize_kernel for its peers' partial sums.  Ranks are driven by independent host
+  // processes, so a peer can legitimately be seconds behind (NCCL itself waits for ever); the bound only exists so that a
+  // dead peer surfaces as vbmc_b200:exchange instead of a kernel that never ends.  VBMC_B200_P2P_TIMEOUT_S, default 120.
+  double tmo_s = 120.0;
+  if (const char* e = getenv("VBMC_B200_P2P_TIMEOUT_S")) tmo_s = atof(e) > 0.0 ? atof(e) : tmo_s;
+  c->xdev.timeout_cycles = static_cast<long long>(static_cast<double>(khz > 0 ? khz : 2000000) * 1000.0 * tmo_s);
+  c->p2p_ready = true;
+  return VBMC_B200_OK;
+}
+
 void comm_destroy(vbmc_b200_ctx* c) {
+  p2p_teardown(c);
   if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
   c->comm = nullptr;
   c->nranks = 1;
   c->rank = 0;
+  c->eps_key.valid = false;  // the shard of the pair axis this rank generates changes with the communicator
 }
 
 // ---- FP64 FMA peak: 8 independent DFMA chains per thread ----
@@ -105,12 +197,20 @@ int vbmc_b200_comm_init(vbmc_b200_ctx* c, int nranks, int rank, const void* id12
   VB_NCCL(g_nccl.initrank(&c->comm, nranks, uid, rank));
   c->nranks = nranks;
   c->rank = rank;
+  c->eps_key.valid = false;
+  VB_TRY(p2p_setup(c));
   return VBMC_B200_OK;
 }
 
 int vbmc_b200_shard_range(int total, int nranks, int rank, int* begin, int* end) {
   if (total < 0 || nranks < 1 || rank < 0 || rank >= nranks || !begin || !end) VB_FAIL(VBMC_B200_EINVAL, "shard_range: bad arguments");
   shard_range(total, nranks, rank, begin, end);
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_comm_p2p(vbmc_b200_ctx* c, int* peer_memory) {
+  if (!c || !peer_memory) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  *peer_memory = (c->nranks > 1 && c->p2p_ready) ? 1 : 0;
   return VBMC_B200_OK;
 }
 

@@ -30,6 +30,7 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 struct PhiloxArgs {
   int D, K, half, pair_begin, pair_end;
   uint64_t seed, stream;
+  uint64_t stream_add;  // added to the stream id (1 when generating the NEXT step's draws ahead of time)
   const uint64_t* dyn;  // optional device pointer to {seed, stream} (graph replay: values change, the node does not)
   double* eps;  // [K][half][D]  (floats in FP32 mode)
 };
@@ -40,7 +41,7 @@ __global__ void philox_normal_kernel(const PhiloxArgs a) {
   const long long e_begin = (static_cast<long long>(j) * a.half + a.pair_begin) * a.D;
   const long long e_end = (static_cast<long long>(j) * a.half + a.pair_end) * a.D;
   const long long c_begin = e_begin >> 1, c_end = (e_end + 1) >> 1;
-  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = a.dyn ? a.dyn[1] : a.stream;
+  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = (a.dyn ? a.dyn[1] : a.stream) + a.stream_add;
   for (long long c = c_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; c < c_end;
        c += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 ctr = make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
@@ -65,7 +66,7 @@ __global__ void philox_normal_f32_kernel(const PhiloxArgs a) {
   const long long e_begin = (static_cast<long long>(j) * a.half + a.pair_begin) * a.D;
   const long long e_end = (static_cast<long long>(j) * a.half + a.pair_end) * a.D;
   const long long c_begin = e_begin >> 2, c_end = (e_end + 3) >> 2;
-  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = a.dyn ? a.dyn[1] : a.stream;
+  const uint64_t seed = a.dyn ? a.dyn[0] : a.seed, strm = (a.dyn ? a.dyn[1] : a.stream) + a.stream_add;
   for (long long c = c_begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; c < c_end;
        c += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 ctr = make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32),
@@ -97,12 +98,14 @@ __global__ void philox_raw_kernel(uint4 ctr, uint2 key, uint32_t* out) {
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
-int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st, const uint64_t* dyn) {
+int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st, const uint64_t* dyn,
+                  uint64_t stream_add) {
   PhiloxArgs a;
   a.D = D; a.K = K; a.half = Ns / 2;
   shard_range(a.half, c->nranks, c->rank, &a.pair_begin, &a.pair_end);
   a.seed = seed; a.stream = stream_id;
   a.dyn = dyn;
+  a.stream_add = stream_add;
   a.eps = c->eps.d();
   if (a.pair_end <= a.pair_begin) return VBMC_B200_OK;
   const bool f32 = c->precision == 32;
