@@ -451,7 +451,10 @@ def main():
     ent_tflops = counts["entmc_flops"] * shard / (ent_ms * 1e-3) / 1e12 if ent_ms > 0 else None
     ent_gbs = counts["entmc_bytes"] * shard / (ent_ms * 1e-3) / 1e9 if ent_ms > 0 else None
     roofline = {"kernel": "entmc_kernel", "bound": "fp64", "achieved": ent_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ent_tflops / fp64_peak if ent_tflops else None, "traffic": None,
+                "frac": ent_tflops / fp64_peak if ent_tflops else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at c3 on one GPU (profiles/r1_ncu_summary.md, capture
+                # entmc_r1f: 65.61 MB + 0.20 MB); other configurations were not captured
+                "traffic": 65.61e6 + 0.204e6 if (cfg_name == "c3" and world == 1) else None,
                 "peak_source": "DFMA micro-benchmark run live on this device (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"achieved": ent_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ent_gbs / peaks["hbm_gbs"] if ent_gbs else None,
                         "peak_source": peak_src + " MEASURED_PEAKS.json"},
@@ -477,7 +480,10 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")},
                    "parallelism": f"mc-pair-shard x{world} + hyp-sample shard, 1 all-reduce/step" if world > 1 else "single GPU",
-                   "eps": "device Philox4x32-10, fresh draws every step (reference: randn per call)",
+                   "allreduce": (("peer memory over NVLink, fused into finalize_kernel (CUDA IPC, no NCCL call per step)" if ctx.comm_p2p()
+                                  else "ncclAllReduce") if world > 1 else None),
+                   "eps": "device Philox4x32-10 + 1024-strip ziggurat, fresh draws every step (reference: randn per call), generated "
+                          "ahead of time in the tail of the previous step",
                    "l2": "flushed (256 MB memset) between timed steps, outside the CUDA events",
                    "gp_posterior_from": gp_source, "setup_s": round(t_setup, 2)},
         "clocks": clocks,

@@ -115,6 +115,13 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreate(&c->ev_t0));
   VB_CUDA(cudaEventCreate(&c->ev_t1));
+  {
+    const int rc = vb::philox_init_tables(c);
+    if (rc != VBMC_B200_OK) {
+      vbmc_b200_destroy(c);
+      return rc;
+    }
+  }
   if (const char* g = getenv("VBMC_B200_GRAPHS")) c->graphs_enabled = strcmp(g, "0") != 0;
   if (const char* pc = getenv("VBMC_B200_ENTMC_PRUNE")) c->entmc_prune_c = atof(pc);
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
@@ -136,7 +143,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->predWork};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->predWork, &c->zigTab};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);

@@ -239,6 +239,7 @@ struct vbmc_b200_ctx {
 
   // eps
   vb::DevBuf eps;
+  vb::DevBuf zigTab;  // ziggurat tables of the draw generator (philox.cu)
   int epsD = 0, epsK = 0, epsNs = 0;
   bool eps_ready = false;
   bool eps_f32 = false;  // the resident draws are floats (generated by the device generator in FP32 mode)
@@ -313,6 +314,7 @@ int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st);
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
 int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
 int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
+int philox_init_tables(vbmc_b200_ctx* c);
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
                   const uint64_t* dyn = nullptr, uint64_t stream_add = 0);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
