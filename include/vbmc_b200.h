@@ -51,6 +51,11 @@ const char* vbmc_b200_last_error(void);
 /* device: CUDA ordinal; fails with ENODEV when the device is not compute capability 10.x. */
 int vbmc_b200_create(vbmc_b200_ctx** out, int device);
 int vbmc_b200_destroy(vbmc_b200_ctx* ctx);
+/* Process-wide context of `device`, created on first use and owned by the library (do not destroy it; released by
+ * vbmc_b200_shared_release or at process exit).  Every MEX gateway of mex/ is its own shared object but links this one
+ * library, so this is how negelcbo_vbmc, gplite_post, gplite_pred ... see the same resident GP posterior and draws. */
+int vbmc_b200_shared(vbmc_b200_ctx** out, int device);
+int vbmc_b200_shared_release(void);
 int vbmc_b200_sync(vbmc_b200_ctx* ctx);
 /* number of kernels this library launched on the context since creation (bench: gpu_launches) */
 int vbmc_b200_launch_count(vbmc_b200_ctx* ctx, long long* count);
@@ -106,6 +111,13 @@ typedef struct vbmc_b200_gp_desc {
  * L: N x N x S upper factors (gp.post(s).L) or NULL when variances are never requested. */
 int vbmc_b200_gp_attach(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const double* alpha,
                         const double* sW1, const int* Lchol, const double* L);
+
+/* Caller's fingerprint of the resident posterior (e.g. the address of gp.post(1).alpha's data in MATLAB, whose
+ * copy-on-write keeps it stable until the posterior is recomputed).  The library only stores it and resets it to 0
+ * whenever the resident posterior changes (gp_attach, gp_post, gp_post_update1, gp_nlz*), so that several gateways
+ * sharing one context agree on whether `gp` has to be attached again. */
+int vbmc_b200_gp_tag_set(vbmc_b200_ctx* ctx, unsigned long long tag);
+int vbmc_b200_gp_tag_get(vbmc_b200_ctx* ctx, unsigned long long* tag);
 
 /* gplite_post(hyp,X,y,covfun,meanfun,noisefun,s2)  — gplite/gplite_post.m:94-172, i.e. S x
  * gplite_core(hyp,gp,0,0) (gplite/private/gplite_core.m:33-102,278-285): SE-ARD Gram, Cholesky
@@ -174,8 +186,10 @@ int vbmc_b200_thetabnd_set(vbmc_b200_ctx* ctx, int n, const double* lb, const do
  * entropy draws.  The reference draws epsilon = randn(D,1,Ns/2) per component from MATLAB's
  * global stream (ent/entmc_vbmc.m:53).  Two sources:
  *   parity mode : the caller supplies the draws (host buffer, D x Ns/2 x K column-major);
- *   device mode : counter-based Philox4x32-10 + Box-Muller keyed by (seed, call counter,
- *                 element index) — independent of the number of GPUs and of the sharding.
+ *   device mode : counter-based Philox4x32-10 feeding a 1024-strip ziggurat (FP32 mode: Box-Muller), keyed by
+ *                 (seed, call counter, element index) — independent of the number of GPUs and of the sharding.
+ *                 A caller whose call counter advances by one per call gets the next call's draws generated
+ *                 ahead of time, in the tail of the current call.
  * ------------------------------------------------------------------------------------- */
 enum { VBMC_B200_EPS_HOST = 0, VBMC_B200_EPS_RESIDENT = 1, VBMC_B200_EPS_PHILOX = 2 };
 /* copy draws to the device once; later calls may use VBMC_B200_EPS_RESIDENT */

@@ -164,6 +164,35 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   return VBMC_B200_OK;
 }
 
+int vbmc_b200_gp_tag_set(vbmc_b200_ctx* c, unsigned long long tag) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  c->gp_tag = c->gp_ready ? tag : 0;
+  return VBMC_B200_OK;
+}
+int vbmc_b200_gp_tag_get(vbmc_b200_ctx* c, unsigned long long* tag) {
+  if (!c || !tag) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  *tag = c->gp_ready ? c->gp_tag : 0;
+  return VBMC_B200_OK;
+}
+
+// process-wide contexts, one per device (see include/vbmc_b200.h)
+static vbmc_b200_ctx* g_shared[64] = {nullptr};
+int vbmc_b200_shared(vbmc_b200_ctx** out, int device) {
+  if (!out) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_shared: out is NULL");
+  *out = nullptr;
+  if (device < 0 || device >= 64) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_shared: device %d out of range", device);
+  if (!g_shared[device]) VB_TRY(vbmc_b200_create(&g_shared[device], device));
+  *out = g_shared[device];
+  return VBMC_B200_OK;
+}
+int vbmc_b200_shared_release(void) {
+  for (int d = 0; d < 64; ++d) {
+    if (g_shared[d]) vbmc_b200_destroy(g_shared[d]);
+    g_shared[d] = nullptr;
+  }
+  return VBMC_B200_OK;
+}
+
 int vbmc_b200_sync(vbmc_b200_ctx* c) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
   VB_CUDA(cudaSetDevice(c->device));
@@ -290,6 +319,7 @@ extern "C" {
 int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const double* alpha, const double* sW1,
                         const int* Lchol, const double* L) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  c->gp_tag = 0;  // the resident posterior is about to change: a caller's fingerprint of it no longer holds
   int Ncov, Nnoise, Nmean;
   VB_TRY(gp_check_desc(g, &Ncov, &Nnoise, &Nmean));
   if (!alpha) VB_FAIL(VBMC_B200_EINVAL, "gp_attach: alpha is required");

@@ -208,6 +208,7 @@ struct vbmc_b200_ctx {
 
   // GP
   bool gp_ready = false;
+  unsigned long long gp_tag = 0;  // opaque caller fingerprint of the resident posterior (vbmc_b200_gp_tag_*); 0 = none
   vb::GpDev gp{};
   vb::DevBuf gpX, gpHyp, gpAlpha, gpDerived, gpL, gpY, gpS2, gpWork;
   std::vector<int> gpLchol;

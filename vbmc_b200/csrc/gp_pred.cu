@@ -273,6 +273,7 @@ extern "C" int vbmc_b200_gp_set_sn2_mult(vbmc_b200_ctx* c, const double* sn2_mul
 extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, double ystar, double* alpha_out,
                                          double* Lcol_out, double* sW_out) {
   if (!c || !xstar) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  c->gp_tag = 0;  // the resident posterior is about to change: a caller's fingerprint of it no longer holds
   if (!c->gp_ready)
     VB_FAIL(VBMC_B200_EREFERENCE, "gplite_post:NoGP: GPLITE_POST can perform rank-one update only with an existing GP struct.");
   if (!c->gpHasL) VB_FAIL(VBMC_B200_ESTATE, "gplite_post (rank-one): the factors gp.post(s).L must be resident (gp_attach with L, or gp_post)");

@@ -996,6 +996,7 @@ extern "C" {
 int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alpha, double* L, double* sW1,
                       double* sn2_mult, int* Lchol) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  c->gp_tag = 0;  // the resident posterior is about to change: a caller's fingerprint of it no longer holds
   int Ncov, Nnoise, Nmean;
   VB_TRY(check_desc(gd, &Ncov, &Nnoise, &Nmean, "gp_post"));
   if (gd->Nhyp != Ncov + Nnoise + Nmean)
@@ -1075,6 +1076,7 @@ static double nlz_value(const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hpr
 int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hprior, double* nlZ,
                      double* dnlZ) {
   if (!c || !nlZ) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  c->gp_tag = 0;  // the resident posterior is about to change: a caller's fingerprint of it no longer holds
   int Ncov, Nnoise, Nmean;
   VB_TRY(check_desc(gd, &Ncov, &Nnoise, &Nmean, "gp_nlz"));
   if (gd->Nhyp != Ncov + Nnoise + Nmean)
@@ -1173,6 +1175,7 @@ int vbmc_b200_gp_nlz(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b
 // gpoptimize_fun -> gplite_nlZ, Ninit vectors) and every slice-sampler step (gplite_train.m:318-330).
 int vbmc_b200_gp_nlz_batch(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, const vbmc_b200_hprior* hprior, double* nlZ) {
   if (!c || !nlZ) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  c->gp_tag = 0;  // the resident posterior is about to change: a caller's fingerprint of it no longer holds
   int Ncov, Nnoise, Nmean;
   VB_TRY(check_desc(gd, &Ncov, &Nnoise, &Nmean, "gp_nlz_batch"));
   if (gd->Nhyp != Ncov + Nnoise + Nmean)
