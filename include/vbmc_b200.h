@@ -211,7 +211,8 @@ typedef struct vbmc_b200_negelcbo_args {
   const double* theta;   /* ntheta (host)                                                 */
   int ntheta;
   double beta;           /* 0 or non-finite => 0 (negelcbo_vbmc.m:15)                      */
-  int Ns;                /* MC draws per component; made even like entmc_vbmc.m:45; must be > 0 */
+  int Ns;                /* MC draws per component, made even like entmc_vbmc.m:45; 0 = deterministic entropy
+                            lower bound entlb_vbmc instead of the Monte-Carlo estimate (negelcbo_vbmc.m:102-109) */
   int compute_grad;      /* 0/1                                                            */
   int compute_var;       /* 0 none, 1 full, 2 diagonal (gplogjoint.m:273,306)              */
   int separate_K;        /* nargout > 9: fill I_sk (and J_sjk when compute_var)            */
@@ -276,6 +277,12 @@ int vbmc_b200_fminadam(vbmc_b200_ctx* ctx, const vbmc_b200_fminadam_args* args);
  * Uses the vp last set (no theta unpacking).  grad_flags[4]; dH length = D*K*gf0 + K*gf1 + D*gf2 + K*gf3. */
 int vbmc_b200_entmc(vbmc_b200_ctx* ctx, int Ns, const int grad_flags[4], int jacobian_flag, int eps_mode,
                     const double* eps, uint64_t seed, uint64_t stream, double* H, double* dH);
+
+/* [H,dH] = entlb_vbmc(vp,grad_flags,jacobian_flag) — ent/entlb_vbmc.m:1-147, the deterministic entropy lower bound that
+ * negelcbo_vbmc uses instead of entmc_vbmc when Ns == 0 (negelcbo_vbmc.m:102-109; misc/vpsieve_vbmc.m:76 scores every
+ * candidate posterior that way).  Uses the vp last set; dH layout as vbmc_b200_entmc.  vbmc_b200_negelcbo handles
+ * Ns == 0 itself (same outputs as for Ns > 0, H and dH being the bound and its gradient). */
+int vbmc_b200_entlb(vbmc_b200_ctx* ctx, const int grad_flags[4], int jacobian_flag, double* H, double* dH);
 
 /* [F,dF,varF,dvarF,varss,I_sk,J_sjk] = gplogjoint(vp,gp,grad_flags,avg_flag,jacobian_flag,compute_var,separate_K)
  * misc/gplogjoint.m:1-413.  avg_flag must be 1 when S > 1.  dvarF: compute_var == 2 only

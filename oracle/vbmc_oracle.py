@@ -286,6 +286,81 @@ def entmc_vbmc(vp, Ns, grad_flags=True, jacobian_flag=True, epsilon=None, nargou
     return H, dH
 
 
+def entlb_vbmc(vp, grad_flags=None, jacobian_flag=True, nargout=2):
+    """[H,dH] = entlb_vbmc(vp,grad_flags,jacobian_flag) — ent/entlb_vbmc.m:1-147, the deterministic entropy lower bound of
+    Gershman et al. (2012) that negelcbo_vbmc uses when Ns == 0 (negelcbo_vbmc.m:102-109): vpsieve_vbmc.m:76 scores every
+    candidate with it (NSentFast = 0, vbmc.m:216), and the whole optimisation does when K == 1 or EntropySwitch is on
+    (vpsieve_vbmc.m:29-33).  Vectorised like the .m code (K x K temporaries); the BigK branch (:48-66) is dead (BigK = Inf)."""
+    if nargout < 2:  # :8-9
+        gf = [False] * 4
+    elif grad_flags is None:  # :10-11
+        gf = [True] * 4
+    else:
+        gf = list(np.atleast_1d(grad_flags).astype(bool))
+        if len(gf) == 1:  # :13
+            gf = gf * 4
+    D, K = vp["D"], vp["K"]
+    mu = np.asarray(vp["mu"], dtype=np.float64).reshape(D, K)
+    sigma = np.asarray(vp["sigma"], dtype=np.float64).ravel()
+    lam = np.asarray(vp["lambda"], dtype=np.float64).ravel()
+    w = np.asarray(vp["w"], dtype=np.float64).ravel()
+    mu_grad = np.zeros((D, K)) if gf[0] else np.zeros((0,))
+    sigma_grad = np.zeros(K) if gf[1] else np.zeros((0,))
+    lambda_grad = np.zeros(D) if gf[2] else np.zeros((0,))
+    w_grad = np.zeros(K) if gf[3] else np.zeros((0,))
+    if K == 1:  # :32-47 exact entropy of one Gaussian
+        H = 0.5 * D * (1 + math.log(2 * math.pi)) + D * np.sum(np.log(sigma)) + np.sum(np.log(lam))
+        if gf[1]:
+            sigma_grad[:] = D / sigma
+        if gf[2]:
+            lambda_grad[:] = 1.0  # :42-43 (already the log-lambda gradient)
+        if gf[3]:
+            w_grad = np.zeros(1)  # :46
+    else:  # :68-135
+        # index convention of the .m code: dim 2 = j (row of gammasum), dim 3 = k
+        sumsigma2 = sigma[:, None] ** 2 + sigma[None, :] ** 2  # (j,k)  :76
+        sumsigma = np.sqrt(sumsigma2)
+        nconst = 1.0 / (2 * math.pi) ** (D / 2) / np.prod(lam)  # :79
+        dmu_jk = mu[:, :, None] - mu[:, None, :]  # (D,j,k) = mu_j - mu_k   (bsxfun(@minus, mu, mu_3), :81)
+        d2 = np.sum((dmu_jk / (sumsigma[None, :, :] * lam[:, None, None])) ** 2, axis=0)  # (j,k)  :81
+        gamma = nconst / sumsigma**D * np.exp(-0.5 * d2)  # (j,k)  :82
+        gammasum = np.sum(w[:, None] * gamma, axis=0)  # (k,): sum over dim 2 (j) of w(1,j).*gamma(1,j,k)  :83 (gamma is symmetric)
+        H = -np.sum(w * np.log(gammasum))  # :85
+        if any(gf):
+            # :90 divides gamma(1,j,k) by gammasum(1,1,k) (gammasum is 1x1xK): element (j,k) -> gamma(j,k)/gammasum(k)
+            gammafrac = gamma / gammasum[None, :]
+            wgammafrac = w[None, :] * gammafrac  # w_3(k) * gamma(j,k)/gammasum(k)  :91
+            if gf[0]:
+                dmu = (mu[:, None, :] - mu[:, :, None]) / (sumsigma2[None, :, :] * (lam**2)[:, None, None])  # (D,j,k) = (mu_k-mu_j)/..  :94
+            if gf[1]:
+                dsigma = -D / sumsigma2 + 1.0 / sumsigma2**2 * np.sum((dmu_jk / lam[:, None, None]) ** 2, axis=0)  # (j,k)  :97
+            for j in range(K):  # :101-115
+                if gf[0]:
+                    m1 = np.sum(wgammafrac[j, :][None, :] * dmu[:, j, :], axis=1)  # :104
+                    m2 = np.sum(dmu[:, j, :] * (gamma[j, :] * w)[None, :], axis=1) / gammasum[j]  # :105
+                    mu_grad[:, j] = -w[j] * (m1 + m2)  # :106
+                if gf[1]:
+                    s1 = np.sum(wgammafrac[j, :] * dsigma[j, :])  # :111
+                    s2 = np.sum(dsigma[j, :] * gamma[j, :] * w) / gammasum[j]  # :112
+                    sigma_grad[j] = -w[j] * sigma[j] * (s1 + s2)  # :113
+            if gf[2]:
+                dmu2 = (mu[:, None, :] - mu[:, :, None]) ** 2 / (sumsigma2[None, :, :] * (lam**2)[:, None, None])  # (D,j,k)  :118
+                inner = np.sum((dmu2 - 1.0) * (gamma * w[:, None])[None, :, :], axis=1)  # sum over j of (.)*gamma(j,k)*w(j) -> (D,k)  :120
+                lambda_grad[:] = -np.sum(w[None, :] * inner / gammasum[None, :], axis=1)  # :119-121
+            if gf[3]:
+                w_grad[:] = -np.log(gammasum) - np.sum(wgammafrac, axis=1)  # :126  sum over dim 3 (k), result indexed by j
+    dH = None
+    if nargout > 1:  # :137-145
+        if jacobian_flag and gf[1]:
+            sigma_grad = sigma_grad * sigma
+        if (not jacobian_flag) and gf[2]:
+            lambda_grad = lambda_grad / lam
+        if jacobian_flag and gf[3]:
+            w_grad = _softmax_jacobian(vp["eta"]) @ np.atleast_1d(w_grad)
+        dH = np.concatenate([mu_grad.T.ravel(), np.ravel(sigma_grad), np.ravel(lambda_grad), np.ravel(w_grad)])
+    return H, dH
+
+
 def entlb_K1(vp):
     """ent/entlb_vbmc.m:32-34: exact entropy of a single component (known answer for entmc)."""
     D = vp["D"]
@@ -608,7 +683,7 @@ def negelcbo_vbmc(theta, beta, vp, gp, Ns=0, compute_grad=None, compute_var=None
     if Ns > 0:
         H, dH = entmc_vbmc(vp, Ns, gflags, True, epsilon=epsilon, nargout=2)
     else:
-        raise OracleError("vbmc_b200:OutOfScope", "entlb_vbmc (Ns==0) is out of scope (SURVEY.md 2 #4)")
+        H, dH = entlb_vbmc(vp, gflags, True, nargout=2)  # deterministic lower bound (negelcbo_vbmc.m:107-109)
     F = -G - H
     dF = (-dG - dH) if compute_grad else None
     varH = 0.0

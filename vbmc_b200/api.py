@@ -454,6 +454,26 @@ def entmc_vbmc(vp, Ns=10, grad_flags=None, jacobian_flag=True, *, epsilon=None, 
     return (H.value, dH)[:max(1, nargout)]
 
 
+def entlb_vbmc(vp, grad_flags=None, jacobian_flag=True, *, nargout=2, ctx=None):
+    """[H,dH] = entlb_vbmc(vp,grad_flags,jacobian_flag), ent/entlb_vbmc.m:1-147: the deterministic entropy lower bound
+    negelcbo_vbmc uses when Ns == 0 (negelcbo_vbmc.m:102-109)."""
+    ctx = ctx or default_context()
+    if nargout < 2:
+        grad_flags = False
+    elif grad_flags is None:
+        grad_flags = True
+    if np.isscalar(grad_flags):
+        grad_flags = [bool(grad_flags)] * 4
+    gf = (C.c_int * 4)(*[int(bool(g)) for g in grad_flags])
+    ctx.vp_set(vp)
+    D, K = int(vp["D"]), int(vp["K"])
+    n = D * K * gf[0] + K * gf[1] + D * gf[2] + K * gf[3]
+    H = C.c_double()
+    dH = np.zeros(n) if nargout > 1 else None
+    _lib.check(ctx.lib.vbmc_b200_entlb(ctx.handle, gf, int(bool(jacobian_flag)), C.byref(H), dptr(dH)))
+    return (H.value, dH)[:max(1, nargout)]
+
+
 def gplogjoint(vp, gp, grad_flags=None, avg_flag=True, jacobian_flag=True, compute_var=None, separate_K=None, *,
                nargout=2, ctx=None):
     """[F,dF,varF,dvarF,varss,I_sk,J_sjk] = gplogjoint(...), misc/gplogjoint.m:1-413."""

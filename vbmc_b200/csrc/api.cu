@@ -143,7 +143,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->predWork, &c->zigTab};
+                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->predWork, &c->zigTab, &c->entlbWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -644,8 +644,8 @@ static int negelcbo_validate(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a,
     VB_FAIL(VBMC_B200_EUNSUPPORTED,
             "vbmc_b200:OutOfScope: weights-only optimisation (gplogjoint_weights.m) is outside this build (SURVEY.md 2 #5)");
   if (a->Ns <= 0)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED,
-            "vbmc_b200:OutOfScope: Ns == 0 selects entlb_vbmc (deterministic entropy bound), outside this build");
+    VB_FAIL(VBMC_B200_EINVAL, "negelcbo: Ns must be positive here (Ns == 0, the deterministic entropy bound entlb_vbmc, is handled by "
+                              "vbmc_b200_negelcbo only; the device fminadam loop and the resident loop need Monte-Carlo draws)");
   if (a->compute_var != 0 && a->compute_var != 1 && a->compute_var != 2)
     VB_FAIL(VBMC_B200_EINVAL, "negelcbo: compute_var must be 0, 1 (full) or 2 (diagonal)");
 
@@ -830,8 +830,9 @@ static int check_exchange(vbmc_b200_ctx* c) {
 static int step_with_graph(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a, int Ns, int gmask, int nth, bool sync = true) {
   const bool philox = a->eps_mode == VBMC_B200_EPS_PHILOX;
   const bool hit = philox && eps_key_matches(c, a->seed, a->stream, Ns);
-  const bool trail = philox && c->prefetch_enabled &&
-                     (hit || (c->have_last_key && c->last_seed == a->seed && c->last_stream + 1 == a->stream));
+  // ahead-of-time generation only for a caller that is seen to stream (previous call had stream - 1): a repeated key — e.g. the
+  // token draws of Ns == 0 calls — must not trigger it
+  const bool trail = philox && c->prefetch_enabled && c->have_last_key && c->last_seed == a->seed && c->last_stream + 1 == a->stream;
   const int rc = step_with_graph_impl(c, a, Ns, gmask, nth, sync, hit, trail);
   if (rc != VBMC_B200_OK) {  // whatever was enqueued, the buffer is not trusted any more
     c->eps_key.valid = false;
@@ -956,7 +957,22 @@ static int assemble_vargrad(vbmc_b200_ctx* c, int gmask, int jacobian, const std
   return VBMC_B200_OK;
 }
 
-int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
+int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a_in) {
+  if (!c || !a_in) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  // Ns == 0: negelcbo_vbmc.m:102-109 replaces the Monte-Carlo entropy by the deterministic lower bound entlb_vbmc (what
+  // vpsieve_vbmc.m:76 evaluates for every candidate).  Everything but the entropy term is the ordinary step, so the step
+  // runs with a token two-draw entropy estimate, and H, dH are then exchanged for the bound:
+  //     F_lb = F + H_mc - H_lb,   dF_lb = dF + dH_mc - dH_lb        (F = -G - H + penalties, negelcbo_vbmc.m:116-117)
+  const bool lower_bound = a_in->Ns == 0;
+  vbmc_b200_negelcbo_args a_lb = *a_in;
+  if (lower_bound) {
+    a_lb.Ns = 2;
+    a_lb.eps_mode = VBMC_B200_EPS_PHILOX;
+    a_lb.eps = nullptr;
+    a_lb.seed = 0xE17B;
+    a_lb.stream = 0;
+  }
+  const vbmc_b200_negelcbo_args* a = lower_bound ? &a_lb : a_in;
   double beta;
   int Ns, gmask;
   VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
@@ -964,6 +980,20 @@ int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a) {
   const int nth = grad_mask_len(c, gmask);
   VB_TRY(step_with_graph(c, a, Ns, gmask, nth));
   scatter_negelcbo(c, a, nth);
+  if (lower_bound) {
+    OutLayout ol;
+    ol.init(nth, c->gp.S, c->K);
+    const double Hmc = c->out_pinned[ol.oH];
+    std::vector<double> dHmc(c->out_pinned + ol.oDH, c->out_pinned + ol.oDH + nth), dHlb(nth > 0 ? nth : 1);
+    double Hlb = 0.0;
+    VB_TRY(run_entlb(c, gmask, 1, &Hlb, nth ? dHlb.data() : nullptr));
+    if (a->F) *a->F += Hmc - Hlb;
+    if (a->H) *a->H = Hlb;
+    for (int i = 0; i < nth; ++i) {
+      if (a->dF) a->dF[i] += dHmc[i] - dHlb[i];
+      if (a->dH) a->dH[i] = dHlb[i];
+    }
+  }
   if (a->compute_var) {
     // varG (and J_sjk) from the factors; F = F + beta*sqrt(varF)   (negelcbo_vbmc.m:119-130)
     std::vector<double> vF, J, vg;

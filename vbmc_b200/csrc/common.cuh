@@ -271,6 +271,7 @@ struct vbmc_b200_ctx {
   size_t theta_pinned_cap = 0, out_pinned_cap = 0;
   vb::DevBuf flush;  // L2 flush scratch
   vb::DevBuf varWork;  // variance path: Z/V, Gram, J, varF(s)
+  vb::DevBuf entlbWork;  // entlb_vbmc: gamma[K][K], gsum, wraw, out
 
   // CUDA graph of one negelcbo step (single rank): replayed while the step signature is unchanged
   bool graphs_enabled = true;
@@ -319,6 +320,7 @@ int philox_init_tables(vbmc_b200_ctx* c);
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
                   const uint64_t* dyn = nullptr, uint64_t stream_add = 0);
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
+int run_entlb(vbmc_b200_ctx* c, int gmask, int jacobian, double* H, double* dH);
 int launch_adam_step(vbmc_b200_ctx* c, const AdamArgs& a, cudaStream_t st);
 int launch_adam_check(vbmc_b200_ctx* c, const AdamArgs& a, int iter, double TolFun, cudaStream_t st);
 int launch_adam_final(vbmc_b200_ctx* c, const AdamArgs& a, int iter, cudaStream_t st);
