@@ -1,4 +1,6 @@
-"""Multi-GPU parity check, launched with torchrun (one rank per GPU):
+"""Multi-GPU parity check (a script, not collected by pytest; it lives under tests/ because it uses the oracle as its checker),
+launched with torchrun, one rank per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mgpu_check.py
 every rank evaluates the same negelcbo_vbmc step on its shard (MC pair axis, hyper-parameter samples);
 after the single NCCL all-reduce all ranks must hold the same F, dF, equal to the oracle's (rank 0 checks)."""
 import os

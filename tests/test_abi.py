@@ -54,3 +54,8 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "vbmc_b200" / "csrc").glob("*"):
         if p.suffix in (".cu", ".cuh", ".h", ".cpp"):
             assert "oracle" not in p.read_text(), p
+    # the same holds for the helper scripts and the gateways: only tests/, smoke() and bench.py's CPU-baseline / reference
+    # legs may touch oracle/
+    for p in list((ROOT / "tools").glob("*.py")) + list((ROOT / "mex").glob("*")):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
