@@ -1,5 +1,5 @@
 """Committed vectors (tests/golden/*.npz, made by tests/golden/make_golden.py — read its header for what they are):
-the NumPy oracle, the C/OpenMP port and the CUDA path must all reproduce them; the K = 1 file also carries closed-form
+the NumPy oracle, the C/OpenMP port (here) and the CUDA path (tests/test_zz_golden_gpu.py) must all reproduce them; the K = 1 file also carries closed-form
 known answers derived from the reference's formulas (ent/entmc_vbmc.m:60-67,82-88)."""
 import importlib.util
 import os
@@ -67,17 +67,3 @@ def test_closed_form_known_answers():
     assert abs(float(g["H"]) - float(g["closed_H"])) < 1e-12 * max(1.0, abs(float(g["closed_H"])))
     D = 4
     assert np.max(np.abs(g["dH"][:D] - g["closed_dH_mu"])) < 1e-13
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", NAMES)
-def test_cuda_path_reproduces_golden(gpu_ctx, name):
-    import vbmc_b200
-    g, shape, w = load(name)
-    vp, gp, eps, Ns = w["vp"], w["gp"], w["epsilon"], shape["Ns"]
-    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
-    F, dF, G, H, varF, dH = vbmc_b200.negelcbo_vbmc(g["theta"], 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
-    assert rel(F, g["F"]) < 1e-10 and rel(dF, g["dF"]) < 1e-10 and rel(G, g["G"]) < 1e-10
-    assert rel(H, g["H"]) < 1e-10 and rel(dH, g["dH"]) < 1e-10
-    if name == "k1_closed_form_D4":
-        assert abs(H - float(g["closed_H"])) < 1e-10 * max(1.0, abs(float(g["closed_H"])))

@@ -1,0 +1,23 @@
+"""CUDA leg of the committed vectors (tests/golden/*.npz; CPU legs and loader in tests/test_golden.py).
+(File name: runs after the long-validated GPU tests under `pytest -x`.)"""
+import os
+
+import numpy as np
+import pytest
+
+from test_golden import HERE, NAMES, load, rel
+from vbmc_b200 import workloads
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_path_reproduces_golden(gpu_ctx, name):
+    import vbmc_b200
+    g, shape, w = load(name)
+    vp, gp, eps, Ns = w["vp"], w["gp"], w["epsilon"], shape["Ns"]
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    F, dF, G, H, varF, dH = vbmc_b200.negelcbo_vbmc(g["theta"], 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
+    assert rel(F, g["F"]) < 1e-10 and rel(dF, g["dF"]) < 1e-10 and rel(G, g["G"]) < 1e-10
+    assert rel(H, g["H"]) < 1e-10 and rel(dH, g["dH"]) < 1e-10
+    if name == "k1_closed_form_D4":
+        assert abs(H - float(g["closed_H"])) < 1e-10 * max(1.0, abs(float(g["closed_H"])))
