@@ -308,9 +308,12 @@ def main():
     l0 = ctx.launch_count()
     t_wall0 = time.perf_counter()
     tot_ms = 0.0
+    per_step_ms = []
     for i in range(args.steps):
         ctx.flush_l2()               # outside the timed events
-        tot_ms += resident_step(args.warmup + i)
+        v = resident_step(args.warmup + i)
+        tot_ms += v
+        per_step_ms.append(v)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - l0
@@ -476,7 +479,9 @@ def main():
     nth = theta.size
     line = {
         "metric": "negelcbo_vbmc grad-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "ms_per_step_percentiles_rank0": {f"p{q}": float(np.percentile(per_step_ms, q)) for q in (10, 50, 90)} if per_step_ms else None,
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")},
                    "parallelism": f"mc-pair-shard x{world} + hyp-sample shard, 1 all-reduce/step" if world > 1 else "single GPU",
