@@ -37,6 +37,48 @@ def _fingerprint(*arrays):
     return hash(tuple(a.tobytes() if isinstance(a, np.ndarray) else repr(a) for a in arrays))
 
 
+# ---- cheap "did this dict change since the last call" probes -----------------------------------------------------------
+# A gradient step calls negelcbo_vbmc with the SAME vp / thetabnd objects a few thousand times; re-marshalling and hashing
+# them costs more host time than everything else in the wrapper.  The probe is (identity of the dict and of its arrays,
+# a dot product of every array with fixed pseudo-random weights): an in-place edit of any entry changes it (a permutation
+# too), and a new object always takes the full path.
+_PROBE_W = np.random.Generator(np.random.Philox(20260925)).standard_normal(1 << 14)
+
+
+def _probe(entries):
+    """(ids, value) for a tuple of dict entries, or None when an entry is not a float64 ndarray small enough to probe."""
+    ids, val = [], 0.0
+    for x in entries:
+        if x is None:
+            ids.append(0)
+            continue
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.size <= _PROBE_W.size):
+            return None
+        ids.append(id(x))
+        val += float(x.ravel() @ _PROBE_W[:x.size]) + 0.125 * x.size
+    return tuple(ids), val
+
+
+class _CallFrame:
+    """Pre-marshalled argument block of one negelcbo_vbmc signature: the ctypes struct, its output buffers and the pointers
+    between them are built once; a call copies theta in, sets the scalars and copies the results out."""
+    __slots__ = ("a", "theta", "sc", "dF", "dH", "Isk", "Jsjk")
+
+    def __init__(self, ntheta, K, S, grad, var, sepK):
+        self.a = a = _lib.NegelcboArgs()
+        self.theta = np.zeros(ntheta)
+        self.sc = np.zeros(8)
+        self.dF = np.zeros(ntheta) if grad else None
+        self.dH = np.zeros(ntheta) if grad else None
+        self.Isk = np.zeros((K, S)) if sepK else None
+        self.Jsjk = np.zeros((K, K, S)) if (sepK and var) else None
+        a.theta, a.ntheta = dptr(self.theta), ntheta
+        p = self.sc.ctypes.data_as(_lib.c_double_p)
+        off = lambda i: C.cast(C.addressof(p.contents) + 8 * i, _lib.c_double_p)
+        a.F, a.G, a.H, a.varF, a.varGss, a.varG, a.varH = off(0), off(1), off(2), off(3), off(4), off(5), off(6)
+        a.dF, a.dH, a.I_sk, a.J_sjk = dptr(self.dF), dptr(self.dH), dptr(self.Isk), dptr(self.Jsjk)
+
+
 class Context:
     """One GPU context (vbmc_b200_create).  Caches which gp / vp / thetabnd are resident."""
 
@@ -49,6 +91,9 @@ class Context:
         self._vp_key = None
         self._bnd_key = None
         self._keep = []  # host arrays referenced by in-flight descriptors
+        self._vp_probe = None    # (id(vp), flags, ids, value) of the vp dict last marshalled (see _probe)
+        self._bnd_probe = None
+        self._frames = {}        # negelcbo_vbmc call frames by signature
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -159,6 +204,12 @@ class Context:
     # -- VP ---------------------------------------------------------------------------------
     def vp_set(self, vp):
         D, K = int(vp["D"]), int(vp["K"])
+        flags = tuple(int(bool(vp[f])) for f in ("optimize_mu", "optimize_sigma", "optimize_lambda", "optimize_weights"))
+        pr = _probe((vp["mu"], vp["sigma"], vp["lambda"], vp["w"], vp.get("eta"), vp.get("delta")))
+        probe = None if pr is None else (id(vp), D, K, flags) + pr
+        if probe is not None and probe == getattr(self, "_vp_probe", None) and self._vp_key is not None:
+            return
+        self._vp_probe = None
         mu = np.ascontiguousarray(f64(vp["mu"]).reshape(D, K).T)  # column-major D x K
         sigma = f64(vp["sigma"]).ravel()
         lam = f64(vp["lambda"]).ravel()
@@ -169,30 +220,41 @@ class Context:
             delta = f64(delta).ravel() * np.ones(D)
         else:
             delta = None
-        flags = tuple(int(bool(vp[f])) for f in ("optimize_mu", "optimize_sigma", "optimize_lambda", "optimize_weights"))
         key = (D, K, flags, _fingerprint(mu, sigma, lam, w, eta, delta))
         if key == self._vp_key:
+            self._vp_probe = probe
             return
         d = _lib.VpDesc()
         d.D, d.K = D, K
         d.mu, d.sigma, d.lambda_, d.w, d.eta, d.delta = dptr(mu), dptr(sigma), dptr(lam), dptr(w), dptr(eta), dptr(delta)
         d.optimize_mu, d.optimize_sigma, d.optimize_lambda, d.optimize_weights = flags
+        self._vp_key = None
         _lib.check(self.lib.vbmc_b200_vp_set(self._h, C.byref(d)))
         self._vp_key = key
+        self._vp_probe = probe
 
     def thetabnd_set(self, thetabnd):
         if thetabnd is None:
+            self._bnd_probe = None
             if self._bnd_key is not None:
                 _lib.check(self.lib.vbmc_b200_thetabnd_set(self._h, 0, None, None, 0.0, 0.0, 0.0))
                 self._bnd_key = None
             return
-        lb, ub = f64(thetabnd["lb"]).ravel(), f64(thetabnd["ub"]).ravel()
         wt, wp = float(thetabnd.get("WeightThreshold", 0.0)), float(thetabnd.get("WeightPenalty", 0.0))
+        pr = _probe((thetabnd["lb"], thetabnd["ub"]))
+        probe = None if pr is None else (id(thetabnd), float(thetabnd["TolCon"]), wt, wp) + pr
+        if probe is not None and probe == getattr(self, "_bnd_probe", None) and self._bnd_key is not None:
+            return
+        self._bnd_probe = None
+        lb, ub = f64(thetabnd["lb"]).ravel(), f64(thetabnd["ub"]).ravel()
         key = (_fingerprint(lb, ub), float(thetabnd["TolCon"]), wt, wp)
         if key == self._bnd_key:
+            self._bnd_probe = probe
             return
+        self._bnd_key = None
         _lib.check(self.lib.vbmc_b200_thetabnd_set(self._h, lb.size, dptr(lb), dptr(ub), float(thetabnd["TolCon"]), wt, wp))
         self._bnd_key = key
+        self._bnd_probe = probe
 
     # -- draws ------------------------------------------------------------------------------
     def eps_upload(self, epsilon):
@@ -363,27 +425,34 @@ def negelcbo_vbmc(theta, beta, vp, gp, Ns=0, compute_grad=None, compute_var=None
     ctx.gp_attach(gp, want_L=bool(compute_var))
     ctx.thetabnd_set(thetabnd)
     S, K = len(gp["post"]), int(vp["K"])
-    a = _lib.NegelcboArgs()
-    a.theta, a.ntheta = dptr(theta), theta.size
+    grad, var = bool(compute_grad), int(compute_var)
+    frames = ctx.__dict__.setdefault("_frames", {})
+    fkey = (theta.size, K, S, grad, bool(var), bool(separate_K))
+    fr = frames.get(fkey)
+    if fr is None:
+        if len(frames) > 64:
+            frames.clear()
+        fr = frames[fkey] = _CallFrame(theta.size, K, S, grad, bool(var), bool(separate_K))
+    a = fr.a
+    np.copyto(fr.theta, theta)
     a.beta, a.Ns = float(beta), int(Ns)
-    a.compute_grad, a.compute_var, a.separate_K = int(bool(compute_grad)), int(compute_var), int(separate_K)
+    a.compute_grad, a.compute_var, a.separate_K = int(grad), var, int(separate_K)
     a.use_thetabnd = int(thetabnd is not None)
     if Ns > 0:
         mode, e, seed, stream = _eps_args(vp, Ns, epsilon, rng)
     else:
         mode, e, seed, stream = _lib.EPS_RESIDENT, None, 0, 0
     a.eps_mode, a.eps, a.seed, a.stream = mode, dptr(e), seed, stream
-    sc = np.zeros(8)
-    dF = np.zeros(theta.size) if compute_grad else None
-    dH = np.zeros(theta.size) if compute_grad else None
-    Isk = np.zeros((K, S)) if separate_K else None
-    Jsjk = np.zeros((K, K, S)) if (separate_K and compute_var) else None
-    p = sc.ctypes.data_as(_lib.c_double_p)
-    off = lambda i: C.cast(C.addressof(p.contents) + 8 * i, _lib.c_double_p)
-    a.F, a.G, a.H, a.varF, a.varGss, a.varG, a.varH = off(0), off(1), off(2), off(3), off(4), off(5), off(6)
-    a.dF, a.dH, a.I_sk, a.J_sjk = dptr(dF), dptr(dH), dptr(Isk), dptr(Jsjk)
-    _lib.check(ctx.lib.vbmc_b200_negelcbo(ctx.handle, C.byref(a)))
-    out = (float(sc[0]), dF, float(sc[1]), float(sc[2]), float(sc[3]), dH, float(sc[4]), float(sc[5]), float(sc[6]),
+    sc = fr.sc
+    sc[:] = 0.0
+    try:
+        _lib.check(ctx.lib.vbmc_b200_negelcbo(ctx.handle, C.byref(a)))
+    finally:
+        a.eps = None   # do not keep the caller's draws alive through the cached struct
+    # results are handed out as fresh arrays: the frame's buffers are overwritten by the next call
+    Isk, Jsjk = fr.Isk, fr.Jsjk
+    out = (float(sc[0]), fr.dF.copy() if grad else None, float(sc[1]), float(sc[2]), float(sc[3]), fr.dH.copy() if grad else None,
+           float(sc[4]), float(sc[5]), float(sc[6]),
            None if Isk is None else Isk.T.copy(), None if Jsjk is None else Jsjk.transpose(2, 1, 0).copy())
     return out[:max(1, nargout)]
 
