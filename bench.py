@@ -139,6 +139,28 @@ def adam_update(state, x, grad):
     return x - step * mhat / (np.sqrt(vhat) + math.sqrt(np.finfo(float).eps))
 
 
+def numpy_stand_in(w, cfg):
+    """The NumPy restatement that materialises the same D x Ns x K temporaries as the .m code (oracle/vbmc_oracle.py) — the
+    stand-in for "the reference's MATLAB CPU path" (MATLAB cannot run here) — on a bounded sample: one
+    evaluation with Ns = 2048 draws per component, the entropy part (linear in Ns) scaled to the configuration's Ns."""
+    from oracle import vbmc_oracle as orc
+    from vbmc_b200 import workloads
+    vp, gp, theta = w["vp"], w["gp"], w["theta"]
+    _, tb = orc.vpbounds(dict(vp), gp, workloads.VP_OPTIONS)
+    Ns_s = min(cfg["Ns"], 2048)
+    eps = workloads.make_epsilon(cfg, Ns=Ns_s)
+    t0 = time.perf_counter()
+    orc.negelcbo_vbmc(theta, 0.0, vp, gp, Ns_s, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)
+    t_small = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.gplogjoint(vp, gp, [1, 1, 1, 1], True, True, 0, nargout=2)
+    t_glj = time.perf_counter() - t0
+    t_step = t_glj + max(t_small - t_glj, 0.0) * cfg["Ns"] / Ns_s
+    return {"value": 1.0 / t_step, "unit": "steps/s", "cores": 1, "kind": "port",
+            "sample": f"NumPy restatement vectorised like the .m code (elementwise NumPy is single-threaded): one evaluation at Ns={Ns_s} "
+                      f"({t_small:.2f} s, of which gplogjoint {t_glj:.2f} s), entropy part scaled x{cfg['Ns'] // Ns_s} to Ns={cfg['Ns']}"}
+
+
 def run_reference(args, cfg_name, emit):
     """Reference arm: the reference's CPU algorithm (oracle C/OpenMP port) on the host cores."""
     from vbmc_b200 import workloads
@@ -476,6 +498,12 @@ def main():
             cpu = {"value": r["steps_per_s"], "unit": "steps/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
         except Exception as e:  # the baseline is reporting only; never let it kill the bench line
             cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"unavailable: {e}"}
+    cpu_numpy = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu_numpy = numpy_stand_in(dict(w, gp=gp), cfg)
+        except Exception as e:
+            cpu_numpy = {"value": None, "unit": "steps/s", "kind": "port", "sample": f"unavailable: {str(e)[:200]}"}
     nth = theta.size
     line = {
         "metric": "negelcbo_vbmc grad-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
@@ -506,6 +534,7 @@ def main():
         "c4": c4,
         "c5": c5,
         "cpu_baseline": cpu,
+        "cpu_baseline_numpy": cpu_numpy,
     }
     emit(line)
     if dist is not None:
