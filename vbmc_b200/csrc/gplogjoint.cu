@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "glj_multi.cuh"
 
 namespace vb {
 
@@ -379,6 +380,44 @@ static int launch_glj_pairs(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st)
   return VBMC_B200_OK;
 }
 
+// Variant "multi" (glj_multi.cuh): several components per CTA with the points in registers; shares the chunk-sum and epilogue
+// kernels of the thread-per-pair variant.  VBMC_B200_GLJ_VARIANT=multi, group size VBMC_B200_GLJ_KG (default 10).
+template <int DP>
+static int launch_glj_multi(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
+  constexpr int P = 4;
+  static const int kg_env = getenv("VBMC_B200_GLJ_KG") ? atoi(getenv("VBMC_B200_GLJ_KG")) : 10;
+  const int kg = kg_env < 1 ? 1 : (kg_env > a.K ? a.K : kg_env);
+  const int npairs = a.s_count * a.K;
+  const int nchunks = (a.N + P * GLJM_THREADS - 1) / (P * GLJM_THREADS), kgroups = (a.K + kg - 1) / kg;
+  const size_t nval = 1 + 2 * a.D;
+  VB_TRY(c->glj_part.reserve(sizeof(double) * (nchunks + 1) * nval * npairs));
+  double* sums = c->glj_part.d() + static_cast<size_t>(nchunks) * nval * npairs;
+  GljMultiArgs m;
+  m.N = a.N; m.D = a.D; m.K = a.K; m.s_begin = a.s_begin; m.npairs = npairs; m.kg = kg;
+  m.X = a.gp.X; m.alpha = a.gp.alpha; m.ell = a.gp.ell; m.lnc = a.gp.lnc;
+  m.mu = a.vp.mu; m.sigma = a.vp.sigma; m.lambda = a.vp.lambda; m.delta = a.vp.delta;
+  m.part = c->glj_part.d();
+  const size_t smem = sizeof(double) * glj_multi_smem_doubles(a.D, DP, kg);
+  auto kern = glj_multi_kernel<DP, P>;
+  if (smem > 48 * 1024)
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  {
+    KernelScope ks(c, "gplogjoint", st);
+    kern<<<dim3(nchunks, kgroups, a.s_count), GLJM_THREADS, smem, st>>>(m);
+    VB_CUDA(cudaGetLastError());
+  }
+  {
+    KernelScope ks(c, "gplogjoint_epilogue", st);
+    glj_pairs_sum_kernel<<<dim3((npairs + 127) / 128, static_cast<unsigned>(nval)), 128, 0, st>>>(nchunks, static_cast<int>(nval), npairs,
+                                                                                                 c->glj_part.d(), sums);
+    VB_CUDA(cudaGetLastError());
+    c->launches++;
+    glj_pairs_epilogue_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(a, sums);
+    VB_CUDA(cudaGetLastError());
+  }
+  return VBMC_B200_OK;
+}
+
 int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
   (void)need_grad;
   GljArgs a;
@@ -394,6 +433,20 @@ int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
   VB_TRY(c->glj_out.reserve(sizeof(double) * static_cast<size_t>(a.S) * a.K * a.ostride));
   a.out = c->glj_out.d();
   if (a.s_count <= 0) return VBMC_B200_OK;
+  static const bool multi = getenv("VBMC_B200_GLJ_VARIANT") && !strcmp(getenv("VBMC_B200_GLJ_VARIANT"), "multi");
+  if (multi) {
+    switch (pick_dp(a.D)) {
+      case 2: return launch_glj_multi<2>(c, a, st);
+      case 4: return launch_glj_multi<4>(c, a, st);
+      case 6: return launch_glj_multi<6>(c, a, st);
+      case 8: return launch_glj_multi<8>(c, a, st);
+      case 10: return launch_glj_multi<10>(c, a, st);
+      case 12: return launch_glj_multi<12>(c, a, st);
+      case 16: return launch_glj_multi<16>(c, a, st);
+      case 20: return launch_glj_multi<20>(c, a, st);
+      case 24: return launch_glj_multi<24>(c, a, st);
+    }
+  }
   if (!getenv("VBMC_B200_GLJ_THREAD_PER_PAIR")) {  // default: one CTA per (s,k); the thread-per-pair variant measured slower end to end
     switch (pick_dp(a.D)) {
       case 2: return launch_glj<2>(c, a, st);
