@@ -3,6 +3,10 @@
 // element against the NumPy restatement without a GPU.  Test infrastructure only; never part of the product library.
 #include <vector>
 
+// libvbmc_b200.so (often loaded in the same test process) exports nvcc's host-side launch stubs under the same mangled names as
+// these kernels; without a private namespace the dynamic linker would bind the calls below to those stubs.
+#define vb vb_host_harness
+
 #define VB_HD inline
 #include "../../vbmc_b200/csrc/entlb_math.cuh"
 

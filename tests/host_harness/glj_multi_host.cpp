@@ -1,5 +1,9 @@
 // Host run of vbmc_b200/csrc/glj_multi.cuh through the thread-per-CUDA-thread shim (see cuda_shim.h).
 #include "cuda_shim.h"
+
+// libvbmc_b200.so (often loaded in the same test process) exports nvcc's host-side launch stubs under the same mangled names as
+// these kernels; without a private namespace the dynamic linker would bind the calls below to those stubs.
+#define vb vb_host_harness
 #include "../../vbmc_b200/csrc/glj_multi.cuh"
 
 template <int DP, int P>

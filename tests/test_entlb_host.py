@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not ava
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     so = tmp_path_factory.mktemp("entlb") / "libentlb_host.so"
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-shared", "-fPIC", "-o", str(so),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-Wl,-Bsymbolic", "-shared", "-fPIC", "-o", str(so),
                            str(ROOT / "tests" / "host_harness" / "entlb_host.cpp")])
     lib = C.CDLL(str(so))
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not ava
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     so = tmp_path_factory.mktemp("gljm") / "libglj_multi_host.so"
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", str(so),
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-Wl,-Bsymbolic", "-shared", "-fPIC", "-o", str(so),
                            str(ROOT / "tests" / "host_harness" / "glj_multi_host.cpp")])
     lib = C.CDLL(str(so))
     dp = C.POINTER(C.c_double)
