@@ -117,3 +117,29 @@ def test_gplogjoint_in_40_digits():
     Go, dGo = orc.gplogjoint(vp, gp, [1, 1, 1, 1], True, True, 0, nargout=2)[:2]
     assert abs(Go - float(G)) < 1e-12 * max(1.0, abs(float(G)))
     assert rel(dGo, ref) < 1e-11
+
+
+def test_gplite_core_in_40_digits():
+    """nlZ = 1/2 r'(K + sn2 I)^-1 r + 1/2 log det(K + sn2 I) + N/2 log 2 pi and alpha = (K + sn2 I)^-1 r with the SE-ARD kernel and
+    the negative-quadratic mean (gplite/private/gplite_core.m:33-102,193), evaluated with mpmath matrices."""
+    D, N = 2, 9
+    w = problem(D, 2, N, 1, 4, 91)
+    gp = w["gp"]
+    X, y, hyp = gp["X"], gp["y"], np.asarray(gp["post"][0]["hyp"], dtype=float)
+    h = [mp.mpf(float(v)) for v in hyp]
+    ell = [mp.e ** h[d] for d in range(D)]
+    sf2, sn2 = mp.e ** (2 * h[D]), mp.e ** (2 * h[D + 1])
+    m0, xm, om = h[D + 2], h[D + 3:D + 3 + D], [mp.e ** v for v in h[D + 3 + D:D + 3 + 2 * D]]
+    Xm = [[mp.mpf(float(v)) for v in row] for row in X]
+    K = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(N):
+            K[i, j] = sf2 * mp.e ** (-sum(((Xm[i][d] - Xm[j][d]) / ell[d]) ** 2 for d in range(D)) / 2) + (sn2 if i == j else 0)
+    r = mp.matrix([mp.mpf(float(y[i])) - (m0 - sum(((Xm[i][d] - xm[d]) / om[d]) ** 2 for d in range(D)) / 2) for i in range(N)])
+    alpha = mp.lu_solve(K, r)
+    nlZ = (r.T * alpha)[0] / 2 + mp.log(mp.det(K)) / 2 + N * mp.log(2 * mp.pi) / 2
+    nlZo = orc.gplite_nlZ(hyp, gp, None, nargout=1)[0]
+    assert abs(nlZo - float(nlZ)) < 1e-9 * max(1.0, abs(float(nlZ)))
+    ao = np.asarray(gp["post"][0]["alpha"], dtype=float)
+    ref = np.array([float(v) for v in alpha])
+    assert np.max(np.abs(ao - ref)) < 1e-7 * np.max(np.abs(ref))      # cond(K + sn2 I) ~ sf2/sn2
