@@ -21,3 +21,12 @@ def test_cuda_path_reproduces_golden(gpu_ctx, name):
     assert rel(H, g["H"]) < 1e-10 and rel(dH, g["dH"]) < 1e-10
     if name == "k1_closed_form_D4":
         assert abs(H - float(g["closed_H"])) < 1e-10 * max(1.0, abs(float(g["closed_H"])))
+
+
+@pytest.mark.gpu
+def test_cuda_component_relabelling_and_antithetic_draws(gpu_ctx):
+    """Size-independent properties (tests/test_properties.py) through the CUDA path."""
+    import vbmc_b200
+    from test_properties import check_antithetic, check_permutation
+    check_permutation(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds)
+    check_antithetic(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds)
