@@ -31,7 +31,7 @@ def permuted_problem(D=4, K=6, N=60, S=3, Ns=128, seed=5):
     return w, vp2, theta2, eps2, idx
 
 
-def check_permutation(negelcbo, vpbounds):
+def check_permutation(negelcbo, vpbounds, tol=1e-12):
     w, vp2, theta2, eps2, idx = permuted_problem()
     vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
     assert np.array_equal(theta[idx], theta2)
@@ -39,17 +39,17 @@ def check_permutation(negelcbo, vpbounds):
     _, tb2 = vpbounds(vp2, gp, workloads.VP_OPTIONS)
     a = negelcbo(theta, 0.0, vp, gp, 128, 1, 0, 0, tb, 0, epsilon=eps, nargout=4)
     b = negelcbo(theta2, 0.0, vp2, gp, 128, 1, 0, 0, tb2, 0, epsilon=eps2, nargout=4)
-    assert rel(b[0], a[0]) < 1e-12 and rel(b[2], a[2]) < 1e-12 and rel(b[3], a[3]) < 1e-12
+    assert rel(b[0], a[0]) < tol and rel(b[2], a[2]) < tol and rel(b[3], a[3]) < tol
     assert rel(b[1], np.asarray(a[1])[idx]) < 1e-10
 
 
-def check_antithetic(negelcbo, vpbounds):
+def check_antithetic(negelcbo, vpbounds, tol=1e-13):
     w, *_ = permuted_problem(seed=9)
     vp, gp, theta, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
     _, tb = vpbounds(vp, gp, workloads.VP_OPTIONS)
     a = negelcbo(theta, 0.0, vp, gp, 128, 1, 0, 0, tb, 0, epsilon=eps, nargout=4)
     b = negelcbo(theta, 0.0, vp, gp, 128, 1, 0, 0, tb, 0, epsilon=-eps, nargout=4)
-    assert rel(b[3], a[3]) < 1e-13 and rel(b[1], a[1]) < 1e-11 and rel(b[0], a[0]) < 1e-13
+    assert rel(b[3], a[3]) < tol and rel(b[1], a[1]) < 1e-10 and rel(b[0], a[0]) < tol
 
 
 def test_oracle_component_relabelling():

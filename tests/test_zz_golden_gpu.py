@@ -28,5 +28,5 @@ def test_cuda_component_relabelling_and_antithetic_draws(gpu_ctx):
     """Size-independent properties (tests/test_properties.py) through the CUDA path."""
     import vbmc_b200
     from test_properties import check_antithetic, check_permutation
-    check_permutation(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds)
-    check_antithetic(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds)
+    check_permutation(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds, tol=1e-11)   # different summation order over k
+    check_antithetic(vbmc_b200.negelcbo_vbmc, vbmc_b200.vpbounds, tol=1e-12)
