@@ -27,7 +27,7 @@ def test_entlb_matches_oracle(gpu_ctx, D, K, jac):
     vp = mk(D, max(30, K + 5), K, 1)["vp"]
     H, dH = vbmc_b200.entlb_vbmc(vp, [1, 1, 1, 1], jac)
     Ho, dHo = orc.entlb_vbmc(vp, [1, 1, 1, 1], jac)
-    assert rel(H, Ho) < 1e-12 and dH.shape == dHo.shape and rel(dH, dHo) < TOL
+    assert rel(H, Ho) < 1e-11 and dH.shape == dHo.shape and rel(dH, dHo) < TOL
     (H1,) = vbmc_b200.entlb_vbmc(vp, nargout=1)
     assert H1 == H
 
@@ -38,7 +38,7 @@ def test_entlb_grad_flag_subsets(gpu_ctx):
     for gf in [(1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1), (1, 0, 1, 1), (0, 0, 0, 0)]:
         H, dH = vbmc_b200.entlb_vbmc(vp, list(gf), True)
         Ho, dHo = orc.entlb_vbmc(vp, list(gf), True)
-        assert rel(H, Ho) < 1e-12 and dH.shape == dHo.shape
+        assert rel(H, Ho) < 1e-11 and dH.shape == dHo.shape
         assert dH.size == 0 or rel(dH, dHo) < TOL
 
 
