@@ -291,6 +291,12 @@ def main():
         refit = {"gplite_post_wall_ms": t_refit * 1e3, "S": S_, "N": N_, "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
                  "potrf_update_dmma_tflops": upd_flops / (kt["potrf_update"] * 1e-3) / 1e12 if kt["potrf_update"] > 0 else None,
                  "chol_flops_N3_over_3_x_S": S_ * N_ ** 3 / 3.0}
+        if refit["potrf_update_dmma_tflops"]:
+            # the N^3/3 contraction runs on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA); peak = tools/dmma_probe.cu on B200
+            refit["roofline"] = {"kernel": "gp_update_kernel", "bound": "tensor", "achieved": refit["potrf_update_dmma_tflops"], "peak": 37.1,
+                                 "unit": "TFLOP/s", "frac": refit["potrf_update_dmma_tflops"] / 37.1,
+                                 "peak_source": "FP64 DMMA micro-benchmark tools/dmma_probe.cu, measured on B200 (profiles/r1_ncu_summary.md); "
+                                                "ncu: tensor sub-pipe 63.8 % active on the large trailing updates"}
     _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
     Ns = cfg["Ns"]
     counts = algorithmic_counts(cfg)
