@@ -14,7 +14,9 @@ import numpy as np
 
 _DIR = Path(__file__).resolve().parent / "c"
 _LIB = _DIR / "libvbmc_oracle.so"
+_LIB128 = _DIR / "libvbmc_truth128.so"   # the same C source compiled in IEEE binary128 (make -C oracle/c): "truth"
 _lib = None
+_lib128 = None
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
@@ -32,10 +34,23 @@ def host_threads():
     return aff
 
 
+def load_truth128():
+    global _lib128
+    if _lib128 is None:
+        load()
+        if not _LIB128.exists():
+            subprocess.check_call(["make", "-C", str(_DIR)])
+        _lib128 = C.CDLL(str(_LIB128))
+        _lib128.vbmc_truth128_negelcbo.restype = C.c_int
+    return _lib128
+
+
 def load():
     global _lib
     if _lib is None:
-        os.environ.setdefault("OMP_NUM_THREADS", str(host_threads()))
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must not inherit that,
+        # so the thread count is set explicitly unless the caller asks for one with VBMC_ORACLE_THREADS.
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("VBMC_ORACLE_THREADS", str(host_threads()))
         if not _LIB.exists():
             subprocess.check_call(["make", "-C", str(_DIR)])
         _lib = C.CDLL(str(_LIB))
@@ -80,15 +95,17 @@ class Prepared:
             self.wt, self.wp = float(thetabnd.get("WeightThreshold", 0.0)), float(thetabnd.get("WeightPenalty", 0.0))
 
 
-def negelcbo(prep: Prepared, theta, Ns, eps, compute_grad=True):
-    """(F, dF, G, H, dH, I_sk) of negelcbo_vbmc(theta,0,vp,gp,Ns,compute_grad,0,0,thetabnd)."""
-    lib = load()
+def negelcbo(prep: Prepared, theta, Ns, eps, compute_grad=True, truth128=False):
+    """(F, dF, G, H, dH, I_sk) of negelcbo_vbmc(theta,0,vp,gp,Ns,compute_grad,0,0,thetabnd).
+    ``truth128``: evaluate every intermediate in IEEE binary128 (results rounded to double at the end)."""
+    lib = load_truth128() if truth128 else load()
     theta = _c(theta).ravel()
     eps = _c(eps)
     F, G, H = C.c_double(), C.c_double(), C.c_double()
     dF, dH = np.zeros(theta.size), np.zeros(theta.size)
     Isk = np.zeros((prep.S, prep.K))
-    rc = lib.vbmc_oracle_negelcbo(
+    fn = lib.vbmc_truth128_negelcbo if truth128 else lib.vbmc_oracle_negelcbo
+    rc = fn(
         prep.D, prep.K, prep.N, prep.S, prep.Nhyp, prep.Ncov, prep.Nnoise, prep.meanfun, _p(prep.X), _p(prep.hyp), _p(prep.alpha),
         _p(theta), theta.size, prep.opt.ctypes.data_as(ip), _p(prep.mu), _p(prep.sigma), _p(prep.lam), _p(prep.w), _p(prep.eta),
         _p(prep.delta), int(Ns), _p(eps), prep.nbnd, _p(prep.lb), _p(prep.ub), C.c_double(prep.tol), C.c_double(prep.wt),

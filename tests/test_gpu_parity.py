@@ -8,6 +8,8 @@ import pytest
 from oracle import vbmc_oracle as orc
 from vbmc_b200 import workloads
 
+from _truth import errs_vs_truth, truth_negelcbo
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
@@ -47,8 +49,13 @@ def test_negelcbo_matches_oracle(gpu_ctx, shape):
     F, dF, G, H, varF, dH = got
     Fo, dFo, Go, Ho, _, dHo = ref[:6]
     assert rel(H, Ho) < TOL and rel(dH, dHo) < TOL
-    assert rel(G, Go) < TOL
-    assert rel(F, Fo) < TOL and rel(dF, dFo) < TOL
+    # log-joint side: the gate is against the binary128 evaluation (tests/test_truth128.py explains why); the FP64 NumPy oracle
+    # must agree with the CUDA path to within ITS OWN distance from that truth
+    t = truth_negelcbo(vp, gp, theta, Ns, eps, tb)
+    e = errs_vs_truth(dict(F=F, dF=dF, G=G, H=H, dH=dH), t)
+    eo = errs_vs_truth(dict(F=Fo, dF=dFo, G=Go, H=Ho, dH=dHo), t)
+    assert max(e.values()) < TOL, e
+    assert rel(G, Go) < TOL + 2 * eo["G"] and rel(F, Fo) < TOL + 2 * eo["F"] and rel(dF, dFo) < TOL + 2 * eo["dF"], (e, eo)
     assert varF == 0.0
 
 

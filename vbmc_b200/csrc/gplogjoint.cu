@@ -6,14 +6,21 @@
 // (SURVEY.md Appendix B.1):
 //     zeta_n = exp(lnnf_sk - 0.5*sum_d Delta_dn^2) * alpha_sn,  Delta_dn = (mu_kd - X_nd)/tau_skd
 //     A = sum zeta_n,   B_d = sum zeta_n Delta_dn,   C_d = sum zeta_n (Delta_dn^2 - 1)
-// One CTA per (s,k): X (N x D column-major => unit stride over n) and alpha_s are streamed once,
-// coalesced; the CTA then turns (A,B,C) into I_sk and the un-weighted gradient pieces
-// (gplogjoint.m:169-174, 206-210, 227-231, 248-252).  The whole working set (X, alpha) is < 1 MB
-// and stays in L2; the kernel is latency/FP64-pipe bound, not HBM bound.
+// A CTA owns one (s, k, slice of N): X (N x D column-major => unit stride over n) and alpha_s are streamed
+// coalesced; the working set (X, alpha) is < 1 MB and stays in L2, the kernel is FP64-pipe bound.
+//
+// Accuracy (dd_math.cuh): alpha_n ~ 1e4 while the sums are O(1), so every n-dependent quantity is carried as a
+// two-word (h, l) value -- the terms, the three running sums, the block and slice reductions -- and the results
+// are the correctly rounded sums of the exact formula to ~1e-20 * sum|zeta_n|.  tests/test_truth128.py checks the
+// outputs against an IEEE binary128 evaluation on ill-conditioned posteriors (plain FP64 is off by 1e-11..5e-9 there).
+//
+// The N axis is split over gridDim.z slices when S_local*K CTAs would not fill the GPU (multi-GPU shards of S);
+// slice partials go to global memory and the LAST slice to finish (atomic ticket) adds them in slice order and
+// runs the per-(s,k) epilogue (gplogjoint.m:169-174, 206-210, 227-231, 248-252) -- no second launch, deterministic.
 #include <stdlib.h>
 
 #include "common.cuh"
-#include "glj_multi.cuh"
+#include "dd_math.cuh"
 
 namespace vb {
 
@@ -27,22 +34,46 @@ struct GljArgs {
   double* out;  // [S][K][ostride] (only rows s_begin..s_begin+s_count-1 written)
   const double* wvec;  // optional [S][K][N] weight vectors replacing alpha_s (variance gradient: K^-1 z_k)
   int raw;             // 1: epilogue without the mean-function terms (derivative contractions only)
+  int nsplit;          // slices of the N axis (gridDim.z)
+  double* part;        // [S*K][nsplit][2*(1+2D)] slice partials (nsplit > 1)
+  unsigned* ticket;    // [S*K] arrival counters, zero between launches
 };
 
 constexpr int GLJ_THREADS = 128;
+constexpr int GLJ_PARTS = 8;  // block reduction: 8 ordered partial sums of 16 threads each, then the 8 in order
 
-template <int DP>
+__device__ const double2 g_exp2_tab[64] = {VB_EXP2_TABLE_ROWS};
+
+// dynamic shared memory (doubles): exp2 table [128] | mu [DP] | itau [DP] | misc [4] | red [2*nval][COLS+1] | red2 [2*nval][GLJ_PARTS]
+static size_t glj_smem_bytes(int D, int DP, int halves) {
+  const size_t nval2 = 2 * (1 + 2 * static_cast<size_t>(D));
+  return sizeof(double) * (128 + 2 * DP + 4 + nval2 * (GLJ_THREADS / halves + 1) + nval2 * GLJ_PARTS);
+}
+
+// DPH dimensions per thread, HALVES threads per training point (HALVES = 2 for D > 12: the 4*D + 2 accumulator words of one
+// thread would not fit the register file; the lane pair exchanges its two partial sum_d Delta^2 with one shuffle and both
+// lanes evaluate the exponential).
+template <int DPH, int HALVES>
 __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
   extern __shared__ __align__(16) double sm[];
+  constexpr int DP = DPH * HALVES;
+  constexpr int COLS = GLJ_THREADS / HALVES;  // training points per sweep iteration
+  constexpr int RS = COLS + 1;
   const int D = a.D, N = a.N;
   const int k = blockIdx.x;
   const int s = a.s_begin + blockIdx.y;
   const int tid = threadIdx.x;
-  double* s_mu = sm;            // [DP]
-  double* s_itau = sm + DP;     // [DP]
-  double* s_misc = sm + 2 * DP; // [4]: lnnf
-  double* red = sm + 2 * DP + 4;  // [(1+2D)][GLJ_THREADS+1]
+  const int half = HALVES == 2 ? (tid & 1) : 0, col = HALVES == 2 ? (tid >> 1) : tid;
+  const int d0 = half * DPH;
+  double2* s_tab = reinterpret_cast<double2*>(sm);  // [64]
+  double* s_mu = sm + 128;          // [DP]
+  double* s_itau = s_mu + DP;       // [DP]
+  double* s_misc = s_itau + DP;     // [4]: lnnf, last-slice flag
+  double* red = s_misc + 4;         // [2*nval][RS]
+  const int nval = 1 + 2 * D, nval2 = 2 * nval;
+  double* red2 = red + static_cast<size_t>(nval2) * RS;  // [2*nval][GLJ_PARTS]
 
+  if (tid < 64) s_tab[tid] = g_exp2_tab[tid];
   const double sigk = a.vp.sigma[k];
   if (tid < DP) {
     double mu = 0.0, itau = 0.0;
@@ -63,66 +94,123 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
   }
   __syncthreads();
   const double lnnf = s_misc[0];
-  double mu[DP], itau[DP];
+  double Ah = 0.0, Al = 0.0, Bh[DPH], Bl[DPH], Qh[DPH], Ql[DPH];
 #pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    mu[d] = s_mu[d];
-    itau[d] = s_itau[d];
-  }
-  double A = 0.0, B[DP], C[DP];
-#pragma unroll
-  for (int d = 0; d < DP; ++d) B[d] = C[d] = 0.0;
+  for (int d = 0; d < DPH; ++d) Bh[d] = Bl[d] = Qh[d] = Ql[d] = 0.0;
   const double* __restrict__ X = a.gp.X;
   const double* __restrict__ alpha = a.wvec ? a.wvec + (static_cast<size_t>(s) * a.K + k) * N : a.gp.alpha + static_cast<size_t>(s) * N;
-  for (int n = tid; n < N; n += GLJ_THREADS) {
-    double dl[DP];
-    double ss = 0.0;
+  // slice of the N axis owned by this CTA (multiples of the block size except the last)
+  const int per = ((N + a.nsplit - 1) / a.nsplit + GLJ_THREADS - 1) / GLJ_THREADS * GLJ_THREADS;
+  const int n0 = blockIdx.z * per;
+  const int n1 = min(N, n0 + per);
+  for (int base = n0; base < n1; base += COLS) {  // warp-uniform trip count: the lane pairs shuffle inside
+    const int n = base + col;
+    const bool live = n < n1;
+    double x[DPH], dh[DPH], dl[DPH];
 #pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const double x = d < D ? __ldg(X + static_cast<size_t>(d) * N + n) : 0.0;
-      dl[d] = (mu[d] - x) * itau[d];
-      ss = fma(dl[d], dl[d], ss);
+    for (int d = 0; d < DPH; ++d) x[d] = (live && d0 + d < D) ? __ldg(X + static_cast<size_t>(d0 + d) * N + n) : 0.0;
+    const double al_n = live ? __ldg(alpha + n) : 0.0;
+    double ssh, ssl;
+    glj_delta<DPH>(s_mu + d0, s_itau + d0, x, dh, dl, ssh, ssl);
+    if (HALVES == 2) {
+      const double oh = __shfl_xor_sync(0xffffffffu, ssh, 1), ol = __shfl_xor_sync(0xffffffffu, ssl, 1);
+      double th, tl;
+      two_sum(ssh, oh, th, tl);  // symmetric: both lanes of the pair get the same (ssh, ssl)
+      ssl = tl + (ssl + ol);
+      ssh = th;
     }
-    const double zeta = exp(lnnf - 0.5 * ss) * __ldg(alpha + n);  // z_k(n)*alpha(n)  (:167-169)
-    A += zeta;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      B[d] = fma(zeta, dl[d], B[d]);
-      C[d] = fma(zeta, fma(dl[d], dl[d], -1.0), C[d]);
-    }
+    double zh, zl;
+    glj_zeta(ssh, ssl, lnnf, al_n, s_tab, zh, zl);  // z_k(n)*alpha(n)  (:167-169)
+    if (half == 0) acc_add(Ah, Al, zh, zl);
+    glj_accumulate<DPH>(dh, dl, zh, zl, Bh, Bl, Qh, Ql);
   }
-  // ---- block reduction in fixed order ----
-  constexpr int RS = GLJ_THREADS + 1;
-  red[0 * RS + tid] = A;
+  // ---- block reduction in fixed order, two-word: value v of column `col` -> red[2v][col], red[2v+1][col] ----
+  if (half == 0) {
+    red[0 * RS + col] = Ah;
+    red[1 * RS + col] = Al;
+  }
 #pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    if (d < D) {
-      red[(1 + d) * RS + tid] = B[d];
-      red[(1 + D + d) * RS + tid] = C[d];
+  for (int d = 0; d < DPH; ++d) {
+    if (d0 + d < D) {
+      red[(2 + 2 * (d0 + d)) * RS + col] = Bh[d];
+      red[(3 + 2 * (d0 + d)) * RS + col] = Bl[d];
+      red[(2 + 2 * D + 2 * (d0 + d)) * RS + col] = Qh[d];
+      red[(3 + 2 * D + 2 * (d0 + d)) * RS + col] = Ql[d];
     }
   }
   __syncthreads();
-  const int nval = 1 + 2 * D;
-  // two-stage ordered sum: 4 partial sums of 32 per value, then the 4 parts in order (deterministic)
-  double* red2 = red + static_cast<size_t>(nval) * RS;  // [nval][4]
-  for (int idx = tid; idx < nval * 4; idx += GLJ_THREADS) {
-    const int i = idx >> 2, part = idx & 3;
-    const double* rr = red + i * RS + part * (GLJ_THREADS / 4);
-    double sacc = 0.0;
-    for (int t = 0; t < GLJ_THREADS / 4; ++t) sacc += rr[t];
-    red2[idx] = sacc;
+  constexpr int PER = COLS / GLJ_PARTS;
+  for (int idx = tid; idx < nval * GLJ_PARTS; idx += GLJ_THREADS) {
+    const int i = idx / GLJ_PARTS, part = idx - i * GLJ_PARTS;
+    const double* rh = red + (2 * i) * RS + part * PER;
+    const double* rl = red + (2 * i + 1) * RS + part * PER;
+    double h = rh[0], l = rl[0];
+    for (int t = 1; t < PER; ++t) acc_add(h, l, rh[t], rl[t]);
+    red2[(2 * i) * GLJ_PARTS + part] = h;
+    red2[(2 * i + 1) * GLJ_PARTS + part] = l;
   }
   __syncthreads();
-  for (int i = tid; i < nval; i += GLJ_THREADS) red[i * RS] = (red2[4 * i] + red2[4 * i + 1]) + (red2[4 * i + 2] + red2[4 * i + 3]);
+  // totals of this CTA -> red[2*i*RS], red[(2*i+1)*RS] (renormalised)
+  for (int i = tid; i < nval; i += GLJ_THREADS) {
+    double h = red2[(2 * i) * GLJ_PARTS], l = red2[(2 * i + 1) * GLJ_PARTS];
+    for (int p = 1; p < GLJ_PARTS; ++p) acc_add(h, l, red2[(2 * i) * GLJ_PARTS + p], red2[(2 * i + 1) * GLJ_PARTS + p]);
+    double nh, nl;
+    fast_two_sum(h, l, nh, nl);
+    red[(2 * i) * RS] = nh;
+    red[(2 * i + 1) * RS] = nl;
+  }
+  __syncthreads();
+  const int pair = s * a.K + k;
+  if (a.nsplit > 1) {
+    double* mine = a.part + (static_cast<size_t>(pair) * a.nsplit + blockIdx.z) * nval2;
+    for (int i = tid; i < nval2; i += GLJ_THREADS) __stcg(mine + i, red[i * RS]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(a.ticket + pair, 1u);
+      const bool last = t == static_cast<unsigned>(a.nsplit - 1);
+      if (last) a.ticket[pair] = 0;  // ready for the next launch (kernels of one context are stream-ordered)
+      s_misc[1] = last ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (s_misc[1] == 0.0) return;
+    __threadfence();
+    const double* all = a.part + static_cast<size_t>(pair) * a.nsplit * nval2;
+    for (int i = tid; i < nval; i += GLJ_THREADS) {
+      double h = __ldcg(all + 2 * i), l = __ldcg(all + 2 * i + 1);
+      for (int z = 1; z < a.nsplit; ++z) acc_add(h, l, __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i), __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i + 1));
+      double nh, nl;
+      fast_two_sum(h, l, nh, nl);
+      red[(2 * i) * RS] = nh;
+      red[(2 * i + 1) * RS] = nl;
+    }
+    __syncthreads();
+  }
+  // ---- C_d = Q_d - A in two-word arithmetic, then everything rounds to one double ----
+  // red2[0] = A, red2[1 + d] = B_d, red2[1 + D + d] = C_d
+  if (tid < nval) {
+    const double Ah_ = red[0], Al_ = red[RS];
+    double v;
+    if (tid == 0) {
+      v = Ah_ + Al_;
+    } else if (tid <= D) {
+      v = red[(2 * tid) * RS] + red[(2 * tid + 1) * RS];
+    } else {
+      double h, l;
+      dd_add(red[(2 * tid) * RS], red[(2 * tid + 1) * RS], -Ah_, -Al_, h, l);
+      v = h + l;
+    }
+    red2[tid] = v;
+  }
   __syncthreads();
   // ---- per-(s,k) epilogue ----
-  double* o = a.out + (static_cast<size_t>(s) * a.K + k) * a.ostride;
+  double* o = a.out + static_cast<size_t>(pair) * a.ostride;
   const bool quad = a.meanfun == 4 && !a.raw;
   if (tid < D) {
     const int d = tid;
     const double lam = a.vp.lambda[d];
     const double it = s_itau[d];
-    const double Bd = red[(1 + d) * RS], Cd = red[(1 + D + d) * RS];
+    const double Bd = red2[1 + d], Cd = red2[1 + D + d];
     double gmu = -Bd * it;                                  // w(k)*dz_dmu*alpha / w(k)   (:206-208)
     double glam = sigk * sigk * lam * (Cd * it * it);       // (:248-249) / w(k)
     if (quad) {
@@ -134,11 +222,11 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
     o[2 + D + d] = glam;
   }
   if (tid == 32) {
-    double I = red[0] + ((a.meanfun > 0 && !a.raw) ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
+    double I = red2[0] + ((a.meanfun > 0 && !a.raw) ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
     double gs = 0.0;
     for (int d = 0; d < D; ++d) {
       const double lam = a.vp.lambda[d], it = s_itau[d], dl = a.vp.delta[d];
-      gs += (lam * it) * (lam * it) * red[(1 + D + d) * RS];  // sum (lambda/tau)^2 (Delta^2-1) z alpha (:227-229)
+      gs += (lam * it) * (lam * it) * red2[1 + D + d];  // sum (lambda/tau)^2 (Delta^2-1) z alpha (:227-229)
       if (quad) {
         const double io2 = a.gp.iom2[s * D + d], xm = a.gp.xm[s * D + d], m = s_mu[d];
         I -= 0.5 * io2 * (m * m + sigk * sigk * lam * lam - 2.0 * m * xm + xm * xm + dl * dl);  // nu_k (:172-174)
@@ -191,231 +279,53 @@ static int pick_dp(int D) {
   return -1;
 }
 
-template <int DP>
-static int launch_glj(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (2 * DP + 4 + static_cast<size_t>(1 + 2 * a.D) * (GLJ_THREADS + 1 + 4));
-  auto kern = glj_kernel<DP>;
+template <int DPH, int HALVES>
+static int launch_glj_t(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
+  const size_t smem = glj_smem_bytes(a.D, DPH * HALVES, HALVES);
+  auto kern = glj_kernel<DPH, HALVES>;
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(a.K, a.s_count);
+  dim3 grid(a.K, a.s_count, a.nsplit);
   KernelScope ks(c, "gplogjoint", st);
   kern<<<grid, GLJ_THREADS, smem, st>>>(a);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// Fast path of the step (alpha-weighted contraction, all samples of this rank): one THREAD per (s,k) pair, the CTA's
-// threads sweep the same chunk of training points, so X[n][:] is a CTA-uniform (broadcast) load and the 2D+1 sums of
-// a pair live in registers with no cross-thread reduction at all.  The N axis is split into chunks across CTAs
-// (grid.x) to fill the machine; a second kernel adds the chunk partials in chunk order (deterministic) and applies
-// the per-(s,k) epilogue.  Compared with one CTA per (s,k) this removes 1000 block reductions and the S*K-fold
-// re-read of X from L2: 60-80 us -> ~10 us at c3, short enough to hide behind the draw generator.
-// ------------------------------------------------------------------------------------------------
-constexpr int GLJ2_THREADS = 128;
-
-template <int DP>
-__global__ void __launch_bounds__(GLJ2_THREADS) glj_pairs_kernel(const GljArgs a, int chunk, double* __restrict__ part) {
-  const int D = a.D, N = a.N, K = a.K;
-  const int npairs = a.s_count * K;
-  const int i = blockIdx.y * GLJ2_THREADS + threadIdx.x;
-  const bool live = i < npairs;
-  const int sl = live ? i / K : 0, k = live ? i - sl * K : 0;
-  const int s = a.s_begin + sl;
-  const double sigk = a.vp.sigma[k];
-  double mu[DP], itau[DP];
-  double slt = 0.0;
-#pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    mu[d] = 0.0;
-    itau[d] = 0.0;
-    if (d < D) {
-      const double lam = a.vp.lambda[d], ell = a.gp.ell[s * D + d], dl = a.vp.delta[d];
-      const double tau = sqrt(sigk * sigk * lam * lam + ell * ell + dl * dl);  // gplogjoint.m:164
-      mu[d] = a.vp.mu[k * D + d];
-      itau[d] = 1.0 / tau;
-      slt += log(1.0 / itau[d]);
-    }
+// slices of the N axis: enough CTAs for ~4 per SM, at least 2*GLJ_THREADS points per slice; region 0 of the scratch buffers
+// belongs to the step's own launch, region 1 to the weighted (variance-gradient) launch, which may be enqueued on another stream.
+static int glj_dispatch(vbmc_b200_ctx* c, GljArgs& a, int region, cudaStream_t st) {
+  const int pairs = a.K * a.s_count;
+  int nsplit = (4 * c->num_sms + pairs - 1) / pairs;
+  const int max_split = (a.N + 2 * GLJ_THREADS - 1) / (2 * GLJ_THREADS);
+  nsplit = nsplit > max_split ? max_split : nsplit;
+  nsplit = nsplit > 16 ? 16 : (nsplit < 1 ? 1 : nsplit);
+  static const int force = getenv("VBMC_B200_GLJ_NSPLIT") ? atoi(getenv("VBMC_B200_GLJ_NSPLIT")) : 0;
+  if (force > 0) nsplit = force > 16 ? 16 : force;
+  a.nsplit = nsplit;
+  const size_t npair_all = static_cast<size_t>(a.S) * a.K;
+  const size_t nval2 = 2 * (1 + 2 * static_cast<size_t>(a.D));
+  const size_t part_doubles = npair_all * 16 * nval2;  // capacity for the largest nsplit: the buffer never moves between launches
+  const size_t tick_bytes = 2 * npair_all * sizeof(unsigned);
+  if (c->glj_part.cap < 2 * part_doubles * sizeof(double) + tick_bytes) {
+    VB_CUDA(cudaStreamSynchronize(st));
+    VB_TRY(c->glj_part.reserve(2 * part_doubles * sizeof(double) + tick_bytes));
+    VB_CUDA(cudaMemsetAsync(c->glj_part.p, 0, c->glj_part.cap, st));
   }
-  const double lnnf = a.gp.lnc[s] - slt;  // lnnf_k = ln_sf2 + sum_lnell - sum(log(tau_k))  (:165)
-  const int n0 = blockIdx.x * chunk;
-  int n1 = n0 + chunk;
-  n1 = n1 > N ? N : n1;
-  const double* __restrict__ X = a.gp.X;
-  const double* __restrict__ alpha = a.gp.alpha + static_cast<size_t>(s) * N;
-  double A = 0.0, B[DP], C[DP];
-#pragma unroll
-  for (int d = 0; d < DP; ++d) B[d] = C[d] = 0.0;
-  int n = n0;
-  for (; n + 1 < n1; n += 2) {  // two points per iteration: two independent exp chains
-    double d0[DP], d1[DP];
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const double x0 = d < D ? __ldg(X + static_cast<size_t>(d) * N + n) : 0.0;
-      const double x1 = d < D ? __ldg(X + static_cast<size_t>(d) * N + n + 1) : 0.0;
-      d0[d] = (mu[d] - x0) * itau[d];
-      d1[d] = (mu[d] - x1) * itau[d];
-      s0 = fma(d0[d], d0[d], s0);
-      s1 = fma(d1[d], d1[d], s1);
-    }
-    const double z0 = exp(lnnf - 0.5 * s0) * __ldg(alpha + n);  // z_k(n)*alpha(n)  (:167-169)
-    const double z1 = exp(lnnf - 0.5 * s1) * __ldg(alpha + n + 1);
-    A += z0;
-    A += z1;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      B[d] = fma(z0, d0[d], B[d]);
-      C[d] = fma(z0, fma(d0[d], d0[d], -1.0), C[d]);
-      B[d] = fma(z1, d1[d], B[d]);
-      C[d] = fma(z1, fma(d1[d], d1[d], -1.0), C[d]);
-    }
+  a.part = c->glj_part.d() + static_cast<size_t>(region) * part_doubles;
+  a.ticket = reinterpret_cast<unsigned*>(c->glj_part.d() + 2 * part_doubles) + static_cast<size_t>(region) * npair_all;
+  switch (pick_dp(a.D)) {
+    case 2: return launch_glj_t<2, 1>(c, a, st);
+    case 4: return launch_glj_t<4, 1>(c, a, st);
+    case 6: return launch_glj_t<6, 1>(c, a, st);
+    case 8: return launch_glj_t<8, 1>(c, a, st);
+    case 10: return launch_glj_t<10, 1>(c, a, st);
+    case 12: return launch_glj_t<12, 1>(c, a, st);
+    case 16: return launch_glj_t<8, 2>(c, a, st);
+    case 20: return launch_glj_t<10, 2>(c, a, st);
+    case 24: return launch_glj_t<12, 2>(c, a, st);
   }
-  if (n < n1) {
-    double d0[DP];
-    double s0 = 0.0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      const double x0 = d < D ? __ldg(X + static_cast<size_t>(d) * N + n) : 0.0;
-      d0[d] = (mu[d] - x0) * itau[d];
-      s0 = fma(d0[d], d0[d], s0);
-    }
-    const double z0 = exp(lnnf - 0.5 * s0) * __ldg(alpha + n);
-    A += z0;
-#pragma unroll
-    for (int d = 0; d < DP; ++d) {
-      B[d] = fma(z0, d0[d], B[d]);
-      C[d] = fma(z0, fma(d0[d], d0[d], -1.0), C[d]);
-    }
-  }
-  if (!live) return;
-  // partials: [chunk][value][pair] => consecutive threads write consecutive addresses
-  double* o = part + static_cast<size_t>(blockIdx.x) * (1 + 2 * D) * npairs + i;
-  o[0] = A;
-#pragma unroll
-  for (int d = 0; d < DP; ++d) {
-    if (d < D) {
-      o[static_cast<size_t>(1 + d) * npairs] = B[d];
-      o[static_cast<size_t>(1 + D + d) * npairs] = C[d];
-    }
-  }
-}
-
-// chunk partials -> totals, one thread per (value, pair): the nchunks loads of a thread are independent and coalesced
-// across the warp; fixed chunk order => deterministic
-__global__ void __launch_bounds__(128) glj_pairs_sum_kernel(int nchunks, int nval, int npairs, const double* __restrict__ part,
-                                                            double* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int v = blockIdx.y;
-  if (i >= npairs) return;
-  const double* p = part + static_cast<size_t>(v) * npairs + i;
-  const size_t stride = static_cast<size_t>(nval) * npairs;
-  double acc = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < nchunks; ++c) acc += p[c * stride];
-  sums[static_cast<size_t>(v) * npairs + i] = acc;
-}
-
-// totals -> [I, gsig, gmu[D], glam[D]] per (s,k)   (gplogjoint.m:169-174, 206-210, 227-231, 248-252)
-__global__ void __launch_bounds__(128) glj_pairs_epilogue_kernel(const GljArgs a, const double* __restrict__ sums) {
-  const int D = a.D, K = a.K;
-  const int npairs = a.s_count * K;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npairs) return;
-  const int sl = i / K, k = i - sl * K, s = a.s_begin + sl;
-  const double sigk = a.vp.sigma[k];
-  double* o = a.out + (static_cast<size_t>(s) * K + k) * a.ostride;
-  const bool quad = a.meanfun == 4;
-  double I = sums[i] + (a.meanfun > 0 ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
-  double gs = 0.0;
-  for (int d = 0; d < D; ++d) {
-    const double lam = a.vp.lambda[d], ell = a.gp.ell[s * D + d], dl = a.vp.delta[d];
-    const double it = 1.0 / sqrt(sigk * sigk * lam * lam + ell * ell + dl * dl);
-    const double Bd = sums[static_cast<size_t>(1 + d) * npairs + i], Cd = sums[static_cast<size_t>(1 + D + d) * npairs + i];
-    const double m = a.vp.mu[k * D + d];
-    double gmu = -Bd * it;                             // (:206-208) / w(k)
-    double glam = sigk * sigk * lam * (Cd * it * it);  // (:248-249) / w(k)
-    gs += (lam * it) * (lam * it) * Cd;                // (:227-229)
-    if (quad) {
-      const double io2 = a.gp.iom2[s * D + d], xm = a.gp.xm[s * D + d];
-      gmu -= io2 * (m - xm);                           // (:210)
-      glam -= sigk * sigk * lam * io2;                 // (:252)
-      I -= 0.5 * io2 * (m * m + sigk * sigk * lam * lam - 2.0 * m * xm + xm * xm + dl * dl);  // nu_k (:172-174)
-      gs -= io2 * lam * lam;                           // (:231)
-    }
-    o[2 + d] = gmu;
-    o[2 + D + d] = glam;
-  }
-  o[0] = I;
-  o[1] = sigk * gs;
-}
-
-template <int DP>
-static int launch_glj_pairs(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
-  const int npairs = a.s_count * a.K;
-  const int by = (npairs + GLJ2_THREADS - 1) / GLJ2_THREADS;
-  int nchunks = (4 * c->num_sms + by - 1) / by;          // ~4 CTAs (16 warps) per SM
-  const int max_chunks = (a.N + 15) / 16;                // at least 16 points per chunk
-  nchunks = nchunks > max_chunks ? max_chunks : (nchunks < 1 ? 1 : nchunks);
-  const int chunk = (a.N + nchunks - 1) / nchunks;
-  nchunks = (a.N + chunk - 1) / chunk;
-  const size_t nval = 1 + 2 * a.D;
-  VB_TRY(c->glj_part.reserve(sizeof(double) * (nchunks + 1) * nval * npairs));
-  double* sums = c->glj_part.d() + static_cast<size_t>(nchunks) * nval * npairs;
-  {
-    KernelScope ks(c, "gplogjoint", st);
-    glj_pairs_kernel<DP><<<dim3(nchunks, by), GLJ2_THREADS, 0, st>>>(a, chunk, c->glj_part.d());
-    VB_CUDA(cudaGetLastError());
-  }
-  {
-    KernelScope ks(c, "gplogjoint_epilogue", st);
-    glj_pairs_sum_kernel<<<dim3((npairs + 127) / 128, static_cast<unsigned>(nval)), 128, 0, st>>>(nchunks, static_cast<int>(nval), npairs,
-                                                                                                 c->glj_part.d(), sums);
-    VB_CUDA(cudaGetLastError());
-    c->launches++;
-    glj_pairs_epilogue_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(a, sums);
-    VB_CUDA(cudaGetLastError());
-  }
-  return VBMC_B200_OK;
-}
-
-// Variant "multi" (glj_multi.cuh): several components per CTA with the points in registers; shares the chunk-sum and epilogue
-// kernels of the thread-per-pair variant.  VBMC_B200_GLJ_VARIANT=multi, group size VBMC_B200_GLJ_KG (default 10).
-template <int DP>
-static int launch_glj_multi(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
-  constexpr int P = 4;
-  static const int kg_env = getenv("VBMC_B200_GLJ_KG") ? atoi(getenv("VBMC_B200_GLJ_KG")) : 10;
-  const int kg = kg_env < 1 ? 1 : (kg_env > a.K ? a.K : kg_env);
-  const int npairs = a.s_count * a.K;
-  const int nchunks = (a.N + P * GLJM_THREADS - 1) / (P * GLJM_THREADS), kgroups = (a.K + kg - 1) / kg;
-  const size_t nval = 1 + 2 * a.D;
-  VB_TRY(c->glj_part.reserve(sizeof(double) * (nchunks + 1) * nval * npairs));
-  double* sums = c->glj_part.d() + static_cast<size_t>(nchunks) * nval * npairs;
-  GljMultiArgs m;
-  m.N = a.N; m.D = a.D; m.K = a.K; m.s_begin = a.s_begin; m.npairs = npairs; m.kg = kg;
-  m.X = a.gp.X; m.alpha = a.gp.alpha; m.ell = a.gp.ell; m.lnc = a.gp.lnc;
-  m.mu = a.vp.mu; m.sigma = a.vp.sigma; m.lambda = a.vp.lambda; m.delta = a.vp.delta;
-  m.part = c->glj_part.d();
-  const size_t smem = sizeof(double) * glj_multi_smem_doubles(a.D, DP, kg);
-  auto kern = glj_multi_kernel<DP, P>;
-  if (smem > 48 * 1024)
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  {
-    KernelScope ks(c, "gplogjoint", st);
-    kern<<<dim3(nchunks, kgroups, a.s_count), GLJM_THREADS, smem, st>>>(m);
-    VB_CUDA(cudaGetLastError());
-  }
-  {
-    KernelScope ks(c, "gplogjoint_epilogue", st);
-    glj_pairs_sum_kernel<<<dim3((npairs + 127) / 128, static_cast<unsigned>(nval)), 128, 0, st>>>(nchunks, static_cast<int>(nval), npairs,
-                                                                                                 c->glj_part.d(), sums);
-    VB_CUDA(cudaGetLastError());
-    c->launches++;
-    glj_pairs_epilogue_kernel<<<(npairs + 127) / 128, 128, 0, st>>>(a, sums);
-    VB_CUDA(cudaGetLastError());
-  }
-  return VBMC_B200_OK;
+  VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:gplogjoint: D=%d > 24 is not supported by this build", a.D);
 }
 
 int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
@@ -433,45 +343,7 @@ int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
   VB_TRY(c->glj_out.reserve(sizeof(double) * static_cast<size_t>(a.S) * a.K * a.ostride));
   a.out = c->glj_out.d();
   if (a.s_count <= 0) return VBMC_B200_OK;
-  static const bool multi = getenv("VBMC_B200_GLJ_VARIANT") && !strcmp(getenv("VBMC_B200_GLJ_VARIANT"), "multi");
-  if (multi) {
-    switch (pick_dp(a.D)) {
-      case 2: return launch_glj_multi<2>(c, a, st);
-      case 4: return launch_glj_multi<4>(c, a, st);
-      case 6: return launch_glj_multi<6>(c, a, st);
-      case 8: return launch_glj_multi<8>(c, a, st);
-      case 10: return launch_glj_multi<10>(c, a, st);
-      case 12: return launch_glj_multi<12>(c, a, st);
-      case 16: return launch_glj_multi<16>(c, a, st);
-      case 20: return launch_glj_multi<20>(c, a, st);
-      case 24: return launch_glj_multi<24>(c, a, st);
-    }
-  }
-  if (!getenv("VBMC_B200_GLJ_THREAD_PER_PAIR")) {  // default: one CTA per (s,k); the thread-per-pair variant measured slower end to end
-    switch (pick_dp(a.D)) {
-      case 2: return launch_glj<2>(c, a, st);
-      case 4: return launch_glj<4>(c, a, st);
-      case 6: return launch_glj<6>(c, a, st);
-      case 8: return launch_glj<8>(c, a, st);
-      case 10: return launch_glj<10>(c, a, st);
-      case 12: return launch_glj<12>(c, a, st);
-      case 16: return launch_glj<16>(c, a, st);
-      case 20: return launch_glj<20>(c, a, st);
-      case 24: return launch_glj<24>(c, a, st);
-    }
-  }
-  switch (pick_dp(a.D)) {
-    case 2: return launch_glj_pairs<2>(c, a, st);
-    case 4: return launch_glj_pairs<4>(c, a, st);
-    case 6: return launch_glj_pairs<6>(c, a, st);
-    case 8: return launch_glj_pairs<8>(c, a, st);
-    case 10: return launch_glj_pairs<10>(c, a, st);
-    case 12: return launch_glj_pairs<12>(c, a, st);
-    case 16: return launch_glj_pairs<16>(c, a, st);
-    case 20: return launch_glj_pairs<20>(c, a, st);
-    case 24: return launch_glj_pairs<24>(c, a, st);
-  }
-  VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:gplogjoint: D=%d > 24 is not supported by this build", a.D);
+  return glj_dispatch(c, a, 0, st);
 }
 
 // same contraction with per-(s,k) weight vectors w_sk (N each) and the raw epilogue; all S samples, out [S][K][2+2D]
@@ -486,18 +358,7 @@ int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out
   a.wvec = wvec;
   a.raw = 1;
   a.out = out;
-  switch (pick_dp(a.D)) {
-    case 2: return launch_glj<2>(c, a, st);
-    case 4: return launch_glj<4>(c, a, st);
-    case 6: return launch_glj<6>(c, a, st);
-    case 8: return launch_glj<8>(c, a, st);
-    case 10: return launch_glj<10>(c, a, st);
-    case 12: return launch_glj<12>(c, a, st);
-    case 16: return launch_glj<16>(c, a, st);
-    case 20: return launch_glj<20>(c, a, st);
-    case 24: return launch_glj<24>(c, a, st);
-  }
-  VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:gplogjoint: D=%d > 24 is not supported by this build", a.D);
+  return glj_dispatch(c, a, 1, st);
 }
 
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st) {
