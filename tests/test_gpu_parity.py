@@ -399,8 +399,11 @@ def test_variance_more_points_than_eight_columns_fit(gpu_ctx):
     w = mk(D=2, N=3600, K=3, S=1, Ns=8, log_sn=math.log(0.3))
     got = vbmc_b200.gplogjoint(w["vp"], w["gp"], True, True, True, 2, nargout=7)
     ref = orc.gplogjoint(w["vp"], w["gp"], True, True, True, 2, nargout=7)
+    # the value itself against the binary128 evaluation (the FP64 oracle is ~1e-9 away from it at N = 3600)
+    t = truth_negelcbo(w["vp"], w["gp"], w["theta"], 2, np.zeros((3, 1, 2)), None, compute_grad=False)
+    assert rel(got[0], t["G"]) < TOL, (rel(got[0], t["G"]), rel(ref[0], t["G"]))
     # J = prior term (O(1)) - z K^-1 z cancels four digits here, on top of the conditioning of a 3600-point Gram matrix
-    assert rel(got[0], ref[0]) < 1e-9 and rel(got[2], ref[2]) < 1e-5 and rel(got[6], ref[6]) < 1e-5
+    assert rel(got[2], ref[2]) < 1e-5 and rel(got[6], ref[6]) < 1e-5
     assert rel(got[3], ref[3]) < 1e-4
 
 

@@ -305,15 +305,19 @@ static int glj_dispatch(vbmc_b200_ctx* c, GljArgs& a, int region, cudaStream_t s
   a.nsplit = nsplit;
   const size_t npair_all = static_cast<size_t>(a.S) * a.K;
   const size_t nval2 = 2 * (1 + 2 * static_cast<size_t>(a.D));
-  const size_t part_doubles = npair_all * 16 * nval2;  // capacity for the largest nsplit: the buffer never moves between launches
-  const size_t tick_bytes = 2 * npair_all * sizeof(unsigned);
-  if (c->glj_part.cap < 2 * part_doubles * sizeof(double) + tick_bytes) {
+  const size_t part_doubles = npair_all * 16 * nval2;  // capacity for the largest nsplit: the buffer does not move between launches
+  if (c->glj_part.cap < 2 * part_doubles * sizeof(double)) {
     VB_CUDA(cudaStreamSynchronize(st));
-    VB_TRY(c->glj_part.reserve(2 * part_doubles * sizeof(double) + tick_bytes));
-    VB_CUDA(cudaMemsetAsync(c->glj_part.p, 0, c->glj_part.cap, st));
+    VB_TRY(c->glj_part.reserve(2 * part_doubles * sizeof(double)));
+  }
+  // arrival counters live in their own buffer: they must stay zero between launches whatever shape comes next
+  if (c->glj_ticket.cap < 2 * npair_all * sizeof(unsigned)) {
+    VB_CUDA(cudaStreamSynchronize(st));
+    VB_TRY(c->glj_ticket.reserve(2 * npair_all * sizeof(unsigned) + 4096));
+    VB_CUDA(cudaMemset(c->glj_ticket.p, 0, c->glj_ticket.cap));
   }
   a.part = c->glj_part.d() + static_cast<size_t>(region) * part_doubles;
-  a.ticket = reinterpret_cast<unsigned*>(c->glj_part.d() + 2 * part_doubles) + static_cast<size_t>(region) * npair_all;
+  a.ticket = static_cast<unsigned*>(c->glj_ticket.p) + static_cast<size_t>(region) * (c->glj_ticket.cap / (2 * sizeof(unsigned)));
   switch (pick_dp(a.D)) {
     case 2: return launch_glj_t<2, 1>(c, a, st);
     case 4: return launch_glj_t<4, 1>(c, a, st);
