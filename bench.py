@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--config", default=None, help="c2|c3|c4 (default: c3 at 1 GPU, c4 at >1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs under ncu only; such a line says so)")
     return p.parse_args()
 
 
@@ -119,6 +120,47 @@ def scipy_gp_post(hyp, X, y, covfun, meanfun, noisefun, s2):
             "Nmean": 2 * D + 1, "post": post}
 
 
+def library_cholesky_bar(w, cfg, local):
+    """The on-box library bar for the refit's factorisation (hard part 3): the same S matrices K/sl + diag(sn2/sl)
+    factored by the vendor library through torch.linalg.cholesky (cuSOLVER potrfBatched / potrf as torch dispatches; FP64).
+    Bench-only: the product never links cuSOLVER.  Factorisation only -- no Gram, no solves -- so it is a LOWER bound of a
+    library-built gplite_post."""
+    try:
+        import torch
+        dev = torch.device("cuda", local)
+        X = torch.tensor(w["X"], device=dev, dtype=torch.float64)
+        hyp = torch.tensor(w["hyp"], device=dev, dtype=torch.float64)
+        D, N, S = cfg["D"], cfg["N"], cfg["S"]
+        mats = []
+        for s_ in range(S):
+            h = hyp[:, s_]
+            Z = X / torch.exp(h[:D])
+            sq = torch.cdist(Z, Z).pow(2)
+            sn2 = torch.exp(2 * h[D + 1]) + (1.0 if w["s2"] is not None else 0.0)
+            mats.append(torch.exp(2 * h[D]) * torch.exp(-0.5 * sq) / sn2 + torch.eye(N, device=dev, dtype=torch.float64))
+        A = torch.stack(mats)
+        del mats
+        torch.linalg.cholesky(A, upper=True)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(3):
+            e0.record()
+            torch.linalg.cholesky(A, upper=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        flops = S * N ** 3 / 3.0
+        out = {"torch_linalg_cholesky_ms": best, "tflops": flops / (best * 1e-3) / 1e12, "S": S, "N": N,
+               "what": "torch.linalg.cholesky(upper=True) on the S x N x N batch, FP64, best of 3, CUDA events (factorisation only)"}
+        del A
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # reporting only
+        return {"error": str(e)[:200]}
+
+
 def algorithmic_counts(cfg):
     """per grad-step."""
     D, K, Ns, N, S = cfg["D"], cfg["K"], cfg["Ns"], cfg["N"], cfg["S"]
@@ -161,6 +203,115 @@ def numpy_stand_in(w, cfg):
                       f"({t_small:.2f} s, of which gplogjoint {t_glj:.2f} s), entropy part scaled x{cfg['Ns'] // Ns_s} to Ns={cfg['Ns']}"}
 
 
+
+TRAFFIC_C3_BYTES = 65.61e6 + 0.204e6
+TRAFFIC_C3_SOURCE = "ncu --set full capture entmc_r1f (profiles/r1_ncu_summary.md): dram read 65.61 MB + write 0.20 MB per launch"
+PARITY_TOL = 1e-10      # FP64 gate (BASELINE.json north_star); FP32 sweep: 1e-4
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
+
+
+def parity_gate(ctx, vbmc_b200, w, tb, cfg, dist, local, rank, world, *, full=True, truth_Ns=128, truth_S=None, precision=64,
+                reduced_Ns=None):
+    """Checked BEFORE anything is timed: one GPU step of this configuration against the CPU restatements, same draws.
+
+    full      : the configuration's own Ns, device Philox draws dumped to the host, vs the C port in FP64 (entropy side: no
+                cancellation, the port is good to 1e-13; log-joint side: the port itself is ~1e-10 from the truth, reported).
+    truth     : theta, GP and the first `truth_Ns` draws per component vs the binary128 evaluation (oracle/c -DVBMC_ORACLE_QUAD):
+                the whole of F, dF, G, H, dH at 1e-10 (optionally on the first `truth_S` hyper-parameter samples only).
+    N > 1     : F, dF must be bit-identical on all ranks and within 1e-12 of a 1-rank evaluation of the same Philox draws.
+    Raises on failure; returns the dict that goes into the bench line as "parity"."""
+    from oracle import cport
+    vp, gp, theta = w["vp"], w["gp"], w["theta"]
+    D, K, Ns = cfg["D"], cfg["K"], (reduced_Ns or cfg["Ns"])
+    tol = PARITY_TOL if precision == 64 else 1e-4
+    seed, stream = 990001, 7
+    out = {"tol": tol, "sweep_bits": precision}
+    c1 = ctx if world == 1 else vbmc_b200.Context(local)      # 1-rank evaluator of the same draws
+    ctx.set_precision(precision)
+    try:
+        if full:
+            got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, rng=(seed, stream), nargout=6, ctx=ctx)
+            F, dF, G, H, _, dH = got
+            if world > 1:
+                import torch
+                t = torch.tensor(np.concatenate([[F, G, H], dF, dH]), device=f"cuda:{local}")
+                allt = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                same = all(torch.equal(allt[0], x) for x in allt)
+                out["ranks_bit_identical"] = bool(same)
+                if not same:
+                    raise RuntimeError("parity gate: F/dF differ between ranks")
+                c1.set_precision(precision)
+                F1, dF1, G1, H1, _, dH1 = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, rng=(seed, stream), nargout=6, ctx=c1)
+                out["vs_one_rank_same_draws"] = dict(F=_rel(F, F1), dF=_rel(dF, dF1), G=_rel(G, G1), H=_rel(H, H1), dH=_rel(dH, dH1))
+                lim = 1e-12 if precision == 64 else 1e-5
+                if max(out["vs_one_rank_same_draws"].values()) > lim:
+                    raise RuntimeError(f"parity gate: {world}-rank step differs from the 1-rank step on the same draws: {out['vs_one_rank_same_draws']}")
+            if rank == 0:
+                c1.set_precision(precision)
+                eps = c1.eps_philox(D, K, Ns, seed, stream, readback=True)
+                c1.set_precision(64)
+                prep = cport.Prepared(vp, gp, tb)
+                Fp, dFp, Gp, Hp, dHp, _ = cport.negelcbo(prep, theta, Ns, eps)
+                e = dict(F=_rel(F, Fp), dF=_rel(dF, dFp), G=_rel(G, Gp), H=_rel(H, Hp), dH=_rel(dH, dHp))
+                out["vs_cport_fp64_full"] = dict(e, Ns=Ns, what="C/OpenMP port in FP64 on the dumped device draws; its own log-joint "
+                                                 "side is ~1e-10 from the binary128 truth at this conditioning, so only H, dH are gated here")
+                if max(e["H"], e["dH"]) > tol:
+                    raise RuntimeError(f"parity gate ({cfg.get('name', '')} Ns={Ns}, {precision}-bit sweep): entropy side off: {e}")
+                if max(e["F"], e["dF"], e["G"]) > max(1e-8, tol):
+                    raise RuntimeError(f"parity gate: log-joint side far from the FP64 port: {e}")
+        # ---- truth: binary128 on a reduced number of draws (and optionally of hyper-parameter samples) ----
+        gp_t = gp if truth_S is None else dict(gp, post=list(gp["post"][:truth_S]))
+        c1.set_precision(64)
+        eps_t = c1.eps_philox(D, K, truth_Ns, seed, stream + 1, readback=True)
+        c1.set_precision(precision)
+        got = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp_t, truth_Ns, 1, 0, 0, tb, 0, epsilon=eps_t, nargout=6, ctx=ctx)
+        F, dF, G, H, _, dH = got
+        if rank == 0:
+            prep = cport.Prepared(vp, gp_t, tb)
+            Ft, dFt, Gt, Ht, dHt, _ = cport.negelcbo(prep, theta, truth_Ns, eps_t, truth128=True)
+            e = dict(F=_rel(F, Ft), dF=_rel(dF, dFt), G=_rel(G, Gt), H=_rel(H, Ht), dH=_rel(dH, dHt))
+            Fp, dFp, Gp, Hp, dHp, _ = cport.negelcbo(prep, theta, truth_Ns, eps_t)
+            out["vs_binary128"] = dict(e, Ns=truth_Ns, S=len(gp_t["post"]))
+            out["fp64_port_vs_binary128"] = dict(F=_rel(Fp, Ft), dF=_rel(dFp, dFt), G=_rel(Gp, Gt), H=_rel(Hp, Ht), dH=_rel(dHp, dHt))
+            if max(e.values()) > tol:
+                raise RuntimeError(f"parity gate: CUDA step vs binary128 truth: {e}")
+        if truth_S is not None:   # make the full posterior resident again
+            ctx.gp_attach(gp)
+    finally:
+        ctx.set_precision(64)
+        if c1 is not ctx:
+            c1.close()
+    out["ok"] = True
+    return out
+
+
+def guarded_gate(name, dist, local, *a, **kw):
+    """Run parity_gate on every rank; a failure on any rank stops all of them (no rank is left waiting in a collective)."""
+    err, res = None, None
+    try:
+        res = parity_gate(*a, **kw)
+    except Exception as e:   # noqa: BLE001
+        err = f"{name}: {e}"
+    bad = 1.0 if err else 0.0
+    if dist is not None:
+        import torch
+        t = torch.tensor([bad], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bad = float(t.item())
+    if bad:
+        sys.stderr.write(f"[bench] PARITY GATE FAILED ({err or 'on another rank'}) -- nothing is timed\n")
+        sys.stderr.flush()
+        if dist is not None:
+            dist.destroy_process_group()
+        sys.exit(3)
+    return res
+
+
 def run_reference(args, cfg_name, emit):
     """Reference arm: the reference's CPU algorithm (oracle C/OpenMP port) on the host cores."""
     from vbmc_b200 import workloads
@@ -181,13 +332,16 @@ def run_reference(args, cfg_name, emit):
     emit(line)
 
 
-def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=64):
-    """Device-resident steps/s of another configuration (same protocol as the headline `value`)."""
+def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=64, gate=None, rank=0, world=1):
+    """Device-resident steps/s of another configuration (same protocol as the headline `value`), behind its own parity gate."""
     import ctypes as C
     from vbmc_b200 import _lib, workloads
     cfg = dict(workloads.CONFIGS[cfg_name])
     w = workloads.build(cfg, lambda *a: vbmc_b200.gplite_post(*a, ctx=ctx, want_L=False), with_eps=False)
     _, tb = vbmc_b200.vpbounds(w["vp"], w["gp"], workloads.VP_OPTIONS)
+    parity = None
+    if gate is not None:
+        parity = guarded_gate(f"{cfg_name}/{precision}", dist, local, ctx, vbmc_b200, w, tb, cfg, dist, local, rank, world, precision=precision, **gate)
     ctx.vp_set(w["vp"]); ctx.gp_attach(w["gp"]); ctx.thetabnd_set(tb)
     theta = np.ascontiguousarray(w["theta"])
     F, dF, ms = C.c_double(), np.zeros_like(theta), C.c_float()
@@ -213,7 +367,7 @@ def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot = float(t.item())
     return {"workload": cfg_name, **{k: cfg[k] for k in ("D", "N", "K", "Ns", "S")}, "steps": steps, "entropy_sweep_bits": precision,
-            "ms_per_step": tot / steps, "value": 1e3 * steps / tot, "unit": "steps/s"}
+            "ms_per_step": tot / steps, "value": 1e3 * steps / tot, "unit": "steps/s", "parity": parity}
 
 
 def main():
@@ -297,9 +451,15 @@ def main():
                                  "unit": "TFLOP/s", "frac": refit["potrf_update_dmma_tflops"] / 37.1,
                                  "peak_source": "FP64 DMMA micro-benchmark tools/dmma_probe.cu, measured on B200 (profiles/r1_ncu_summary.md); "
                                                 "ncu: tensor sub-pipe 63.8 % active on the large trailing updates"}
+        refit["library_bar"] = library_cholesky_bar(w, cfg, local)
     _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
     Ns = cfg["Ns"]
     counts = algorithmic_counts(cfg)
+
+    # ---- parity gate: nothing is timed unless this configuration's step matches the CPU restatements ----
+    parity = None
+    if not args.no_parity:
+        parity = guarded_gate(cfg_name, dist, local, ctx, vbmc_b200, dict(w, gp=gp), tb, cfg, dist, local, rank, world, full=True, truth_Ns=128)
 
     # ---- make everything resident, build the args struct for the device-resident loop ----
     ctx.vp_set(vp)
@@ -352,6 +512,25 @@ def main():
         tot_ms = float(t.item())
     ms_per_step = tot_ms / args.steps
     value = 1e3 / ms_per_step
+
+    # ---- the same steps as ONE resident loop of >= 200 consecutive steps, wall clock between two device syncs (no L2 flush, no gaps):
+    # what a caller that keeps theta on the device sees; the per-step events above cannot hide work in un-timed gaps here ----
+    nloop = max(200, args.steps)
+    barrier()
+    tl0 = time.perf_counter()
+    a.stream = 300_000
+    _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), nloop, C.byref(ms)))
+    barrier()
+    loop_wall = time.perf_counter() - tl0
+    loop_dev_ms = ms.value
+    if dist is not None:
+        import torch
+        t = torch.tensor([loop_wall, loop_dev_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        loop_wall, loop_dev_ms = float(t[0].item()), float(t[1].item())
+    resident_loop = {"steps": nloop, "wall_s": loop_wall, "steps_per_s_wall": nloop / loop_wall, "steps_per_s_device_events": 1e3 * nloop / loop_dev_ms,
+                     "what": "vbmc_b200_negelcbo_resident_loop: consecutive steps, fresh device draws each, host sync every step for F/dF; "
+                             "L2 NOT flushed (a step's 65.5 MB of draws are written by the generator right before they are read)"}
 
     # ---- per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
     ctx.profile_reset()
@@ -460,13 +639,15 @@ def main():
     # ---- c4 (Ns=131072): the MC-shard configuration BASELINE.json names for 2/4/8 GPUs, same protocol ----
     c4 = None
     if args.config is None:
-        c4 = quick_value(ctx, vbmc_b200, "c4", max(10, args.steps // 5), 3, dist, local)
+        c4 = quick_value(ctx, vbmc_b200, "c4", max(10, args.steps // 5), 3, dist, local, rank=rank, world=world,
+                         gate=None if args.no_parity else dict(full=True, truth_Ns=64))
     # ---- c5 (D=20, N=4000, K=100, Ns=262144, S=40): BASELINE.json's FP32 configuration, FP32 and FP64 sweeps ----
     c5 = None
     if args.config is None and os.environ.get("VBMC_B200_BENCH_C5", "1") != "0":
         try:
-            c5 = {"fp32": quick_value(ctx, vbmc_b200, "c5", 5, 2, dist, local, precision=32),
-                  "fp64": quick_value(ctx, vbmc_b200, "c5", 3, 1, dist, local, precision=64)}
+            g5 = None if args.no_parity else dict(full=True, reduced_Ns=2048, truth_Ns=64, truth_S=2)
+            c5 = {"fp32": quick_value(ctx, vbmc_b200, "c5", 5, 2, dist, local, precision=32, gate=g5, rank=rank, world=world),
+                  "fp64": quick_value(ctx, vbmc_b200, "c5", 3, 1, dist, local, precision=64, gate=g5, rank=rank, world=world)}
         except Exception as e:   # a sub-measurement must never cost the headline line (every rank fails alike: no collective is left hanging)
             c5 = {"error": str(e)[:300]}
     clocks = sampler.stop() if rank == 0 else None
@@ -481,20 +662,23 @@ def main():
     shard = 1.0 / world
     ent_tflops = counts["entmc_flops"] * shard / (ent_ms * 1e-3) / 1e12 if ent_ms > 0 else None
     ent_gbs = counts["entmc_bytes"] * shard / (ent_ms * 1e-3) / 1e9 if ent_ms > 0 else None
-    roofline = {"kernel": "entmc_kernel", "bound": "fp64", "achieved": ent_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ent_tflops / fp64_peak if ent_tflops else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at c3 on one GPU (profiles/r1_ncu_summary.md, capture
-                # entmc_r1f: 65.61 MB + 0.20 MB); other configurations were not captured
-                "traffic": 65.61e6 + 0.204e6 if (cfg_name == "c3" and world == 1) else None,
+    exec_tflops = ent_tflops * kept_frac if ent_tflops else None
+    roofline = {"kernel": "entmc_kernel", "bound": "fp64", "achieved": exec_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": exec_tflops / fp64_peak if exec_tflops else None,
+                "frac_is": "EXECUTED flops (scored (pair, component) blocks only) / measured DFMA peak; the algorithmic fraction is in `algorithmic`",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at c3 on one GPU: NOT measured in this run, copied from the
+                # ncu capture named in traffic_source (the kernel reads each draw exactly once, so the figure is shape-determined)
+                "traffic": TRAFFIC_C3_BYTES if (cfg_name == "c3" and world == 1) else None,
+                "traffic_source": TRAFFIC_C3_SOURCE if (cfg_name == "c3" and world == 1) else None,
                 "peak_source": "DFMA micro-benchmark run live on this device (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"achieved": ent_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ent_gbs / peaks["hbm_gbs"] if ent_gbs else None,
                         "peak_source": peak_src + " MEASURED_PEAKS.json"},
                 "algorithmic": {"flops_per_launch": counts["entmc_flops"] * shard, "bytes_per_launch": counts["entmc_bytes"] * shard,
-                                "ms_per_launch": ent_ms},
+                                "ms_per_launch": ent_ms, "tflops": ent_tflops, "frac": ent_tflops / fp64_peak if ent_tflops else None},
                 "executed": {"kept_fraction": kept_frac, "tflops": ent_tflops * kept_frac if ent_tflops else None,
                              "frac": ent_tflops * kept_frac / fp64_peak if ent_tflops else None,
                              "what": "components whose term is < exp(-50) of q for a whole warp of draws are skipped (below FP64 round-off; "
-                                     "parity-tested); `achieved` counts the ALGORITHMIC K^2 Ns (5D+12) flops, `executed` only the scored ones"},
+                                     "parity-tested); `algorithmic` counts the K^2 Ns (5D+12) flops of SURVEY 8d, `executed` (= achieved/frac) only the scored ones"},
                 "note": "entmc at K=50 has ~78 flop/B: FP64-pipe bound, not HBM bound (SURVEY.md 8d); both fractions reported"}
     cpu = None
     if not args.no_cpu_baseline:
@@ -530,10 +714,12 @@ def main():
                 "includes": "host theta H2D, F/dF D2H, host Adam update (fminadam.m:51-60); draws from the device generator",
                 "host_eps_variant_steps_per_s": e2e_host_eps,
                 "host_eps_variant_h2d_bytes_per_step": counts["entmc_bytes"] if e2e_host_eps else None},
+        "parity": parity if parity is not None else {"ok": None, "skipped": "--no-parity"},
         "fminadam_device_loop": fmin,
         "next_rows": nxt,
         "gpu_launches": launches,
         "wall_s_timed_region": t_wall,
+        "resident_loop": resident_loop,
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in prof.items()},
         "roofline": roofline,
         "refit": refit,

@@ -112,12 +112,17 @@ typedef struct vbmc_b200_gp_desc {
 int vbmc_b200_gp_attach(vbmc_b200_ctx* ctx, const vbmc_b200_gp_desc* gp, const double* alpha,
                         const double* sW1, const int* Lchol, const double* L);
 
-/* Caller's fingerprint of the resident posterior (e.g. the address of gp.post(1).alpha's data in MATLAB, whose
- * copy-on-write keeps it stable until the posterior is recomputed).  The library only stores it and resets it to 0
- * whenever the resident posterior changes (gp_attach, gp_post, gp_post_update1, gp_nlz*), so that several gateways
- * sharing one context agree on whether `gp` has to be attached again. */
+/* Caller's fingerprint of the resident posterior.  The MEX gateways hash the data addresses of every gp.post(s).alpha (MATLAB's
+ * copy-on-write keeps them stable until a posterior is recomputed), S, N, D, Nhyp, covfun/meanfun/noisefun and the CONTENT of
+ * every hyper-parameter vector plus first/last alpha values (mex/vbmc_b200_mex_common.h); the address of post(1).alpha alone is
+ * NOT a fingerprint -- `gp1 = gp; gp1.post = gp.post(1)` (activeimportancesampling_vbmc.m:170-171) shares it with another S.
+ * The library only stores the tag and resets it to 0 whenever the resident posterior changes (gp_attach, gp_post,
+ * gp_post_update1, gp_nlz*), so that several gateways sharing one context agree on whether `gp` has to be attached again. */
 int vbmc_b200_gp_tag_set(vbmc_b200_ctx* ctx, unsigned long long tag);
 int vbmc_b200_gp_tag_get(vbmc_b200_ctx* ctx, unsigned long long* tag);
+/* Shape of the resident posterior (all 0 when none): callers that size output arrays from their own struct must check it
+ * matches before a compute call -- the library always computes with the RESIDENT N, D, S. */
+int vbmc_b200_gp_shape(vbmc_b200_ctx* ctx, int* N, int* D, int* S);
 
 /* gplite_post(hyp,X,y,covfun,meanfun,noisefun,s2)  — gplite/gplite_post.m:94-172, i.e. S x
  * gplite_core(hyp,gp,0,0) (gplite/private/gplite_core.m:33-102,278-285): SE-ARD Gram, Cholesky

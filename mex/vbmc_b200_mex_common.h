@@ -94,18 +94,63 @@ inline void gp_model(const mxArray* gp, vbmc_b200_gp_desc* g) {
     for (int i = 0; i < 3 && i < (int)mxGetNumberOfElements(nf); ++i) g->noisefun[i] = (int)mxGetDoubles(nf)[i];
 }
 
-// Make gp.post resident when it is not already.  Fingerprint: data pointer of gp.post(1).alpha (MATLAB's copy-on-write
-// keeps it stable until the posterior is recomputed), low bit = "the factors L were uploaded too".  The fingerprint is kept
-// by the library next to the posterior itself (vbmc_b200_gp_tag_*) — every gateway is a separate shared object, a static
-// here would not be seen by the others — and the library clears it whenever the resident posterior changes.
+// Fingerprint of a gp struct (FNV-1a): shape, model switches, the data address AND first/last value of every gp.post(s).alpha, the
+// address of gp.X, and the content of every hyper-parameter vector, sn2_mult and Lchol.  MATLAB arrays are copy-on-write, so any
+// edit of alpha / X gives a new address; the small fields are hashed by value.  Low bit = "the factors L were uploaded too".
+inline unsigned long long fnv1a(unsigned long long h, const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) {
+    h ^= b[i];
+    h *= 1099511628211ULL;
+  }
+  return h;
+}
+inline unsigned long long gp_fingerprint(const mxArray* gp, const mxArray* post, int S) {
+  unsigned long long h = 1469598103934665603ULL;
+  vbmc_b200_gp_desc g;
+  gp_model(gp, &g);
+  const int dims[8] = {S, g.N, g.D, g.covfun, g.meanfun, g.noisefun[0], g.noisefun[1], g.noisefun[2]};
+  h = fnv1a(h, dims, sizeof(dims));
+  const void* px[3] = {g.X, g.y, g.s2};
+  h = fnv1a(h, px, sizeof(px));
+  for (int s = 0; s < S; ++s) {
+    const mxArray* a = mxGetField(post, s, "alpha");
+    const mxArray* hy = mxGetField(post, s, "hyp");
+    if (!a || !hy) mexErrMsgIdAndTxt("vbmc_b200:gp", "gp.post(%d) has no alpha / hyp.", s + 1);
+    const void* pa = mxGetData(a);
+    const size_t na = mxGetNumberOfElements(a), nh = mxGetNumberOfElements(hy);
+    h = fnv1a(h, &pa, sizeof(pa));
+    h = fnv1a(h, &na, sizeof(na));
+    if (na) {
+      h = fnv1a(h, mxGetDoubles(a), sizeof(double));
+      h = fnv1a(h, mxGetDoubles(a) + na - 1, sizeof(double));
+    }
+    h = fnv1a(h, mxGetDoubles(hy), sizeof(double) * nh);
+    const double m = dbl(post, s, "sn2_mult") ? dbl(post, s, "sn2_mult")[0] : 1.0;
+    const double lc = mxGetField(post, s, "Lchol") ? mxGetScalar(mxGetField(post, s, "Lchol")) : 1.0;
+    h = fnv1a(h, &m, sizeof(m));
+    h = fnv1a(h, &lc, sizeof(lc));
+  }
+  return h & ~1ULL;
+}
+
+// Make gp.post resident when it is not already.  The fingerprint is kept by the library next to the posterior itself
+// (vbmc_b200_gp_tag_*) -- every gateway is a separate shared object, a static here would not be seen by the others -- and the
+// library clears it whenever the resident posterior changes.  A hit is only trusted when the RESIDENT shape equals the struct's
+// (the gateways size their outputs from the struct; the library computes with the resident N, D, S).
 inline int gp_attach(vbmc_b200_ctx* c, const mxArray* gp, bool want_L) {
   const mxArray* post = fld(gp, 0, "post");
   if (!post) mexErrMsgIdAndTxt("vbmc_b200:gp", "gp.post is missing or empty.");
   const int S = (int)mxGetNumberOfElements(post);
-  const unsigned long long key = (unsigned long long)(size_t)mxGetData(mxGetField(post, 0, "alpha")) & ~1ULL;
+  const unsigned long long key = gp_fingerprint(gp, post, S);
   unsigned long long have = 0;
   check(vbmc_b200_gp_tag_get(c, &have));
-  if (have && (have & ~1ULL) == key && ((have & 1ULL) || !want_L)) return S;
+  if (have && (have & ~1ULL) == key && ((have & 1ULL) || !want_L)) {
+    int rN = 0, rD = 0, rS = 0;
+    check(vbmc_b200_gp_shape(c, &rN, &rD, &rS));
+    const mxArray* X = fld(gp, 0, "X");
+    if (X && rS == S && rN == (int)mxGetM(X) && rD == (int)mxGetN(X)) return S;
+  }
   vbmc_b200_gp_desc g;
   gp_model(gp, &g);
   g.S = S;

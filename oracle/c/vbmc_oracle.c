@@ -51,6 +51,15 @@ int FN(threads)(void) {
 #endif
 }
 
+/* explicit thread count: torchrun exports OMP_NUM_THREADS=1 to every rank and libgomp may already be initialised */
+void FN(set_threads)(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 typedef struct {
   int D, K;
   real *mu, *sigma, *lambda, *w, *eta; /* mu[K][D] */

@@ -42,6 +42,7 @@ def load_truth128():
             subprocess.check_call(["make", "-C", str(_DIR)])
         _lib128 = C.CDLL(str(_LIB128))
         _lib128.vbmc_truth128_negelcbo.restype = C.c_int
+        _lib128.vbmc_truth128_set_threads(int(os.environ.get("VBMC_ORACLE_THREADS", host_threads())))
     return _lib128
 
 
@@ -56,6 +57,7 @@ def load():
         _lib = C.CDLL(str(_LIB))
         _lib.vbmc_oracle_threads.restype = C.c_int
         _lib.vbmc_oracle_negelcbo.restype = C.c_int
+        _lib.vbmc_oracle_set_threads(int(os.environ.get("VBMC_ORACLE_THREADS", host_threads())))
     return _lib
 
 

@@ -1,5 +1,5 @@
-"""Multi-GPU parity check (a script, not collected by pytest; it lives under tests/ because it uses the oracle as its checker),
-launched with torchrun, one rank per GPU:
+"""Multi-GPU parity check, launched with torchrun, one rank per GPU (tests/test_mgpu.py runs it under pytest -m gpu on every
+box that has at least two GPUs; it lives under tests/ because it uses the oracle as its checker):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/mgpu_check.py
 every rank evaluates the same negelcbo_vbmc step on its shard (MC pair axis, hyper-parameter samples);
 after the single NCCL all-reduce all ranks must hold the same F, dF, equal to the oracle's (rank 0 checks)."""
@@ -53,11 +53,29 @@ def main():
         # device Philox draws do not depend on the sharding: compare against a single-GPU style evaluation of the dump
         F2, dF2 = vbmc_b200.negelcbo_vbmc(theta, 0.0, vp, gp, cfg["Ns"], 1, 0, 0, tb, 0, rng=(42, 3), nargout=2, ctx=ctx)
         if rank == 0:
+            # checker: the binary128 evaluation (tests/test_truth128.py); the FP64 NumPy oracle's own distance is printed beside it
+            from oracle import cport
+            Ft, dFt, Gt, Ht, _, _ = cport.negelcbo(cport.Prepared(vp, gp, tb), theta, cfg["Ns"], eps, truth128=True)
             Fo, dFo, Go, Ho = orc.negelcbo_vbmc(theta, 0.0, vp, gp, cfg["Ns"], 1, 0, 0, tb, 0, epsilon=eps, nargout=4)[:4]
             rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
-            errs = (rel(F, Fo), rel(dF, dFo), rel(G, Go), rel(H, Ho))
+            errs = (rel(F, Ft), rel(dF, dFt), rel(G, Gt), rel(H, Ht))
             worst = max(worst, *errs)
-            print(f"[mgpu_check] world={world} {shape}: rel errors F,dF,G,H = {errs}", flush=True)
+            print(f"[mgpu_check] world={world} {shape}: rel errors vs binary128 F,dF,G,H = {errs}; FP64 oracle vs binary128 = "
+                  f"{(rel(Fo, Ft), rel(dFo, dFt), rel(Go, Gt), rel(Ho, Ht))}", flush=True)
+        dist.barrier()
+        # beta != 0 with the diagonal variance and its gradient (negelcbo_vbmc.m:119-130): the per-sample gradients of ALL hyper-
+        # parameter samples are needed on every rank although the step shards them (stale rows of glj_out)
+        Fb, dFb = vbmc_b200.negelcbo_vbmc(theta, 0.7, vp, gp, cfg["Ns"], 1, 2, 0, tb, 0, epsilon=eps, nargout=2, ctx=ctx)
+        t = torch.tensor(np.concatenate([[Fb], dFb]), device=f"cuda:{local}")
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(t, ref), f"rank {rank}: beta != 0 results differ from rank 0"
+        if rank == 0:
+            Fbo, dFbo = orc.negelcbo_vbmc(theta, 0.7, vp, gp, cfg["Ns"], 1, 2, 0, tb, 0, epsilon=eps, nargout=2)[:2]
+            eb = (rel(Fb, Fbo), rel(dFb, dFbo))
+            print(f"[mgpu_check] world={world} {shape}: beta=0.7, compute_var=2: rel errors F,dF vs oracle = {eb}", flush=True)
+            assert max(eb) < 1e-6, eb   # the variance goes through K^-1 (cond ~ sf2/sn2): 1e-7..1e-6 is the FP64 floor (test_gpu_parity.py)
+        dist.barrier()
     # streaming generator-mode calls (stream advancing by one): ahead-of-time draws + graph replay of the multi-GPU step
     # (the all-reduce is inside finalize_kernel).  Every call must equal parity mode on that stream's dumped draws, on every rank.
     refs = []

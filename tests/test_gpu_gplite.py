@@ -92,6 +92,39 @@ def test_gplite_post_ill_conditioned_realistic(gpu_ctx):
         assert rel(a["L"].T @ a["L"], b["L"].T @ b["L"]) < 1e-13
 
 
+@pytest.mark.parametrize("name,S", [("c3", 3), ("c5", 2)], ids=["c3_N2000_D10", "c5_N4000_D20_noisy"])
+def test_gplite_post_at_benchmark_sizes(gpu_ctx, name, S):
+    """The refit at the training-set sizes the benchmark uses (c3: N = 2000, c5: N = 4000 with per-point noise), realistic noise
+    floor (sn2 = 1e-5 => cond ~ 1e8).  Criteria that do not depend on the conditioning: backward error of the factor
+    (L'L == K/sl + diag) and of the solution ((K + Sigma) alpha == y - m), each 1e-13; against the LAPACK-based oracle a
+    cond-scaled forward bound (any backward-stable solver, MATLAB's included, has forward error ~ cond * eps)."""
+    import vbmc_b200
+    cfg = dict(workloads.CONFIGS[name], S=S)
+    X, y, s2 = workloads.make_training_set(cfg, 101)
+    hyp = workloads.make_hyp_samples(cfg, X, y, 102)
+    nf = [1, 1, 0] if s2 is not None else [1, 0, 0]
+    N, D = X.shape
+    gp = vbmc_b200.gplite_post(hyp, X, y, 1, 4, nf, s2)
+    ref = orc.gplite_post(hyp, X, y, 1, 4, nf, s2)
+    for s in range(S):
+        a, b = gp["post"][s], ref["post"][s]
+        assert a["Lchol"] and b["Lchol"] and a["sn2_mult"] == b["sn2_mult"]
+        assert rel(a["sW"], b["sW"]) < 1e-14
+        _, _, _, K_mat, _ = orc.gplite_core(hyp[:, s], ref, False, False)
+        sn2 = math.exp(2 * hyp[D + 1, s]) + (s2 if s2 is not None else 0.0) * np.ones(N)
+        A = K_mat + np.diag(sn2 * a["sn2_mult"])
+        m = orc.gplite_meanfun(hyp[D + 2:, s], X, 4)
+        ev = np.linalg.eigvalsh(A)            # symmetric positive definite: ||A||_2 = ev[-1], cond = ev[-1] / ev[0]
+        nA = float(ev[-1])
+        resid = np.linalg.norm(A @ a["alpha"] - (y - m)) / (nA * np.linalg.norm(a["alpha"]) + np.linalg.norm(y - m))
+        resid_ref = np.linalg.norm(A @ b["alpha"] - (y - m)) / (nA * np.linalg.norm(b["alpha"]) + np.linalg.norm(y - m))
+        assert resid < 1e-13, (resid, resid_ref)
+        sl = float(np.min(sn2)) * a["sn2_mult"]
+        assert rel(a["L"].T @ a["L"], A / sl) < 1e-13
+        cond = float(ev[-1] / ev[0])
+        assert rel(a["alpha"], b["alpha"]) < 50 * cond * np.finfo(float).eps, (rel(a["alpha"], b["alpha"]), cond)
+
+
 def test_gplite_post_cholesky_retry(gpu_ctx):
     """Duplicate points + tiny noise: chol fails, sn2_mult is multiplied by 10 until it works (gplite_core.m:78-81)."""
     import vbmc_b200

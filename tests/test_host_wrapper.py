@@ -189,3 +189,62 @@ def test_change_probes_never_skip_a_needed_upload(problem):
     vp_list = dict(vp, sigma=list(vp["sigma"]))  # entries that are not float64 arrays always take the full path (content key)
     call(vp_list); call(vp_list)
     assert ctx.lib.calls["negelcbo"] > 0
+
+
+def test_gp_attach_never_reuses_a_stale_posterior(problem):
+    """the device posterior must be re-uploaded after ANY change of the gp dict -- in-place edits of a middle
+    sample, scalar fields, replaced arrays -- and must not be re-uploaded when nothing changed (content equal, frozen or not)."""
+    import copy
+    w = problem
+    cfg = dict(D=3, N=30, K=4, S=3, Ns=16, target="rosenbrock", noisy=False)
+    gp = workloads.build(cfg, orc.gplite_post)["gp"]
+    ctx = FakeCtx(3, 4)
+    n = lambda: ctx.lib.calls["gp_attach"]
+    ctx.gp_attach(gp)
+    assert n() == 1
+    ctx.gp_attach(gp)
+    assert n() == 1                                     # unchanged (content probe: the oracle's arrays are writable)
+    gp["post"][1]["alpha"][7] += 1e-9                   # in-place edit of a MIDDLE sample, middle element
+    ctx.gp_attach(gp)
+    assert n() == 2
+    gp["post"][1]["hyp"][2] += 1e-12
+    ctx.gp_attach(gp)
+    assert n() == 3
+    gp["meanfun"] = 1
+    ctx.gp_attach(gp)
+    assert n() == 4
+    gp["meanfun"] = 4
+    gp["post"][2]["sn2_mult"] = 10.0
+    ctx.gp_attach(gp)
+    assert n() == 6 - 1
+    gp["X"][3, 1] += 1e-9
+    ctx.gp_attach(gp)
+    assert n() == 6
+    gp["y"][5] -= 1e-9
+    ctx.gp_attach(gp)
+    assert n() == 7
+    gp2 = copy.deepcopy(gp)                             # a NEW dict (CPython may reuse ids) with the same content: no upload
+    ctx.gp_attach(gp2)
+    assert n() == 7
+    gp2["post"][0]["alpha"] = gp2["post"][0]["alpha"] * (1 + 1e-15)   # replaced array
+    ctx.gp_attach(gp2)
+    assert n() == 8
+    # a posterior attached for S = 3 is not the resident one of its one-sample sub-struct (activeimportancesampling_vbmc.m:170-171)
+    gp1 = dict(gp2, post=[gp2["post"][0]])
+    ctx.gp_attach(gp1)
+    assert n() == 9
+    ctx.gp_attach(gp2)
+    assert n() == 10
+    # frozen arrays (what gplite_post returns): identity is enough, and an attempted in-place edit raises instead of going unnoticed
+    api._freeze(gp2["X"], gp2["y"], *[a for p in gp2["post"] for a in (p["alpha"], p["hyp"], p["sW"], p["L"])])
+    ctx.gp_attach(gp2)
+    assert n() == 10 and ctx._gp_key.frozen is True     # same content: no upload; from now on identity alone decides
+    ctx.gp_attach(gp2)
+    assert n() == 10
+    with pytest.raises(ValueError):
+        gp2["post"][1]["alpha"][0] = 0.0
+    # the factors: a posterior attached without L is not enough for a caller that needs them
+    ctx.gp_attach(gp2, want_L=True)
+    assert n() == 11
+    ctx.gp_attach(gp2, want_L=False)
+    assert n() == 11

@@ -59,6 +59,68 @@ def _probe(entries):
     return tuple(ids), val
 
 
+# ---- "is this gp the posterior that is resident on the device?" -------------------------------------------------------------
+# Two levels.  (1) identity: the same array OBJECTS in the same places, all of them read-only (the arrays of a gp dict built by
+# gplite_post / gplite_post_update1 are frozen, so they cannot have been edited in place) plus every scalar field -- no data is
+# read, ~10 us.  (2) content: shapes, scalars and a weighted sum of EVERY array (X, y, s2 and hyp, alpha, sW(1), sn2_mult, Lchol of
+# every sample): any edit, in place or not, of any sample changes it; used for dicts that did not come from this module or that
+# hold a writable array.  A stale device posterior is never reused silently.
+def _probe_big(x):
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    n, m = x.size, _PROBE_W.size
+    val = 0.125 * n
+    for o in range(0, n, m):
+        c = x[o:o + m]
+        val += float(c @ _PROBE_W[:c.size]) * (1.0 + 1e-3 * (o // m))
+    return val
+
+
+def _gp_scalars(gp):
+    cov = gp.get("covfun", 1)
+    cov = int(cov[0] if isinstance(cov, (list, tuple, np.ndarray)) else cov)
+    return (cov, int(gp.get("meanfun", 1)), tuple(int(v) for v in gp.get("noisefun", [1, 0, 0])), len(gp["post"]))
+
+
+def _gp_identity(gp):
+    """(key, frozen): ids of every array + scalars; frozen is True when no array can be edited in place."""
+    arrs = [gp["X"], gp.get("y"), gp.get("s2")]
+    key = [id(a) for a in arrs]
+    for p in gp["post"]:
+        pa = (p["alpha"], p["hyp"], p.get("sW"), p.get("L"))
+        arrs.extend(pa)
+        key.extend(id(a) for a in pa)
+        key.append((id(p), float(p.get("sn2_mult", 1.0) or 1.0), bool(p.get("Lchol", True))))
+    frozen = all(a is None or (isinstance(a, np.ndarray) and not a.flags.writeable) for a in arrs)
+    return (_gp_scalars(gp), tuple(key)), frozen
+
+
+def _gp_content(gp, with_L):
+    X = np.asarray(gp["X"])
+    vals = [X.shape, _gp_scalars(gp), _probe_big(X)]
+    for name in ("y", "s2"):
+        vals.append(None if gp.get(name) is None else _probe_big(gp[name]))
+    for p in gp["post"]:
+        vals.append((_probe_big(p["hyp"]), _probe_big(p["alpha"]), float(np.ravel(p["sW"])[0]), float(p.get("sn2_mult", 1.0) or 1.0),
+                     bool(p.get("Lchol", True)), _probe_big(p["L"]) if (with_L and p.get("L") is not None) else None))
+    return tuple(vals)
+
+
+def _freeze(*arrays):
+    for a in arrays:
+        if isinstance(a, np.ndarray):
+            a.flags.writeable = False
+
+
+class _GpResident:
+    __slots__ = ("ident", "frozen", "content", "content_L", "has_L")
+
+    def __init__(self, gp, has_L):
+        self.ident, self.frozen = _gp_identity(gp)
+        self.content = _gp_content(gp, False)
+        self.content_L = _gp_content(gp, True) if (has_L and all(p.get("L") is not None for p in gp["post"])) else None
+        self.has_L = has_L
+
+
 class _CallFrame:
     """Pre-marshalled argument block of one negelcbo_vbmc signature: the ctypes struct, its output buffers and the pointers
     between them are built once; a call copies theta in, sets the scalars and copies the results out."""
@@ -173,15 +235,25 @@ class Context:
         keep += [Xc, hyp, y, s2]
         return d, (N, D, S, Nhyp)
 
+    def gp_is_resident(self, gp, want_L=False):
+        """True when the device holds exactly this posterior (see _gp_identity / _gp_content above)."""
+        r = self._gp_key
+        if r is None or (want_L and not r.has_L):
+            return False
+        ident, frozen = _gp_identity(gp)
+        if frozen and r.frozen and ident == r.ident:
+            return True
+        if _gp_content(gp, False) != r.content:
+            return False
+        if want_L and r.content_L is not None and all(p.get("L") is not None for p in gp["post"]) and _gp_content(gp, True) != r.content_L:
+            return False
+        r.ident, r.frozen = ident, frozen      # same content under new objects: remember them
+        return True
+
     def gp_attach(self, gp, want_L=False):
-        """Make ``gp`` (with a posterior computed elsewhere) resident; no-op when unchanged."""
+        """Make ``gp`` (with a posterior computed elsewhere) resident; no-op when the device already holds exactly this posterior."""
         post = gp["post"]
-        a0, a1 = np.asarray(post[0]["alpha"]), np.asarray(post[-1]["alpha"])
-        h0, h1 = np.asarray(post[0]["hyp"]), np.asarray(post[-1]["hyp"])
-        # cheap fingerprint (no copies): identity of the struct + first/last values (SURVEY.md 8b)
-        key = (id(gp), gp["X"].shape, len(post), float(a0.flat[0]), float(a1.flat[-1]), float(h0.flat[0]),
-               float(h1.flat[-1]), bool(want_L))
-        if self._gp_key is not None and key[:-1] == self._gp_key[:-1] and (self._gp_key[-1] or not want_L):
+        if self.gp_is_resident(gp, want_L):
             return
         if want_L and any(p.get("L") is None for p in post):
             raise VbmcB200Error(_lib.ESTATE, "vbmc_b200:noL: the variance path needs gp.post(s).L (call gplite_post with want_L=True, "
@@ -195,11 +267,12 @@ class Context:
         L = None
         if want_L:
             L = np.ascontiguousarray(np.stack([f64(p["L"]).T for p in post]))  # each column-major
+        self._gp_key = None
         _lib.check(self.lib.vbmc_b200_gp_attach(self._h, C.byref(d), dptr(alpha), dptr(sW1),
                                                 Lchol.ctypes.data_as(_lib.c_int_p), dptr(L)))
         mult = f64([float(p.get("sn2_mult", 1.0) or 1.0) for p in post])
         _lib.check(self.lib.vbmc_b200_gp_set_sn2_mult(self._h, dptr(mult)))
-        self._gp_key = key
+        self._gp_key = _GpResident(gp, bool(want_L))
 
     # -- VP ---------------------------------------------------------------------------------
     def vp_set(self, vp):
@@ -593,8 +666,8 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     N x N x S device->host copy of the factors (gp.post(s).L is then None).
     """
     ctx = ctx or default_context()
-    X = f64(X)
-    y = f64(y).ravel()
+    X = np.array(X, dtype=np.float64, order="C")        # the struct owns frozen copies (MATLAB value semantics): an in-place edit of
+    y = np.array(y, dtype=np.float64).ravel()           # the caller's arrays cannot silently diverge from the device posterior
     N, D = X.shape
     hyp = f64(hyp)
     if hyp.ndim == 1:
@@ -604,7 +677,7 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     meanfun = 1 if meanfun is None else meanfun
     if noisefun is None:
         noisefun = [1, 0, 0] if s2 is None else [1, 1, 0]
-    gp = {"X": X, "y": y, "s2": None if s2 is None else f64(s2).ravel(), "covfun": covfun, "meanfun": meanfun,
+    gp = {"X": X, "y": y, "s2": None if s2 is None else np.array(s2, dtype=np.float64).ravel(), "covfun": covfun, "meanfun": meanfun,
           "noisefun": list(noisefun), "Ncov": D + 1, "Nnoise": _noise_count(noisefun), "Nmean": _mean_count(D, meanfun),
           "meanfun_extras": None, "intmeanfun": 0}
     keep = []
@@ -618,8 +691,8 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     gp["post"] = [{"hyp": hyp[:, s].copy(), "alpha": alpha[s].copy(), "sW": np.full(N, sW1[s]),
                    "L": None if L is None else L[s].T.copy(), "sn2_mult": float(mult[s]), "Lchol": bool(Lchol[s])}
                   for s in range(S)]
-    ctx._gp_key = (id(gp), gp["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(hyp[0, 0]),
-                   float(hyp[-1, -1]), True)   # the factors stay on the device whether or not they were copied out
+    _freeze(gp["X"], gp["y"], gp["s2"], *[a for p in gp["post"] for a in (p["hyp"], p["alpha"], p["sW"], p["L"])])
+    ctx._gp_key = _GpResident(gp, True)   # the factors stay on the device whether or not they were copied out
     return gp
 
 
@@ -645,8 +718,7 @@ def gplite_post_update1(gp, xstar, ystar, s2star=None, *, ctx=None):
         return gplite_post(hyp, np.vstack([X, xs[None, :]]), np.append(y, ystar), gp["covfun"], gp["meanfun"], gp["noisefun"], s2,
                            ctx=ctx, want_L=any(p.get("L") is not None for p in post))
     have_L = all(p.get("L") is not None for p in post)
-    resident = ctx._gp_key is not None and ctx._gp_key[0] == id(gp) and ctx._gp_key[-1]
-    if not resident:
+    if not ctx.gp_is_resident(gp, want_L=True):
         ctx.gp_attach(gp, want_L=True)   # raises vbmc_b200:noL when the factors are neither resident nor in the struct
     alpha = np.zeros((S, N + 1))
     Lcol = np.zeros((S, N + 1))
@@ -668,8 +740,8 @@ def gplite_post_update1(gp, xstar, ystar, s2star=None, *, ctx=None):
         else:
             q["L"] = None
         new["post"].append(q)
-    h0, h1 = np.asarray(new["post"][0]["hyp"]), np.asarray(new["post"][-1]["hyp"])
-    ctx._gp_key = (id(new), new["X"].shape, S, float(alpha[0, 0]), float(alpha[-1, -1]), float(h0.flat[0]), float(h1.flat[-1]), True)
+    _freeze(new["X"], new["y"], *[a for p in new["post"] for a in (p["alpha"], p["sW"], p["L"])])
+    ctx._gp_key = _GpResident(new, True)
     return new
 
 

@@ -175,6 +175,14 @@ int vbmc_b200_gp_tag_get(vbmc_b200_ctx* c, unsigned long long* tag) {
   return VBMC_B200_OK;
 }
 
+int vbmc_b200_gp_shape(vbmc_b200_ctx* c, int* N, int* D, int* S) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  if (N) *N = c->gp_ready ? c->gp.N : 0;
+  if (D) *D = c->gp_ready ? c->gp.D : 0;
+  if (S) *S = c->gp_ready ? c->gp.S : 0;
+  return VBMC_B200_OK;
+}
+
 // process-wide contexts, one per device (see include/vbmc_b200.h)
 static vbmc_b200_ctx* g_shared[64] = {nullptr};
 int vbmc_b200_shared(vbmc_b200_ctx** out, int device) {
@@ -543,7 +551,7 @@ static bool step_uses_nccl(const vbmc_b200_ctx* c) {
 
 // enqueue the device part of one evaluation; `what` selects negelcbo / entmc / gplogjoint
 static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int jacobian, int what, bool have_theta) {
-  const bool doH = what != FIN_GPLOGJOINT, doG = what != FIN_ENTMC;
+  const bool doH = what != FIN_GPLOGJOINT && what != FIN_NEGELCBO_NOENT, doG = what != FIN_ENTMC;
   RLayout rl;
   rl.init(c->D, c->K, (doG || c->gp_ready) ? c->gp.S : 0);
   if (what == FIN_ENTMC) rl.init(c->D, c->K, 0);
@@ -565,7 +573,7 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   if (doG) {
     VB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     VB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    VB_TRY(launch_gplogjoint(c, gmask != 0, c->stream2));
+    VB_TRY(launch_gplogjoint(c, 0, c->stream2));
     VB_CUDA(cudaEventRecord(c->ev_glj, c->stream2));
     VB_TRY(launch_glj_reduce(c, c->stream2));
     VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
@@ -859,6 +867,8 @@ static int assemble_vargrad(vbmc_b200_ctx* c, int gmask, int jacobian, const std
   const int D = c->D, K = c->K, S = c->gp.S, os = 2 + 2 * D;
   std::vector<double> vpc(static_cast<size_t>(D) * K + 3 * K + D + 2 * K + 2 * D), der(static_cast<size_t>(S) * (3 * D + 3)),
       go(static_cast<size_t>(S) * K * os);
+  // the step filled only this rank's shard of the per-sample results: every rank needs all of them here
+  if (c->nranks > 1) VB_TRY(launch_gplogjoint(c, 1, c->stream));
   VB_CUDA(cudaMemcpyAsync(vpc.data(), c->vp.mu, sizeof(double) * vpc.size(), cudaMemcpyDeviceToHost, c->stream));
   VB_CUDA(cudaMemcpyAsync(der.data(), c->gpDerived.p, sizeof(double) * der.size(), cudaMemcpyDeviceToHost, c->stream));
   VB_CUDA(cudaMemcpyAsync(go.data(), c->glj_out.p, sizeof(double) * go.size(), cudaMemcpyDeviceToHost, c->stream));
@@ -960,37 +970,40 @@ static int assemble_vargrad(vbmc_b200_ctx* c, int gmask, int jacobian, const std
 int vbmc_b200_negelcbo(vbmc_b200_ctx* c, const vbmc_b200_negelcbo_args* a_in) {
   if (!c || !a_in) VB_FAIL(VBMC_B200_EINVAL, "null argument");
   // Ns == 0: negelcbo_vbmc.m:102-109 replaces the Monte-Carlo entropy by the deterministic lower bound entlb_vbmc (what
-  // vpsieve_vbmc.m:76 evaluates for every candidate).  Everything but the entropy term is the ordinary step, so the step
-  // runs with a token two-draw entropy estimate, and H, dH are then exchanged for the bound:
-  //     F_lb = F + H_mc - H_lb,   dF_lb = dF + dH_mc - dH_lb        (F = -G - H + penalties, negelcbo_vbmc.m:116-117)
+  // vpsieve_vbmc.m:76 evaluates for every candidate).  The step runs WITHOUT the entropy sweep (no draws are generated, the
+  // resident draw buffer and its bookkeeping are untouched): F0 = -G + penalties, dF0 likewise; then
+  //     F = F0 - H_lb,   dF = dF0 - dH_lb        (F = -G - H + penalties, negelcbo_vbmc.m:116-117)
   const bool lower_bound = a_in->Ns == 0;
   vbmc_b200_negelcbo_args a_lb = *a_in;
-  if (lower_bound) {
-    a_lb.Ns = 2;
-    a_lb.eps_mode = VBMC_B200_EPS_PHILOX;
-    a_lb.eps = nullptr;
-    a_lb.seed = 0xE17B;
-    a_lb.stream = 0;
-  }
+  if (lower_bound) a_lb.Ns = 2;  // passes the Ns > 0 validation below; no draw is ever made
   const vbmc_b200_negelcbo_args* a = lower_bound ? &a_lb : a_in;
   double beta;
   int Ns, gmask;
   VB_TRY(negelcbo_validate(c, a, &beta, &Ns, &gmask));
   VB_CUDA(cudaSetDevice(c->device));
   const int nth = grad_mask_len(c, gmask);
-  VB_TRY(step_with_graph(c, a, Ns, gmask, nth));
+  if (lower_bound) {
+    const size_t nstage = static_cast<size_t>(c->ntheta) + 2;
+    VB_TRY(c->theta_dev.reserve(sizeof(double) * nstage));
+    VB_TRY(ensure_pinned(&c->theta_pinned, &c->theta_pinned_cap, sizeof(double) * nstage));
+    memcpy(c->theta_pinned, a->theta, sizeof(double) * c->ntheta);
+    memset(c->theta_pinned + c->ntheta, 0, 2 * sizeof(double));
+    VB_CUDA(cudaMemcpyAsync(c->theta_dev.p, c->theta_pinned, sizeof(double) * nstage, cudaMemcpyHostToDevice, c->stream));
+    VB_TRY(enqueue_step(c, Ns, gmask, a->use_thetabnd, 1, FIN_NEGELCBO_NOENT, true));
+    VB_TRY(fetch_out(c, nth, c->gp.S));
+    if (c->nranks > 1 && c->out_pinned[0] != c->out_pinned[0]) VB_TRY(check_exchange(c));
+  } else {
+    VB_TRY(step_with_graph(c, a, Ns, gmask, nth));
+  }
   scatter_negelcbo(c, a, nth);
   if (lower_bound) {
-    OutLayout ol;
-    ol.init(nth, c->gp.S, c->K);
-    const double Hmc = c->out_pinned[ol.oH];
-    std::vector<double> dHmc(c->out_pinned + ol.oDH, c->out_pinned + ol.oDH + nth), dHlb(nth > 0 ? nth : 1);
+    std::vector<double> dHlb(nth > 0 ? nth : 1);
     double Hlb = 0.0;
     VB_TRY(run_entlb(c, gmask, 1, &Hlb, nth ? dHlb.data() : nullptr));
-    if (a->F) *a->F += Hmc - Hlb;
+    if (a->F) *a->F -= Hlb;
     if (a->H) *a->H = Hlb;
     for (int i = 0; i < nth; ++i) {
-      if (a->dF) a->dF[i] += dHmc[i] - dHlb[i];
+      if (a->dF) a->dF[i] -= dHlb[i];
       if (a->dH) a->dH[i] = dHlb[i];
     }
   }

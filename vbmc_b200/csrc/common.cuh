@@ -312,7 +312,7 @@ int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, in
 int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);
 int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st);
 int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st);
-int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st);
+int launch_gplogjoint(vbmc_b200_ctx* c, int all_samples, cudaStream_t st);
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
 int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
 int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
@@ -334,6 +334,6 @@ void shard_range(int total, int nranks, int rank, int* begin, int* end);
 int entmc_pick_dp(int D);
 
 enum { NEED_MU = 1, NEED_E = 2, NEED_W = 4 };
-enum { FIN_NEGELCBO = 0, FIN_ENTMC = 1, FIN_GPLOGJOINT = 2 };
+enum { FIN_NEGELCBO = 0, FIN_ENTMC = 1, FIN_GPLOGJOINT = 2, FIN_NEGELCBO_NOENT = 3 };  // NOENT: F = -G + penalties (the caller adds the entropy bound)
 
 }  // namespace vb

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   }
   const double* R = a.stage_R ? sR : a.R;
   __syncthreads();
-  const bool doH = a.what != FIN_GPLOGJOINT, doG = a.what != FIN_ENTMC;
+  const bool doH = a.what != FIN_GPLOGJOINT && a.what != FIN_NEGELCBO_NOENT, doG = a.what != FIN_ENTMC;
   const double invNs = 1.0 / static_cast<double>(a.Ns > 0 ? a.Ns : 1);
   const double invS = 1.0 / static_cast<double>(S > 0 ? S : 1);
 
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   }
   __syncthreads();
   // ------------------------------------------------------------------ F, dF
-  if (a.what == FIN_NEGELCBO) {
+  if (a.what == FIN_NEGELCBO || a.what == FIN_NEGELCBO_NOENT) {
 #pragma unroll 1
     for (int i = tid; i < a.ntheta_out; i += nt)
       out[ol.oDF + i] = -out[ol.oDG + i] - out[ol.oDH + i] + out[ol.oDF + i];  // dF = -dG - dH (+ dL)

@@ -332,12 +332,18 @@ static int glj_dispatch(vbmc_b200_ctx* c, GljArgs& a, int region, cudaStream_t s
   VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:gplogjoint: D=%d > 24 is not supported by this build", a.D);
 }
 
-int launch_gplogjoint(vbmc_b200_ctx* c, int need_grad, cudaStream_t st) {
-  (void)need_grad;
+// all_samples: ignore the rank's shard and evaluate every hyper-parameter sample (the variance gradient needs the per-sample
+// gradients of ALL samples on every rank: gplogjoint.m:407-410)
+int launch_gplogjoint(vbmc_b200_ctx* c, int all_samples, cudaStream_t st) {
   GljArgs a;
   a.N = c->gp.N; a.D = c->D; a.K = c->K; a.S = c->gp.S;
-  shard_range(a.S, c->nranks, c->rank, &a.s_begin, &a.s_count);
-  a.s_count -= a.s_begin;
+  if (all_samples) {
+    a.s_begin = 0;
+    a.s_count = a.S;
+  } else {
+    shard_range(a.S, c->nranks, c->rank, &a.s_begin, &a.s_count);
+    a.s_count -= a.s_begin;
+  }
   a.meanfun = c->gp.meanfun;
   a.ostride = 2 + 2 * a.D;
   a.gp = c->gp;
