@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       }
   }
   // ------------------------------------------------------------------ penalties (FIN_NEGELCBO only)
-  const bool doP = a.what == FIN_NEGELCBO && a.use_bnd && a.nbnd > 0;
+  const bool doP = (a.what == FIN_NEGELCBO || a.what == FIN_NEGELCBO_NOENT) && a.use_bnd && a.nbnd > 0;
   if (doP) {
     // theta_ext = [mu(:); lnscale(:); eta(:)]   (vpbndloss.m:34-38)
     int b_mu = 0, b_ls = 0, b_eta = 0, nb = 0;
