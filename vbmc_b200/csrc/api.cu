@@ -143,7 +143,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->zigTab, &c->entlbWork};
+                        &c->ent_partial, &c->ent_partial2, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->zigTab, &c->entlbWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -722,7 +722,7 @@ static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask
                                 c->opt[0] + 2 * c->opt[1] + 4 * c->opt[2] + 8 * c->opt[3], c->gp.meanfun,
                                 reinterpret_cast<long long>(c->theta_dev.p), reinterpret_cast<long long>(c->out_dev.p),
                                 reinterpret_cast<long long>(c->R_dev.p), reinterpret_cast<long long>(c->eps.p),
-                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->glj_out.p), reinterpret_cast<long long>(c->glj_part.p), reinterpret_cast<long long>(c->glj_ticket.p),
+                                reinterpret_cast<long long>(c->ent_partial.p), reinterpret_cast<long long>(c->ent_partial2.p), reinterpret_cast<long long>(c->glj_out.p), reinterpret_cast<long long>(c->glj_part.p), reinterpret_cast<long long>(c->glj_ticket.p),
                                 reinterpret_cast<long long>(c->ent_tables.p),
                                 reinterpret_cast<long long>(c->vpCur.p), reinterpret_cast<long long>(c->vpBase.p),
                                 reinterpret_cast<long long>(c->gpAlpha.p), reinterpret_cast<long long>(c->gpX.p),

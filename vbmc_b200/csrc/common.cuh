@@ -264,7 +264,7 @@ struct vbmc_b200_ctx {
   uint64_t last_seed = 0, last_stream = 0;
 
   // step buffers
-  vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, glj_out, glj_part, glj_ticket;
+  vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, ent_partial2, glj_out, glj_part, glj_ticket;
   vb::DevBuf ent_tables;  // FP32 sweep: per-step tables (entmc_f32.cu)
   double* theta_pinned = nullptr;
   double* out_pinned = nullptr;

@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
 // R.Hs[j], R.M[j][d], R.E[j][d], Wj[j][l] (Wj goes to R.oWc region sized K*K)
 __global__ void entmc_reduce_kernel(const double* __restrict__ partial, int tiles_per_comp, int pstride, int D, int K,
                                     double* __restrict__ Hs, double* __restrict__ M, double* __restrict__ E,
-                                    double* __restrict__ Wj) {
+                                    double* __restrict__ Wj, const int* __restrict__ skip_if_expanded) {
+  if (skip_if_expanded && *skip_if_expanded == 2) return;  // the second-generation sweep (entmc2.cu) produced this step's sums
   const int j = blockIdx.x;
   for (int i = threadIdx.x; i < pstride; i += blockDim.x) {
     double s = 0.0;
@@ -558,13 +559,13 @@ int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_pe
 }
 
 template <int DP>
-static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
+static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st, bool expanded_done) {
   auto kdir = entmc_kernel<DP, 8, false>;
   auto kexp = entmc_kernel<DP, 8, true>;
   VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   const int grid = pl.ntiles < c->num_sms ? pl.ntiles : c->num_sms;
   VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
-  {
+  if (!expanded_done) {
     KernelScope ks(c, "entmc", st);  // expanded form, tables in shared memory (default when the guard allows)
     kexp<<<grid, pl.nw * 32, pl.smem, st>>>(pl.a);
     VB_CUDA(cudaGetLastError());
@@ -577,7 +578,15 @@ static int launch_one(vbmc_b200_ctx* c, const EntmcPlan& pl, cudaStream_t st) {
   return VBMC_B200_OK;
 }
 
+bool entmc2_enabled(vbmc_b200_ctx* c);
+int launch_entmc2(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st, bool* handled);
+int launch_entmc2_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st, bool* handled);
+
 int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
+  // expanded formulation: the second-generation sweep (entmc2.cu) when it covers the shape; the kernels of this file then only
+  // stand by for a step whose device guard selects the direct formulation
+  bool v2 = false;
+  if (entmc2_enabled(c)) VB_TRY(launch_entmc2(c, Ns, need_mask, st, &v2));
   EntmcPlan pl;
   VB_TRY(make_plan(c, Ns, &pl));
   if (pl.ntiles == 0) return VBMC_B200_OK;
@@ -600,15 +609,15 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   if (c->eps_f32)
     VB_FAIL(VBMC_B200_ESTATE, "entmc: the resident draws were generated in FP32 mode; upload or regenerate them for the FP64 sweep");
   switch (pl.DP) {
-    case 2: return launch_one<2>(c, pl, st);
-    case 4: return launch_one<4>(c, pl, st);
-    case 6: return launch_one<6>(c, pl, st);
-    case 8: return launch_one<8>(c, pl, st);
-    case 10: return launch_one<10>(c, pl, st);
-    case 12: return launch_one<12>(c, pl, st);
-    case 16: return launch_one<16>(c, pl, st);
-    case 20: return launch_one<20>(c, pl, st);
-    case 24: return launch_one<24>(c, pl, st);
+    case 2: return launch_one<2>(c, pl, st, v2);
+    case 4: return launch_one<4>(c, pl, st, v2);
+    case 6: return launch_one<6>(c, pl, st, v2);
+    case 8: return launch_one<8>(c, pl, st, v2);
+    case 10: return launch_one<10>(c, pl, st, v2);
+    case 12: return launch_one<12>(c, pl, st, v2);
+    case 16: return launch_one<16>(c, pl, st, v2);
+    case 20: return launch_one<20>(c, pl, st, v2);
+    case 24: return launch_one<24>(c, pl, st, v2);
   }
   VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: unsupported padded dimension %d", pl.DP);
 }
@@ -620,9 +629,11 @@ int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st)
   rl.init(c->D, c->K, S_layout);
   double* R = c->R_dev.d();
   if (pl.ntiles == 0) return VBMC_B200_OK;  // R was zeroed at the start of the step
-  KernelScope ks(c, "reduce", st);
+  bool v2 = false;
+  if (entmc2_enabled(c)) VB_TRY(launch_entmc2_reduce(c, Ns, S_layout, st, &v2));
+  KernelScope ks(c, v2 ? "reduce_direct" : "reduce", st);
   entmc_reduce_kernel<<<c->K, 128, 0, st>>>(c->ent_partial.d(), pl.tiles_per_comp, pl.a.pstride, c->D, c->K,
-                                            R + rl.oHs, R + rl.oM, R + rl.oE, R + rl.oWc);
+                                            R + rl.oHs, R + rl.oM, R + rl.oE, R + rl.oWc, v2 ? c->vp.form_flag : nullptr);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
