@@ -555,8 +555,11 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   RLayout rl;
   rl.init(c->D, c->K, (doG || c->gp_ready) ? c->gp.S : 0);
   if (what == FIN_ENTMC) rl.init(c->D, c->K, 0);
-  VB_TRY(c->R_dev.reserve(sizeof(double) * rl.total));
+  VB_TRY(c->R_dev.reserve(sizeof(double) * rl.total_all));
   VB_CUDA(cudaMemsetAsync(c->R_dev.p, 0, sizeof(double) * rl.total, c->stream));
+  // multi-GPU over peer memory: when the step produces every entry of R (entropy AND log-joint), the reduction kernels write
+  // their values straight into the peers' inboxes and finalize_kernel only publishes, waits and sums
+  const bool pushed = doH && doG && step_push_target(c, rl.S, true).peer != nullptr;
   // the draws do not depend on theta: generate them on a third stream while vp_unpack (and then gplogjoint) run
   const bool philox_now = doH && c->philox_pending;
   const bool trail = doH && c->philox_trail;
@@ -575,7 +578,7 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     VB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     VB_TRY(launch_gplogjoint(c, 0, c->stream2));
     VB_CUDA(cudaEventRecord(c->ev_glj, c->stream2));
-    VB_TRY(launch_glj_reduce(c, c->stream2));
+    VB_TRY(launch_glj_reduce(c, c->stream2, doH && doG));
     VB_CUDA(cudaEventRecord(c->ev_join, c->stream2));
   }
   if (doH) {
@@ -609,7 +612,7 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   // multi-GPU: the partial sums are all-reduced inside finalize_kernel over NVLink peer memory (finalize.cu exchange_sum);
   // NCCL only when the peer mapping is unavailable or R exceeds the exchange slots
   if (c->nranks > 1 && !(c->p2p_ready && rl.total <= c->xdev.cap)) VB_TRY(allreduce_R(c, rl.total, c->stream));
-  VB_TRY(launch_finalize(c, Ns, gmask, use_bnd, jacobian, what, c->stream));
+  VB_TRY(launch_finalize(c, Ns, gmask, use_bnd, jacobian, what, c->stream, pushed));
   return VBMC_B200_OK;
 }
 

@@ -101,21 +101,27 @@ struct GpDev {  // attached GP posterior
   const double* sn2eff; // [S]     1/sW(1)^2
 };
 
-// partial-sum vector R that is all-reduced across ranks
+// partial-sum vector R that is all-reduced across ranks.  Compact: the K x K matrix of column sums W_jl and
+// the K x D lambda-gradient pieces are contracted with the weights BEFORE the exchange (every rank knows w), so the exchanged
+// vector is O(KD + SK) -- 2660 doubles at c3 (it was 5110), 10 320 at c5 (it was 22 320).
 struct RLayout {
   int D, K, S;
   int oHs, oM, oE, oWc, oI, oGmu, oGsig, oGlam, total;
+  int oWfull;     // scratch behind the exchanged part: un-contracted W_jl [K][K] (first-generation / FP32 sweeps only)
+  int total_all;
   __host__ __device__ void init(int D_, int K_, int S_) {
     D = D_; K = K_; S = S_;
     oHs = 0;
     oM = oHs + K;
     oE = oM + K * D;
     oWc = oE + K * D;
-    oI = oWc + K * K;  // per-source column sums W_jl (weighted by w_j in finalize)
+    oI = oWc + K;        // Wc[l] = sum_j w_j W_jl
     oGmu = oI + S * K;
     oGsig = oGmu + K * D;
     oGlam = oGsig + K;
-    total = oGlam + K * D;  // GlamK[k][d]: the sum over k is taken in finalize
+    total = oGlam + D;   // Glam[d] = sum_k w_k sum_s glam[s][k][d]
+    oWfull = total;
+    total_all = total + K * K;
   }
 };
 
@@ -167,6 +173,19 @@ struct XchgDev {
   unsigned long long* const* peer = nullptr;  // device array [nranks]: base of every rank's exchange buffer
   long long timeout_cycles = 0;        // give up waiting for a peer after this many SM cycles
 };
+
+#ifdef __CUDACC__
+// Producer side of the peer-memory all-reduce (finalize.cu): a reduction kernel writes each value of R it produces straight
+// into slot [parity][my rank] of EVERY rank's inbox, so the single-CTA finalize_kernel only has to publish the flags, wait and
+// sum -- the 8 x 21 KB push is spread over all the threads that produce R instead of one CTA.  No-op when xc.peer is null.
+__device__ __forceinline__ void xchg_push(const XchgDev& xc, int idx, double v) {
+  if (xc.peer == nullptr) return;
+  const unsigned long long* me = xc.peer[xc.rank];
+  const unsigned long long seq = me[XCHG_SEQ] + 1;   // finalize_kernel of the previous step stored it (stream order)
+  const size_t at = (static_cast<size_t>(seq & 1) * xc.nranks + xc.rank) * xc.cap + idx;
+  for (int r = 0; r < xc.nranks; ++r) reinterpret_cast<double*>(xc.peer[r] + XCHG_HDR)[at] = v;
+}
+#endif
 
 struct Prof {
   double ms = 0;
@@ -313,9 +332,10 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);
 int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st);
 int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st);
 int launch_gplogjoint(vbmc_b200_ctx* c, int all_samples, cudaStream_t st);
-int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st);
+int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st, bool whole_step);
+XchgDev step_push_target(vbmc_b200_ctx* c, int S_layout, bool whole_step);
 int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out, cudaStream_t st);
-int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st);
+int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st, bool pushed = false);
 int philox_init_tables(vbmc_b200_ctx* c);
 int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_t stream_id, cudaStream_t st,
                   const uint64_t* dyn = nullptr, uint64_t stream_add = 0);

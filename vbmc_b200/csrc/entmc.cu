@@ -426,10 +426,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) entmc_kernel(const EntmcArgs a) 
 }
 
 // Sum the tile partials of each component in tile order.  grid = K CTAs.
-// R.Hs[j], R.M[j][d], R.E[j][d], Wj[j][l] (Wj goes to R.oWc region sized K*K)
+// R.Hs[j], R.M[j][d], R.E[j][d] (also pushed to the peers' inboxes, common.cuh xchg_push) and the un-contracted column sums
+// Wfull[j][l] (scratch behind R); wc_contract_kernel then forms R.Wc[l] = sum_j w_j Wfull[j][l].
 __global__ void entmc_reduce_kernel(const double* __restrict__ partial, int tiles_per_comp, int pstride, int D, int K,
-                                    double* __restrict__ Hs, double* __restrict__ M, double* __restrict__ E,
-                                    double* __restrict__ Wj, const int* __restrict__ skip_if_expanded) {
+                                    double* __restrict__ R, int oHs, int oM, int oE, int oWfull, XchgDev xc,
+                                    const int* __restrict__ skip_if_expanded) {
   if (skip_if_expanded && *skip_if_expanded == 2) return;  // the second-generation sweep (entmc2.cu) produced this step's sums
   const int j = blockIdx.x;
   for (int i = threadIdx.x; i < pstride; i += blockDim.x) {
@@ -437,15 +438,32 @@ __global__ void entmc_reduce_kernel(const double* __restrict__ partial, int tile
     const double* p = partial + static_cast<size_t>(j) * tiles_per_comp * pstride + i;
 #pragma unroll 8
     for (int t = 0; t < tiles_per_comp; ++t) s += p[static_cast<size_t>(t) * pstride];
-    if (i == 0)
-      Hs[j] = s;
-    else if (i < 1 + D)
-      M[j * D + (i - 1)] = s;
-    else if (i < 1 + 2 * D)
-      E[j * D + (i - 1 - D)] = s;
-    else
-      Wj[j * K + (i - 1 - 2 * D)] = s;
+    if (i < 1 + 2 * D) {
+      const int at = i == 0 ? oHs + j : (i < 1 + D ? oM + j * D + (i - 1) : oE + j * D + (i - 1 - D));
+      R[at] = s;
+      xchg_push(xc, at, s);
+    } else {
+      R[oWfull + j * K + (i - 1 - 2 * D)] = s;
+    }
   }
+  if (xc.peer) __threadfence_system();
+}
+
+// one warp per l: Wc[l] = sum_j w_j Wfull[j][l], lanes take j = lane, lane + 32, ...; fixed order
+__global__ void __launch_bounds__(128) wc_contract_kernel(int K, const double* __restrict__ w, double* __restrict__ R, int oWfull, int oWc,
+                                                           XchgDev xc, const int* __restrict__ skip_if_expanded) {
+  if (skip_if_expanded && *skip_if_expanded == 2) return;
+  const int l = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (l >= K) return;
+  double acc = 0.0;
+  for (int j = lane; j < K; j += 32) acc = fma(w[j], R[oWfull + j * K + l], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    R[oWc + l] = acc;
+    xchg_push(xc, oWc + l, acc);
+  }
+  if (xc.peer) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,9 +649,13 @@ int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st)
   if (pl.ntiles == 0) return VBMC_B200_OK;  // R was zeroed at the start of the step
   bool v2 = false;
   if (entmc2_enabled(c)) VB_TRY(launch_entmc2_reduce(c, Ns, S_layout, st, &v2));
+  const XchgDev xc = step_push_target(c, S_layout, S_layout > 0);
   KernelScope ks(c, v2 ? "reduce_direct" : "reduce", st);
-  entmc_reduce_kernel<<<c->K, 128, 0, st>>>(c->ent_partial.d(), pl.tiles_per_comp, pl.a.pstride, c->D, c->K,
-                                            R + rl.oHs, R + rl.oM, R + rl.oE, R + rl.oWc, v2 ? c->vp.form_flag : nullptr);
+  entmc_reduce_kernel<<<c->K, 128, 0, st>>>(c->ent_partial.d(), pl.tiles_per_comp, pl.a.pstride, c->D, c->K, R, rl.oHs, rl.oM, rl.oE,
+                                            rl.oWfull, xc, v2 ? c->vp.form_flag : nullptr);
+  VB_CUDA(cudaGetLastError());
+  c->launches++;
+  wc_contract_kernel<<<(c->K + 3) / 4, 128, 0, st>>>(c->K, c->vp.w, R, rl.oWfull, rl.oWc, xc, v2 ? c->vp.form_flag : nullptr);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }

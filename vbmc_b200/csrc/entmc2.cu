@@ -123,7 +123,7 @@ __device__ __forceinline__ double reduce8(double (&v)[8], int lane) {
   return v[0];
 }
 
-template <int DP, int KW>
+template <int DP, int KW, bool ROT>
 __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
   if (*a.form_flag != 2) return;  // the direct formulation (entmc.cu) handles this step
   extern __shared__ __align__(16) unsigned char smem[];
@@ -286,6 +286,12 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
         }
       }
       // ---- component loop: two components per iteration => four independent exp chains (ka, kb) x (+, -) ----
+      // ROT: software-pipelined by one iteration.  The gradient sums A(+-)_d += t(+-) v_d of the PREVIOUS component pair (40
+      // independent DFMAs, rows re-read from the table) sit in the same basic block as the exponentials of the current pair
+      // (four 12-deep dependency chains), so the instruction scheduler fills the chains' latency slots with them; the rows of
+      // the current pair are dead after the dot products instead of staying live across the exponential.
+      double tpv[4] = {0.0, 0.0, 0.0, 0.0};   // (a_k / r) e(+-) of the previous pair
+      int kpv = K2, kbpv = K2;                // its rows (K2: all-zero dummy row)
 #pragma unroll 1
       for (int ia = 0; ia < nact; ia += 2) {
         const unsigned kk = *reinterpret_cast<const unsigned short*>(klist + ia);  // two byte indices, one broadcast load
@@ -312,6 +318,23 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
         double x[4], ex[4];
         x[0] = xba - rta; x[1] = xba + rta;   // -0.5||u + r eps||^2,  -0.5||u - r eps||^2
         x[2] = xbb - rtb; x[3] = xbb + rtb;
+        if (ROT && needT) {   // previous pair's gradient sums: independent of everything above
+          const double* pa = tab_v + kpv * DP;
+          const double* pb = tab_v + kbpv * DP;
+#pragma unroll
+          for (int d = 0; d < DP; d += 2) {
+            const double2 a2 = *reinterpret_cast<const double2*>(pa + d);
+            const double2 b2 = *reinterpret_cast<const double2*>(pb + d);
+            Ap[d] = fma(tpv[0], a2.x, Ap[d]);
+            Am[d] = fma(tpv[1], a2.x, Am[d]);
+            Ap[d + 1] = fma(tpv[0], a2.y, Ap[d + 1]);
+            Am[d + 1] = fma(tpv[1], a2.y, Am[d + 1]);
+            Ap[d] = fma(tpv[2], b2.x, Ap[d]);
+            Am[d] = fma(tpv[3], b2.x, Am[d]);
+            Ap[d + 1] = fma(tpv[2], b2.y, Ap[d + 1]);
+            Am[d + 1] = fma(tpv[3], b2.y, Am[d + 1]);
+          }
+        }
         exp2_neg4(x, ex, t16);
         if (needW) {
           stage[ia * 32 + lane] = make_double2(ex[0], ex[1]);
@@ -327,16 +350,32 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
           Bm = fma(tma, sa.x, Bm);
           Bp = fma(tpb, sb.x, Bp);
           Bm = fma(tmb, sb.x, Bm);
+          if (ROT) {
+            tpv[0] = tpa; tpv[1] = tma; tpv[2] = tpb; tpv[3] = tmb;
+            kpv = k; kbpv = kb;
+          } else {
 #pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            Ap[d] = fma(tpa, va[d], Ap[d]);   // a_k e u_d
-            Am[d] = fma(tma, va[d], Am[d]);
-          }
+            for (int d = 0; d < DP; ++d) {
+              Ap[d] = fma(tpa, va[d], Ap[d]);   // a_k e u_d
+              Am[d] = fma(tma, va[d], Am[d]);
+            }
 #pragma unroll
-          for (int d = 0; d < DP; ++d) {
-            Ap[d] = fma(tpb, vb[d], Ap[d]);
-            Am[d] = fma(tmb, vb[d], Am[d]);
+            for (int d = 0; d < DP; ++d) {
+              Ap[d] = fma(tpb, vb[d], Ap[d]);
+              Am[d] = fma(tmb, vb[d], Am[d]);
+            }
           }
+        }
+      }
+      if (ROT && needT) {   // drain: the last pair's gradient sums
+        const double* pa = tab_v + kpv * DP;
+        const double* pb = tab_v + kbpv * DP;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          Ap[d] = fma(tpv[0], pa[d], Ap[d]);
+          Am[d] = fma(tpv[1], pa[d], Am[d]);
+          Ap[d] = fma(tpv[2], pb[d], Ap[d]);
+          Am[d] = fma(tpv[3], pb[d], Am[d]);
         }
       }
       const double iqp = valid ? 1.0 / qp : 0.0;
@@ -431,32 +470,58 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
   }
 }
 
-// Sum the run partials of each component in CTA order.  grid = K CTAs.
+// Run partials -> R (compact layout, common.cuh), every sum in a fixed order.
 // Component j's tiles [j*tpc, (j+1)*tpc) belong to the CTAs owner(j*tpc) .. owner((j+1)*tpc - 1), owner(t) = floor(t*G/T);
 // inside CTA b the run of component j has index j - first_j(b), first_j(b) = ceil(b*T/G) / tpc.
-__global__ void entmc2_reduce_kernel(const double* __restrict__ partial, const int* __restrict__ form_flag, int G, int tpc, int ntiles, int rmax,
-                                     int pstride, int D, int K, double* __restrict__ Hs, double* __restrict__ M, double* __restrict__ E,
-                                     double* __restrict__ Wj) {
-  if (*form_flag != 2) return;
-  const int j = blockIdx.x;
-  const long long T = ntiles;
-  const int b_lo = static_cast<int>((static_cast<long long>(j) * tpc * G) / T);
-  const int b_hi = static_cast<int>(((static_cast<long long>(j + 1) * tpc - 1) * G) / T);
-  for (int i = threadIdx.x; i < pstride; i += blockDim.x) {
-    double s = 0.0;
-    for (int b = b_lo; b <= b_hi; ++b) {
-      const int first_j = static_cast<int>((b * T + G - 1) / G) / tpc;
-      s += partial[(static_cast<size_t>(b) * rmax + (j - first_j)) * pstride + i];
-    }
-    if (i == 0)
-      Hs[j] = s;
-    else if (i < 1 + D)
-      M[j * D + (i - 1)] = s;
-    else if (i < 1 + 2 * D)
-      E[j * D + (i - 1 - D)] = s;
-    else
-      Wj[j * K + (i - 1 - 2 * D)] = s;
+//   blocks [0, nb1): one THREAD per (j, i), i < 1 + 2D  ->  Hs[j], M[j][d], E[j][d]
+//   blocks [nb1, ..): one WARP per l  ->  Wc[l] = sum_j w_j W_jl  (lanes take j = lane, lane + 32, ...; butterfly over the lanes)
+// Each value is also written into every peer's exchange inbox when xc.peer is set (multi-GPU, common.cuh xchg_push).
+struct Entmc2Red {
+  const double* partial;
+  const int* form_flag;
+  int G, tpc, ntiles, rmax, pstride, D, K, nb1;
+  const double* w;
+  double* R;
+  int oHs, oM, oE, oWc;
+  XchgDev xc;
+};
+
+__device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, int j, int i) {
+  const long long T = a.ntiles;
+  const int b_lo = static_cast<int>((static_cast<long long>(j) * a.tpc * a.G) / T);
+  const int b_hi = static_cast<int>(((static_cast<long long>(j + 1) * a.tpc - 1) * a.G) / T);
+  double s = 0.0;
+  for (int b = b_lo; b <= b_hi; ++b) {
+    const int first_j = static_cast<int>((b * T + a.G - 1) / a.G) / a.tpc;
+    s += a.partial[(static_cast<size_t>(b) * a.rmax + (j - first_j)) * a.pstride + i];
   }
+  return s;
+}
+
+__global__ void __launch_bounds__(128) entmc2_reduce_kernel(const Entmc2Red a) {
+  if (*a.form_flag != 2) return;
+  const int D = a.D, K = a.K, nv = 1 + 2 * D;
+  if (static_cast<int>(blockIdx.x) < a.nb1) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K * nv) return;
+    const int j = o / nv, i = o - j * nv;
+    const double s = entmc2_run_sum(a, j, i);
+    const int at = i == 0 ? a.oHs + j : (i < 1 + D ? a.oM + j * D + (i - 1) : a.oE + j * D + (i - 1 - D));
+    a.R[at] = s;
+    xchg_push(a.xc, at, s);
+  } else {
+    const int l = (blockIdx.x - a.nb1) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (l >= K) return;
+    double acc = 0.0;
+    for (int j = lane; j < K; j += 32) acc = fma(a.w[j], entmc2_run_sum(a, j, nv + l), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      a.R[a.oWc + l] = acc;
+      xchg_push(a.xc, a.oWc + l, acc);
+    }
+  }
+  if (a.xc.peer) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,7 +559,7 @@ static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
   off = round_up2(off, 16);
   a.off_warp = off;
   const int eps_bytes = round_up2(32 * D * 8, 16);
-  const int klist_bytes = round_up2(K2 + 2, 16);
+  const int klist_bytes = round_up2(K2 + 4, 16);
   int stage_bytes = K2 * 32 * 16;
   const int res_bytes = round_up2(a.pstride * 8, 16);
   if (stage_bytes < res_bytes) stage_bytes = res_bytes;
@@ -529,7 +594,8 @@ bool entmc2_enabled(vbmc_b200_ctx* c) {
 
 template <int DP, int KW>
 static int launch2(vbmc_b200_ctx* c, const Entmc2Plan& pl, cudaStream_t st) {
-  auto kern = entmc2_kernel<DP, KW>;
+  static const bool rot = !(getenv("VBMC_B200_ENTMC_ROT") && atoi(getenv("VBMC_B200_ENTMC_ROT")) == 0);
+  auto kern = rot ? entmc2_kernel<DP, KW, true> : entmc2_kernel<DP, KW, false>;
   VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
   KernelScope ks(c, "entmc", st);
   kern<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
@@ -571,10 +637,18 @@ int launch_entmc2_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st
   if (pl.a.ntiles == 0) return VBMC_B200_OK;
   RLayout rl;
   rl.init(c->D, c->K, S_layout);
-  double* R = c->R_dev.d();
+  Entmc2Red r;
+  r.partial = c->ent_partial2.d();
+  r.form_flag = c->vp.form_flag;
+  r.G = pl.grid; r.tpc = pl.a.tpc; r.ntiles = pl.a.ntiles; r.rmax = pl.a.rmax; r.pstride = pl.a.pstride;
+  r.D = c->D; r.K = c->K;
+  r.nb1 = (c->K * (1 + 2 * c->D) + 127) / 128;
+  r.w = c->vp.w;
+  r.R = c->R_dev.d();
+  r.oHs = rl.oHs; r.oM = rl.oM; r.oE = rl.oE; r.oWc = rl.oWc;
+  r.xc = step_push_target(c, S_layout, S_layout > 0);
   KernelScope ks(c, "reduce", st);
-  entmc2_reduce_kernel<<<c->K, 128, 0, st>>>(c->ent_partial2.d(), c->vp.form_flag, pl.grid, pl.a.tpc, pl.a.ntiles, pl.a.rmax, pl.a.pstride, c->D,
-                                             c->K, R + rl.oHs, R + rl.oM, R + rl.oE, R + rl.oWc);
+  entmc2_reduce_kernel<<<r.nb1 + (c->K + 3) / 4, 128, 0, st>>>(r);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }

@@ -5,6 +5,8 @@
 //                      (misc/vpbndloss.m:9-71, utils/softbndloss.m:9-28, negelcbo_vbmc.m:136-164),
 //                      F = -G - H + L, dF = -dG - dH + dL (negelcbo_vbmc.m:116-117).
 // O(DK) work; they exist so that a step needs no host round trip between kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -178,6 +180,7 @@ struct FinArgs {
   const double* R;
   double* Rw;      // == R, writable: receives the all-reduced sums when they do not fit in shared memory
   XchgDev xc;      // nranks > 1: all-reduce R across ranks over peer memory before it is used (common.cuh)
+  int pushed;      // the reduction kernels already wrote this rank's R into every peer's inbox (xchg_push): only publish, wait, sum
   const double* lb;
   const double* ub;
   const double* cn;  // [K+1]
@@ -231,14 +234,14 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // sequence number in every rank's flag word (release, system scope), wait until all ranks' flags show it in the local
 // buffer (acquire), then sum the nranks local slots in rank order into dst.  No kernel launch and no NCCL call between the
 // partial sums and their use; every rank adds the same numbers in the same order => identical results everywhere.
-__device__ __noinline__ void exchange_sum(const XchgDev& xc, const double* __restrict__ R, int total, double* dst) {
+__device__ __noinline__ void exchange_sum(const XchgDev& xc, const double* __restrict__ R, int total, double* dst, int pushed) {
   const int tid = threadIdx.x, nt = blockDim.x, nr = xc.nranks;
   unsigned long long* me = xc.peer[xc.rank];
   const unsigned long long seq = me[XCHG_SEQ] + 1;
   const int par = static_cast<int>(seq & 1);
   const size_t slot = (static_cast<size_t>(par) * nr + xc.rank) * xc.cap;
 #pragma unroll 1
-  for (int i0 = tid; i0 < total; i0 += 4 * nt) {
+  for (int i0 = tid; i0 < (pushed ? 0 : total); i0 += 4 * nt) {
     double v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = (i0 + u * nt < total) ? R[i0 + u * nt] : 0.0;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     v_lnlambda[d] = a.vp.lnlambda[d];
   }
   if (a.xc.nranks > 1) {
-    exchange_sum(a.xc, a.R, rl.total, a.stage_R ? sR : a.Rw);
+    exchange_sum(a.xc, a.R, rl.total, a.stage_R ? sR : a.Rw, a.pushed);
   } else if (a.stage_R) {
     // 8 independent loads in flight per thread: the staging is one L2 round trip per 2048 doubles, not one per 256
     int i = tid;
@@ -427,12 +430,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
       }
     if (a.gf[3])
 #pragma unroll 1
-      for (int l = tid; l < K; l += nt) {
-        double acc = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < K; ++j) acc += v_w[j] * R[rl.oWc + j * K + l];
-        gHw[l] = -R[rl.oHs + l] * invNs - v_cn[l] * acc * invNs;  // :97, :100
-      }
+      for (int l = tid; l < K; l += nt)
+        gHw[l] = -R[rl.oHs + l] * invNs - v_cn[l] * R[rl.oWc + l] * invNs;  // :97, :100  (Wc[l] = sum_j w_j W_jl, contracted upstream)
   }
   // ------------------------------------------------------------------ expected log joint
   if (doG) {
@@ -468,10 +467,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     if (a.gf[2])
 #pragma unroll 1
       for (int d = tid; d < D; d += nt) {
-        double g = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) g += R[rl.oGlam + k * D + d];  // sum_k w_k (...)  (gplogjoint.m:248-252)
-        g *= invS;
+        double g = R[rl.oGlam + d] * invS;  // sum_k w_k (...), contracted upstream  (gplogjoint.m:248-252)
         if (a.jacobian) g *= v_lambda[d];  // :361-363
         out[ol.oDG + o_lam + d] = g;
       }
@@ -610,7 +606,16 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   return VBMC_B200_OK;
 }
 
-int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st) {
+// where the reduction kernels of a step should push their values (empty: single GPU, NCCL path, or a call that does not produce all of R)
+XchgDev step_push_target(vbmc_b200_ctx* c, int S_layout, bool whole_step) {
+  RLayout rl;
+  rl.init(c->D, c->K, S_layout);
+  static const bool off = getenv("VBMC_B200_XCHG_PUSH") && atoi(getenv("VBMC_B200_XCHG_PUSH")) == 0;
+  if (off || !whole_step || c->nranks <= 1 || !c->p2p_ready || rl.total > c->xdev.cap) return XchgDev{};
+  return c->xdev;
+}
+
+int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int jacobian, int what, cudaStream_t st, bool pushed) {
   // compute_grad: bit mask of gradient blocks (bit i = grad_flags(i+1))
   FinArgs a;
   a.D = c->D; a.K = c->K; a.S = c->gp_ready ? c->gp.S : 0; a.Ns = Ns;
@@ -631,6 +636,7 @@ int launch_finalize(vbmc_b200_ctx* c, int Ns, int compute_grad, int use_bnd, int
   a.R = c->R_dev.d();
   a.Rw = c->R_dev.d();
   a.xc = XchgDev{};
+  a.pushed = pushed ? 1 : 0;
   a.lb = c->bnd.d();
   a.ub = c->bnd.d() + c->nbnd;
   a.cn = c->vp.cn;

@@ -238,38 +238,58 @@ __global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
   }
 }
 
-// R.I[s][k] (all S rows: zero outside the local shard), R.Gmu[k][d], R.Gsig[k], R.GlamK[k][d] = w_k * sum_s glam[s][k][d]
-// (finalize adds the K rows of GlamK).  One thread per output, the <= S loads of a thread are independent.
+// R.I[s][k] (all S rows: zero outside the local shard), R.Gmu[k][d], R.Gsig[k]: one thread per output, the <= S loads of a thread
+// are independent.  R.Glam[d] = sum_k w_k sum_s glam[s][k][d]: one warp per d (blocks >= nb1), lanes take k = lane, lane + 32, ...
+// Every value also goes to the peers' exchange inboxes when xc.peer is set (common.cuh xchg_push).
 __global__ void __launch_bounds__(128) glj_reduce_kernel(const double* __restrict__ out, int ostride, int D, int K, int S,
-                                                         int s_begin, int s_count, const double* __restrict__ w,
-                                                         double* __restrict__ RI, double* __restrict__ Gmu,
-                                                         double* __restrict__ Gsig, double* __restrict__ GlamK) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                         int s_begin, int s_count, const double* __restrict__ w, double* __restrict__ R,
+                                                         int oI, int oGmu, int oGsig, int oGlam, int nb1, XchgDev xc) {
   const int nI = S * K, nM = K * D;
-  if (i < nI) {
-    const int s = i / K;
-    RI[i] = (s >= s_begin && s < s_begin + s_count) ? out[static_cast<size_t>(i) * ostride] : 0.0;
-    return;
-  }
-  int r = i - nI, off, k;
-  double scale = 1.0;
-  double* dst;
-  if (r < nM) {
-    k = r / D; off = 2 + (r - k * D); dst = Gmu + r;
-  } else if (r < nM + K) {
-    k = r - nM; off = 1; dst = Gsig + k;
-  } else if (r < 2 * nM + K) {
-    r -= nM + K;
-    k = r / D; off = 2 + D + (r - k * D); dst = GlamK + r; scale = w[k];
-  } else {
-    return;
-  }
-  const double* o = out + (static_cast<size_t>(s_begin) * K + k) * ostride + off;
-  const size_t step = static_cast<size_t>(K) * ostride;
-  double acc = 0.0;
+  if (static_cast<int>(blockIdx.x) < nb1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int at;
+    double v;
+    if (i < nI) {
+      const int s = i / K;
+      at = oI + i;
+      v = (s >= s_begin && s < s_begin + s_count) ? out[static_cast<size_t>(i) * ostride] : 0.0;
+    } else {
+      int r = i - nI, off, k;
+      if (r < nM) {
+        k = r / D; off = 2 + (r - k * D); at = oGmu + r;
+      } else if (r < nM + K) {
+        k = r - nM; off = 1; at = oGsig + k;
+      } else {
+        return;
+      }
+      const double* o = out + (static_cast<size_t>(s_begin) * K + k) * ostride + off;
+      const size_t step = static_cast<size_t>(K) * ostride;
+      double acc = 0.0;
 #pragma unroll 8
-  for (int s = 0; s < s_count; ++s) acc += o[s * step];
-  *dst = scale * acc;
+      for (int s = 0; s < s_count; ++s) acc += o[s * step];
+      v = acc;
+    }
+    R[at] = v;
+    xchg_push(xc, at, v);
+  } else {
+    const int d = (blockIdx.x - nb1) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (d >= D) return;
+    double acc = 0.0;
+    for (int k = lane; k < K; k += 32) {
+      const double* o = out + (static_cast<size_t>(s_begin) * K + k) * ostride + 2 + D + d;
+      const size_t step = static_cast<size_t>(K) * ostride;
+      double a2 = 0.0;
+      for (int s = 0; s < s_count; ++s) a2 += o[s * step];
+      acc = fma(w[k], a2, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      R[oGlam + d] = acc;
+      xchg_push(xc, oGlam + d, acc);
+    }
+  }
+  if (xc.peer) __threadfence_system();
 }
 
 static int pick_dp(int D) {
@@ -371,16 +391,17 @@ int launch_gplogjoint_weighted(vbmc_b200_ctx* c, const double* wvec, double* out
   return glj_dispatch(c, a, 1, st);
 }
 
-int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st) {
+int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st, bool whole_step) {
   RLayout rl;
   rl.init(c->D, c->K, c->gp.S);
   int sb, se;
   shard_range(c->gp.S, c->nranks, c->rank, &sb, &se);
   double* R = c->R_dev.d();
   KernelScope ks(c, "reduce", st);
-  const int nout = c->gp.S * c->K + 2 * c->K * c->D + c->K;
-  glj_reduce_kernel<<<(nout + 127) / 128, 128, 0, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w,
-                                                       R + rl.oI, R + rl.oGmu, R + rl.oGsig, R + rl.oGlam);
+  const int nout = c->gp.S * c->K + c->K * c->D + c->K;
+  const int nb1 = (nout + 127) / 128;
+  glj_reduce_kernel<<<nb1 + (c->D + 3) / 4, 128, 0, st>>>(c->glj_out.d(), 2 + 2 * c->D, c->D, c->K, c->gp.S, sb, se - sb, c->vp.w, R, rl.oI,
+                                                         rl.oGmu, rl.oGsig, rl.oGlam, nb1, step_push_target(c, c->gp.S, whole_step));
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
