@@ -106,30 +106,36 @@ def test_cuda_hits_truth_at_benchmark_shapes(gpu_ctx, name, over):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nsplit", [1, 2, 3, 7, 16])
-def test_slices_of_the_training_set_do_not_change_the_result(nsplit):
-    """VBMC_B200_GLJ_NSPLIT forces the number of N-slices (normally chosen from the grid size): the two-word partials make the
-    result independent of the slicing to 1e-15."""
+@pytest.mark.parametrize("min_points,warps_per_sm", [(32, 12), (100, 12), (777, 3), (5000, 12), (10 ** 9, 12)])
+def test_segmentation_of_the_training_set_does_not_change_the_result(min_points, warps_per_sm):
+    """The (pair, n) space is cut into contiguous ranges, one warp each (csrc/gplogjoint.cu); VBMC_B200_GLJ_MIN_POINTS /
+    VBMC_B200_GLJ_WARPS_PER_SM force other cuts -- from 32-point segments (up to 25 per pair) to ONE warp for everything: the
+    two-word segment partials make the result independent of the cut to 1e-14, and every cut hits the binary128 truth."""
     import json
     import os
     import subprocess
     import sys
     code = (
-        "import json, numpy as np, vbmc_b200\n"
+        "import json, sys, numpy as np, vbmc_b200\n"
+        "sys.path.insert(0, 'tests')\n"
         "from vbmc_b200 import workloads\n"
+        "from _truth import truth_negelcbo, errs_vs_truth\n"
         "w = workloads.build('c2', vbmc_b200.gplite_post, overrides=dict(Ns=64, N=777))\n"
         "_, tb = vbmc_b200.vpbounds(w['vp'], w['gp'], workloads.VP_OPTIONS)\n"
         "F, dF, G, H = vbmc_b200.negelcbo_vbmc(w['theta'], 0.0, w['vp'], w['gp'], 64, 1, 0, 0, tb, 0, epsilon=w['epsilon'], nargout=4)\n"
-        "print(json.dumps(dict(F=F, G=G, dF=list(map(float, dF)))))\n")
+        "t = truth_negelcbo(w['vp'], w['gp'], w['theta'], 64, w['epsilon'], tb)\n"
+        "print(json.dumps(dict(F=F, G=G, dF=list(map(float, dF)), err=errs_vs_truth(dict(F=F, dF=dF, G=G, H=H), t))))\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for ns in (0, nsplit):
+    for forced in (False, True):
         env = dict(os.environ, PYTHONPATH=root)
-        if ns:
-            env["VBMC_B200_GLJ_NSPLIT"] = str(ns)
-        else:
-            env.pop("VBMC_B200_GLJ_NSPLIT", None)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        env.pop("VBMC_B200_GLJ_MIN_POINTS", None)
+        env.pop("VBMC_B200_GLJ_WARPS_PER_SM", None)
+        if forced:
+            env["VBMC_B200_GLJ_MIN_POINTS"] = str(min_points)
+            env["VBMC_B200_GLJ_WARPS_PER_SM"] = str(warps_per_sm)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd=root)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert rel(outs[1]["dF"], outs[0]["dF"]) < 1e-14 and abs(outs[1]["G"] - outs[0]["G"]) < 1e-14 * abs(outs[0]["G"])
+    assert max(outs[1]["err"].values()) < TOL, outs[1]["err"]

@@ -6,17 +6,20 @@
 // (SURVEY.md Appendix B.1):
 //     zeta_n = exp(lnnf_sk - 0.5*sum_d Delta_dn^2) * alpha_sn,  Delta_dn = (mu_kd - X_nd)/tau_skd
 //     A = sum zeta_n,   B_d = sum zeta_n Delta_dn,   C_d = sum zeta_n (Delta_dn^2 - 1)
-// A CTA owns one (s, k, slice of N): X (N x D column-major => unit stride over n) and alpha_s are streamed
-// coalesced; the working set (X, alpha) is < 1 MB and stays in L2, the kernel is FP64-pipe bound.
+// X (N x D column-major => unit stride over n) and alpha_s are streamed coalesced; the working set (X, alpha) is
+// < 1 MB and stays in L2, the kernel is FP64-pipe bound.
 //
 // Accuracy (dd_math.cuh): alpha_n ~ 1e4 while the sums are O(1), so every n-dependent quantity is carried as a
-// two-word (h, l) value -- the terms, the three running sums, the block and slice reductions -- and the results
+// two-word (h, l) value -- the terms, the three running sums, the warp and segment reductions -- and the results
 // are the correctly rounded sums of the exact formula to ~1e-20 * sum|zeta_n|.  tests/test_truth128.py checks the
 // outputs against an IEEE binary128 evaluation on ill-conditioned posteriors (plain FP64 is off by 1e-11..5e-9 there).
 //
-// The N axis is split over gridDim.z slices when S_local*K CTAs would not fill the GPU (multi-GPU shards of S);
-// slice partials go to global memory and the LAST slice to finish (atomic ticket) adds them in slice order and
-// runs the per-(s,k) epilogue (gplogjoint.m:169-174, 206-210, 227-231, 248-252) -- no second launch, deterministic.
+// Schedule: the flattened (pair, n) space of this rank -- pair = (local s, k), n = training point -- is cut into W
+// equal contiguous ranges, ONE WARP per range (4 warps per CTA, no block barrier after the table load).  A range touches
+// at most a few pairs; for each it sweeps its segment of the N axis, reduces the 2D+1 two-word sums inside the warp and
+// writes them to the pair's segment slot.  The LAST segment of a pair to finish (atomic ticket) adds the segments in
+// order and runs the per-(s,k) epilogue (gplogjoint.m:169-174, 206-210, 227-231, 248-252): perfectly balanced whatever
+// S_local * K is (a multi-GPU shard of 2-3 samples fills the machine like the full problem), one launch, deterministic.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -34,207 +37,221 @@ struct GljArgs {
   double* out;  // [S][K][ostride] (only rows s_begin..s_begin+s_count-1 written)
   const double* wvec;  // optional [S][K][N] weight vectors replacing alpha_s (variance gradient: K^-1 z_k)
   int raw;             // 1: epilogue without the mean-function terms (derivative contractions only)
-  int nsplit;          // slices of the N axis (gridDim.z)
-  double* part;        // [S*K][nsplit][2*(1+2D)] slice partials (nsplit > 1)
-  unsigned* ticket;    // [S*K] arrival counters, zero between launches
+  int W;               // number of ranges (= warps in the grid)
+  int maxseg;          // segment slots per pair
+  double* part;        // [s_count*K][maxseg][2*(1+2D)] segment partials
+  unsigned* ticket;    // [s_count*K] arrival counters, zero between launches
 };
 
-constexpr int GLJ_THREADS = 128;
-constexpr int GLJ_PARTS = 8;  // block reduction: 8 ordered partial sums of 16 threads each, then the 8 in order
+constexpr int GLJ_THREADS = 128;   // 4 independent warps
 
 __device__ const double2 g_exp2_tab[64] = {VB_EXP2_TABLE_ROWS};
 
-// dynamic shared memory (doubles): exp2 table [128] | mu [DP] | itau [DP] | misc [4] | red [2*nval][COLS+1] | red2 [2*nval][GLJ_PARTS]
-static size_t glj_smem_bytes(int D, int DP, int halves) {
-  const size_t nval2 = 2 * (1 + 2 * static_cast<size_t>(D));
-  return sizeof(double) * (128 + 2 * DP + 4 + nval2 * (GLJ_THREADS / halves + 1) + nval2 * GLJ_PARTS);
+// per-warp shared memory (doubles): mu [DP] | itau [DP] | red [2*(1+2D)][COLS+1]   (+ the CTA's exp2 table [128] in front)
+static size_t glj_warp_doubles(int D, int DP, int halves) {
+  return 2 * static_cast<size_t>(DP) + 2 * (1 + 2 * static_cast<size_t>(D)) * (32 / halves + 1);
 }
+static size_t glj_smem_bytes(int D, int DP, int halves) { return sizeof(double) * (128 + 4 * glj_warp_doubles(D, DP, halves)); }
 
-// DPH dimensions per thread, HALVES threads per training point (HALVES = 2 for D > 12: the 4*D + 2 accumulator words of one
+// first range that owns a point of flattened index q:  range w covers [ceil(w*T/W), ceil((w+1)*T/W))  <=>  owner(q) = floor(q*W/T)
+__device__ __forceinline__ int glj_owner(long long q, long long T, int W) { return static_cast<int>((q * W) / T); }
+
+// DPH dimensions per lane, HALVES lanes per training point (HALVES = 2 for D > 12: the 4*D + 2 accumulator words of one
 // thread would not fit the register file; the lane pair exchanges its two partial sum_d Delta^2 with one shuffle and both
 // lanes evaluate the exponential).
 template <int DPH, int HALVES>
-__global__ void __launch_bounds__(GLJ_THREADS) glj_kernel(const GljArgs a) {
+__global__ void __launch_bounds__(GLJ_THREADS, 2) glj_kernel(const GljArgs a) {
   extern __shared__ __align__(16) double sm[];
   constexpr int DP = DPH * HALVES;
-  constexpr int COLS = GLJ_THREADS / HALVES;  // training points per sweep iteration
+  constexpr int COLS = 32 / HALVES;  // training points per warp iteration
   constexpr int RS = COLS + 1;
-  const int D = a.D, N = a.N;
-  const int k = blockIdx.x;
-  const int s = a.s_begin + blockIdx.y;
-  const int tid = threadIdx.x;
-  const int half = HALVES == 2 ? (tid & 1) : 0, col = HALVES == 2 ? (tid >> 1) : tid;
+  const int D = a.D, N = a.N, K = a.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = HALVES == 2 ? (lane & 1) : 0, col = HALVES == 2 ? (lane >> 1) : lane;
   const int d0 = half * DPH;
-  double2* s_tab = reinterpret_cast<double2*>(sm);  // [64]
-  double* s_mu = sm + 128;          // [DP]
-  double* s_itau = s_mu + DP;       // [DP]
-  double* s_misc = s_itau + DP;     // [4]: lnnf, last-slice flag
-  double* red = s_misc + 4;         // [2*nval][RS]
   const int nval = 1 + 2 * D, nval2 = 2 * nval;
-  double* red2 = red + static_cast<size_t>(nval2) * RS;  // [2*nval][GLJ_PARTS]
+  double2* s_tab = reinterpret_cast<double2*>(sm);  // [64]
+  double* wsm = sm + 128 + static_cast<size_t>(warp) * (2 * DP + static_cast<size_t>(nval2) * RS);
+  double* s_mu = wsm;              // [DP]
+  double* s_itau = s_mu + DP;      // [DP]
+  double* red = s_itau + DP;       // [2*nval][RS]
 
   if (tid < 64) s_tab[tid] = g_exp2_tab[tid];
-  const double sigk = a.vp.sigma[k];
-  if (tid < DP) {
-    double mu = 0.0, itau = 0.0;
-    if (tid < D) {
-      const double lam = a.vp.lambda[tid], ell = a.gp.ell[s * D + tid], dl = a.vp.delta[tid];
-      const double tau = sqrt(sigk * sigk * lam * lam + ell * ell + dl * dl);  // gplogjoint.m:164
-      mu = a.vp.mu[k * D + tid];
-      itau = 1.0 / tau;
-    }
-    s_mu[tid] = mu;
-    s_itau[tid] = itau;
-  }
   __syncthreads();
-  if (tid == 0) {
-    double slt = 0.0;
-    for (int d = 0; d < D; ++d) slt += log(1.0 / s_itau[d]);
-    s_misc[0] = a.gp.lnc[s] - slt;  // lnnf_k = ln_sf2 + sum_lnell - sum(log(tau_k))  (:165)
-  }
-  __syncthreads();
-  const double lnnf = s_misc[0];
-  double Ah = 0.0, Al = 0.0, Bh[DPH], Bl[DPH], Qh[DPH], Ql[DPH];
-#pragma unroll
-  for (int d = 0; d < DPH; ++d) Bh[d] = Bl[d] = Qh[d] = Ql[d] = 0.0;
+
+  const int w = blockIdx.x * (GLJ_THREADS / 32) + warp;
+  if (w >= a.W) return;
+  const long long T = static_cast<long long>(a.s_count) * K * N;
+  const long long q0 = (static_cast<long long>(w) * T + a.W - 1) / a.W, q1 = (static_cast<long long>(w + 1) * T + a.W - 1) / a.W;
   const double* __restrict__ X = a.gp.X;
-  const double* __restrict__ alpha = a.wvec ? a.wvec + (static_cast<size_t>(s) * a.K + k) * N : a.gp.alpha + static_cast<size_t>(s) * N;
-  // slice of the N axis owned by this CTA (multiples of the block size except the last)
-  const int per = ((N + a.nsplit - 1) / a.nsplit + GLJ_THREADS - 1) / GLJ_THREADS * GLJ_THREADS;
-  const int n0 = blockIdx.z * per;
-  const int n1 = min(N, n0 + per);
-  for (int base = n0; base < n1; base += COLS) {  // warp-uniform trip count: the lane pairs shuffle inside
-    const int n = base + col;
-    const bool live = n < n1;
-    double x[DPH], dh[DPH], dl[DPH];
+
+  for (long long q = q0; q < q1;) {
+    const int pl = static_cast<int>(q / N);             // local pair index
+    const int n0 = static_cast<int>(q - static_cast<long long>(pl) * N);
+    const int n1 = static_cast<int>(min(static_cast<long long>(N), q1 - static_cast<long long>(pl) * N));
+    q += n1 - n0;
+    const int sl = pl / K, k = pl - sl * K, s = a.s_begin + sl;
+    const int pair = s * K + k;
+    // ---- per-pair constants: lane d owns dimension d (gplogjoint.m:164-165) ----
+    const double sigk = a.vp.sigma[k];
+    double tau2 = 1.0;
+    if (lane < DP) {
+      double mu = 0.0, itau = 0.0;
+      if (lane < D) {
+        const double lam = a.vp.lambda[lane], ell = a.gp.ell[s * D + lane], dl = a.vp.delta[lane];
+        tau2 = sigk * sigk * lam * lam + ell * ell + dl * dl;
+        mu = a.vp.mu[k * D + lane];
+        itau = 1.0 / sqrt(tau2);
+      }
+      s_mu[lane] = mu;
+      s_itau[lane] = itau;
+    }
+    // sum_d log tau_d = 0.5 log prod_d tau_d^2: one logarithm (the product of <= 24 squared length scales cannot leave the
+    // double range); xor-butterfly => every lane holds the same product
 #pragma unroll
-    for (int d = 0; d < DPH; ++d) x[d] = (live && d0 + d < D) ? __ldg(X + static_cast<size_t>(d0 + d) * N + n) : 0.0;
-    const double al_n = live ? __ldg(alpha + n) : 0.0;
-    double ssh, ssl;
-    glj_delta<DPH>(s_mu + d0, s_itau + d0, x, dh, dl, ssh, ssl);
-    if (HALVES == 2) {
-      const double oh = __shfl_xor_sync(0xffffffffu, ssh, 1), ol = __shfl_xor_sync(0xffffffffu, ssl, 1);
-      double th, tl;
-      two_sum(ssh, oh, th, tl);  // symmetric: both lanes of the pair get the same (ssh, ssl)
-      ssl = tl + (ssl + ol);
-      ssh = th;
-    }
-    double zh, zl;
-    glj_zeta(ssh, ssl, lnnf, al_n, s_tab, zh, zl);  // z_k(n)*alpha(n)  (:167-169)
-    if (half == 0) acc_add(Ah, Al, zh, zl);
-    glj_accumulate<DPH>(dh, dl, zh, zl, Bh, Bl, Qh, Ql);
-  }
-  // ---- block reduction in fixed order, two-word: value v of column `col` -> red[2v][col], red[2v+1][col] ----
-  if (half == 0) {
-    red[0 * RS + col] = Ah;
-    red[1 * RS + col] = Al;
-  }
+    for (int off = 16; off > 0; off >>= 1) tau2 *= __shfl_xor_sync(0xffffffffu, tau2, off);
+    const double lnnf = a.gp.lnc[s] - 0.5 * log(tau2);  // lnnf_k = ln_sf2 + sum_lnell - sum(log(tau_k))  (:165)
+    __syncwarp();
+
+    double Ah = 0.0, Al = 0.0, Bh[DPH], Bl[DPH], Qh[DPH], Ql[DPH];
 #pragma unroll
-  for (int d = 0; d < DPH; ++d) {
-    if (d0 + d < D) {
-      red[(2 + 2 * (d0 + d)) * RS + col] = Bh[d];
-      red[(3 + 2 * (d0 + d)) * RS + col] = Bl[d];
-      red[(2 + 2 * D + 2 * (d0 + d)) * RS + col] = Qh[d];
-      red[(3 + 2 * D + 2 * (d0 + d)) * RS + col] = Ql[d];
+    for (int d = 0; d < DPH; ++d) Bh[d] = Bl[d] = Qh[d] = Ql[d] = 0.0;
+    const double* __restrict__ alpha = a.wvec ? a.wvec + (static_cast<size_t>(s) * K + k) * N : a.gp.alpha + static_cast<size_t>(s) * N;
+    // software-pipelined loads (when the registers allow it): the next iteration's coordinates are in flight while this one
+    // is evaluated
+    constexpr bool PREFETCH = true;
+    double xn[PREFETCH ? DPH : 1], aln = 0.0;
+    if (PREFETCH) {
+      const int n = n0 + col;
+      const bool live = n < n1;
+#pragma unroll
+      for (int d = 0; d < DPH; ++d) xn[PREFETCH ? d : 0] = (live && d0 + d < D) ? __ldg(X + static_cast<size_t>(d0 + d) * N + n) : 0.0;
+      aln = live ? __ldg(alpha + n) : 0.0;
     }
-  }
-  __syncthreads();
-  constexpr int PER = COLS / GLJ_PARTS;
-  for (int idx = tid; idx < nval * GLJ_PARTS; idx += GLJ_THREADS) {
-    const int i = idx / GLJ_PARTS, part = idx - i * GLJ_PARTS;
-    const double* rh = red + (2 * i) * RS + part * PER;
-    const double* rl = red + (2 * i + 1) * RS + part * PER;
-    double h = rh[0], l = rl[0];
-    for (int t = 1; t < PER; ++t) acc_add(h, l, rh[t], rl[t]);
-    red2[(2 * i) * GLJ_PARTS + part] = h;
-    red2[(2 * i + 1) * GLJ_PARTS + part] = l;
-  }
-  __syncthreads();
-  // totals of this CTA -> red[2*i*RS], red[(2*i+1)*RS] (renormalised)
-  for (int i = tid; i < nval; i += GLJ_THREADS) {
-    double h = red2[(2 * i) * GLJ_PARTS], l = red2[(2 * i + 1) * GLJ_PARTS];
-    for (int p = 1; p < GLJ_PARTS; ++p) acc_add(h, l, red2[(2 * i) * GLJ_PARTS + p], red2[(2 * i + 1) * GLJ_PARTS + p]);
-    double nh, nl;
-    fast_two_sum(h, l, nh, nl);
-    red[(2 * i) * RS] = nh;
-    red[(2 * i + 1) * RS] = nl;
-  }
-  __syncthreads();
-  const int pair = s * a.K + k;
-  if (a.nsplit > 1) {
-    double* mine = a.part + (static_cast<size_t>(pair) * a.nsplit + blockIdx.z) * nval2;
-    for (int i = tid; i < nval2; i += GLJ_THREADS) __stcg(mine + i, red[i * RS]);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned t = atomicAdd(a.ticket + pair, 1u);
-      const bool last = t == static_cast<unsigned>(a.nsplit - 1);
-      if (last) a.ticket[pair] = 0;  // ready for the next launch (kernels of one context are stream-ordered)
-      s_misc[1] = last ? 1.0 : 0.0;
+    for (int base = n0; base < n1; base += COLS) {  // warp-uniform trip count: the lane pairs shuffle inside
+      double x[DPH], dh[DPH], dl[DPH];
+      double al_n;
+      if (PREFETCH) {
+#pragma unroll
+        for (int d = 0; d < DPH; ++d) x[d] = xn[PREFETCH ? d : 0];
+        al_n = aln;
+        const int n = base + COLS + col;
+        const bool live = n < n1;
+#pragma unroll
+        for (int d = 0; d < DPH; ++d) xn[PREFETCH ? d : 0] = (live && d0 + d < D) ? __ldg(X + static_cast<size_t>(d0 + d) * N + n) : 0.0;
+        aln = live ? __ldg(alpha + n) : 0.0;
+      } else {
+        const int n = base + col;
+        const bool live = n < n1;
+#pragma unroll
+        for (int d = 0; d < DPH; ++d) x[d] = (live && d0 + d < D) ? __ldg(X + static_cast<size_t>(d0 + d) * N + n) : 0.0;
+        al_n = live ? __ldg(alpha + n) : 0.0;
+      }
+      double ssh, ssl;
+      glj_delta<DPH>(s_mu + d0, s_itau + d0, x, dh, dl, ssh, ssl);
+      if (HALVES == 2) {
+        const double oh = __shfl_xor_sync(0xffffffffu, ssh, 1), ol = __shfl_xor_sync(0xffffffffu, ssl, 1);
+        double th, tl;
+        two_sum(ssh, oh, th, tl);  // symmetric: both lanes of the pair get the same (ssh, ssl)
+        ssl = tl + (ssl + ol);
+        ssh = th;
+      }
+      double zh, zl;
+      glj_zeta(ssh, ssl, lnnf, al_n, s_tab, zh, zl);  // z_k(n)*alpha(n)  (:167-169); alpha = 0 beyond the segment
+      if (half == 0) acc_add(Ah, Al, zh, zl);
+      glj_accumulate<DPH>(dh, dl, zh, zl, Bh, Bl, Qh, Ql);
     }
-    __syncthreads();
-    if (s_misc[1] == 0.0) return;
-    __threadfence();
-    const double* all = a.part + static_cast<size_t>(pair) * a.nsplit * nval2;
-    for (int i = tid; i < nval; i += GLJ_THREADS) {
-      double h = __ldcg(all + 2 * i), l = __ldcg(all + 2 * i + 1);
-      for (int z = 1; z < a.nsplit; ++z) acc_add(h, l, __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i), __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i + 1));
-      double nh, nl;
-      fast_two_sum(h, l, nh, nl);
-      red[(2 * i) * RS] = nh;
-      red[(2 * i + 1) * RS] = nl;
+    // ---- warp reduction in fixed order, two-word: value v of column `col` -> red[2v][col], red[2v+1][col] ----
+    if (half == 0) {
+      red[0 * RS + col] = Ah;
+      red[1 * RS + col] = Al;
     }
-    __syncthreads();
-  }
-  // ---- C_d = Q_d - A in two-word arithmetic, then everything rounds to one double ----
-  // red2[0] = A, red2[1 + d] = B_d, red2[1 + D + d] = C_d
-  if (tid < nval) {
-    const double Ah_ = red[0], Al_ = red[RS];
-    double v;
-    if (tid == 0) {
-      v = Ah_ + Al_;
-    } else if (tid <= D) {
-      v = red[(2 * tid) * RS] + red[(2 * tid + 1) * RS];
-    } else {
-      double h, l;
-      dd_add(red[(2 * tid) * RS], red[(2 * tid + 1) * RS], -Ah_, -Al_, h, l);
-      v = h + l;
-    }
-    red2[tid] = v;
-  }
-  __syncthreads();
-  // ---- per-(s,k) epilogue ----
-  double* o = a.out + static_cast<size_t>(pair) * a.ostride;
-  const bool quad = a.meanfun == 4 && !a.raw;
-  if (tid < D) {
-    const int d = tid;
-    const double lam = a.vp.lambda[d];
-    const double it = s_itau[d];
-    const double Bd = red2[1 + d], Cd = red2[1 + D + d];
-    double gmu = -Bd * it;                                  // w(k)*dz_dmu*alpha / w(k)   (:206-208)
-    double glam = sigk * sigk * lam * (Cd * it * it);       // (:248-249) / w(k)
-    if (quad) {
-      const double io2 = a.gp.iom2[s * D + d], xm = a.gp.xm[s * D + d];
-      gmu -= io2 * (s_mu[d] - xm);                          // (:210)
-      glam -= sigk * sigk * lam * io2;                      // (:252)
-    }
-    o[2 + d] = gmu;
-    o[2 + D + d] = glam;
-  }
-  if (tid == 32) {
-    double I = red2[0] + ((a.meanfun > 0 && !a.raw) ? a.gp.m0[s] : 0.0);  // I_k = z_k*alpha + m0   (:169)
-    double gs = 0.0;
-    for (int d = 0; d < D; ++d) {
-      const double lam = a.vp.lambda[d], it = s_itau[d], dl = a.vp.delta[d];
-      gs += (lam * it) * (lam * it) * red2[1 + D + d];  // sum (lambda/tau)^2 (Delta^2-1) z alpha (:227-229)
-      if (quad) {
-        const double io2 = a.gp.iom2[s * D + d], xm = a.gp.xm[s * D + d], m = s_mu[d];
-        I -= 0.5 * io2 * (m * m + sigk * sigk * lam * lam - 2.0 * m * xm + xm * xm + dl * dl);  // nu_k (:172-174)
-        gs -= io2 * lam * lam;                                                                 // (:231)
+#pragma unroll
+    for (int d = 0; d < DPH; ++d) {
+      if (d0 + d < D) {
+        red[(2 + 2 * (d0 + d)) * RS + col] = Bh[d];
+        red[(3 + 2 * (d0 + d)) * RS + col] = Bl[d];
+        red[(2 + 2 * D + 2 * (d0 + d)) * RS + col] = Qh[d];
+        red[(3 + 2 * D + 2 * (d0 + d)) * RS + col] = Ql[d];
       }
     }
-    o[0] = I;
-    o[1] = sigk * gs;
+    __syncwarp();
+    for (int i = lane; i < nval; i += 32) {   // lane i sums value i over the columns, in column order
+      const double* rh = red + (2 * i) * RS;
+      const double* rl = red + (2 * i + 1) * RS;
+      double h = rh[0], l = rl[0];
+#pragma unroll 4
+      for (int t = 1; t < COLS; ++t) acc_add(h, l, rh[t], rl[t]);
+      double nh, nl;
+      fast_two_sum(h, l, nh, nl);
+      red[(2 * i) * RS] = nh;          // column 0 of the rows: the segment totals
+      red[(2 * i + 1) * RS] = nl;
+    }
+    __syncwarp();
+    // ---- segments of this pair: [w_first, w_last]; the last one to arrive combines them ----
+    const int w_first = glj_owner(static_cast<long long>(pl) * N, T, a.W), w_last = glj_owner(static_cast<long long>(pl + 1) * N - 1, T, a.W);
+    const int nseg = w_last - w_first + 1;
+    if (nseg > 1) {
+      double* mine = a.part + (static_cast<size_t>(pl) * a.maxseg + (w - w_first)) * nval2;
+      for (int i = lane; i < nval2; i += 32) __stcg(mine + i, red[i * RS]);
+      __threadfence();
+      __syncwarp();
+      unsigned tk = 0;
+      if (lane == 0) {
+        tk = atomicAdd(a.ticket + pl, 1u);
+        if (tk == static_cast<unsigned>(nseg - 1)) a.ticket[pl] = 0;  // ready for the next launch (stream-ordered)
+      }
+      tk = __shfl_sync(0xffffffffu, tk, 0);
+      if (tk != static_cast<unsigned>(nseg - 1)) continue;   // not the last segment: next pair of this range
+      __threadfence();
+      const double* all = a.part + static_cast<size_t>(pl) * a.maxseg * nval2;
+      for (int i = lane; i < nval; i += 32) {
+        double h = __ldcg(all + 2 * i), l = __ldcg(all + 2 * i + 1);
+        for (int z = 1; z < nseg; ++z) acc_add(h, l, __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i), __ldcg(all + static_cast<size_t>(z) * nval2 + 2 * i + 1));
+        double nh, nl;
+        fast_two_sum(h, l, nh, nl);
+        red[(2 * i) * RS] = nh;
+        red[(2 * i + 1) * RS] = nl;
+      }
+      __syncwarp();
+    }
+    // ---- C_d = Q_d - A in two-word arithmetic, then everything rounds to one double; per-(s,k) epilogue, lane d owns d ----
+    const double A_h = red[0], A_l = red[RS];
+    const double Aval = A_h + A_l;
+    double gs = 0.0, Iq = 0.0;
+    double* o = a.out + static_cast<size_t>(pair) * a.ostride;
+    const bool quad = a.meanfun == 4 && !a.raw;
+    if (lane < D) {
+      const int d = lane;
+      const double Bd = red[(2 + 2 * d) * RS] + red[(3 + 2 * d) * RS];
+      double ch, cl;
+      dd_add(red[(2 + 2 * D + 2 * d) * RS], red[(3 + 2 * D + 2 * d) * RS], -A_h, -A_l, ch, cl);
+      const double Cd = ch + cl;
+      const double lam = a.vp.lambda[d], it = s_itau[d], dlt = a.vp.delta[d], m = s_mu[d];
+      double gmu = -Bd * it;                                  // w(k)*dz_dmu*alpha / w(k)   (:206-208)
+      double glam = sigk * sigk * lam * (Cd * it * it);       // (:248-249) / w(k)
+      gs = (lam * it) * (lam * it) * Cd;                      // sum (lambda/tau)^2 (Delta^2-1) z alpha (:227-229)
+      if (quad) {
+        const double io2 = a.gp.iom2[s * D + d], xm = a.gp.xm[s * D + d];
+        gmu -= io2 * (m - xm);                                // (:210)
+        glam -= sigk * sigk * lam * io2;                      // (:252)
+        Iq = -0.5 * io2 * (m * m + sigk * sigk * lam * lam - 2.0 * m * xm + xm * xm + dlt * dlt);  // nu_k (:172-174)
+        gs -= io2 * lam * lam;                                // (:231)
+      }
+      o[2 + d] = gmu;
+      o[2 + D + d] = glam;
+    }
+    // sums over d in ascending lane order (sequential adds through shuffles: same order as a serial loop)
+    double gsum = 0.0, isum = 0.0;
+    for (int d = 0; d < D; ++d) {
+      gsum += __shfl_sync(0xffffffffu, gs, d);
+      isum += __shfl_sync(0xffffffffu, Iq, d);
+    }
+    if (lane == 0) {
+      o[0] = Aval + ((a.meanfun > 0 && !a.raw) ? a.gp.m0[s] : 0.0) + isum;  // I_k = z_k*alpha + m0 + nu_k   (:169-174)
+      o[1] = sigk * gsum;
+    }
+    __syncwarp();  // red / s_mu are rewritten by the next pair
   }
 }
 
@@ -305,30 +322,33 @@ static int launch_glj_t(vbmc_b200_ctx* c, const GljArgs& a, cudaStream_t st) {
   auto kern = glj_kernel<DPH, HALVES>;
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(a.K, a.s_count, a.nsplit);
   KernelScope ks(c, "gplogjoint", st);
-  kern<<<grid, GLJ_THREADS, smem, st>>>(a);
+  kern<<<(a.W + 3) / 4, GLJ_THREADS, smem, st>>>(a);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
 
-// slices of the N axis: enough CTAs for ~4 per SM, at least 2*GLJ_THREADS points per slice; region 0 of the scratch buffers
-// belongs to the step's own launch, region 1 to the weighted (variance-gradient) launch, which may be enqueued on another stream.
+// number of ranges: one warp each; 12 warps per SM fill the register file (168 registers per thread); at least
+// GLJ_MIN_POINTS points per range so that the per-segment reduction stays a small fraction of the sweep.
+// Region 0 of the scratch buffers belongs to the step's own launch, region 1 to the weighted (variance-gradient) launch,
+// which may be enqueued on another stream.
 static int glj_dispatch(vbmc_b200_ctx* c, GljArgs& a, int region, cudaStream_t st) {
-  const int pairs = a.K * a.s_count;
-  int nsplit = (4 * c->num_sms + pairs - 1) / pairs;
-  const int max_split = (a.N + 2 * GLJ_THREADS - 1) / (2 * GLJ_THREADS);
-  nsplit = nsplit > max_split ? max_split : nsplit;
-  nsplit = nsplit > 16 ? 16 : (nsplit < 1 ? 1 : nsplit);
-  static const int force = getenv("VBMC_B200_GLJ_NSPLIT") ? atoi(getenv("VBMC_B200_GLJ_NSPLIT")) : 0;
-  if (force > 0) nsplit = force > 16 ? 16 : force;
-  a.nsplit = nsplit;
+  const long long T = static_cast<long long>(a.s_count) * a.K * a.N;
+  static const int min_pts = getenv("VBMC_B200_GLJ_MIN_POINTS") ? atoi(getenv("VBMC_B200_GLJ_MIN_POINTS")) : 512;
+  static const int wps = getenv("VBMC_B200_GLJ_WARPS_PER_SM") ? atoi(getenv("VBMC_B200_GLJ_WARPS_PER_SM")) : 8;
+  long long W = static_cast<long long>(wps) * c->num_sms;
+  const long long wmax = (T + min_pts - 1) / (min_pts > 0 ? min_pts : 1);
+  if (W > wmax) W = wmax;
+  if (W < 1) W = 1;
+  a.W = static_cast<int>(W);
+  const long long per = (T + W - 1) / W;                       // points per range
+  a.maxseg = static_cast<int>((a.N + per - 1) / per) + 1;       // a pair can straddle that many ranges
   const size_t npair_all = static_cast<size_t>(a.S) * a.K;
   const size_t nval2 = 2 * (1 + 2 * static_cast<size_t>(a.D));
-  const size_t part_doubles = npair_all * 16 * nval2;  // capacity for the largest nsplit: the buffer does not move between launches
+  const size_t part_doubles = npair_all * static_cast<size_t>(a.maxseg) * nval2;
   if (c->glj_part.cap < 2 * part_doubles * sizeof(double)) {
     VB_CUDA(cudaStreamSynchronize(st));
-    VB_TRY(c->glj_part.reserve(2 * part_doubles * sizeof(double)));
+    VB_TRY(c->glj_part.reserve(2 * part_doubles * sizeof(double) + (1 << 20)));
   }
   // arrival counters live in their own buffer: they must stay zero between launches whatever shape comes next
   if (c->glj_ticket.cap < 2 * npair_all * sizeof(unsigned)) {
