@@ -107,6 +107,8 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork0, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_philox, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_glj, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_la_main, cudaEventDisableTiming));
+  VB_CUDA(cudaEventCreateWithFlags(&c->ev_la_side, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_trail_fork, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_trail, cudaEventDisableTiming));
   if (const char* pf = getenv("VBMC_B200_PREFETCH")) c->prefetch_enabled = strcmp(pf, "0") != 0;
@@ -158,6 +160,8 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   cudaEventDestroy(c->ev_fork0);
   cudaEventDestroy(c->ev_philox);
   cudaEventDestroy(c->ev_glj);
+  cudaEventDestroy(c->ev_la_main);
+  cudaEventDestroy(c->ev_la_side);
   cudaEventDestroy(c->ev_trail_fork);
   cudaEventDestroy(c->ev_trail);
   delete c;

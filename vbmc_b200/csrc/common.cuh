@@ -207,6 +207,7 @@ struct vbmc_b200_ctx {
   cudaStream_t stream3 = nullptr;  // draw generation (independent of theta)
   cudaEvent_t ev_fork0 = nullptr, ev_philox = nullptr;
   cudaEvent_t ev_glj = nullptr;  // log-joint kernel done (before its reduction)
+  cudaEvent_t ev_la_main = nullptr, ev_la_side = nullptr;  // refit look-ahead: panel stream <-> trailing-update stream (gp_refit.cu)
   cudaEvent_t ev_trail_fork = nullptr, ev_trail = nullptr;  // ahead-of-time draw generation (forked after the entropy sweep)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   long long launches = 0;

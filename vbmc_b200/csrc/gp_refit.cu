@@ -17,6 +17,8 @@
 
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -366,7 +368,7 @@ __device__ __forceinline__ void load_pblock_async(double* dst, const double* src
 // trailing update — one read-modify-write of C per 128 panel rows doubles the flop/byte (8 instead of 4), which
 // is what lifts the kernel off the HBM roof (B200: DMMA peak 37 TFLOP/s needs > 5.7 flop/B).
 template <int KD>
-__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int krow0, int Ifirst, int Icount, int chunk) {
+__global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int krow0, int Ifirst, int Icount, int chunk, int nitems) {
   extern __shared__ __align__(16) double usm[];
   constexpr int LD = KD + 4;
   double* PI = usm;              // PI[m*LD + k] = P_I(k, m)
@@ -375,8 +377,11 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kro
   const int s = g.active[blockIdx.y];
   const int Np = g.Np, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = Np / TB;
+  // a CTA takes the work items blockIdx.x, blockIdx.x + gridDim.x, ...: with gridDim.x * gridDim.y below the SM count the
+  // kernel leaves SMs free for the panel kernels that run beside it (look-ahead, refit_core)
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
   // decode work item -> (ii, chunk): row I = Ifirst+ii has ceil((nb-I)/UPD_CHUNK) chunks
-  int t = blockIdx.x, ii = 0;
+  int t = item, ii = 0;
   for (;;) {
     const int nch = (nb - (Ifirst + ii) + chunk - 1) / chunk;
     if (t < nch) break;
@@ -442,6 +447,7 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kro
       }
     __syncthreads();  // all warps done with PJ before the ring slot is refilled
   }
+  }  // work items
 }
 
 // number of CTAs (work items) of gp_update_kernel for block rows Ifirst .. Ifirst+Icount-1
@@ -839,8 +845,17 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
         KernelScope ks(c, "gram", st);
         gp_gram_kernel<<<grid, 256, sizeof(double) * 2 * D * TB, st>>>(g);
       }
-      // 128-wide panels: two 64-steps share one big trailing update of depth 128
-      for (int kb = 0; kb < nb; kb += 2) {
+      // 128-wide panels: two 64-steps share one big trailing update of depth 128.
+      // LOOK-AHEAD: the panel work (diagonal-block factorisation on `nact` CTAs, row-panel solves) is latency bound and leaves
+      // the GPU nearly idle.  After panel kb is done, only the two block rows of the NEXT panel are updated on the panel stream;
+      // the rest of the trailing update runs on a second stream while the next panel is factored (they touch disjoint rows:
+      // the update reads panel rows kb, kb+1 and writes rows >= kb+4; the next panel reads and writes rows kb+2, kb+3).
+      static const bool la_env = !(getenv("VBMC_B200_REFIT_LOOKAHEAD") && atoi(getenv("VBMC_B200_REFIT_LOOKAHEAD")) == 0);
+      // (measured: 6.40 -> 5.96 ms at c3, S=20 x N=2000; at N=4000 the update dominates and giving up SMs costs more than the
+      // hidden panels return: 52.1 -> 54.4 ms, so it is used up to Np = 2560 only)
+      const bool lookahead = la_env && !c->profiling && Np <= 2560;   // per-kernel event timing needs the serial order
+      cudaStream_t side = c->stream2;
+      auto panel = [&](int kb) -> int {
         for (int h = 0; h < 2 && kb + h < nb; ++h) {
           const int k = kb + h, nr = nb - k - 1;
           {  // (a fused potf2+trsm kernel, gp_panel_kernel, was measured slower: 2.6 vs 2.2 ms at c3)
@@ -856,16 +871,45 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
             const int ch = update_chunk(nb, kb + 1, 1, nact, c->num_sms);
             dim3 grid(update_work_items(nb, kb + 1, 1, ch), nact);
             KernelScope ks(c, "potrf_update", st);
-            gp_update_kernel<64><<<grid, 256, UPDATE_SMEM64, st>>>(g, kb * TB, kb + 1, 1, ch);
-          }
-          if (h == 1 && nr > 0) {  // trailing update with both panel rows (depth 128)
-            const int ch = update_chunk(nb, kb + 2, nb - kb - 2, nact, c->num_sms);
-            dim3 grid(update_work_items(nb, kb + 2, nb - kb - 2, ch), nact);
-            KernelScope ks(c, "potrf_update", st);
-            gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, st>>>(g, kb * TB, kb + 2, nb - kb - 2, ch);
+            gp_update_kernel<64><<<grid, 256, UPDATE_SMEM64, st>>>(g, kb * TB, kb + 1, 1, ch, grid.x);
           }
         }
+        return VBMC_B200_OK;
+      };
+      // rows Ifirst.. with panel rows kb, kb+1; max_ctas > 0: persistent CTAs on at most that many SMs
+      auto update128 = [&](int kb, int Ifirst, int Icount, cudaStream_t sx, int max_ctas) -> int {
+        const int ch = update_chunk(nb, Ifirst, Icount, nact, c->num_sms);
+        const int items = update_work_items(nb, Ifirst, Icount, ch);
+        int gx = items;
+        if (max_ctas > 0 && gx * nact > max_ctas) gx = max_ctas / nact > 0 ? max_ctas / nact : 1;
+        dim3 grid(gx, nact);
+        KernelScope ks(c, "potrf_update", sx);
+        gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, sx>>>(g, kb * TB, Ifirst, Icount, ch, items);
+        return VBMC_B200_OK;
+      };
+      static const int reserve = getenv("VBMC_B200_REFIT_PANEL_SMS") ? atoi(getenv("VBMC_B200_REFIT_PANEL_SMS")) : 28;
+      bool side_busy = false;
+      for (int kb = 0; kb < nb; kb += 2) {
+        VB_TRY(panel(kb));
+        const int nrest = nb - kb - 2;   // block rows behind the panel
+        if (nrest <= 0) break;
+        if (!lookahead) {
+          VB_TRY(update128(kb, kb + 2, nrest, st, 0));
+          continue;
+        }
+        if (side_busy) VB_CUDA(cudaStreamWaitEvent(st, c->ev_la_side, 0));   // the previous trailing update wrote these rows
+        side_busy = false;
+        const int la = nrest < 2 ? nrest : 2;
+        VB_TRY(update128(kb, kb + 2, la, st, 0));
+        if (nrest > la) {
+          VB_CUDA(cudaEventRecord(c->ev_la_main, st));
+          VB_CUDA(cudaStreamWaitEvent(side, c->ev_la_main, 0));
+          VB_TRY(update128(kb, kb + 2 + la, nrest - la, side, c->num_sms - reserve));
+          VB_CUDA(cudaEventRecord(c->ev_la_side, side));
+          side_busy = true;
+        }
       }
+      if (side_busy) VB_CUDA(cudaStreamWaitEvent(st, c->ev_la_side, 0));
       return VBMC_B200_OK;
     };
     // ~100 dependent launches: replay them as one CUDA graph while shapes and buffers are unchanged
