@@ -34,7 +34,9 @@ SHAPES = [
     dict(D=10, N=300, K=50, S=4, Ns=512, target="lumpy"),   # c3 shape, reduced N/Ns/S
     dict(D=20, N=128, K=12, S=2, Ns=96, target="lumpy"),    # c5 dimension
     dict(D=20, N=160, K=100, S=2, Ns=128, target="lumpy"),  # c5 dimension and component count (K=100)
-    dict(D=7, N=140, K=128, S=1, Ns=66),                    # largest supported K
+    dict(D=7, N=140, K=128, S=1, Ns=66),
+    dict(D=4, N=200, K=160, S=2, Ns=64),                    # K = N^(2/3) at N = 2000 (vbmc.m:247): five list rounds of 32
+    dict(D=3, N=260, K=252, S=1, Ns=34),                    # K = N^(2/3) at N = 4000; one warp per CTA (the stage takes 126 KB)
 ]
 
 
@@ -188,6 +190,32 @@ def test_exp_underflow_matches_reference_semantics(gpu_ctx):
     H, dH = vbmc_b200.entmc_vbmc(vp, Ns, True, True, epsilon=eps)
     Ho, dHo = orc.entmc_vbmc(vp, Ns, True, True, epsilon=eps)
     assert np.isfinite(H) and rel(H, Ho) < TOL and rel(dH, dHo) < TOL
+
+
+def test_direct_formulation_forced_matches_oracle():
+    """VBMC_B200_ENTMC_FORM=direct runs the subtract-then-square instantiation (normally only selected by the device guard for
+    huge ||u||^2) on ordinary shapes; the switch is read at context creation, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, vbmc_b200
+from oracle import vbmc_oracle as orc
+from vbmc_b200 import workloads
+rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1e-300, np.max(np.abs(b))))
+for shape in (dict(D=2, N=50, K=2, S=8, Ns=100), dict(D=5, N=60, K=7, S=2, Ns=200), dict(D=10, N=80, K=50, S=2, Ns=256), dict(D=20, N=60, K=12, S=1, Ns=64),
+              dict(D=3, N=200, K=140, S=1, Ns=34)):
+    cfg = dict(shape, target="rosenbrock", noisy=False)
+    w = workloads.build(cfg, orc.gplite_post)
+    vp, eps = w["vp"], w["epsilon"]
+    H, dH = vbmc_b200.entmc_vbmc(vp, shape["Ns"], True, True, epsilon=eps)
+    Ho, dHo = orc.entmc_vbmc(vp, shape["Ns"], True, True, epsilon=eps)
+    assert rel(H, Ho) < 1e-10 and rel(dH, dHo) < 1e-10, (shape, rel(H, Ho), rel(dH, dHo))
+print("OK")
+'''
+    env = dict(os.environ, VBMC_B200_ENTMC_FORM="direct", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_device_rng_equals_parity_mode_on_dumped_draws(gpu_ctx):

@@ -601,10 +601,16 @@ int launch_entmc2(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st, bool
 int launch_entmc2_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st, bool* handled);
 
 int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
-  // expanded formulation: the second-generation sweep (entmc2.cu) when it covers the shape; the kernels of this file then only
-  // stand by for a step whose device guard selects the direct formulation
-  bool v2 = false;
-  if (entmc2_enabled(c)) VB_TRY(launch_entmc2(c, Ns, need_mask, st, &v2));
+  // FP64: the second-generation sweep (entmc2.cu, both formulations, K <= 256).  The kernels of this file serve the FP32 sweep
+  // (entmc_f32.cu shares the plan and the tile partials) and VBMC_B200_ENTMC_V1=1 (first-generation FP64 kernel, A/B runs).
+  if (entmc2_enabled(c)) {
+    if (c->eps_f32)
+      VB_FAIL(VBMC_B200_ESTATE, "entmc: the resident draws were generated in FP32 mode; upload or regenerate them for the FP64 sweep");
+    bool v2 = false;
+    VB_TRY(launch_entmc2(c, Ns, need_mask, st, &v2));
+    if (v2) return VBMC_B200_OK;
+    VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: D=%d, K=%d is not supported by this build (D <= 24, K <= 256)", c->D, c->K);
+  }
   EntmcPlan pl;
   VB_TRY(make_plan(c, Ns, &pl));
   if (pl.ntiles == 0) return VBMC_B200_OK;
@@ -627,35 +633,38 @@ int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st) {
   if (c->eps_f32)
     VB_FAIL(VBMC_B200_ESTATE, "entmc: the resident draws were generated in FP32 mode; upload or regenerate them for the FP64 sweep");
   switch (pl.DP) {
-    case 2: return launch_one<2>(c, pl, st, v2);
-    case 4: return launch_one<4>(c, pl, st, v2);
-    case 6: return launch_one<6>(c, pl, st, v2);
-    case 8: return launch_one<8>(c, pl, st, v2);
-    case 10: return launch_one<10>(c, pl, st, v2);
-    case 12: return launch_one<12>(c, pl, st, v2);
-    case 16: return launch_one<16>(c, pl, st, v2);
-    case 20: return launch_one<20>(c, pl, st, v2);
-    case 24: return launch_one<24>(c, pl, st, v2);
+    case 2: return launch_one<2>(c, pl, st, false);
+    case 4: return launch_one<4>(c, pl, st, false);
+    case 6: return launch_one<6>(c, pl, st, false);
+    case 8: return launch_one<8>(c, pl, st, false);
+    case 10: return launch_one<10>(c, pl, st, false);
+    case 12: return launch_one<12>(c, pl, st, false);
+    case 16: return launch_one<16>(c, pl, st, false);
+    case 20: return launch_one<20>(c, pl, st, false);
+    case 24: return launch_one<24>(c, pl, st, false);
   }
   VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:entmc: unsupported padded dimension %d", pl.DP);
 }
 
 int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st) {
+  if (entmc2_enabled(c)) {
+    bool v2 = false;
+    VB_TRY(launch_entmc2_reduce(c, Ns, S_layout, st, &v2));
+    return VBMC_B200_OK;
+  }
   EntmcPlan pl;
   VB_TRY(make_plan(c, Ns, &pl));
   RLayout rl;
   rl.init(c->D, c->K, S_layout);
   double* R = c->R_dev.d();
   if (pl.ntiles == 0) return VBMC_B200_OK;  // R was zeroed at the start of the step
-  bool v2 = false;
-  if (entmc2_enabled(c)) VB_TRY(launch_entmc2_reduce(c, Ns, S_layout, st, &v2));
   const XchgDev xc = step_push_target(c, S_layout, S_layout > 0);
-  KernelScope ks(c, v2 ? "reduce_direct" : "reduce", st);
+  KernelScope ks(c, "reduce", st);
   entmc_reduce_kernel<<<c->K, 128, 0, st>>>(c->ent_partial.d(), pl.tiles_per_comp, pl.a.pstride, c->D, c->K, R, rl.oHs, rl.oM, rl.oE,
-                                            rl.oWfull, xc, v2 ? c->vp.form_flag : nullptr);
+                                            rl.oWfull, xc, nullptr);
   VB_CUDA(cudaGetLastError());
   c->launches++;
-  wc_contract_kernel<<<(c->K + 3) / 4, 128, 0, st>>>(c->K, c->vp.w, R, rl.oWfull, rl.oWc, xc, v2 ? c->vp.form_flag : nullptr);
+  wc_contract_kernel<<<(c->K + 3) / 4, 128, 0, st>>>(c->K, c->vp.w, R, rl.oWfull, rl.oWc, xc, nullptr);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }

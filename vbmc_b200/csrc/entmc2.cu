@@ -18,8 +18,11 @@
 //  * The per-group sums of log q, M_d, E_d go through the same packed butterfly into ONE register per lane and pass;
 //    the W_jl sums are kept by owner lanes (k mod 32) in registers.  Nothing is written to shared memory per group
 //    except the stage itself.
-// Results are sums in a fixed order => bit-reproducible run to run.  The direct (subtract-then-square) formulation the
-// device guard selects for huge ||u||^2 stays in entmc.cu (entmc_kernel<DP, 8, false>).
+// Results are sums in a fixed order => bit-reproducible run to run.  DIRECT = true instantiates the reference's own
+// subtract-then-square formulation, which the device guard (vp_unpack_kernel) selects when ||u||^2 is so large that the
+// expanded form's cancellation error (~eps_mach * ||u||^2) could matter.  K <= 256 (vbmc.m:247: K <= N^(2/3) = 252 at N = 4000);
+// the thread-private stage needs K * 512 B of shared memory per warp, so the warps per CTA shrink as K grows (8 up to K = 50,
+// 4 at K = 100, 1 at K = 256).
 #include "entmc_shared.cuh"
 
 namespace vb {
@@ -123,9 +126,12 @@ __device__ __forceinline__ double reduce8(double (&v)[8], int lane) {
   return v[0];
 }
 
-template <int DP, int KW, bool ROT>
+template <int KW> struct KlistIndex { typedef unsigned char type; };
+template <> struct KlistIndex<8> { typedef unsigned short type; };
+
+template <int DP, int KW, bool DIRECT>
 __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
-  if (*a.form_flag != 2) return;  // the direct formulation (entmc.cu) handles this step
+  if (*a.form_flag != (DIRECT ? 1 : 2)) return;  // the other instantiation handles this step (device guard, vp_unpack_kernel)
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NV = 1 + 2 * DP;        // log q, M[DP], E[DP] (padded dimensions carry zeros)
   constexpr int NB = (NV + 7) / 8;      // packed-butterfly passes for them
@@ -135,14 +141,15 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
   const int nw = blockDim.x >> 5;
 
   double* tab_v = reinterpret_cast<double*>(smem + a.off_v);    // [K2+1][DP]  r_jk * u_jk
-  double4* tab_s = reinterpret_cast<double4*>(smem + a.off_s);  // [K2+1] {r^2, -0.5||u||^2, ck, ak/r}
+  double4* tab_s = reinterpret_cast<double4*>(smem + a.off_s);  // [K2+1] {r^2, -0.5||u||^2 (DIRECT: 1/r^2), ck, ak/r}
   double* t16 = reinterpret_cast<double*>(smem + a.off_t16);    // [16]
   float2* tab_m = reinterpret_cast<float2*>(smem + a.off_m);    // [K] {||u|| (rounded down), prune_c + log(ck_k/ck_j) (rounded up)}
   float* tab_r = reinterpret_cast<float*>(smem + a.off_m) + 2 * K;  // [K] r (rounded up)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a.off_bar) + warp;
   unsigned char* wbase = smem + a.off_warp + static_cast<size_t>(warp) * a.warp_bytes;
   double* eps_s = reinterpret_cast<double*>(wbase + a.woff_eps);      // [32*D]
-  unsigned char* klist = wbase + a.woff_klist;                        // [K2+2]
+  using KI = typename KlistIndex<KW>::type;   // byte indices up to K = 128 (the shared-memory budget at K = 50 is counted in bytes)
+  KI* klist = reinterpret_cast<KI*>(wbase + a.woff_klist);  // [K2+4]
   double2* stage = reinterpret_cast<double2*>(wbase + a.woff_stage);  // [K2][32] {e+, e-} by list position, thread-private columns
   double* wtmp = reinterpret_cast<double*>(wbase + a.woff_stage);     // [K] mailbox of the W totals / [pstride] run result (aliases stage)
 
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
         for (int d = 0; d < D; ++d) uu = fma(tab_v[k * DP + d], tab_v[k * DP + d], uu);
         if (k < K) {
           const double r = sj / a.sigma[k];
-          tab_s[k] = make_double4(r * r, -0.5 * uu, a.ck[k], a.ak[k] / r);
+          tab_s[k] = make_double4(r * r, DIRECT ? 1.0 / (r * r) : -0.5 * uu, a.ck[k], a.ak[k] / r);
           // pruning test operands in FP32, rounded so that the test can only err towards keeping a component
           tab_m[k] = make_float2(__double2float_rd(sqrt(uu) * 0.999999), __double2float_ru(a.prune_c + log(a.ck[k]) - log(a.ck[j]) + 0.5));
           tab_r[k] = __double2float_ru(r);
@@ -275,10 +282,10 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
             keep = !(bb + he2 + m.y < 0.0f) || a.prune_c <= 0.0;   // NaN keeps
           }
           const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) klist[nact + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned char>(k);  // compacted, ascending
+          if (keep) klist[nact + __popc(bal & ((1u << lane) - 1u))] = static_cast<KI>(k);  // compacted, ascending
           nact += __popc(bal);
         }
-        if (lane == 0) klist[nact] = static_cast<unsigned char>(K2);  // dummy partner when the count is odd (ck = ak = 0)
+        if (lane == 0) klist[nact] = static_cast<KI>(K2);  // dummy partner when the count is odd (ck = ak = 0)
         __syncwarp();
         if (a.prune_stats && lane == 0) {
           atomicAdd(a.prune_stats, static_cast<unsigned long long>(nact));
@@ -286,17 +293,19 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
         }
       }
       // ---- component loop: two components per iteration => four independent exp chains (ka, kb) x (+, -) ----
-      // ROT: software-pipelined by one iteration.  The gradient sums A(+-)_d += t(+-) v_d of the PREVIOUS component pair (40
-      // independent DFMAs, rows re-read from the table) sit in the same basic block as the exponentials of the current pair
-      // (four 12-deep dependency chains), so the instruction scheduler fills the chains' latency slots with them; the rows of
-      // the current pair are dead after the dot products instead of staying live across the exponential.
-      double tpv[4] = {0.0, 0.0, 0.0, 0.0};   // (a_k / r) e(+-) of the previous pair
-      int kpv = K2, kbpv = K2;                // its rows (K2: all-zero dummy row)
+      // (a software-pipelined variant -- gradient sums of the previous pair interleaved with the exponentials of the current
+      // one, rows re-read from the table -- was measured slower: 0.272 vs 0.246 ms at c3)
 #pragma unroll 1
       for (int ia = 0; ia < nact; ia += 2) {
-        const unsigned kk = *reinterpret_cast<const unsigned short*>(klist + ia);  // two byte indices, one broadcast load
-        const int k = kk & 0xff, kb = kk >> 8;
-        const double4 sa = tab_s[k], sb = tab_s[kb];  // {r^2, -0.5||u||^2, ck, ak/r}
+        int k, kb;   // two indices, one broadcast load
+        if (sizeof(KI) == 1) {
+          const unsigned kk = *reinterpret_cast<const unsigned short*>(klist + ia);
+          k = kk & 0xff; kb = kk >> 8;
+        } else {
+          const unsigned kk = *reinterpret_cast<const unsigned*>(klist + ia);
+          k = kk & 0xffff; kb = kk >> 16;
+        }
+        const double4 sa = tab_s[k], sb = tab_s[kb];  // {r^2, -0.5||u||^2 | 1/r^2, ck, ak/r}
         double va[DP], vb[DP];
 #pragma unroll
         for (int d = 0; d < DP; d += 2) {
@@ -305,35 +314,36 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
           va[d] = a2.x; va[d + 1] = a2.y;
           vb[d] = b2.x; vb[d + 1] = b2.y;
         }
-        double ta0 = 0.0, ta1 = 0.0, tb0 = 0.0, tb1 = 0.0;
-#pragma unroll
-        for (int d = 0; d < DP; d += 2) {
-          ta0 = fma(e[d], va[d], ta0);
-          tb0 = fma(e[d], vb[d], tb0);
-          ta1 = fma(e[d + 1], va[d + 1], ta1);
-          tb1 = fma(e[d + 1], vb[d + 1], tb1);
-        }
-        const double rta = ta0 + ta1, rtb = tb0 + tb1;                              // r (eps.u)
-        const double xba = fma(sa.x, mhee, sa.y), xbb = fma(sb.x, mhee, sb.y);      // -0.5 (||u||^2 + r^2 ||eps||^2)
         double x[4], ex[4];
-        x[0] = xba - rta; x[1] = xba + rta;   // -0.5||u + r eps||^2,  -0.5||u - r eps||^2
-        x[2] = xbb - rtb; x[3] = xbb + rtb;
-        if (ROT && needT) {   // previous pair's gradient sums: independent of everything above
-          const double* pa = tab_v + kpv * DP;
-          const double* pb = tab_v + kbpv * DP;
+        if (!DIRECT) {
+          double ta0 = 0.0, ta1 = 0.0, tb0 = 0.0, tb1 = 0.0;
 #pragma unroll
           for (int d = 0; d < DP; d += 2) {
-            const double2 a2 = *reinterpret_cast<const double2*>(pa + d);
-            const double2 b2 = *reinterpret_cast<const double2*>(pb + d);
-            Ap[d] = fma(tpv[0], a2.x, Ap[d]);
-            Am[d] = fma(tpv[1], a2.x, Am[d]);
-            Ap[d + 1] = fma(tpv[0], a2.y, Ap[d + 1]);
-            Am[d + 1] = fma(tpv[1], a2.y, Am[d + 1]);
-            Ap[d] = fma(tpv[2], b2.x, Ap[d]);
-            Am[d] = fma(tpv[3], b2.x, Am[d]);
-            Ap[d + 1] = fma(tpv[2], b2.y, Ap[d + 1]);
-            Am[d + 1] = fma(tpv[3], b2.y, Am[d + 1]);
+            ta0 = fma(e[d], va[d], ta0);
+            tb0 = fma(e[d], vb[d], tb0);
+            ta1 = fma(e[d + 1], va[d + 1], ta1);
+            tb1 = fma(e[d + 1], vb[d + 1], tb1);
           }
+          const double rta = ta0 + ta1, rtb = tb0 + tb1;                              // r (eps.u)
+          const double xba = fma(sa.x, mhee, sa.y), xbb = fma(sb.x, mhee, sb.y);      // -0.5 (||u||^2 + r^2 ||eps||^2)
+          x[0] = xba - rta; x[1] = xba + rta;   // -0.5||u + r eps||^2,  -0.5||u - r eps||^2
+          x[2] = xbb - rtb; x[3] = xbb + rtb;
+        } else {
+          // the reference's own subtract-then-square (entmc_vbmc.m:62): r z(+-)_d = v_d +- r^2 eps_d, ||z||^2 = sum (.)^2 / r^2
+          double da[4] = {0.0, 0.0, 0.0, 0.0}, db[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for (int d = 0; d < DP; d += 2) {
+            const double zap0 = fma(sa.x, e[d], va[d]), zam0 = fma(-sa.x, e[d], va[d]);
+            const double zbp0 = fma(sb.x, e[d], vb[d]), zbm0 = fma(-sb.x, e[d], vb[d]);
+            const double zap1 = fma(sa.x, e[d + 1], va[d + 1]), zam1 = fma(-sa.x, e[d + 1], va[d + 1]);
+            const double zbp1 = fma(sb.x, e[d + 1], vb[d + 1]), zbm1 = fma(-sb.x, e[d + 1], vb[d + 1]);
+            da[0] = fma(zap0, zap0, da[0]); da[1] = fma(zam0, zam0, da[1]);
+            db[0] = fma(zbp0, zbp0, db[0]); db[1] = fma(zbm0, zbm0, db[1]);
+            da[2] = fma(zap1, zap1, da[2]); da[3] = fma(zam1, zam1, da[3]);
+            db[2] = fma(zbp1, zbp1, db[2]); db[3] = fma(zbm1, zbm1, db[3]);
+          }
+          x[0] = -0.5 * sa.y * (da[0] + da[2]); x[1] = -0.5 * sa.y * (da[1] + da[3]);
+          x[2] = -0.5 * sb.y * (db[0] + db[2]); x[3] = -0.5 * sb.y * (db[1] + db[3]);
         }
         exp2_neg4(x, ex, t16);
         if (needW) {
@@ -350,32 +360,16 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
           Bm = fma(tma, sa.x, Bm);
           Bp = fma(tpb, sb.x, Bp);
           Bm = fma(tmb, sb.x, Bm);
-          if (ROT) {
-            tpv[0] = tpa; tpv[1] = tma; tpv[2] = tpb; tpv[3] = tmb;
-            kpv = k; kbpv = kb;
-          } else {
 #pragma unroll
-            for (int d = 0; d < DP; ++d) {
-              Ap[d] = fma(tpa, va[d], Ap[d]);   // a_k e u_d
-              Am[d] = fma(tma, va[d], Am[d]);
-            }
-#pragma unroll
-            for (int d = 0; d < DP; ++d) {
-              Ap[d] = fma(tpb, vb[d], Ap[d]);
-              Am[d] = fma(tmb, vb[d], Am[d]);
-            }
+          for (int d = 0; d < DP; ++d) {
+            Ap[d] = fma(tpa, va[d], Ap[d]);   // a_k e u_d
+            Am[d] = fma(tma, va[d], Am[d]);
           }
-        }
-      }
-      if (ROT && needT) {   // drain: the last pair's gradient sums
-        const double* pa = tab_v + kpv * DP;
-        const double* pb = tab_v + kbpv * DP;
 #pragma unroll
-        for (int d = 0; d < DP; ++d) {
-          Ap[d] = fma(tpv[0], pa[d], Ap[d]);
-          Am[d] = fma(tpv[1], pa[d], Am[d]);
-          Ap[d] = fma(tpv[2], pb[d], Ap[d]);
-          Am[d] = fma(tpv[3], pb[d], Am[d]);
+          for (int d = 0; d < DP; ++d) {
+            Ap[d] = fma(tpb, vb[d], Ap[d]);
+            Am[d] = fma(tmb, vb[d], Am[d]);
+          }
         }
       }
       const double iqp = valid ? 1.0 / qp : 0.0;
@@ -499,7 +493,6 @@ __device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, int j, int 
 }
 
 __global__ void __launch_bounds__(128) entmc2_reduce_kernel(const Entmc2Red a) {
-  if (*a.form_flag != 2) return;
   const int D = a.D, K = a.K, nv = 1 + 2 * D;
   if (static_cast<int>(blockIdx.x) < a.nb1) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -535,13 +528,13 @@ struct Entmc2Plan {
   Entmc2Args a;
 };
 
-// false: this shape is left to the first-generation kernel (not enough shared memory for even one warp, K > 128)
+// false: no plan (D > 24, K > 256, or not enough shared memory for even one warp)
 static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
   const int D = c->D, K = c->K;
   const int half = Ns / 2;
   pl->DP = entmc_pick_dp(D);
-  if (pl->DP < 0 || K > 128) return false;
-  pl->KW = K <= 64 ? 2 : 4;
+  if (pl->DP < 0 || K > 256) return false;
+  pl->KW = K <= 64 ? 2 : (K <= 128 ? 4 : 8);
   Entmc2Args& a = pl->a;
   memset(&a, 0, sizeof(a));
   a.D = D; a.K = K; a.half = half;
@@ -559,7 +552,7 @@ static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
   off = round_up2(off, 16);
   a.off_warp = off;
   const int eps_bytes = round_up2(32 * D * 8, 16);
-  const int klist_bytes = round_up2(K2 + 4, 16);
+  const int klist_bytes = round_up2((pl->KW == 8 ? 2 : 1) * (K2 + 4), 16);
   int stage_bytes = K2 * 32 * 16;
   const int res_bytes = round_up2(a.pstride * 8, 16);
   if (stage_bytes < res_bytes) stage_bytes = res_bytes;
@@ -589,17 +582,25 @@ static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
 
 bool entmc2_enabled(vbmc_b200_ctx* c) {
   static const bool off = getenv("VBMC_B200_ENTMC_V1") && atoi(getenv("VBMC_B200_ENTMC_V1")) != 0;
-  return !off && c->precision == 64 && c->K <= 128;
+  return !off && c->precision == 64;
 }
 
 template <int DP, int KW>
 static int launch2(vbmc_b200_ctx* c, const Entmc2Plan& pl, cudaStream_t st) {
-  static const bool rot = !(getenv("VBMC_B200_ENTMC_ROT") && atoi(getenv("VBMC_B200_ENTMC_ROT")) == 0);
-  auto kern = rot ? entmc2_kernel<DP, KW, true> : entmc2_kernel<DP, KW, false>;
-  VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
-  KernelScope ks(c, "entmc", st);
-  kern<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
-  VB_CUDA(cudaGetLastError());
+  auto kexp = entmc2_kernel<DP, KW, false>;
+  auto kdir = entmc2_kernel<DP, KW, true>;
+  VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  {
+    KernelScope ks(c, "entmc", st);  // expanded form (default when the device guard allows)
+    kexp<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+    VB_CUDA(cudaGetLastError());
+  }
+  {
+    KernelScope ks(c, "entmc_direct", st);  // exits at once unless the guard selected the direct form for this step
+    kdir<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+    VB_CUDA(cudaGetLastError());
+  }
   return VBMC_B200_OK;
 }
 
@@ -619,9 +620,9 @@ int launch_entmc2(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st, bool
   a.partial = c->ent_partial2.d();
   a.prune_c = c->entmc_prune_c;
   a.prune_stats = c->entmc_prune_stats_on ? reinterpret_cast<unsigned long long*>(c->entmc_prune_stats.p) : nullptr;
-#define VB_E2(dp)                                              \
-  case dp:                                                     \
-    return pl.KW == 2 ? launch2<dp, 2>(c, pl, st) : launch2<dp, 4>(c, pl, st);
+#define VB_E2(dp)                                                                                                       \
+  case dp:                                                                                                              \
+    return pl.KW == 2 ? launch2<dp, 2>(c, pl, st) : (pl.KW == 4 ? launch2<dp, 4>(c, pl, st) : launch2<dp, 8>(c, pl, st));
   switch (pl.DP) {
     VB_E2(2) VB_E2(4) VB_E2(6) VB_E2(8) VB_E2(10) VB_E2(12) VB_E2(16) VB_E2(20) VB_E2(24)
   }
