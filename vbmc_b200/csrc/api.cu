@@ -427,6 +427,7 @@ int vbmc_b200_vp_set(vbmc_b200_ctx* c, const vbmc_b200_vp_desc* v) {
   if (v->delta)
     for (int d = 0; d < D; ++d) dl[d] = v->delta[d];
   VB_CUDA(cudaMemcpyAsync(c->vp.delta, dl.data(), sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaMemsetAsync(c->vp.form_flag, 0, 16, c->stream));   // {form flag, arrival ticket, guard maximum} of vp_unpack2_kernel
   VB_CUDA(cudaStreamSynchronize(c->stream));
   c->vp_ready = true;
   c->eps_ready = c->eps_ready && c->epsD == D && c->epsK == K;

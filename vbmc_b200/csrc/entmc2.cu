@@ -130,8 +130,7 @@ template <int KW> struct KlistIndex { typedef unsigned char type; };
 template <> struct KlistIndex<8> { typedef unsigned short type; };
 
 template <int DP, int KW, bool DIRECT>
-__global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
-  if (*a.form_flag != (DIRECT ? 1 : 2)) return;  // the other instantiation handles this step (device guard, vp_unpack_kernel)
+__device__ __forceinline__ void entmc2_body(const Entmc2Args& a) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NV = 1 + 2 * DP;        // log q, M[DP], E[DP] (padded dimensions carry zeros)
   constexpr int NB = (NV + 7) / 8;      // packed-butterfly passes for them
@@ -464,6 +463,15 @@ __global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
   }
 }
 
+// one launch serves both formulations: the device guard (vp_unpack kernels) decides per step
+template <int DP, int KW>
+__global__ void __launch_bounds__(256, 1) entmc2_kernel(const Entmc2Args a) {
+  if (*a.form_flag == 1)
+    entmc2_body<DP, KW, true>(a);
+  else
+    entmc2_body<DP, KW, false>(a);
+}
+
 // Run partials -> R (compact layout, common.cuh), every sum in a fixed order.
 // Component j's tiles [j*tpc, (j+1)*tpc) belong to the CTAs owner(j*tpc) .. owner((j+1)*tpc - 1), owner(t) = floor(t*G/T);
 // inside CTA b the run of component j has index j - first_j(b), first_j(b) = ceil(b*T/G) / tpc.
@@ -587,20 +595,11 @@ bool entmc2_enabled(vbmc_b200_ctx* c) {
 
 template <int DP, int KW>
 static int launch2(vbmc_b200_ctx* c, const Entmc2Plan& pl, cudaStream_t st) {
-  auto kexp = entmc2_kernel<DP, KW, false>;
-  auto kdir = entmc2_kernel<DP, KW, true>;
-  VB_CUDA(cudaFuncSetAttribute(kexp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
-  VB_CUDA(cudaFuncSetAttribute(kdir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
-  {
-    KernelScope ks(c, "entmc", st);  // expanded form (default when the device guard allows)
-    kexp<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
-    VB_CUDA(cudaGetLastError());
-  }
-  {
-    KernelScope ks(c, "entmc_direct", st);  // exits at once unless the guard selected the direct form for this step
-    kdir<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
-    VB_CUDA(cudaGetLastError());
-  }
+  auto kern = entmc2_kernel<DP, KW>;
+  VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_optin)));
+  KernelScope ks(c, "entmc", st);
+  kern<<<pl.grid, pl.nw * 32, pl.smem, st>>>(pl.a);
+  VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
 }
 

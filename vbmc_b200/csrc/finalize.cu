@@ -169,6 +169,129 @@ __global__ void __launch_bounds__(256) vp_unpack_kernel(const UnpackArgs a) {
   }
 }
 
+// Multi-CTA theta -> vp (default; the one-CTA kernel above stays for VBMC_B200_UNPACK_V1=1).  grid = K CTAs of 128 threads.
+// Every CTA recomputes the K + D exponentials it needs (sigma, eta -> softmax normaliser, lambda: a few hundred flops), CTA j
+// then owns component j: its row of mu, sigma_j, w_j, c_j, a_j and row j of the form guard max_k(||u_jk||^2 + r_jk^2 eemax);
+// the rows' maxima meet in one atomicMax on the bit pattern of a non-negative double, and the last CTA to arrive publishes the
+// form flag.  Same formulas as vp_unpack_kernel (the softmax normaliser is summed over 128 instead of 256 threads: last-bit differences).
+__global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
+  extern __shared__ double usm[];
+  const int D = a.D, K = a.K, tid = threadIdx.x, nt = blockDim.x, j = blockIdx.x;
+  double* s_sigma = usm;             // [K]
+  double* s_lambda = s_sigma + K;    // [D]
+  double* s_muj = s_lambda + D;      // [D]
+  __shared__ double part[128];
+  __shared__ double s_es, s_nf;
+  const bool ht = a.have_theta != 0;
+  if (j == 0 && tid < 2 && a.dyn_src) a.vp.dyn_snap[tid] = a.dyn_src[tid];
+  int idx = 0;
+  const int o_mu = 0;
+  if (ht && a.opt[0]) idx += D * K;
+  const int o_sig = idx;
+  if (ht && a.opt[1]) idx += K;
+  const int o_lam = idx;
+  const int o_eta = a.ntheta - K;
+  for (int d = tid; d < D; d += nt) {
+    const double m = (ht && a.opt[0]) ? a.theta[o_mu + j * D + d] : a.base_mu[j * D + d];
+    s_muj[d] = m;
+    a.vp.mu[j * D + d] = m;
+  }
+  // softmax normaliser: the same left-to-right-per-thread + tree order in every CTA => the same es everywhere
+  double es = 0.0;
+  for (int k = tid; k < K; k += nt) {
+    double sg, ls;
+    if (ht && a.opt[1]) {
+      ls = a.theta[o_sig + k];
+      sg = exp(ls);  // vp.sigma(1,:) = exp(theta(idx_start+(1:K)))  (negelcbo_vbmc.m:39-42)
+    } else {
+      sg = a.base_sigma[k];
+      ls = log(sg);
+    }
+    s_sigma[k] = sg;
+    const double et = (ht && a.opt[3]) ? a.theta[o_eta + k] : a.base_eta[k];
+    es += exp(et);  // (:46-47) no max-shift, like the reference
+    if (k == j) {
+      a.vp.lnsigma[k] = ls;
+      a.vp.sigma[k] = sg;
+      a.vp.eta[k] = et;
+    }
+  }
+  for (int d = tid; d < D; d += nt) {
+    double lm, ll;
+    if (ht && a.opt[2]) {
+      ll = a.theta[o_lam + d];
+      lm = exp(ll);  // (:43)
+    } else {
+      lm = a.base_lambda[d];
+      ll = log(lm);
+    }
+    s_lambda[d] = lm;
+    if (j == 0) {
+      a.vp.lnlambda[d] = ll;
+      a.vp.lambda[d] = lm;
+    }
+  }
+  part[tid] = es;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (tid < off) part[tid] += part[tid + off];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    s_es = part[0];
+    double pl = 1.0;
+    for (int d = 0; d < D; ++d) pl *= s_lambda[d];
+    s_nf = 1.0 / pow(2.0 * 3.14159265358979323846, 0.5 * D) / pl;  // nf (entmc_vbmc.m:40)
+    if (j == 0) a.cn[K] = s_nf;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double et = (ht && a.opt[3]) ? a.theta[o_eta + j] : a.base_eta[j];
+    const double w = (ht && a.opt[3]) ? exp(et) / s_es : a.base_w[j];
+    a.vp.w[j] = w;
+    const double sg = s_sigma[j];
+    const double cn = s_nf / pow(sg, static_cast<double>(D));  // nf/sigma(k)^D  (:63)
+    a.cn[j] = cn;
+    const double ck = w * cn;
+    a.vp.ck[j] = ck;
+    a.vp.ak[j] = ck / sg;
+  }
+  // ---- row j of the form guard (see vp_unpack_kernel) ----
+  const double eemax = D + 12.0 * sqrt(2.0 * D) + 72.0;  // > 12 sigma bound on ||eps||^2
+  double m = 0.0;
+  for (int k = tid; k < K; k += nt) {
+    double uu = 0.0;
+    const double isg = 1.0 / s_sigma[k];
+    for (int d = 0; d < D; ++d) {
+      const double mk = (ht && a.opt[0]) ? a.theta[o_mu + k * D + d] : a.base_mu[k * D + d];
+      const double u = (s_muj[d] - mk) * isg / s_lambda[d];
+      uu = fma(u, u, uu);
+    }
+    const double r = s_sigma[j] * isg;
+    const double v = fma(r * r, eemax, uu);
+    m = (v > m || !(v == v)) ? v : m;
+  }
+  part[tid] = m;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if (tid < off) part[tid] = (part[tid + off] > part[tid] || !(part[tid + off] == part[tid + off])) ? part[tid + off] : part[tid];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    // non-negative doubles order like their bit patterns; a NaN (0x7ff8...) is larger than every finite value
+    unsigned long long* gmax = reinterpret_cast<unsigned long long*>(a.vp.form_flag) + 1;
+    unsigned* ticket = reinterpret_cast<unsigned*>(a.vp.form_flag) + 1;
+    atomicMax(gmax, static_cast<unsigned long long>(__double_as_longlong(part[0] == part[0] ? fabs(part[0]) : part[0])));
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == static_cast<unsigned>(K - 1)) {
+      __threadfence();
+      const double gm = __longlong_as_double(static_cast<long long>(atomicExch(gmax, 0ULL)));
+      *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((gm <= 2.0e5) ? 2 : 1);
+      *ticket = 0;
+    }
+  }
+}
+
 struct FinArgs {
   int D, K, S, Ns, ntheta_out;
   int gf[4];       // which gradient blocks are produced
@@ -597,10 +720,17 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   a.cn = c->vp.cn;
   a.scratch = c->vp.scratch;
   a.want_cblob = c->entmc_form == 0 ? 1 : 0;
+  static const bool v1 = getenv("VBMC_B200_UNPACK_V1") && atoi(getenv("VBMC_B200_UNPACK_V1")) != 0;
+  KernelScope ks(c, "vp_unpack", c->stream);
+  if (!v1) {
+    a.want_cblob = 0;
+    vp_unpack2_kernel<<<c->K, 128, sizeof(double) * (c->K + 2 * c->D), c->stream>>>(a);
+    VB_CUDA(cudaGetLastError());
+    return VBMC_B200_OK;
+  }
   const size_t smem = sizeof(double) * (2 * static_cast<size_t>(c->D) * c->K + 2 * c->K + c->D);
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(vp_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  KernelScope ks(c, "vp_unpack", c->stream);
   vp_unpack_kernel<<<1, 256, smem, c->stream>>>(a);
   VB_CUDA(cudaGetLastError());
   return VBMC_B200_OK;
