@@ -101,9 +101,16 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
-  VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  VB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  VB_CUDA(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  // The step's own kernels outrank the ahead-of-time draw generator (stream3): the generator fills the whole GPU for 40-150 us
+  // right behind the sweep, and without priorities the small reduction / finalize kernels of the step queue behind its CTAs.
+  {
+    int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority
+    VB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    static const bool flat = getenv("VBMC_B200_STREAM_PRIORITIES") && atoi(getenv("VBMC_B200_STREAM_PRIORITIES")) == 0;
+    VB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, flat ? prio_lo : prio_hi));
+    VB_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, flat ? prio_lo : prio_hi));
+    VB_CUDA(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_lo));
+  }
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_fork0, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_philox, cudaEventDisableTiming));
   VB_CUDA(cudaEventCreateWithFlags(&c->ev_glj, cudaEventDisableTiming));
