@@ -204,8 +204,8 @@ def numpy_stand_in(w, cfg):
 
 
 
-TRAFFIC_C3_BYTES = 65.61e6 + 0.204e6
-TRAFFIC_C3_SOURCE = "ncu --set full capture entmc_r1f (profiles/r1_ncu_summary.md): dram read 65.61 MB + write 0.20 MB per launch"
+TRAFFIC_C3_BYTES = 65.612e6 + 0.257e6
+TRAFFIC_C3_SOURCE = "ncu --set full capture r2_entmc2 (profiles/r2_ncu_summary.md): dram read 65.61 MB + write 0.26 MB per launch"
 PARITY_TOL = 1e-10      # FP64 gate (BASELINE.json north_star); FP32 sweep: 1e-4
 
 
@@ -442,7 +442,12 @@ def main():
         Np_ = (N_ + 1 + 63) // 64 * 64
         nb_ = Np_ // 64
         upd_flops = S_ * sum((nb_ - kb - 1) * (nb_ - kb) // 2 for kb in range(nb_)) * 2.0 * 64 ** 3
-        refit = {"gplite_post_wall_ms": t_refit * 1e3, "S": S_, "N": N_, "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
+        refit = {"gplite_post_wall_ms": t_refit * 1e3, "S": S_, "N": N_,
+                 "end_to_end": {"tflops": S_ * N_ ** 3 / 3.0 / t_refit / 1e12, "frac_of_dmma_peak": S_ * N_ ** 3 / 3.0 / t_refit / 1e12 / 37.1,
+                                "what": "S*N^3/3 over the wall time of the whole gplite_post call (Gram, factorisation with look-ahead, "
+                                        "solves, host<->device copies of X, y, hyp, alpha)"},
+                 "kernels_ms_note": "per-kernel events are taken in the serial (no look-ahead) order",
+                 "kernels_ms": {k: round(v, 4) for k, v in kt.items()},
                  "potrf_update_dmma_tflops": upd_flops / (kt["potrf_update"] * 1e-3) / 1e12 if kt["potrf_update"] > 0 else None,
                  "chol_flops_N3_over_3_x_S": S_ * N_ ** 3 / 3.0}
         if refit["potrf_update_dmma_tflops"]:
@@ -499,6 +504,8 @@ def main():
     per_step_ms = []
     for i in range(args.steps):
         ctx.flush_l2()               # outside the timed events
+        if dist is not None:
+            barrier()                # ranks start each timed step together: a host hiccup on one rank is not billed to its peers' events
         v = resident_step(args.warmup + i)
         tot_ms += v
         per_step_ms.append(v)
