@@ -71,3 +71,21 @@ def test_closed_form_known_answers():
     assert abs(float(g["H"]) - float(g["closed_H"])) < 1e-12 * max(1.0, abs(float(g["closed_H"])))
     D = 4
     assert np.max(np.abs(g["dH"][:D] - g["closed_dH_mu"])) < 1e-13
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_vectors_against_binary128_truth(name, capsys):
+    """every committed vector (an FP64 oracle output, the exact inputs bench/matlab/dump_reference_vectors.m will
+    feed to the real reference) against the IEEE binary128 evaluation of the same formulas (oracle/c -DVBMC_ORACLE_QUAD).  The
+    entropy side must agree to round-off; the log-joint side to the FP64 noise floor of the case, which is printed: this is the
+    distance the MATLAB outputs themselves are expected to have from the truth."""
+    g, shape, w = load(name)
+    vp, gp, eps, Ns = w["vp"], w["gp"], w["epsilon"], shape["Ns"]
+    _, tb = orc.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    prep = cport.Prepared(vp, gp, tb)
+    F, dF, G, H, dH, Isk = cport.negelcbo(prep, g["theta"], Ns, eps, truth128=True)
+    e = dict(F=rel(g["F"], F), dF=rel(g["dF"], dF), G=rel(g["G"], G), H=rel(g["H"], H), dH=rel(g["dH"], dH), I_sk=rel(g["I_sk"], Isk))
+    with capsys.disabled():
+        print(f"\n[golden {name}] committed FP64 vector vs binary128 truth: " + ", ".join(f"{k} {v:.1e}" for k, v in e.items()))
+    assert e["H"] < 1e-13 and e["dH"] < 1e-12
+    assert max(e["F"], e["dF"], e["G"], e["I_sk"]) < 1e-8

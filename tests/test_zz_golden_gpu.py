@@ -17,7 +17,13 @@ def test_cuda_path_reproduces_golden(gpu_ctx, name):
     vp, gp, eps, Ns = w["vp"], w["gp"], w["epsilon"], shape["Ns"]
     _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
     F, dF, G, H, varF, dH = vbmc_b200.negelcbo_vbmc(g["theta"], 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=6)
-    assert rel(F, g["F"]) < 1e-10 and rel(dF, g["dF"]) < 1e-10 and rel(G, g["G"]) < 1e-10
+    # the gate is against the binary128 evaluation of the same inputs; the committed FP64 vector must then agree with the CUDA
+    # result to within ITS OWN distance from that truth (tests/test_golden.py prints it)
+    from oracle import cport
+    Ft, dFt, Gt, Ht, dHt, _ = cport.negelcbo(cport.Prepared(vp, gp, tb), g["theta"], Ns, eps, truth128=True)
+    assert max(rel(F, Ft), rel(dF, dFt), rel(G, Gt), rel(H, Ht), rel(dH, dHt)) < 1e-10
+    assert rel(F, g["F"]) < 1e-10 + 2 * rel(g["F"], Ft) and rel(dF, g["dF"]) < 1e-10 + 2 * rel(g["dF"], dFt)
+    assert rel(G, g["G"]) < 1e-10 + 2 * rel(g["G"], Gt)
     assert rel(H, g["H"]) < 1e-10 and rel(dH, g["dH"]) < 1e-10
     if name == "k1_closed_form_D4":
         assert abs(H - float(g["closed_H"])) < 1e-10 * max(1.0, abs(float(g["closed_H"])))

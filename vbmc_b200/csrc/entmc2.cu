@@ -18,6 +18,10 @@
 //  * The per-group sums of log q, M_d, E_d go through the same packed butterfly into ONE register per lane and pass;
 //    the W_jl sums are kept by owner lanes (k mod 32) in registers.  Nothing is written to shared memory per group
 //    except the stage itself.
+// Measured and NOT adopted (round 2): (a) software-pipelining the gradient sums of the previous component pair into the
+// exponentials of the current one: 0.272 vs 0.246 ms at c3; (b) a lane-pair variant -- two lanes per antithetic pair, each
+// owning half of the dimensions and one sign, 124 registers, 8-byte stage entries, 16 warps per CTA, parity-green: 0.306 vs
+// 0.255 ms (the extra shuffles and 8-byte table loads cost more issue slots than the doubled warp count hides).
 // Results are sums in a fixed order => bit-reproducible run to run.  DIRECT = true instantiates the reference's own
 // subtract-then-square formulation, which the device guard (vp_unpack_kernel) selects when ||u||^2 is so large that the
 // expanded form's cancellation error (~eps_mach * ||u||^2) could matter.  K <= 256 (vbmc.m:247: K <= N^(2/3) = 252 at N = 4000);
