@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_shard_range_matches_c_abi():
-    from vbmc_b200 import _lib, sharding
+    import _sharding as sharding
+    from vbmc_b200 import _lib
     lib = _lib.load()
     for total in (0, 1, 7, 20, 16384, 65536):
         for n in (1, 2, 3, 4, 8):
@@ -31,7 +32,8 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from oracle import vbmc_oracle as orc
-    from vbmc_b200 import sharding, workloads
+    import _sharding as sharding
+    from vbmc_b200 import workloads
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = dict(D=3, N=40, K=4, S=5, Ns=64, target="rosenbrock", noisy=False, log_sn=np.log(0.1))
