@@ -355,6 +355,11 @@ def quick_value(ctx, vbmc_b200, cfg_name, steps, warmup, dist, local, precision=
     try:
         for i in range(warmup + steps):
             ctx.flush_l2()
+            if dist is not None:   # ranks start each timed step together (their L2 flushes are outside everybody's events)
+                ctx.sync()
+                dist.barrier()
+                import torch
+                torch.cuda.synchronize()
             a.stream = 50_000 + i
             _lib.check(ctx.lib.vbmc_b200_negelcbo_resident_loop(ctx.handle, C.byref(a), 1, C.byref(ms)))
             if i >= warmup:
