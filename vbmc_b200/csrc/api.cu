@@ -150,9 +150,11 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->refit_graph) cudaGraphExecDestroy(c->refit_graph);
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
+  for (int i = 0; i < 2; ++i)
+    if (c->trsm_graph[i]) cudaGraphExecDestroy(c->trsm_graph[i]);
   vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->ent_partial2, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->zigTab, &c->entlbWork};
+                        &c->ent_partial, &c->ent_partial2, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->trsmWork, &c->gpXalt, &c->gpAlphaAlt, &c->zigTab, &c->entlbWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -354,8 +356,16 @@ int vbmc_b200_gp_attach(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, const doub
   c->gpHasL = false;
   c->gpLd = g->N;
   if (L) {
-    VB_TRY(c->gpL.reserve(S * N * N * sizeof(double)));
-    VB_CUDA(cudaMemcpyAsync(c->gpL.p, L, S * N * N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // same layout as the factors gp_post leaves behind: leading dimension Np = 64*ceil((N+1)/64), unit diagonal in the padding
+    // (the blocked solves of trsm.cu read whole 64 x 64 tiles in place)
+    const size_t Np = (N + 1 + 63) / 64 * 64;
+    VB_TRY(c->gpL.reserve(S * Np * Np * sizeof(double)));
+    VB_CUDA(cudaMemsetAsync(c->gpL.p, 0, S * Np * Np * sizeof(double), c->stream));
+    for (size_t s = 0; s < S; ++s)
+      VB_CUDA(cudaMemcpy2DAsync(c->gpL.d() + s * Np * Np, Np * sizeof(double), L + s * N * N, N * sizeof(double), N * sizeof(double), N,
+                                cudaMemcpyHostToDevice, c->stream));
+    VB_TRY(vb::pad_identity(c->gpL.d(), static_cast<int>(N), static_cast<int>(Np), static_cast<int>(S), c->stream));
+    c->gpLd = static_cast<int>(Np);
     c->gpHasL = true;
   }
   c->gpLchol.assign(S, 1);

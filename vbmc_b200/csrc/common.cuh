@@ -238,6 +238,10 @@ struct vbmc_b200_ctx {
   std::vector<double> gpHypHost;  // host copy of gp.post(s).hyp ([S][Nhyp]) for O(S) host epilogues
   int gp_noisefun[3] = {1, 0, 0};
   vb::DevBuf predWork;  // gplite_pred: test points, cross-kernel columns, results
+  vb::DevBuf trsmWork;  // blocked forward substitution: padded right-hand sides (trsm.cu)
+  cudaGraphExec_t trsm_graph[2] = {nullptr, nullptr};   // forward / backward sweep of trsm.cu
+  std::vector<long long> trsm_key[2];
+  vb::DevBuf gpXalt, gpAlphaAlt;   // ping-pong partners of gpX / gpAlpha for the rank-one update (no allocation per update)
   bool gpHasL = false;
   int gpLd = 0;  // leading dimension of the factors in gpL (N when attached from the host, Np after gp_post)
 
@@ -350,6 +354,8 @@ int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, 
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
 int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* isfac_dev, cudaStream_t st);
 int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st);
+bool run_trsm_blocked(vbmc_b200_ctx* c, int T, double* Z, const int* isfac_dev, cudaStream_t st, int* rc, bool backward = false);
+int pad_identity(double* L, int N, int Np, int S, cudaStream_t st);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);
 int entmc_pick_dp(int D);

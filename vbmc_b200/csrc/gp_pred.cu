@@ -8,6 +8,8 @@
 // Low-noise posteriors handed over as L = -inv(K+Sigma) use the symmetric product instead (:100-102).
 #include <math.h>
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace vb {
@@ -346,6 +348,7 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
       VB_CUDA(cudaMemcpy2DAsync(nb.d() + static_cast<size_t>(s) * ld2 * ld2, sizeof(double) * ld2,
                                 c->gpL.d() + static_cast<size_t>(s) * ld * ld, sizeof(double) * ld, sizeof(double) * N, N,
                                 cudaMemcpyDeviceToDevice, st));
+    VB_TRY(pad_identity(nb.d(), N, ld2, S, st));   // unit diagonal in the padding (trsm.cu reads whole tiles)
     VB_CUDA(cudaStreamSynchronize(st));
     c->gpL.release();
     c->gpL = nb;
@@ -357,9 +360,11 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
     VB_CUDA(cudaGetLastError());
   }
   VB_TRY(run_rhs_backsolve(c, 1, d_Z, st));                   // alpha_update (old N x N factor)
-  DevBuf na, nx;
-  VB_TRY(na.reserve(sizeof(double) * static_cast<size_t>(S) * N1));
-  VB_TRY(nx.reserve(sizeof(double) * static_cast<size_t>(D) * N1));
+  // the grown alpha / X go into the ping-pong partners of the resident buffers (reserved with room for 256 more points)
+  DevBuf& na = c->gpAlphaAlt;
+  DevBuf& nx = c->gpXalt;
+  if (na.cap < sizeof(double) * static_cast<size_t>(S) * N1) VB_TRY(na.reserve(sizeof(double) * static_cast<size_t>(S) * (N1 + 256)));
+  if (nx.cap < sizeof(double) * static_cast<size_t>(D) * N1) VB_TRY(nx.reserve(sizeof(double) * static_cast<size_t>(D) * (N1 + 256)));
   {
     KernelScope ks(c, "rank1", st);
     rank1_alpha_kernel<<<S, 256, 0, st>>>(N, c->gp.alpha, d_Z, d_par, na.d());
@@ -373,10 +378,8 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
                               sizeof(double) * N1, S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaStreamSynchronize(st));
   if (sW_out) memcpy(sW_out, sw.data(), sizeof(double) * S);
-  c->gpAlpha.release();
-  c->gpAlpha = na;
-  c->gpX.release();
-  c->gpX = nx;
+  std::swap(c->gpAlpha, c->gpAlphaAlt);
+  std::swap(c->gpX, c->gpXalt);
   c->gp.N = N1;
   c->gp.X = c->gpX.d();
   c->gp.alpha = c->gpAlpha.d();

@@ -9,6 +9,8 @@
 // memory, factor columns streamed coalesced from L2), var_gram_kernel (V'V), var_final_kernel (J_sjk, varF_s).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -443,7 +445,11 @@ int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* 
   a.L = c->gpL.d();
   a.gp = c->gp; a.vp = c->vp;
   a.Z = Z; a.W = W; a.isfac = isfac_dev; a.unit_rhs = 0;
-  {
+  static const bool blocked_off = getenv("VBMC_B200_TRSM_BLOCKED") && atoi(getenv("VBMC_B200_TRSM_BLOCKED")) == 0;
+  int rc = VBMC_B200_OK;
+  if (!blocked_off && run_trsm_blocked(c, ncols, Z, isfac_dev, st, &rc)) {
+    VB_TRY(rc);   // blocked DMMA forward substitution (trsm.cu)
+  } else {
     KernelScope ks(c, "pred_trsm", st);
     VB_TRY(launch_var_kernel(c, VK_FWD, a, ncols, S, 64 * 65, 64, st, "gplite_pred"));
   }
@@ -463,6 +469,9 @@ int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st) {
   a.L = c->gpL.d();
   a.gp = c->gp; a.vp = c->vp;
   a.Z = Z;
+  static const bool blocked_off = getenv("VBMC_B200_TRSM_BLOCKED") && atoi(getenv("VBMC_B200_TRSM_BLOCKED")) == 0;
+  int rc = VBMC_B200_OK;
+  if (!blocked_off && run_trsm_blocked(c, ncols, Z, nullptr, st, &rc, true)) return rc;
   KernelScope ks(c, "pred_trsm", st);
   return launch_var_kernel(c, VK_BWD, a, ncols, c->gp.S, 64 * 65, 0, st, "gplite_post");
 }
