@@ -192,9 +192,11 @@ def test_exp_underflow_matches_reference_semantics(gpu_ctx):
     assert np.isfinite(H) and rel(H, Ho) < TOL and rel(dH, dHo) < TOL
 
 
-def test_direct_formulation_forced_matches_oracle():
+@pytest.mark.parametrize("switch", [("VBMC_B200_ENTMC_FORM", "direct"), ("VBMC_B200_ENTMC_TMEM", "1")], ids=["direct", "tmem_stage"])
+def test_direct_formulation_forced_matches_oracle(switch):
     """VBMC_B200_ENTMC_FORM=direct runs the subtract-then-square instantiation (normally only selected by the device guard for
-    huge ||u||^2) on ordinary shapes; the switch is read at context creation, hence the subprocess."""
+    huge ||u||^2) on ordinary shapes; VBMC_B200_ENTMC_TMEM=1 the opt-in variant that parks e(+-) in tensor memory.  The switches
+    are read once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
@@ -213,7 +215,8 @@ for shape in (dict(D=2, N=50, K=2, S=8, Ns=100), dict(D=5, N=60, K=7, S=2, Ns=20
     assert rel(H, Ho) < 1e-10 and rel(dH, dHo) < 1e-10, (shape, rel(H, Ho), rel(dH, dHo))
 print("OK")
 '''
-    env = dict(os.environ, VBMC_B200_ENTMC_FORM="direct", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env[switch[0]] = switch[1]
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
