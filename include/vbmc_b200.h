@@ -144,11 +144,17 @@ int vbmc_b200_gp_pred(vbmc_b200_ctx* ctx, int Nstar, const double* Xstar, const 
 int vbmc_b200_gp_set_sn2_mult(vbmc_b200_ctx* ctx, const double* sn2_mult);
 
 /* gp = gplite_post(gp,xstar,ystar,[],[],[],[],1) — the rank-one update of gplite/gplite_post.m:50-92,173-251 applied to the
- * resident posterior (Cholesky branch; constant or output-dependent noise, no s2: with s2 the reference itself refits).
- * xstar: D values.  Optional outputs: alpha (N+1) x S, the new factor column (N+1) x S (L_new = [L c; 0 d]), sW_new S.
+ * resident posterior (constant or output-dependent noise, no s2: with s2 the reference itself refits).
+ * xstar: D values.  Optional outputs: alpha (N+1) x S, sW_new S, and Lcol (N+1) x S = the last column of the new
+ * gp.post(s).L for the Cholesky samples (:226-233, L_new = [L c; 0 d]).  Low-noise samples (Lchol == 0, :234-238) change
+ * every entry of L = -inv(K + diag): fetch those with vbmc_b200_gp_get_factor; their Lcol is the new column of whatever the device
+ * keeps (the inverse handed over by gp_attach, or the unscaled factor a device refit left).
  * The context's GP then has N+1 training points (private/activesample_vbmc.m:483 calls this once per acquired point). */
 int vbmc_b200_gp_post_update1(vbmc_b200_ctx* ctx, const double* xstar, double ystar, double* alpha, double* Lcol,
                               double* sW_new);
+/* gp.post(s).L of the resident posterior as the reference stores it (gplite/private/gplite_core.m:67-100): the upper Cholesky
+ * factor, or -inv(K + sn2_mult*diag(sn2)) for a low-noise sample.  L: N x N column-major, N = the resident point count. */
+int vbmc_b200_gp_get_factor(vbmc_b200_ctx* ctx, int s, double* L);
 
 /* Hyper-prior of gplite_nlZ (gplite/gplite_hypprior.m:18-58); arrays of length Nhyp. */
 typedef struct vbmc_b200_hprior {
@@ -247,8 +253,9 @@ int vbmc_b200_negelcbo(vbmc_b200_ctx* ctx, const vbmc_b200_negelcbo_args* args);
  * misc/vpoptimize_vbmc.m:71 builds and passes at :127.  The iterate, the Adam moments and
  * the histories stay on the device: one call = one whole stochastic optimisation, no per-iteration host copies;
  * the host only reads the termination flag every 20 iterations (:65-83).
- * vp / gp / thetabnd are the ones last set on the context.  beta must be 0 (VBMC's default ELCBOWeight = 0; the
- * variance gradient needs a host assembly): otherwise EUNSUPPORTED and the caller keeps the per-step path.
+ * vp / gp / thetabnd are the ones last set on the context.  With beta ~= 0 (compute_var must be 2, negelcbo_vbmc.m:19-20; the
+ * factors gp.post(s).L must be resident) every iteration also runs the variance path and its O(S K^2) host assembly
+ * (negelcbo_vbmc.m:119-130): the loop is then host-driven with one synchronisation per iteration instead of a replayed graph.
  * ------------------------------------------------------------------------------------- */
 typedef struct vbmc_b200_fminadam_args {
   /* inputs */
@@ -261,7 +268,7 @@ typedef struct vbmc_b200_fminadam_args {
   double stepsize_max, stepsize_min, stepsize_decay; /* <= 0 or NaN => 0.1, 0.001, 200 (fminadam.m:11-18) */
   double beta;            /* objective arguments, as vbmc_b200_negelcbo_args                            */
   int Ns;
-  int compute_var;        /* accepted; has no effect on F, dF when beta == 0                            */
+  int compute_var;        /* no effect on F, dF when beta == 0; must be 2 (diagonal) when beta ~= 0     */
   int use_thetabnd;
   int eps_mode;           /* EPS_HOST / EPS_RESIDENT: the same draws every iteration (parity mode);
                              EPS_PHILOX: iteration i (0-based) draws from Philox stream `stream + i`     */

@@ -3,8 +3,8 @@
 // == fminadam(@(t) negelcbo_vbmc(t,beta,vp,gp,Ns,1,compute_var,altent,thetabnd,entropy_alpha), theta0, LB, UB, TolFun,
 //             MaxIter, master_stepsize)                                                         (utils/fminadam.m:1-102)
 // fminadam receives a function handle, which cannot be evaluated on the device, so the integration point is the call
-// site.  beta ~= 0 is answered with vbmc_b200:OutOfScope: the caller falls through to the
-// unchanged fminadam + per-step negelcbo_vbmc gateway.
+// site.  beta ~= 0 (compute_var == 2) runs the variance-penalised objective of negelcbo_vbmc.m:119-130
+// every iteration; the factors gp.post(s).L are attached for it.
 // Build: mex -R2018a mex/fminadam_negelcbo_mex.cpp -Iinclude -Lvbmc_b200/lib -lvbmc_b200 -output utils/fminadam_negelcbo_mex
 #include "vbmc_b200_mex_common.h"
 
@@ -14,7 +14,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   vbmc_b200_ctx* c = context();
   VpHold vh;
   vp_set(c, prhs[2], &vh);
-  gp_attach(c, prhs[3], false);
+  const int cvar = given(nrhs, prhs, 5) ? (int)mxGetScalar(prhs[5]) : 0;
+  gp_attach(c, prhs[3], /*want_L=*/cvar != 0);
   const mxArray* tb = given(nrhs, prhs, 6) ? prhs[6] : nullptr;
   thetabnd_set(c, tb);
   const int n = (int)mxGetNumberOfElements(prhs[0]);
@@ -24,7 +25,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   a.nvars = n;
   a.beta = mxIsEmpty(prhs[1]) ? 0.0 : mxGetScalar(prhs[1]);
   a.Ns = (int)mxGetScalar(prhs[4]);
-  a.compute_var = given(nrhs, prhs, 5) ? (int)mxGetScalar(prhs[5]) : 0;
+  a.compute_var = cvar;
   a.use_thetabnd = tb != nullptr;
   if (given(nrhs, prhs, 7)) {
     if ((int)mxGetNumberOfElements(prhs[7]) != n) mexErrMsgIdAndTxt("fminadam:bounds", "LB must have numel(x0) entries.");

@@ -73,15 +73,21 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
       memcpy(mxGetDoubles(sW), dbl(post_in, s, "sW"), sizeof(double) * N);
       mxGetDoubles(sW)[N] = sWn[s];                                     // [sW; 1/sqrt(sn2_eff)]   (gplite_post.m:238)
       mxSetFieldByNumber(plhs[0], s, 2, sW);
-      mxArray* Ls = mxCreateDoubleMatrix(N + 1, N + 1, mxREAL);         // [L, c; 0, d]            (gplite_post.m:228-230)
+      mxArray* Ls = mxCreateDoubleMatrix(N + 1, N + 1, mxREAL);
       double* Ld = mxGetDoubles(Ls);
-      const double* Lo = dbl(post_in, s, "L");
-      for (size_t j = 0; j < N; ++j) memcpy(Ld + j * (N + 1), Lo + j * N, sizeof(double) * N);   // last row stays 0
-      memcpy(Ld + N * (N + 1), &col[s * (N + 1)], sizeof(double) * (N + 1));
+      const mxArray* lc = mxGetField(post_in, s, "Lchol");
+      const bool is_chol = !lc || mxGetScalar(lc) != 0;   // mxGetScalar reads logicals as 0/1
+      if (is_chol) {                                                    // [L, c; 0, d]            (gplite_post.m:228-230)
+        const double* Lo = dbl(post_in, s, "L");
+        for (size_t j = 0; j < N; ++j) memcpy(Ld + j * (N + 1), Lo + j * N, sizeof(double) * N);   // last row stays 0
+        memcpy(Ld + N * (N + 1), &col[s * (N + 1)], sizeof(double) * (N + 1));
+      } else {                                                          // [L + v*a', -v; -v', -1/vstar]  (:234-238)
+        check(vbmc_b200_gp_get_factor(c, s, Ld));
+      }
       mxSetFieldByNumber(plhs[0], s, 3, Ls);
       const double* m = dbl(post_in, s, "sn2_mult");
       mxSetFieldByNumber(plhs[0], s, 4, mxCreateDoubleScalar(m ? m[0] : 1.0));
-      mxSetFieldByNumber(plhs[0], s, 5, mxCreateLogicalScalar(true));
+      mxSetFieldByNumber(plhs[0], s, 5, mxCreateLogicalScalar(is_chol));
     }
   }
   // the device holds exactly this posterior, factors included: tag it with the address MATLAB will hand back

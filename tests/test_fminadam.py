@@ -92,6 +92,28 @@ def test_device_fminadam_matches_oracle_loop(gpu_ctx, shape, maxiter):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("beta", [1.5, -0.7])
+def test_device_fminadam_with_variance_penalty(gpu_ctx, beta):
+    """beta ~= 0 (ELCBOWeight, negelcbo_vbmc.m:119-130): F + beta*sqrt(varF) with the diagonal variance and its gradient, every
+    iteration; the loop is host-driven then (one synchronisation per iteration), all N-long work stays on the device."""
+    import vbmc_b200
+    shape, maxiter = dict(D=4, N=60, K=6, S=3, Ns=64), 45
+    w = _mk(**shape)
+    vp, gp, theta0, eps, Ns = w["vp"], w["gp"], w["theta"], w["epsilon"], shape["Ns"]
+    _, tb = vbmc_b200.vpbounds(vp, gp, workloads.VP_OPTIONS)
+    ms = {"max": 0.02, "min": 0.001, "decay": 200}
+    fun = lambda t: orc.negelcbo_vbmc(t, beta, vp, gp, Ns, 1, 2, 0, tb, 0, epsilon=eps, nargout=2)[:2]
+    xo, fo, xtabo, ftabo, ito = orc.fminadam(fun, theta0, None, None, 0.001, maxiter, ms)
+    x, f, xtab, ftab, it = vbmc_b200.fminadam_negelcbo(theta0, beta, vp, gp, Ns, 2, tb, None, None, 0.001, maxiter, ms, epsilon=eps)
+    assert it == ito
+    assert rel(ftab[0], ftabo[0]) < 1e-10 and rel(xtab[:3], xtabo.T[:3]) < 1e-9
+    assert rel(ftab, ftabo) < 1e-8 and rel(xtab, xtabo.T) < 1e-8 and rel(x, xo) < 1e-8 and rel(f, fo) < 1e-8
+    # and it is not the unpenalised path
+    f0 = orc.negelcbo_vbmc(theta0, 0.0, vp, gp, Ns, 1, 0, 0, tb, 0, epsilon=eps, nargout=2)[0]
+    assert abs(ftab[0] - f0) > 1e-6 * abs(f0)
+
+
+@pytest.mark.gpu
 def test_device_fminadam_terminates_like_reference(gpu_ctx):
     """Large TolFun: the slope test passes at iteration 40 in both implementations (fminadam.m:65-83)."""
     import vbmc_b200
@@ -137,9 +159,9 @@ def test_device_fminadam_errors(gpu_ctx):
     import vbmc_b200
     w = _mk(D=2, N=30, K=2, S=2, Ns=32)
     vp, gp, theta0, eps = w["vp"], w["gp"], w["theta"], w["epsilon"]
-    with pytest.raises(vbmc_b200.VbmcB200Error) as e:
-        vbmc_b200.fminadam_negelcbo(theta0, 1.5, vp, gp, 32, 2, None, epsilon=eps)
-    assert e.value.identifier == "vbmc_b200:OutOfScope"
+    with pytest.raises(vbmc_b200.VbmcB200Error) as e:   # negelcbo_vbmc.m:19-20: the gradient of the full variance does not exist
+        vbmc_b200.fminadam_negelcbo(theta0, 1.5, vp, gp, 32, 1, None, epsilon=eps)
+    assert e.value.identifier == "negelcbo_vbmc:vargrad"
     with pytest.raises(vbmc_b200.VbmcB200Error):
         vbmc_b200.fminadam_negelcbo(theta0, 0.0, vp, gp, 32, 0, None, MaxIter=10, epsilon=eps)
     with pytest.raises(vbmc_b200.VbmcB200Error):

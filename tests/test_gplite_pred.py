@@ -174,6 +174,43 @@ def test_rank1_update_matches_oracle(gpu_ctx, resident):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("resident", [True, False], ids=["device_factor", "inverse_from_host"])
+def test_rank1_update_of_a_low_noise_posterior(gpu_ctx, resident):
+    """gplite_post.m:234-238: sample 0 has sn2 < 1e-6, so post.L = -inv(K + sn2*I) and the update touches every entry of it; the
+    other samples take the Cholesky branch in the same call.  After a device refit the low-noise sample lives as an unscaled
+    factor (bordered-factor update, inverse rebuilt on request); attached from the host it lives as the inverse itself."""
+    import vbmc_b200
+    w = _mk(4, 70, 3, log_sn=math.log(0.05))
+    X, y, hyp = w["X"], w["y"], w["hyp"].copy()
+    hyp[5, 0] = math.log(3e-4)
+    n0 = 62
+    ref = orc.gplite_post(hyp, X[:n0], y[:n0], 1, 4, [1, 0, 0], None)
+    assert [p["Lchol"] for p in ref["post"]] == [False, True, True]
+    gp = vbmc_b200.gplite_post(hyp, X[:n0], y[:n0], 1, 4, [1, 0, 0], None, want_L=True) if resident else ref
+    assert [p["Lchol"] for p in gp["post"]] == [False, True, True] and gp["post"][0]["sn2_mult"] == ref["post"][0]["sn2_mult"]
+    ell, sf2, sn2 = np.exp(hyp[:4, 0]), math.exp(2 * hyp[4, 0]), math.exp(2 * hyp[5, 0])
+    for i in range(n0, 70):
+        gp = vbmc_b200.gplite_post_update1(gp, X[i], y[i])
+        ref = orc.gplite_post_update1(ref, X[i], y[i])
+        n = i + 1
+        A = sf2 * np.exp(-0.5 * orc.sq_dist((X[:n] / ell).T)) + sn2 * np.eye(n)
+        bound = 50 * np.linalg.cond(A) * np.finfo(float).eps
+        a, b = gp["post"][0], ref["post"][0]
+        assert a["L"].shape == (n, n) and not a["Lchol"]
+        # it IS the negated inverse of the bordered matrix (the inverse-form recursion accumulates round-off in the oracle too)
+        assert np.max(np.abs(a["L"] @ A + np.eye(n))) < max(bound, 2 * np.max(np.abs(b["L"] @ A + np.eye(n))))
+        assert rel(a["L"], b["L"]) < bound and rel(a["alpha"], b["alpha"]) < bound
+        assert rel(a["sW"], b["sW"]) < 1e-13
+        for s in (1, 2):
+            assert rel(gp["post"][s]["alpha"], ref["post"][s]["alpha"]) < 1e-8
+            assert rel(gp["post"][s]["L"], ref["post"][s]["L"]) < 1e-10
+    Xs = np.random.default_rng(2).standard_normal((5, 4))
+    got = vbmc_b200.gplite_pred(gp, Xs, None, None, True, nargout=4)
+    exp = orc.gplite_pred(ref, Xs, None, None, True, nargout=4)
+    assert rel(got[2], exp[2]) < 1e-6 and np.max(np.abs(got[3] - exp[3])) / sf2 < 1e-6
+
+
+@pytest.mark.gpu
 def test_rank1_update_with_s2_falls_back_to_refit(gpu_ctx):
     import vbmc_b200
     w = _mk(3, 40, 2, noisy=True)

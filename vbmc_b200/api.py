@@ -584,7 +584,7 @@ def fminadam_negelcbo(x0, beta, vp, gp, Ns, compute_var=0, thetabnd=None, LB=Non
     ctx = ctx or default_context()
     x0 = f64(x0).ravel()
     ctx.vp_set(vp)
-    ctx.gp_attach(gp, want_L=False)
+    ctx.gp_attach(gp, want_L=bool(compute_var))   # the variance path needs the factors gp.post(s).L on the device
     ctx.thetabnd_set(thetabnd)
     a = _lib.FminadamArgs()
     a.x0, a.nvars = dptr(x0), x0.size
@@ -772,7 +772,12 @@ def gplite_post_update1(gp, xstar, ystar, s2star=None, *, ctx=None):
         q = dict(p)
         q["alpha"] = alpha[s].copy()
         q["sW"] = np.append(np.ravel(p["sW"]), sWn[s])
-        if have_L:
+        if have_L and not p.get("Lchol", True):
+            # low noise (:234-238): every entry of L = -inv(K + diag) changes; the device hands the new matrix over (symmetric)
+            Ln = np.zeros((N + 1, N + 1))
+            _lib.check(ctx.lib.vbmc_b200_gp_get_factor(ctx.handle, s, dptr(Ln)))
+            q["L"] = Ln.T.copy()   # column-major on the wire
+        elif have_L:
             Ln = np.zeros((N + 1, N + 1))
             Ln[:N, :N] = p["L"]
             Ln[:, N] = Lcol[s]

@@ -107,6 +107,20 @@ __global__ void __launch_bounds__(256) adam_final_kernel(const AdamArgs a, int i
   }
 }
 
+// F += corr[0], dF += corr[1..n]: the variance penalty of negelcbo_vbmc.m:119-130 folded into the step's outputs before the
+// Adam update reads them (beta ~= 0 only)
+__global__ void adam_penalty_kernel(int n, const double* corr, double* fval, double* grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *fval += corr[0];
+  if (i < n) grad[i] += corr[1 + i];
+}
+int launch_adam_penalty(vbmc_b200_ctx* c, const AdamArgs& a, const double* corr, cudaStream_t st) {
+  KernelScope ks(c, "adam", st);
+  adam_penalty_kernel<<<(a.n + 255) / 256, 256, 0, st>>>(a.n, corr, const_cast<double*>(a.fval), const_cast<double*>(a.grad));
+  VB_CUDA(cudaGetLastError());
+  return VBMC_B200_OK;
+}
+
 int launch_adam_step(vbmc_b200_ctx* c, const AdamArgs& a, cudaStream_t st) {
   KernelScope ks(c, "adam", st);
   adam_step_kernel<<<1, 256, 0, st>>>(a);

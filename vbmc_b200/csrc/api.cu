@@ -1110,10 +1110,10 @@ static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   double beta;
   int Ns, gmask;
   VB_TRY(negelcbo_validate(c, &na, &beta, &Ns, &gmask));
-  if (beta != 0.0)
-    VB_FAIL(VBMC_B200_EUNSUPPORTED,
-            "vbmc_b200:OutOfScope: the device-resident fminadam loop supports beta == 0 only (ELCBOWeight default); "
-            "use negelcbo_vbmc per step for the variance-penalised objective");
+  // beta ~= 0 (ELCBOWeight, negelcbo_vbmc.m:119-130): every iteration also runs the variance path (triangular solves + Gram on the
+  // device, O(S K^2) assembly on the host) and folds beta*sqrt(varG) and its gradient into F, dF before the Adam update: the loop
+  // is then driven from the host, one synchronisation per iteration, instead of replaying a graph.
+  const bool penalised = beta != 0.0;
   const double TolFun = (f->TolFun > 0.0) ? f->TolFun : 0.001;        // fminadam.m:6 (NaN compares false)
   const int MaxIter = f->MaxIter > 0 ? f->MaxIter : 10000;            // :7
   const int B = 20;                                                   // batchsize (:24)
@@ -1128,8 +1128,8 @@ static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   ol.init(nth, c->gp.S, c->K);
   VB_TRY(c->out_dev.reserve(sizeof(double) * ol.total));
   VB_TRY(ensure_pinned(&c->out_pinned, &c->out_pinned_cap, sizeof(double) * (ol.total > 16 ? ol.total : 16)));
-  // state: m | v | lb | ub | xout | stats[8] | it (8 bytes) | ftab[MaxIter]
-  const size_t nstate = 5 * static_cast<size_t>(n) + 8 + 1 + MaxIter;
+  // state: m | v | lb | ub | xout | stats[8] | it (8 bytes) | ftab[MaxIter] | corr[1 + n]
+  const size_t nstate = 5 * static_cast<size_t>(n) + 8 + 1 + MaxIter + 1 + n;
   VB_TRY(c->adamState.reserve(sizeof(double) * nstate));
   VB_TRY(c->adamXtab.reserve(sizeof(double) * static_cast<size_t>(n) * MaxIter));
   double* sb = c->adamState.d();
@@ -1150,6 +1150,8 @@ static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
   aa.it = reinterpret_cast<int*>(aa.stats + 8);
   aa.ftab = aa.stats + 9;
   aa.xtab = c->adamXtab.d();
+  double* d_corr = aa.ftab + MaxIter;
+  std::vector<double> corr_h(penalised ? 1 + static_cast<size_t>(n) : 0);
   const bool philox = f->eps_mode == VBMC_B200_EPS_PHILOX;
   aa.dyn = philox ? reinterpret_cast<unsigned long long*>(c->theta_dev.d() + n) : nullptr;
 
@@ -1192,6 +1194,18 @@ static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
     c->philox_dyn = false;
     c->philox_trail = false;
     VB_TRY(rc);
+    if (penalised) {
+      VB_TRY(fetch_out(c, nth, c->gp.S));   // Fs of this iterate (and a synchronisation: vp.cur is this iterate's)
+      std::vector<double> vF, J, vg, dvar;
+      VB_TRY(run_variance(c, na.compute_var, &vF, &J, &vg));
+      double varG, varGss;
+      combine_variance(c->out_pinned + ol.oFs, vF, c->gp.S, &varG, &varGss);
+      VB_TRY(assemble_vargrad(c, gmask, 1, vF, J, vg, c->out_pinned + ol.oFs, &dvar));
+      corr_h[0] = beta * sqrt(varG);                                                    // F = F + beta*sqrt(varF)   (:125)
+      for (int i = 0; i < n; ++i) corr_h[1 + i] = 0.5 * beta * dvar[i] / sqrt(varG);    // dF = dF + 0.5*beta*dvarF/sqrt(varF)  (:128-130)
+      VB_CUDA(cudaMemcpyAsync(d_corr, corr_h.data(), sizeof(double) * corr_h.size(), cudaMemcpyHostToDevice, c->stream));
+      VB_TRY(launch_adam_penalty(c, aa, d_corr, c->stream));
+    }
     VB_TRY(launch_adam_step(c, aa, c->stream));
     VB_TRY(join_trail(c));
     return VBMC_B200_OK;
@@ -1207,7 +1221,7 @@ static int fminadam_impl(vbmc_b200_ctx* c, const vbmc_b200_fminadam_args* f) {
     key.push_back(MaxIter);
     return key;
   };
-  bool use_graph = c->graphs_enabled && !c->profiling && !step_uses_nccl(c);
+  bool use_graph = c->graphs_enabled && !c->profiling && !step_uses_nccl(c) && !penalised;
   double* stats_h = c->out_pinned;  // the pinned output mirror doubles as the read-back slot of the termination test
   int it = 0;
   while (it < MaxIter) {

@@ -347,13 +347,14 @@ int launch_philox(vbmc_b200_ctx* c, int D, int K, int Ns, uint64_t seed, uint64_
 int allreduce_R(vbmc_b200_ctx* c, int count, cudaStream_t st);
 int run_entlb(vbmc_b200_ctx* c, int gmask, int jacobian, double* H, double* dH);
 int launch_adam_step(vbmc_b200_ctx* c, const AdamArgs& a, cudaStream_t st);
+int launch_adam_penalty(vbmc_b200_ctx* c, const AdamArgs& a, const double* corr, cudaStream_t st);
 int launch_adam_check(vbmc_b200_ctx* c, const AdamArgs& a, int iter, double TolFun, cudaStream_t st);
 int launch_adam_final(vbmc_b200_ctx* c, const AdamArgs& a, int iter, cudaStream_t st);
 void comm_destroy(vbmc_b200_ctx* c);
 int run_variance(vbmc_b200_ctx* c, int compute_var, std::vector<double>* varFs, std::vector<double>* J, std::vector<double>* vgrad = nullptr);
 int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double* out);
 int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* isfac_dev, cudaStream_t st);
-int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st);
+int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st, const int* isfac_dev = nullptr);
 bool run_trsm_blocked(vbmc_b200_ctx* c, int T, double* Z, const int* isfac_dev, cudaStream_t st, int* rc, bool backward = false);
 int pad_identity(double* L, int N, int Np, int S, cudaStream_t st);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);

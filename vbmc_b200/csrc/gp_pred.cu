@@ -105,16 +105,19 @@ __global__ void __launch_bounds__(256) pred_var_kernel(const PredArgs a) {
 }
 
 
-// ---- rank-one update of the posterior (gplite_post.m:173-251, Cholesky branch) ----
-// par[s] = {gamma = (mstar - ystar)/vstar, colscale = sqrt(sn2_eff_old)/sn2_eff_new, diagadd = 1 + K/sn2_eff_new}
-// new_L_column = (L'\Ks)/sn2_eff (:229-230) is the forward-substitution result V = L'\(sW.*Ks) rescaled;
-// L(N+1,N+1) = sqrt(1 + K/sn2_eff - c'c) (:231-233).  grid (S), 256 threads.
-__global__ void __launch_bounds__(256) rank1_column_kernel(int N, int ld, double* L, double* Z, const double* par) {
+// ---- rank-one update of the posterior (gplite_post.m:173-251) ----
+// par[s] = {gamma = (mstar - ystar)/vstar, colscale, diagadd, 1/vstar}
+// Device factor (Cholesky branch :226-233, and the low-noise samples a device refit keeps as R'R = K + sn2_mult*sn2*I):
+// new_L_column = (L'\Ks)/sn2_eff (:229-230) is the forward-substitution result V = L'\(sW.*Ks) rescaled by
+// colscale = sqrt(sn2_eff_old)/sn2_eff_new (1 for the unscaled low-noise factor); L(N+1,N+1) = sqrt(diagadd - c'c) with
+// diagadd = 1 + K/sn2_eff (:231-233), respectively K + sn2_eff.  grid (S), 256 threads; inverse-form samples are skipped.
+__global__ void __launch_bounds__(256) rank1_column_kernel(int N, int ld, double* L, double* Z, const double* par, const int* isfac) {
   __shared__ double part[8];
   const int s = blockIdx.x, tid = threadIdx.x;
+  if (!isfac[s]) return;
   double* z = Z + static_cast<size_t>(s) * N;
   double* col = L + static_cast<size_t>(s) * ld * ld + static_cast<size_t>(N) * ld;
-  const double cs = par[3 * s + 1];
+  const double cs = par[4 * s + 1];
   double acc = 0.0;
   for (int n = tid; n < N; n += 256) {
     const double cv = z[n] * cs;
@@ -123,16 +126,33 @@ __global__ void __launch_bounds__(256) rank1_column_kernel(int N, int ld, double
     acc = fma(cv, cv, acc);
   }
   acc = block_sum_256(acc, part);
-  if (tid == 0) col[N] = sqrt(par[3 * s + 2] - acc);
+  if (tid == 0) col[N] = sqrt(par[4 * s + 2] - acc);
+}
+
+// Low-noise posterior in inverse form, L = -inv(K + diag) handed over by gp_attach (:234-238): with a = -L*Ks (= W of
+// var_symv_kernel) and v = -a/vstar,  L <- [L + v a', -v; -v', -1/vstar].  grid (ceil((N+1)/256), N+1, S).
+__global__ void __launch_bounds__(256) rank1_inverse_kernel(int N, int ld, double* L, const double* W, const double* par, const int* isfac) {
+  const int s = blockIdx.z, j = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (isfac[s] || i > N) return;
+  const double* w = W + static_cast<size_t>(s) * N;
+  const double iv = par[4 * s + 3];
+  double* e = L + static_cast<size_t>(s) * ld * ld + static_cast<size_t>(j) * ld + i;
+  if (i < N && j < N)
+    *e = fma(-w[i] * iv, w[j], *e);
+  else if (i == N && j == N)
+    *e = -iv;
+  else
+    *e = w[i < N ? i : j] * iv;   // -v = a/vstar
 }
 
 // alpha = [alpha; 0] + (mstar - ystar)/vstar * [alpha_update; -1]   (:245-247); grid (S)
-__global__ void __launch_bounds__(256) rank1_alpha_kernel(int N, const double* alpha_old, const double* W, const double* par,
-                                                          double* alpha_new) {
+// alpha_update = L\(L'\Ks)/sn2_eff in Z (factor samples) or -L*Ks in Winv (inverse-form samples)
+__global__ void __launch_bounds__(256) rank1_alpha_kernel(int N, const double* alpha_old, const double* Z, const double* Winv,
+                                                          const int* isfac, const double* par, double* alpha_new) {
   const int s = blockIdx.x;
-  const double g = par[3 * s];
+  const double g = par[4 * s];
   const double* ao = alpha_old + static_cast<size_t>(s) * N;
-  const double* w = W + static_cast<size_t>(s) * N;
+  const double* w = (isfac[s] ? Z : Winv) + static_cast<size_t>(s) * N;
   double* an = alpha_new + static_cast<size_t>(s) * (N + 1);
   for (int n = threadIdx.x; n < N; n += 256) an[n] = fma(g, w[n], ao[n]);
   if (threadIdx.x == 0) an[N] = -g;
@@ -282,39 +302,39 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
   if (c->gp_noisefun[1] != 0)
     VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:FullUpdate: rank-one updates are not defined for heteroskedastic noise (gplite_post.m:78-81): refit with gplite_post");
   const int N = c->gp.N, D = c->gp.D, S = c->gp.S;
-  for (int s = 0; s < S; ++s)
-    if (!c->gpLchol[s] || !c->gpLfactor[s])
-      VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:OutOfScope: rank-one update of a low-noise (Lchol == 0) posterior; refit with gplite_post");
+  bool any_inv = false;
+  for (int s = 0; s < S; ++s) any_inv = any_inv || !c->gpLfactor[s];
   VB_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   // ---- [mstar,vstar] = gplite_pred(gp,xstar,y,s2,1,1)  (:191) ----
-  const size_t nhead = static_cast<size_t>(D) + 2 * S + (static_cast<size_t>(S) + 1) / 2 + 3 * static_cast<size_t>(S);
-  VB_TRY(c->predWork.reserve(sizeof(double) * (nhead + static_cast<size_t>(S) * N)));
+  const size_t nhead = static_cast<size_t>(D) + 2 * S + (static_cast<size_t>(S) + 1) / 2 + 4 * static_cast<size_t>(S);
+  VB_TRY(c->predWork.reserve(sizeof(double) * (nhead + (any_inv ? 2 : 1) * static_cast<size_t>(S) * N)));
   double* d_xs = c->predWork.d();
   double* d_fmu = d_xs + D;
   double* d_fs2 = d_fmu + S;
   int* d_isfac = reinterpret_cast<int*>(d_fs2 + S);
   double* d_par = d_fs2 + S + (static_cast<size_t>(S) + 1) / 2;
-  double* d_Z = d_par + 3 * static_cast<size_t>(S);
+  double* d_Z = d_par + 4 * static_cast<size_t>(S);
+  double* d_W = any_inv ? d_Z + static_cast<size_t>(S) * N : nullptr;   // -L*Ks of the inverse-form samples
   VB_CUDA(cudaMemcpyAsync(d_isfac, c->gpLfactor.data(), sizeof(int) * S, cudaMemcpyHostToDevice, st));
   VB_CUDA(cudaMemcpyAsync(d_xs, xstar, sizeof(double) * D, cudaMemcpyHostToDevice, st));
   PredArgs a;
   a.N = N; a.D = D; a.S = S; a.T = 1;
   a.meanfun = c->gp.meanfun; a.Ncov = c->gp.Ncov; a.Nnoise = c->gp.Nnoise; a.Nhyp = c->gp.Nhyp;
   a.X = c->gp.X; a.Xs = d_xs; a.hyp = c->gp.hyp; a.alpha = c->gp.alpha; a.sn2eff = c->gp.sn2eff;
-  a.isfac = d_isfac; a.Z = d_Z; a.W = nullptr; a.fmu = d_fmu; a.fs2 = d_fs2;
+  a.isfac = d_isfac; a.Z = d_Z; a.W = d_W; a.fmu = d_fmu; a.fs2 = d_fs2;
   {
     KernelScope ks(c, "pred_cross", st);
     pred_cross_kernel<<<dim3(1, S), 256, 0, st>>>(a);
     VB_CUDA(cudaGetLastError());
   }
-  VB_TRY(run_rhs_solve(c, 1, d_Z, nullptr, d_isfac, st));
+  VB_TRY(run_rhs_solve(c, 1, d_Z, d_W, d_isfac, st));
   {
     KernelScope ks(c, "pred_var", st);
     pred_var_kernel<<<dim3(1, S), 256, 0, st>>>(a);
     VB_CUDA(cudaGetLastError());
   }
-  std::vector<double> hf(S), hv(S), par(3 * static_cast<size_t>(S)), sw(S);
+  std::vector<double> hf(S), hv(S), par(4 * static_cast<size_t>(S)), sw(S);
   VB_CUDA(cudaMemcpyAsync(hf.data(), d_fmu, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaMemcpyAsync(hv.data(), d_fs2, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaStreamSynchronize(st));
@@ -330,9 +350,15 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
     }
     const double sn2_eff = sn2 * c->gpSn2mult[s];             // gplite_post.m:209
     const double vstar = hv[s] + sn2 * c->gpSn2mult[s];       // ys2 of gplite_pred (:119)
-    par[3 * s] = (hf[s] - ystar) / vstar;                     // :247
-    par[3 * s + 1] = sqrt(c->gpSn2effHost[s]) / sn2_eff;      // V = (L'\Ks)/sqrt(sn2_eff_old)  ->  (L'\Ks)/sn2_eff
-    par[3 * s + 2] = 1.0 + exp(2.0 * h[D]) / sn2_eff;         // :233
+    par[4 * s] = (hf[s] - ystar) / vstar;                     // :247
+    if (c->gpLchol[s]) {
+      par[4 * s + 1] = sqrt(c->gpSn2effHost[s]) / sn2_eff;    // V = (L'\Ks)/sqrt(sn2_eff_old)  ->  (L'\Ks)/sn2_eff
+      par[4 * s + 2] = 1.0 + exp(2.0 * h[D]) / sn2_eff;       // :233
+    } else {                                                  // low-noise sample kept as the unscaled factor of K + sn2_eff*I:
+      par[4 * s + 1] = 1.0;                                   // the bordered matrix [A Ks; Ks' K + sn2_eff] has the factor [R c; 0 d],
+      par[4 * s + 2] = exp(2.0 * h[D]) + sn2_eff;             // c = R'\Ks, d^2 = K + sn2_eff - c'c; its negated inverse is :236
+    }
+    par[4 * s + 3] = 1.0 / vstar;
     sw[s] = 1.0 / sqrt(sn2_eff);                              // :242
   }
   VB_CUDA(cudaMemcpyAsync(d_par, par.data(), sizeof(double) * par.size(), cudaMemcpyHostToDevice, st));
@@ -356,10 +382,11 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
   }
   {
     KernelScope ks(c, "rank1", st);
-    rank1_column_kernel<<<S, 256, 0, st>>>(N, ld, c->gpL.d(), d_Z, d_par);
+    rank1_column_kernel<<<S, 256, 0, st>>>(N, ld, c->gpL.d(), d_Z, d_par, d_isfac);
+    if (any_inv) rank1_inverse_kernel<<<dim3(N / 256 + 1, N + 1, S), 256, 0, st>>>(N, ld, c->gpL.d(), d_W, d_par, d_isfac);
     VB_CUDA(cudaGetLastError());
   }
-  VB_TRY(run_rhs_backsolve(c, 1, d_Z, st));                   // alpha_update (old N x N factor)
+  VB_TRY(run_rhs_backsolve(c, 1, d_Z, st, d_isfac));          // alpha_update (old N x N factor)
   // the grown alpha / X go into the ping-pong partners of the resident buffers (reserved with room for 256 more points)
   DevBuf& na = c->gpAlphaAlt;
   DevBuf& nx = c->gpXalt;
@@ -367,7 +394,7 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
   if (nx.cap < sizeof(double) * static_cast<size_t>(D) * N1) VB_TRY(nx.reserve(sizeof(double) * static_cast<size_t>(D) * (N1 + 256)));
   {
     KernelScope ks(c, "rank1", st);
-    rank1_alpha_kernel<<<S, 256, 0, st>>>(N, c->gp.alpha, d_Z, d_par, na.d());
+    rank1_alpha_kernel<<<S, 256, 0, st>>>(N, c->gp.alpha, d_Z, d_W ? d_W : d_Z, d_isfac, d_par, na.d());
     VB_CUDA(cudaGetLastError());
   }
   VB_CUDA(cudaMemcpy2DAsync(nx.p, sizeof(double) * N1, c->gpX.p, sizeof(double) * N, sizeof(double) * N, D, cudaMemcpyDeviceToDevice, st));

@@ -977,10 +977,15 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
 }
 
 // inv(A) tiles of sample `s` of the last refit: mode 0 -> (S_0..S_D, diagQ) on the host, mode 1 -> -inv(A) into dev_out
+int run_invtiles_ld(vbmc_b200_ctx* c, int N, int D, int Nhyp, int Np, int s, double sl, int mode, std::vector<double>* sums,
+                    std::vector<double>* diagQ, double* dev_out);
 int run_invtiles(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int s, double sl, int mode, std::vector<double>* sums,
                  std::vector<double>* diagQ, double* dev_out) {
-  const int N = gd->N, D = gd->D;
-  const int Np = (N + 1 + TB - 1) / TB * TB;
+  return run_invtiles_ld(c, gd->N, gd->D, gd->Nhyp, (gd->N + 1 + TB - 1) / TB * TB, s, sl, mode, sums, diagQ, dev_out);
+}
+// the same for a resident posterior of N points whose factors have leading dimension Np (grown by rank-one updates)
+int run_invtiles_ld(vbmc_b200_ctx* c, int N, int D, int Nhyp, int Np, int s, double sl, int mode, std::vector<double>* sums,
+                    std::vector<double>* diagQ, double* dev_out) {
   const int nb = (N + TB - 1) / TB, ntiles = nb * (nb + 1) / 2;
   if (D > 24) VB_FAIL(VBMC_B200_EUNSUPPORTED, "vbmc_b200:nlz_grad: D=%d > 24 is not supported by this build", D);
   vb::DevBuf& wk = c->varWork;
@@ -993,7 +998,7 @@ int run_invtiles(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int s, double sl
   VB_TRY(vb::run_factor_inverse(c, N, Np, R, X));
   InvArgs a;
   a.N = N; a.D = D; a.mode = mode;
-  a.Xinv = X; a.Xc = c->gpX.d(); a.hyp = c->gpHyp.d() + static_cast<size_t>(s) * gd->Nhyp;
+  a.Xinv = X; a.Xc = c->gpX.d(); a.hyp = c->gpHyp.d() + static_cast<size_t>(s) * Nhyp;
   a.alpha = c->gpAlpha.d() + static_cast<size_t>(s) * N;
   a.inv_sl = 1.0 / sl;
   a.partial = partial; a.diagQ = dq; a.outL = dev_out;
@@ -1089,6 +1094,31 @@ int vbmc_b200_gp_post(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, double* alp
   c->gp.X = c->gpX.d(); c->gp.hyp = c->gpHyp.d(); c->gp.alpha = c->gpAlpha.d();
   VB_TRY(vb::gp_upload_derived(c, gd, Ncov, Nnoise, h_sw.data(), rr.Lchol.data()));
   c->gp_ready = true;
+  return VBMC_B200_OK;
+}
+
+// gp.post(s).L of the resident posterior in the reference's representation (gplite_core.m:67-100): the upper Cholesky factor
+// (Lchol) or -inv(K + sn2_mult*diag(sn2)) (low noise) -- for a low-noise sample whose factor lives on the device the inverse
+// is built here (R^-T on the tensor path, then X'X tiles).  L_out: N x N, column-major.
+int vbmc_b200_gp_get_factor(vbmc_b200_ctx* c, int s, double* L_out) {
+  if (!c || !L_out) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  if (!c->gp_ready || !c->gpHasL) VB_FAIL(VBMC_B200_ESTATE, "gp_get_L: no posterior with factors is resident (gp_attach with L, or gp_post)");
+  const int N = c->gp.N, S = c->gp.S, ld = c->gpLd;
+  if (s < 0 || s >= S) VB_FAIL(VBMC_B200_EINVAL, "gp_get_L: sample %d of %d", s, S);
+  VB_CUDA(cudaSetDevice(c->device));
+  vb::DevBuf tmp;
+  VB_TRY(tmp.reserve(sizeof(double) * static_cast<size_t>(N) * N));
+  if (c->gpLfactor[s] && !c->gpLchol[s]) {
+    VB_TRY(run_invtiles_ld(c, N, c->gp.D, c->gp.Nhyp, ld, s, 1.0, 1, nullptr, nullptr, tmp.d()));
+  } else {
+    KernelScope ks(c, "extract", c->stream);
+    gp_extract_kernel<<<dim3((N + 255) / 256, N, 1), 256, 0, c->stream>>>(c->gpL.d() + static_cast<size_t>(s) * ld * ld, ld, N, tmp.d(),
+                                                                          c->gpLfactor[s] ? 0 : 1);
+    VB_CUDA(cudaGetLastError());
+  }
+  VB_CUDA(cudaMemcpyAsync(L_out, tmp.p, sizeof(double) * static_cast<size_t>(N) * N, cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  tmp.release();
   return VBMC_B200_OK;
 }
 

@@ -461,17 +461,17 @@ int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* 
 }
 
 // W = R \ Z in place (backward substitution with the resident upper factors), `ncols` right-hand sides per sample
-int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st) {
+int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st, const int* isfac_dev) {
   VarArgs a;
   memset(&a, 0, sizeof(a));
   a.N = c->gp.N; a.D = c->gp.D; a.K = ncols; a.S = c->gp.S; a.ld = c->gpLd;
   a.Lstride = static_cast<size_t>(c->gpLd) * c->gpLd;
   a.L = c->gpL.d();
   a.gp = c->gp; a.vp = c->vp;
-  a.Z = Z;
+  a.Z = Z; a.isfac = isfac_dev;
   static const bool blocked_off = getenv("VBMC_B200_TRSM_BLOCKED") && atoi(getenv("VBMC_B200_TRSM_BLOCKED")) == 0;
   int rc = VBMC_B200_OK;
-  if (!blocked_off && run_trsm_blocked(c, ncols, Z, nullptr, st, &rc, true)) return rc;
+  if (!blocked_off && run_trsm_blocked(c, ncols, Z, isfac_dev, st, &rc, true)) return rc;
   KernelScope ks(c, "pred_trsm", st);
   return launch_var_kernel(c, VK_BWD, a, ncols, c->gp.S, 64 * 65, 0, st, "gplite_post");
 }
