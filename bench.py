@@ -442,7 +442,8 @@ def main():
         ctx.profile_reset(); ctx.profile_enable(True)
         gp = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
         ctx.profile_enable(False)
-        kt = {k: ctx.profile_get(k)[0] for k in ("gram", "potrf_panel", "potrf_update", "trsv", "gp_prep")}
+        kt = {k: ctx.profile_get(k)[0] for k in ("gram", "potrf_potf2", "potrf_trsm", "potrf_update", "trsv", "gp_prep")}
+        kt["potrf_panel"] = kt["potrf_potf2"] + kt["potrf_trsm"]   # diagonal-block factorisation + row-panel solve
         N_, S_ = cfg["N"], cfg["S"]
         Np_ = (N_ + 1 + 63) // 64 * 64
         nb_ = Np_ // 64

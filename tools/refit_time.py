@@ -17,3 +17,7 @@ for name in sys.argv[1:] or ("c3", "c5"):
         vbmc_b200.gplite_post(hyp, X, y, 1, 4, nf, s2, ctx=ctx, want_L=False)
         ctx.sync(); best = min(best, time.perf_counter() - t0)
     print(name, "gplite_post wall ms %.3f" % (best * 1e3), "N^3/3*S TFLOP/s %.2f" % (cfg["S"] * cfg["N"] ** 3 / 3 / best / 1e12), flush=True)
+    ctx.profile_reset(); ctx.profile_enable(True)   # per-kernel events, serial order (no look-ahead, no graph)
+    vbmc_b200.gplite_post(hyp, X, y, 1, 4, nf, s2, ctx=ctx, want_L=False)
+    ctx.profile_enable(False)
+    print("   serial ms:", {k: round(ctx.profile_get(k)[0], 3) for k in ("gram", "potrf_potf2", "potrf_trsm", "potrf_update", "trsv", "gp_prep")}, flush=True)

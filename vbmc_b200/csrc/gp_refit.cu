@@ -450,6 +450,168 @@ __global__ void __launch_bounds__(256) gp_update_kernel(const GpBatch g, int kro
   }  // work items
 }
 
+// ---- panel step kb, second generation (round 2) -------------------------------------------------------------------------------
+// The panel is the latency-bound part of the factorisation (64 dependent pivots per step, 32 steps at N = 2000).
+// (1) gp_potf2i_kernel: the 64x64 diagonal block lives in REGISTERS (thread (tx, ty) owns rows ty+16b, columns tx+16a); per pivot
+//     the 16 owners of row p publish it raw, ONE barrier, every thread scales what it needs by rsqrt(d) itself and updates its own
+//     patch -- no shared-memory read-modify-write, no second barrier, block rows/columns that cannot be touched any more are
+//     skipped at compile time.  The same elimination runs on an identity right-hand side, so Z = R_kk^-T (lower triangular) falls
+//     out of the loop with it (R'Z = I) and goes to the scratch buffer.  Same operations in the same order as gp_potf2_kernel:
+//     the factor is bit-identical.  (Measured slower: the owners scaling the row BEFORE the barrier, one rsqrt per pivot instead
+//     of one per thread -- 1.04 vs 0.91 ms over the 32 steps at c3: the loads of the row no longer overlap the rsqrt.)
+// (2) gp_trsmg_kernel (below): the row panel R_kJ = R_kk^-T A_kJ as block substitution on the FP64 tensor path instead of 64
+//     dependent scalar steps.
+__global__ void __launch_bounds__(256) gp_potf2i_kernel(const GpBatch g, int kb) {
+  __shared__ double A[TB][TB + 1];       // A[c][r]: column c, row r; rows of R are stored in place as they are finished
+  __shared__ double rowbuf[2][2 * TB];   // raw pivot row, by pivot parity: [0, 64) A(p, j), [64, 128) E(p, c)
+  const int s = g.active[blockIdx.x];
+  const int Np = g.Np, N = g.N, tid = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* Z = g.dscratch + static_cast<size_t>(s) * TB * TB;   // Z[p*64 + c] = R_kk^-T (p, c)
+  const int k0 = kb * TB;
+  for (int i = tid; i < TB * TB; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    A[c][r] = Ms[static_cast<size_t>(k0 + c) * Np + k0 + r];
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double a[4][4], e[4][4];   // a[ja][ib] = A(ty + 16 ib, tx + 16 ja), e[ca][ib] = E(ty + 16 ib, tx + 16 ca), E = I at the start
+#pragma unroll
+  for (int ja = 0; ja < 4; ++ja)
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) {
+      a[ja][ib] = A[tx + 16 * ja][ty + 16 * ib];
+      e[ja][ib] = (tx + 16 * ja == ty + 16 * ib) ? 1.0 : 0.0;
+    }
+  int bad = 0;
+#pragma unroll
+  for (int pb = 0; pb < 4; ++pb) {
+#pragma unroll 1
+    for (int pt = 0; pt < 16; ++pt) {
+      const int p = 16 * pb + pt, par = p & 1;
+      if (ty == pt) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          rowbuf[par][tx + 16 * q] = a[q][pb];
+          rowbuf[par][TB + tx + 16 * q] = e[q][pb];
+        }
+      }
+      __syncthreads();   // (the buffer of the other parity is free again: everybody passed the previous barrier after reading it)
+      const bool unit = (k0 + p) >= N;
+      const double d = rowbuf[par][p];
+      if (!unit && !(d > 0.0) && bad == 0) bad = k0 + p + 1;
+      const double isq = unit ? 0.0 : rsqrt(d);
+      double lj[4], li[4], zc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        lj[q] = rowbuf[par][tx + 16 * q] * isq;
+        li[q] = rowbuf[par][ty + 16 * q] * isq;
+        zc[q] = rowbuf[par][TB + tx + 16 * q] * isq;
+      }
+      if (!unit) {
+#pragma unroll
+        for (int ib = pb; ib < 4; ++ib) {
+          if (ty + 16 * ib > p) {
+#pragma unroll
+            for (int ja = ib; ja < 4; ++ja) a[ja][ib] = fma(-li[ib], lj[ja], a[ja][ib]);
+#pragma unroll
+            for (int ca = 0; ca <= pb; ++ca) e[ca][ib] = fma(-li[ib], zc[ca], e[ca][ib]);
+          }
+        }
+      }
+      if (ty == pt) {   // off the critical path: row p of R and of Z = R^-T
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = tx + 16 * q;
+          A[j][p] = unit ? (j == p ? 1.0 : 0.0) : (j >= p ? lj[q] : 0.0);   // R(p, j)
+          Z[p * TB + j] = unit ? (j == p ? 1.0 : 0.0) : (j <= p ? zc[q] : 0.0);
+        }
+      }
+    }
+  }
+  if (tid == 0 && bad != 0) atomicCAS(&g.info[s], 0, bad);   // every thread saw the same pivots: `bad` is the first failure
+  __syncthreads();
+  for (int i = tid; i < TB * TB; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    if (r <= c) Ms[static_cast<size_t>(k0 + c) * Np + k0 + r] = A[c][r];
+  }
+}
+
+// Row panel R_kJ = R_kk^-T A_kJ for the block J = kb + 1 + blockIdx.x: block substitution in four 16-row stages,
+//   T_i = B_i - sum_{p < 16 i} R(p, .)' X(p, .)      (DMMA, depth 16 i)
+//   X_i = Z_ii T_i,   Z_ii = inv(R_ii)' = the i-th 16x16 diagonal block of Z      (DMMA, depth 16)
+// so that only the 16x16 diagonal blocks are applied as explicit inverses (their condition number, not the 64x64 block's, enters
+// the error: measured backward error |R'R - A|/|A| of the whole factor 1e-15 like scalar substitution, against 1-2e-14 with the
+// full 64x64 inverse).  A warp owns 8 columns of the block through all four stages: no block barrier after the loads.
+// grid (nb-kb-1, nact), 256 threads; 71.6 KB of shared memory: 3 CTAs per SM.
+constexpr int TG_LDR = 52, TG_LDX = TB + 4, TG_LDZ = 20;
+constexpr int TRSMG_SMEM_BYTES = (TB * TG_LDR + TB * TG_LDX + 4 * 16 * TG_LDZ) * 8;
+__global__ void __launch_bounds__(256) gp_trsmg_kernel(const GpBatch g, int kb) {
+  extern __shared__ __align__(16) double tsm[];
+  double* RA = tsm;                  // RA[r*52 + p] = R_kk(p, r), p < 48
+  double* XS = RA + TB * TG_LDR;     // XS[c*68 + p] = B(p, c), solved in place
+  double* ZD = XS + TB * TG_LDX;     // ZD[i][m*20 + k] = Z(16 i + m, 16 i + k)
+  const int s = g.active[blockIdx.y];
+  const int Np = g.Np, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  const int k0 = kb * TB, jb = kb + 1 + blockIdx.x;
+  double* Bg = Ms + static_cast<size_t>(jb * TB) * Np + k0;
+  load_pblock_async<48>(RA, Ms + static_cast<size_t>(k0) * Np + k0, Np, tid);
+  load_pblock_async<TB>(XS, Bg, Np, tid);
+  {
+    const double* Zg = g.dscratch + static_cast<size_t>(s) * TB * TB;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + 256 * it, i = idx >> 7, m = (idx >> 3) & 15, ch = idx & 7;
+      cp_async16(ZD + i * 16 * TG_LDZ + m * TG_LDZ + 2 * ch, Zg + (16 * i + m) * TB + 16 * i + 2 * ch);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int g4 = lane >> 2, t4 = lane & 3, c0 = warp * 8;
+  const double* xb = XS + (c0 + g4) * TG_LDX;   // B-fragment column of this lane
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double acc[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) acc[a][0] = acc[a][1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16 * i; k += 4) {
+      const double bf = xb[k + t4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) dmma_m8n8k4(acc[a][0], acc[a][1], RA[(16 * i + 8 * a + g4) * TG_LDR + k + t4], bf);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double* t = XS + (c0 + 2 * t4 + j) * TG_LDX + 16 * i + 8 * a + g4;
+        *t -= acc[a][j];
+      }
+    __syncwarp();
+    double x[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) x[a][0] = x[a][1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+      const double bf = xb[16 * i + k + t4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) dmma_m8n8k4(x[a][0], x[a][1], ZD[i * 16 * TG_LDZ + (8 * a + g4) * TG_LDZ + k + t4], bf);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) XS[(c0 + 2 * t4 + j) * TG_LDX + 16 * i + 8 * a + g4] = x[a][j];
+    __syncwarp();
+  }
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) Bg[static_cast<size_t>(c0 + cc) * Np + lane + 32 * h] = XS[(c0 + cc) * TG_LDX + lane + 32 * h];
+}
+
 // number of CTAs (work items) of gp_update_kernel for block rows Ifirst .. Ifirst+Icount-1
 static int update_work_items(int nb, int Ifirst, int Icount, int chunk) {
   int n = 0;
@@ -820,6 +982,10 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   const int UPDATE_SMEM64 = 3 * TB * (64 + 4) * sizeof(double), UPDATE_SMEM128 = 3 * TB * (128 + 4) * sizeof(double);
   VB_CUDA(cudaFuncSetAttribute(gp_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM64));
   VB_CUDA(cudaFuncSetAttribute(gp_update_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, UPDATE_SMEM128));
+  const int TRSMG_SMEM = TRSMG_SMEM_BYTES;
+  VB_CUDA(cudaFuncSetAttribute(gp_trsmg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSMG_SMEM));
+  static const bool panel_v1 = getenv("VBMC_B200_REFIT_PANEL_V1") && atoi(getenv("VBMC_B200_REFIT_PANEL_V1")) != 0;
+  static const bool trsm_v1 = getenv("VBMC_B200_REFIT_TRSM_V1") && atoi(getenv("VBMC_B200_REFIT_TRSM_V1")) != 0;
   for (int attempt = 0; attempt < 10 && !active.empty(); ++attempt) {
     for (int s : active) {
       if (rr->Lchol[s]) {
@@ -859,13 +1025,19 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
         for (int h = 0; h < 2 && kb + h < nb; ++h) {
           const int k = kb + h, nr = nb - k - 1;
           {  // (a fused potf2+trsm kernel, gp_panel_kernel, was measured slower: 2.6 vs 2.2 ms at c3)
-            KernelScope ks(c, "potrf_panel", st);
-            gp_potf2_kernel<<<nact, 256, 0, st>>>(g, k);
+            KernelScope ks(c, "potrf_potf2", st);
+            if (panel_v1)
+              gp_potf2_kernel<<<nact, 256, 0, st>>>(g, k);
+            else   // register-resident factorisation that also yields R_kk^-T
+              gp_potf2i_kernel<<<nact, 256, 0, st>>>(g, k);
           }
           if (nr > 0) {
             dim3 grid(nr, nact);
-            KernelScope ks(c, "potrf_panel", st);
-            gp_trsm_kernel<<<grid, 256, 0, st>>>(g, k);
+            KernelScope ks(c, "potrf_trsm", st);
+            if (panel_v1 || trsm_v1)
+              gp_trsm_kernel<<<grid, 256, 0, st>>>(g, k);
+            else   // the row panel as DMMA products with R_kk^-T
+              gp_trsmg_kernel<<<grid, 256, TRSMG_SMEM, st>>>(g, k);
           }
           if (h == 0 && nr > 0) {  // update block row kb+1 only (needed by the second half of the panel)
             const int ch = update_chunk(nb, kb + 1, 1, nact, c->num_sms);
