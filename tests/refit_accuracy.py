@@ -1,7 +1,7 @@
-"""Accuracy of the refit (factor, alpha, nlZ) against the oracle on the test-suite problem; used to A/B panel variants."""
+"""Accuracy of the refit (factor backward error, alpha, nlZ) against the oracle on the test-suite problems; a script (python tests/refit_accuracy.py on a GPU box) used to A/B the panel variants (VBMC_B200_REFIT_PANEL_V1 / _TRSM_V1)."""
 import sys, os, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import vbmc_b200
 from oracle import vbmc_oracle as orc

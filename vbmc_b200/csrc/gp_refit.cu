@@ -40,7 +40,7 @@ struct GpBatch {
   const double* scale;    // [S] 1/(sn2div*mult)   (Lchol) or 1 (low noise)
   const double* dscale;   // [S] 1/sn2div          (Lchol) or mult (low noise)
   int* info;              // [S] 0 ok, >0 first failing pivot (1-based)
-  double* dscratch;       // [S][64*64] factor of the current diagonal block (written in place one step later)
+  double* dscratch;       // [S][Np/64][64*64] Z_kk = R_kk^-T of every diagonal block (gp_potf2i_kernel; read by the row-panel and back-substitution kernels)
 };
 
 // ---- per-point noise variance and mean (gplite_noisefun.m:176-210, gplite_meanfun.m cases 0,1,4) ----
@@ -234,101 +234,6 @@ __global__ void __launch_bounds__(256) gp_trsm_kernel(const GpBatch g, int kb) {
   for (int i = 0; i < 16; ++i) col[q + 4 * i] = x[i];
 }
 
-// ---- fused panel step: every CTA factors the diagonal block itself (same code as gp_potf2_kernel, ~64 barriers)
-// and then solves its own column block, so a step needs one launch and never runs on only S CTAs.
-// grid (max(1, nb-kb-1), nact); CTA x == 0 writes the factor of the diagonal block back.
-__global__ void __launch_bounds__(256) gp_panel_kernel(const GpBatch g, int kb) {
-  __shared__ double A[TB][TB + 1];
-  __shared__ double lrow[TB];
-  __shared__ double ird[TB];
-  __shared__ int bad;
-  const int s = g.active[blockIdx.y];
-  const int Np = g.Np, N = g.N, tid = threadIdx.x;
-  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
-  const int k0 = kb * TB;
-  const int nr = Np / TB - kb - 1;
-  if (tid == 0) bad = 0;
-  for (int i = tid; i < TB * TB; i += 256) {
-    const int c = i >> 6, r = i & 63;
-    A[c][r] = Ms[static_cast<size_t>(k0 + c) * Np + k0 + r];
-  }
-  // The factor of the previous diagonal block is still in the scratch buffer (it could not be written in place
-  // while the other CTAs of that step were still loading the unfactored block): put it in place now.
-  if (blockIdx.x == 0 && kb > 0) {
-    const double* sc = g.dscratch + static_cast<size_t>(s) * TB * TB;
-    for (int i = tid; i < TB * TB; i += 256) {
-      const int cc = i >> 6, r = i & 63;
-      if (r <= cc) Ms[static_cast<size_t>(k0 - TB + cc) * Np + (k0 - TB) + r] = sc[i];
-    }
-  }
-  // prefetch this CTA's right-hand block into registers (thread (c, q) owns rows q, q+4, ... of column c)
-  const int c = tid >> 2, q = tid & 3;
-  const bool have_rhs = static_cast<int>(blockIdx.x) < nr;
-  const int jb = kb + 1 + blockIdx.x;
-  double* col = Ms + static_cast<size_t>(jb * TB + c) * Np + k0;
-  double x[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = have_rhs ? col[q + 4 * i] : 0.0;
-  __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int p = 0; p < TB; ++p) {
-    const bool unit = (k0 + p) >= N;
-    const double d = A[p][p];
-    if (tid == 0 && !unit && !(d > 0.0) && bad == 0) bad = k0 + p + 1;
-    const double isq = unit ? 0.0 : rsqrt(d);
-    if (tid < TB) {
-      const int j = tid;
-      double v = 0.0;
-      if (j >= p) v = unit ? (j == p ? 1.0 : 0.0) : A[j][p] * isq;
-      lrow[j] = v;
-    }
-    __syncthreads();
-    if (tid < TB) A[tid][p] = lrow[tid];
-    if (!unit) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int j = tx + 16 * a;
-        const double lj = lrow[j];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int i = ty + 16 * b;
-          if (i > p && i <= j) A[j][i] = fma(-lrow[i], lj, A[j][i]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (tid == 0 && bad != 0) atomicCAS(&g.info[s], 0, bad);
-  if (tid < TB) ird[tid] = 1.0 / A[tid][tid];
-  if (blockIdx.x == 0) {
-    if (nr == 0) {  // last block: this is the only CTA of the sample, write in place
-      for (int i = tid; i < TB * TB; i += 256) {
-        const int cc = i >> 6, r = i & 63;
-        if (r <= cc) Ms[static_cast<size_t>(k0 + cc) * Np + k0 + r] = A[cc][r];
-      }
-    } else {
-      double* sc = g.dscratch + static_cast<size_t>(s) * TB * TB;
-      for (int i = tid; i < TB * TB; i += 256) sc[i] = A[i >> 6][i & 63];
-    }
-  }
-  __syncthreads();
-  if (!have_rhs) return;
-  const unsigned lane = tid & 31;
-#pragma unroll
-  for (int p = 0; p < TB; ++p) {
-    double xp = x[p >> 2] * ird[p];
-    xp = __shfl_sync(0xffffffffu, xp, (lane & ~3u) | (p & 3));
-    if (q == (p & 3)) x[p >> 2] = xp;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int r = q + 4 * i;
-      if (r > p) x[i] = fma(-A[r][p], xp, x[i]);   // b_r -= R(p, r) x_p,  R(p, r) = A[r][p]
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) col[q + 4 * i] = x[i];
-}
-
 // ---- trailing update on the FP64 tensor path:  C_IJ -= P_I' P_J  (I <= J, blocks right of kb) ----
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -467,7 +372,7 @@ __global__ void __launch_bounds__(256) gp_potf2i_kernel(const GpBatch g, int kb)
   const int s = g.active[blockIdx.x];
   const int Np = g.Np, N = g.N, tid = threadIdx.x;
   double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
-  double* Z = g.dscratch + static_cast<size_t>(s) * TB * TB;   // Z[p*64 + c] = R_kk^-T (p, c)
+  double* Z = g.dscratch + (static_cast<size_t>(s) * (Np / TB) + kb) * TB * TB;   // Z[p*64 + c] = R_kk^-T (p, c)
   const int k0 = kb * TB;
   for (int i = tid; i < TB * TB; i += 256) {
     const int c = i >> 6, r = i & 63;
@@ -559,7 +464,7 @@ __global__ void __launch_bounds__(256) gp_trsmg_kernel(const GpBatch g, int kb) 
   load_pblock_async<48>(RA, Ms + static_cast<size_t>(k0) * Np + k0, Np, tid);
   load_pblock_async<TB>(XS, Bg, Np, tid);
   {
-    const double* Zg = g.dscratch + static_cast<size_t>(s) * TB * TB;
+    const double* Zg = g.dscratch + (static_cast<size_t>(s) * (Np / TB) + kb) * TB * TB;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       const int idx = tid + 256 * it, i = idx >> 7, m = (idx >> 3) & 15, ch = idx & 7;
@@ -765,6 +670,56 @@ __global__ void __launch_bounds__(1024) gp_bsolve_kernel(const GpBatch g, const 
   for (int i = tid; i < N; i += 1024) alpha[static_cast<size_t>(s) * N + i] = z[i] * sc;
 }
 
+// Second generation: the diagonal blocks are applied through Z_kk = R_kk^-T kept by gp_potf2i_kernel (x_k = Z_kk' y_k: a 64x64
+// matrix-vector product over all 1024 threads instead of 64 dependent divide-and-update steps in one warp), and the update of
+// the rows above keeps four independent sums and 16 loads in flight per thread (one SM streams the 16 MB of a sample's factor).
+__global__ void __launch_bounds__(1024) gp_bsolve2_kernel(const GpBatch g, const double* ascale, double* alpha) {
+  __shared__ double part[16][TB];
+  __shared__ double xk[TB], yk[TB];
+  const int s = blockIdx.x;
+  const int Np = g.Np, N = g.N, tid = threadIdx.x;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* z = Ms + static_cast<size_t>(N) * Np;
+  const int r = tid & 63, pg = tid >> 6;
+  for (int kb = (N + TB - 1) / TB - 1; kb >= 0; --kb) {
+    const int k0 = kb * TB;
+    const double* Zg = g.dscratch + (static_cast<size_t>(s) * (Np / TB) + kb) * TB * TB;   // Z(p, r) at [p*64 + r], zero for r > p
+    if (tid < TB) yk[tid] = (k0 + tid < N) ? z[k0 + tid] : 0.0;
+    double zr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) zr[q] = Zg[(4 * pg + q) * TB + r];
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = fma(zr[q], yk[4 * pg + q], acc);
+    part[pg][r] = acc;
+    __syncthreads();
+    if (tid < TB) {
+      double x = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x += part[q][tid];
+      xk[tid] = x;
+      if (k0 + tid < N) z[k0 + tid] = x;
+    }
+    __syncthreads();
+    for (int i = tid; i < k0; i += 1024) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const double* col = Ms + static_cast<size_t>(k0) * Np + i;
+#pragma unroll 4
+      for (int j = 0; j < TB; j += 4) {
+        a0 = fma(col[static_cast<size_t>(j) * Np], xk[j], a0);
+        a1 = fma(col[static_cast<size_t>(j + 1) * Np], xk[j + 1], a1);
+        a2 = fma(col[static_cast<size_t>(j + 2) * Np], xk[j + 2], a2);
+        a3 = fma(col[static_cast<size_t>(j + 3) * Np], xk[j + 3], a3);
+      }
+      z[i] -= (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+  }
+  const double sc = ascale[s];
+  for (int i = tid; i < N; i += 1024) alpha[static_cast<size_t>(s) * N + i] = z[i] * sc;
+}
+
 __global__ void gp_alpha_kernel(const GpBatch g, const double* ascale, double* alpha) {
   const int s = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -928,7 +883,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   VB_TRY(c->gpAlpha.reserve(sizeof(double) * static_cast<size_t>(S) * N));
   VB_TRY(c->gpL.reserve(sizeof(double) * static_cast<size_t>(S) * Np * Np));
   // work: sn2[S][N] mvec[S][N] scale[S] dscale[S] ascale[S] minsn2[S] logdet[S] zz[S] | info[S] active[S]
-  const size_t nwork = 2 * static_cast<size_t>(S) * N + 6 * S + static_cast<size_t>(S) * TB * TB;
+  const size_t nwork = 2 * static_cast<size_t>(S) * N + 6 * S + static_cast<size_t>(S) * (Np / TB) * TB * TB;
   VB_TRY(c->gpWork.reserve(sizeof(double) * nwork + sizeof(int) * 2 * S + 64));
   VB_CUDA(cudaMemcpyAsync(c->gpX.p, gd->X, sizeof(double) * N * D, cudaMemcpyHostToDevice, st));
   VB_CUDA(cudaMemcpyAsync(c->gpY.p, gd->y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
@@ -951,7 +906,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   double* d_logdet = d_minsn2 + S;
   double* d_zz = d_logdet + S;
   double* d_dscratch = d_zz + S;
-  int* d_info = reinterpret_cast<int*>(d_dscratch + static_cast<size_t>(S) * TB * TB);
+  int* d_info = reinterpret_cast<int*>(d_dscratch + static_cast<size_t>(S) * (Np / TB) * TB * TB);
   int* d_active = d_info + S;
   g.dscratch = d_dscratch;
   g.M = c->gpL.d(); g.scale = d_scale; g.dscale = d_dscale; g.info = d_info; g.active = d_active;
@@ -1024,7 +979,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
       auto panel = [&](int kb) -> int {
         for (int h = 0; h < 2 && kb + h < nb; ++h) {
           const int k = kb + h, nr = nb - k - 1;
-          {  // (a fused potf2+trsm kernel, gp_panel_kernel, was measured slower: 2.6 vs 2.2 ms at c3)
+          {  // (a fused potf2+trsm kernel was measured slower in round 1: 2.6 vs 2.2 ms at c3)
             KernelScope ks(c, "potrf_potf2", st);
             if (panel_v1)
               gp_potf2_kernel<<<nact, 256, 0, st>>>(g, k);
@@ -1059,7 +1014,9 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
         gp_update_kernel<128><<<grid, 256, UPDATE_SMEM128, sx>>>(g, kb * TB, Ifirst, Icount, ch, items);
         return VBMC_B200_OK;
       };
-      static const int reserve = getenv("VBMC_B200_REFIT_PANEL_SMS") ? atoi(getenv("VBMC_B200_REFIT_PANEL_SMS")) : 28;
+      // side-stream budget: num_sms - reserve persistent update CTAs.  0 = one per SM, the panel kernels' CTAs (35 and 72 KB of
+      // shared memory) co-reside with them; measured at c3: reserve 28 -> 5.73 ms, 0 -> 5.30, -92 (240 CTAs) -> 5.69, no look-ahead 5.66
+      static const int reserve = getenv("VBMC_B200_REFIT_PANEL_SMS") ? atoi(getenv("VBMC_B200_REFIT_PANEL_SMS")) : 0;
       bool side_busy = false;
       for (int kb = 0; kb < nb; kb += 2) {
         VB_TRY(panel(kb));
@@ -1137,7 +1094,10 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   }
   {
     KernelScope ks(c, "trsv", st);
-    gp_bsolve_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
+    if (panel_v1)
+      gp_bsolve_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
+    else   // the diagonal blocks through the inverses the panel kernels left behind
+      gp_bsolve2_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
   }
   VB_CUDA(cudaGetLastError());
   rr->logdet.assign(S, 0.0);
