@@ -152,7 +152,7 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   for (int i = 0; i < 2; ++i)
     if (c->trsm_graph[i]) cudaGraphExecDestroy(c->trsm_graph[i]);
-  vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork,
+  vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork, &c->gpFlags,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
                         &c->ent_partial, &c->ent_partial2, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->trsmWork, &c->gpXalt, &c->gpAlphaAlt, &c->zigTab, &c->entlbWork};
   for (auto* b : bufs) b->release();

@@ -231,6 +231,8 @@ struct vbmc_b200_ctx {
   unsigned long long gp_tag = 0;  // opaque caller fingerprint of the resident posterior (vbmc_b200_gp_tag_*); 0 = none
   vb::GpDev gp{};
   vb::DevBuf gpX, gpHyp, gpAlpha, gpDerived, gpL, gpY, gpS2, gpWork;
+  vb::DevBuf gpFlags;      // [S][Np/64] hand-over flags of the multi-CTA back substitution (gp_bsolve3_kernel)
+  int bsolve_epoch = 0;    // value a raised flag carries in the current launch
   std::vector<int> gpLchol;
   std::vector<int> gpLfactor;  // per sample: device L is a Cholesky factor (1) or -inv(K + diag) handed over by the host (0)
   std::vector<double> gpSn2mult;

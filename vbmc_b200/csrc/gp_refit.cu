@@ -720,6 +720,114 @@ __global__ void __launch_bounds__(1024) gp_bsolve2_kernel(const GpBatch g, const
   for (int i = tid; i < N; i += 1024) alpha[static_cast<size_t>(s) * N + i] = z[i] * sc;
 }
 
+// Third generation: P CTAs per sample (P * S <= number of SMs: all of them resident at once).  Block row J of the solution belongs
+// to CTA J mod P, which is the only one that ever writes z_J; the owner of block kb turns it into x_kb = Z_kb' z_kb, stores it in
+// place and raises flag[s][kb] (release); every CTA then subtracts R(J, kb) x_kb from the blocks J < kb it owns.  The factor's
+// entries of a step are loaded BEFORE the flag is awaited (their addresses do not depend on x), so the chain per step is
+// flag -> x -> FMAs -> the next owner's 64x64 product.  `epoch` distinguishes launches (the flags are never reset).
+// A peer that does not arrive within ~2^22 polls (seconds) is reported through info[s] = -7 instead of hanging the GPU.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(1024) gp_bsolve3_kernel(const GpBatch g, const double* ascale, double* alpha, int* flags, int epoch) {
+  __shared__ double part[16][TB];   // partial sums: [16 row groups][64] (solve) or [4 blocks][4 column groups][64] (update)
+  __shared__ double xk[TB], yk[TB];
+  __shared__ int timed_out;
+  const int s = blockIdx.y, me = blockIdx.x, P = gridDim.x;
+  const int Np = g.Np, N = g.N, tid = threadIdx.x;
+  const int nbp = Np / TB, nbN = (N + TB - 1) / TB;
+  double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  double* z = Ms + static_cast<size_t>(N) * Np;
+  int* fl = flags + static_cast<size_t>(s) * nbp;
+  const int r = tid & 63;
+  if (tid == 0) timed_out = 0;
+  __syncthreads();
+  for (int kb = nbN - 1; kb >= 0; --kb) {
+    const int k0 = kb * TB;
+    // prefetch this step's factor entries for the first (up to) four own blocks: thread (blk, cg, r) takes 16 columns of one row
+    const int blk = tid >> 8, cg = (tid >> 6) & 3;
+    int Jfirst = kb - 1 - ((kb - 1 - me) % P + P) % P;   // largest J < kb with J == me (mod P); negative: none
+    if (kb == 0) Jfirst = -1;
+    const int Jmine = Jfirst - blk * P;
+    double rv[16];
+    if (Jmine >= 0) {
+      const double* col = Ms + static_cast<size_t>(k0 + 16 * cg) * Np + Jmine * TB + r;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) rv[q] = __ldcs(col + static_cast<size_t>(q) * Np);
+    }
+    if (kb % P == me) {
+      // ---- my block: x = Z' y (Z(p, c) at [p*64 + c], zero for c > p), thread (pg, r) sums four rows p ----
+      const int pg = tid >> 6;
+      const double* Zg = g.dscratch + (static_cast<size_t>(s) * nbp + kb) * TB * TB;
+      double zr[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) zr[q] = Zg[(4 * pg + q) * TB + r];
+      if (tid < TB) yk[tid] = (k0 + tid < N) ? z[k0 + tid] : 0.0;
+      __syncthreads();
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc = fma(zr[q], yk[4 * pg + q], acc);
+      part[pg][r] = acc;
+      __syncthreads();
+      if (tid < TB) {
+        double x = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x += part[q][tid];
+        xk[tid] = x;
+        if (k0 + tid < N) {
+          z[k0 + tid] = x;
+          alpha[static_cast<size_t>(s) * N + k0 + tid] = x * ascale[s];
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      if (tid == 0 && P > 1) st_release_gpu(fl + kb, epoch);
+    } else {
+      if (tid == 0) {
+        int spins = 0;
+        while (ld_acquire_gpu(fl + kb) != epoch) {
+          if (++spins > (1 << 22)) { timed_out = 1; break; }
+        }
+      }
+      __syncthreads();
+      if (timed_out) {
+        if (tid == 0) atomicExch(&g.info[s], -7);
+        return;
+      }
+      if (tid < TB) xk[tid] = (k0 + tid < N) ? __ldcg(z + k0 + tid) : 0.0;
+      __syncthreads();
+    }
+    // ---- z_J -= R(J, kb) x_kb for my blocks J < kb, four at a time ----
+    for (int J0 = Jfirst; J0 >= 0; J0 -= 4 * P) {
+      const int J = J0 - blk * P;
+      if (J0 != Jfirst && J >= 0) {
+        const double* col = Ms + static_cast<size_t>(k0 + 16 * cg) * Np + J * TB + r;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) rv[q] = __ldcs(col + static_cast<size_t>(q) * Np);
+      }
+      double a0 = 0.0, a1 = 0.0;
+      if (J >= 0) {
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+          a0 = fma(rv[q], xk[16 * cg + q], a0);
+          a1 = fma(rv[q + 1], xk[16 * cg + q + 1], a1);
+        }
+      }
+      part[4 * blk + cg][r] = a0 + a1;
+      __syncthreads();
+      if (tid < 256) {
+        const int b2 = tid >> 6, J2 = J0 - b2 * P;
+        if (J2 >= 0) z[J2 * TB + r] -= (part[4 * b2][r] + part[4 * b2 + 1][r]) + (part[4 * b2 + 2][r] + part[4 * b2 + 3][r]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void gp_alpha_kernel(const GpBatch g, const double* ascale, double* alpha) {
   const int s = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -885,6 +993,11 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   // work: sn2[S][N] mvec[S][N] scale[S] dscale[S] ascale[S] minsn2[S] logdet[S] zz[S] | info[S] active[S]
   const size_t nwork = 2 * static_cast<size_t>(S) * N + 6 * S + static_cast<size_t>(S) * (Np / TB) * TB * TB;
   VB_TRY(c->gpWork.reserve(sizeof(double) * nwork + sizeof(int) * 2 * S + 64));
+  if (c->gpFlags.cap < sizeof(int) * static_cast<size_t>(S) * (Np / TB)) {   // zeroed when (re)allocated; launches are told apart by an epoch
+    VB_TRY(c->gpFlags.reserve(sizeof(int) * static_cast<size_t>(S) * (Np / TB)));
+    VB_CUDA(cudaMemsetAsync(c->gpFlags.p, 0, c->gpFlags.cap, st));
+  }
+  int* d_flags = c->gpFlags.i();
   VB_CUDA(cudaMemcpyAsync(c->gpX.p, gd->X, sizeof(double) * N * D, cudaMemcpyHostToDevice, st));
   VB_CUDA(cudaMemcpyAsync(c->gpY.p, gd->y, sizeof(double) * N, cudaMemcpyHostToDevice, st));
   VB_CUDA(cudaMemcpyAsync(c->gpHyp.p, gd->hyp, sizeof(double) * S * gd->Nhyp, cudaMemcpyHostToDevice, st));
@@ -941,6 +1054,7 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
   VB_CUDA(cudaFuncSetAttribute(gp_trsmg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSMG_SMEM));
   static const bool panel_v1 = getenv("VBMC_B200_REFIT_PANEL_V1") && atoi(getenv("VBMC_B200_REFIT_PANEL_V1")) != 0;
   static const bool trsm_v1 = getenv("VBMC_B200_REFIT_TRSM_V1") && atoi(getenv("VBMC_B200_REFIT_TRSM_V1")) != 0;
+  static const bool bsolve_v2 = getenv("VBMC_B200_REFIT_BSOLVE_V2") && atoi(getenv("VBMC_B200_REFIT_BSOLVE_V2")) != 0;
   for (int attempt = 0; attempt < 10 && !active.empty(); ++attempt) {
     for (int s : active) {
       if (rr->Lchol[s]) {
@@ -1096,15 +1210,25 @@ int refit_core(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* gd, int Ncov, int Nnoi
     KernelScope ks(c, "trsv", st);
     if (panel_v1)
       gp_bsolve_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
-    else   // the diagonal blocks through the inverses the panel kernels left behind
+    else if (bsolve_v2)   // the diagonal blocks through the inverses the panel kernels left behind, one CTA per sample
       gp_bsolve2_kernel<<<S, 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d());
+    else {   // ... and P CTAs per sample that hand the solved blocks to each other through flags
+      const int nbN = (N + TB - 1) / TB;
+      int P = c->num_sms / S;
+      P = P < 1 ? 1 : (P > nbN ? nbN : P);
+      if (P > 8) P = 8;
+      gp_bsolve3_kernel<<<dim3(P, S), 1024, 0, st>>>(g, d_ascale, c->gpAlpha.d(), d_flags, ++c->bsolve_epoch);
+    }
   }
   VB_CUDA(cudaGetLastError());
   rr->logdet.assign(S, 0.0);
   rr->zz.assign(S, 0.0);
   VB_CUDA(cudaMemcpyAsync(rr->logdet.data(), d_logdet, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaMemcpyAsync(rr->zz.data(), d_zz, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+  VB_CUDA(cudaMemcpyAsync(h_info.data(), d_info, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < S; ++s)
+    if (h_info[s] == -7) VB_FAIL(VBMC_B200_ECUDA, "vbmc_b200:backsolve: a CTA of the multi-CTA back substitution did not arrive (sample %d)", s);
   return VBMC_B200_OK;
 }
 
