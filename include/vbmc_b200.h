@@ -72,6 +72,17 @@ int vbmc_b200_set_precision(vbmc_b200_ctx* ctx, int bits);
 int vbmc_b200_entmc_prune(vbmc_b200_ctx* ctx, double log_threshold);
 /* counters of (warp, component) blocks scored / candidate since the last call; enable != 0 keeps counting (bench) */
 int vbmc_b200_entmc_prune_stats(vbmc_b200_ctx* ctx, int enable, unsigned long long* kept, unsigned long long* total);
+/* Entropy sweep schedule (FP64 sweep, K <= 256, D < 20): the K*tpc CTA-tiles of a step (tile = one group of 32 antithetic pairs
+ * per warp, all of one source component j) are cut into one contiguous range per SM.  on != 0 (default): ranges of equal estimated
+ * COST -- per source component the unpack kernel counts the components that survive the pruning test above for a typical warp
+ * of draws, a tile of component j weighs c0 + that count; on == 0: ranges of equal tile count.  c0 <= 0 keeps the current
+ * value (default 16).  Results are sums in a fixed order for a given theta either way; the two schedules differ by round-off.
+ * Also VBMC_B200_ENTMC_BALANCE / VBMC_B200_ENTMC_C0 in the environment.  No counterpart in the reference (ent/entmc_vbmc.m:60-100
+ * is one vectorised loop over components). */
+int vbmc_b200_entmc_balance(vbmc_b200_ctx* ctx, int on, int c0);
+/* the schedule of the LAST step that ran the balanced sweep: tstart[G + 1] tile boundaries, then first / last CTA of every
+ * component (jlo[K], jhi[K]); out holds at least G + 1 + 2 K ints (cap).  G == 0: the last step used equal counts. */
+int vbmc_b200_entmc_plan_get(vbmc_b200_ctx* ctx, int* out, int cap, int* G, int* tpc);
 
 /* ---------------------------------------------------------------------------------------
  * multi-GPU: one context per rank, one all-reduce of the partial sums per negelcbo step.

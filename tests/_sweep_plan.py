@@ -1,0 +1,63 @@
+"""Host restatement of the cost-weighted schedule of the FP64 entropy sweep (vbmc_b200/csrc/finalize.cu, last CTA of
+vp_unpack2_kernel; consumed by entmc2_kernel / entmc2_reduce_kernel).  Test helper: integer arithmetic identical to the device's."""
+import numpy as np
+
+
+def typical_emax(D):
+    """1 - 1/33 quantile of chi^2_D (Wilson-Hilferty), square root: the expected largest ||eps|| of a warp's 32 draws."""
+    z = 1.876
+    wh = 1.0 - 2.0 / (9.0 * D) + z * np.sqrt(2.0 / (9.0 * D))
+    return float(np.sqrt(D * wh ** 3))
+
+
+def survivors(mu, sigma, lam, w, prune_c, emax):
+    """cnt[j] = number of components k that pass the sweep's pruning test for source component j at ||eps||max = emax.
+    mu is (K, D)."""
+    K, D = mu.shape
+    cnt = np.zeros(K, dtype=np.int64)
+    for j in range(K):
+        u = (mu[j][None, :] - mu) / (sigma[:, None] * lam[None, :])
+        un = np.sqrt((u * u).sum(1))
+        r = sigma[j] / sigma
+        tt = un - r * emax
+        bb = np.where(tt > 0, -0.5 * tt * tt, 0.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lck = np.log(w / w[j]) + D * (np.log(sigma[j]) - np.log(sigma))
+        lhs = bb + 0.5 * emax * emax + prune_c + lck + 0.5
+        keep = ~(lhs < 0.0) if prune_c > 0 else np.ones(K, dtype=bool)
+        cnt[j] = max(1, int(keep.sum()))
+    return cnt
+
+
+def plan(weights, tpc, G):
+    """tstart[G+1], jlo[K], jhi[K] for tile weights `weights[j]` (every tile of component j weighs the same)."""
+    K = len(weights)
+    pref = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
+    Wtot = int(pref[K]) * tpc
+    tstart = np.zeros(G + 1, dtype=np.int64)
+    for b in range(G + 1):
+        target = (Wtot * b) // G
+        lo = int(np.searchsorted(pref * tpc, target, side="right")) - 1   # largest jj with pref[jj]*tpc <= target
+        lo = min(lo, K)
+        if lo >= K:
+            t = K * tpc
+        else:
+            q = (target - int(pref[lo]) * tpc) // int(weights[lo])
+            t = lo * tpc + min(q, tpc)
+        tstart[b] = t
+    tstart[0], tstart[G] = 0, K * tpc
+    jlo = np.zeros(K, dtype=np.int64)
+    jhi = np.zeros(K, dtype=np.int64)
+    for j in range(K):
+        tlo, thi = j * tpc, (j + 1) * tpc
+        jlo[j] = min([b for b in range(G) if tstart[b + 1] > tlo], default=G - 1)
+        jhi[j] = max([b for b in range(G) if tstart[b] < thi], default=0)
+    return tstart, jlo, jhi
+
+
+def rmax_bound(K, tpc, G, c0):
+    """slots per CTA the host reserves (entmc2.cu make_plan2)"""
+    T = K * tpc
+    per = (T + G - 1) // G
+    per = (per * (c0 + K) + c0 - 1) // c0 + 2
+    return min(K + 1, (per + tpc - 1) // tpc + 1)

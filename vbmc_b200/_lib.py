@@ -88,7 +88,7 @@ EXPORTS = [
     "vbmc_b200_eps_upload", "vbmc_b200_eps_philox", "vbmc_b200_negelcbo", "vbmc_b200_entmc", "vbmc_b200_gplogjoint",
     "vbmc_b200_negelcbo_resident_loop", "vbmc_b200_profile_enable", "vbmc_b200_profile_get",
     "vbmc_b200_profile_reset", "vbmc_b200_measure_fp64_peak", "vbmc_b200_measure_hbm_copy", "vbmc_b200_flush_l2",
-    "vbmc_b200_philox_raw", "vbmc_b200_shard_range", "vbmc_b200_fminadam", "vbmc_b200_entmc_prune", "vbmc_b200_entmc_prune_stats", "vbmc_b200_gp_pred", "vbmc_b200_gp_post_update1", "vbmc_b200_gp_get_factor", "vbmc_b200_gp_nlz_batch", "vbmc_b200_gp_set_sn2_mult",
+    "vbmc_b200_philox_raw", "vbmc_b200_shard_range", "vbmc_b200_fminadam", "vbmc_b200_entmc_prune", "vbmc_b200_entmc_prune_stats", "vbmc_b200_entmc_balance", "vbmc_b200_entmc_plan_get", "vbmc_b200_gp_pred", "vbmc_b200_gp_post_update1", "vbmc_b200_gp_get_factor", "vbmc_b200_gp_nlz_batch", "vbmc_b200_gp_set_sn2_mult",
     "vbmc_b200_comm_p2p", "vbmc_b200_shared", "vbmc_b200_shared_release", "vbmc_b200_gp_tag_set", "vbmc_b200_gp_tag_get", "vbmc_b200_gp_shape", "vbmc_b200_entlb",
 ]
 
@@ -132,6 +132,8 @@ def load():
     lib.vbmc_b200_negelcbo_resident_loop.argtypes = [vp, C.POINTER(NegelcboArgs), C.c_int, C.POINTER(C.c_float)]
     lib.vbmc_b200_entmc_prune.argtypes = [vp, C.c_double]
     lib.vbmc_b200_entmc_prune_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.vbmc_b200_entmc_balance.argtypes = [vp, C.c_int, C.c_int]
+    lib.vbmc_b200_entmc_plan_get.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vbmc_b200_gp_pred.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p,
                                       c_double_p, c_double_p, c_double_p]
     lib.vbmc_b200_gp_set_sn2_mult.argtypes = [vp, c_double_p]

@@ -228,6 +228,21 @@ class Context:
         _lib.check(self.lib.vbmc_b200_entmc_prune_stats(self._h, int(bool(enable)), C.byref(k), C.byref(t)))
         return k.value, t.value
 
+    def entmc_balance(self, on=True, c0=0):
+        """Cost-weighted (default) or equal-count tile ranges of the FP64 entropy sweep (vbmc_b200_entmc_balance)."""
+        _lib.check(self.lib.vbmc_b200_entmc_balance(self._h, int(bool(on)), int(c0)))
+
+    def entmc_plan(self):
+        """(tstart[G+1], jlo[K], jhi[K], tpc) of the last balanced sweep, or None when the last step used equal counts."""
+        out = np.zeros(2048, dtype=np.int32)
+        G, tpc = C.c_int(), C.c_int()
+        _lib.check(self.lib.vbmc_b200_entmc_plan_get(self._h, out.ctypes.data_as(C.POINTER(C.c_int)), out.size, C.byref(G), C.byref(tpc)))
+        if G.value == 0:
+            return None
+        g, t = G.value, tpc.value
+        K = int(out[g]) // t   # tstart[G] = K * tpc
+        return out[:g + 1].copy(), out[g + 1:g + 1 + K].copy(), out[g + 1 + K:g + 1 + 2 * K].copy(), t
+
     def launch_count(self) -> int:
         n = C.c_longlong()
         _lib.check(self.lib.vbmc_b200_launch_count(self._h, C.byref(n)))

@@ -133,6 +133,8 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   }
   if (const char* g = getenv("VBMC_B200_GRAPHS")) c->graphs_enabled = strcmp(g, "0") != 0;
   if (const char* pc = getenv("VBMC_B200_ENTMC_PRUNE")) c->entmc_prune_c = atof(pc);
+  if (const char* pb = getenv("VBMC_B200_ENTMC_BALANCE")) c->ent_balance = atoi(pb) != 0;
+  if (const char* p0 = getenv("VBMC_B200_ENTMC_C0")) c->ent_balance_c0 = atoi(p0) < 1 ? 1 : (atoi(p0) > 4096 ? 4096 : atoi(p0));
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
     if (!strcmp(f, "separable")) c->entmc_form = 0;
     if (!strcmp(f, "direct")) c->entmc_form = 1;
@@ -152,9 +154,9 @@ int vbmc_b200_destroy(vbmc_b200_ctx* c) {
   if (c->adam_graph) cudaGraphExecDestroy(c->adam_graph);
   for (int i = 0; i < 2; ++i)
     if (c->trsm_graph[i]) cudaGraphExecDestroy(c->trsm_graph[i]);
-  vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork, &c->gpFlags,
+  vb::DevBuf* bufs[] = {&c->gpX, &c->gpHyp, &c->gpAlpha, &c->gpDerived, &c->gpL, &c->gpY, &c->gpS2, &c->gpWork, &c->gpFlags, &c->trsvFlags,
                         &c->vpBase, &c->vpCur, &c->bnd, &c->eps, &c->theta_dev, &c->out_dev, &c->R_dev,
-                        &c->ent_partial, &c->ent_partial2, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->trsmWork, &c->gpXalt, &c->gpAlphaAlt, &c->zigTab, &c->entlbWork};
+                        &c->ent_partial, &c->ent_partial2, &c->ent_plan, &c->glj_out, &c->flush, &c->varWork, &c->adamState, &c->adamXtab, &c->ent_tables, &c->entmc_prune_stats, &c->glj_part, &c->glj_ticket, &c->predWork, &c->trsmWork, &c->gpXalt, &c->gpAlphaAlt, &c->zigTab, &c->entlbWork};
   for (auto* b : bufs) b->release();
   if (c->theta_pinned) cudaFreeHost(c->theta_pinned);
   if (c->out_pinned) cudaFreeHost(c->out_pinned);
@@ -234,6 +236,28 @@ int vbmc_b200_entmc_prune(vbmc_b200_ctx* c, double log_threshold) {
   if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
   if (!(log_threshold >= 0.0)) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_entmc_prune: threshold must be >= 0 (0 disables pruning)");
   c->entmc_prune_c = log_threshold;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_entmc_balance(vbmc_b200_ctx* c, int on, int c0) {
+  if (!c) VB_FAIL(VBMC_B200_EINVAL, "null context");
+  c->ent_balance = on != 0;
+  if (c0 > 0) c->ent_balance_c0 = c0 > 4096 ? 4096 : c0;
+  return VBMC_B200_OK;
+}
+
+int vbmc_b200_entmc_plan_get(vbmc_b200_ctx* c, int* out, int cap, int* G, int* tpc) {
+  if (!c || !out || !G || !tpc) VB_FAIL(VBMC_B200_EINVAL, "null argument");
+  *G = 0;
+  *tpc = 0;
+  if (!c->ent_plan_active || !c->ent_plan.p) return VBMC_B200_OK;
+  const int n = c->ent_plan_req_G + 1 + 2 * c->K;
+  if (cap < n) VB_FAIL(VBMC_B200_EINVAL, "vbmc_b200_entmc_plan_get: out holds %d ints, %d needed", cap, n);
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  VB_CUDA(cudaMemcpy(out, c->ent_plan.p, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  *G = c->ent_plan_req_G;
+  *tpc = c->ent_plan_req_tpc;
   return VBMC_B200_OK;
 }
 
@@ -594,6 +618,8 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     VB_TRY(launch_philox(c, c->D, c->K, Ns, c->philox_seed, c->philox_stream, c->stream3, dyn_src));
     VB_CUDA(cudaEventRecord(c->ev_philox, c->stream3));
   }
+  // cost-weighted schedule of the FP64 sweep: vp_unpack2_kernel builds the tile ranges of this step from theta (entmc2.cu)
+  c->ent_plan_req = doH && entmc2_balance_params(c, Ns, &c->ent_plan_req_tpc, &c->ent_plan_req_G);
   VB_TRY(launch_vp_unpack(c, have_theta));
   if (doG) {
     VB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
@@ -762,6 +788,7 @@ static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask
   key.push_back(c->rank);
   key.push_back(c->p2p_ready ? reinterpret_cast<long long>(c->xchg_peers.p) : 0);
   key.push_back(c->glj_first);
+  key.push_back(c->ent_balance ? c->ent_balance_c0 : 0);
   return key;
 }
 

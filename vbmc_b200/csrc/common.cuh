@@ -233,6 +233,8 @@ struct vbmc_b200_ctx {
   vb::DevBuf gpX, gpHyp, gpAlpha, gpDerived, gpL, gpY, gpS2, gpWork;
   vb::DevBuf gpFlags;      // [S][Np/64] hand-over flags of the multi-CTA back substitution (gp_bsolve3_kernel)
   int bsolve_epoch = 0;    // value a raised flag carries in the current launch
+  vb::DevBuf trsvFlags;    // [S][ld/64 + 1] flags of the single-column sweeps (trsv1_kernel) + one error word at the end
+  bool trsv1_pending = false;  // a single-column sweep ran since the last trsv1_check
   std::vector<int> gpLchol;
   std::vector<int> gpLfactor;  // per sample: device L is a Cholesky factor (1) or -inv(K + diag) handed over by the host (0)
   std::vector<double> gpSn2mult;
@@ -292,6 +294,16 @@ struct vbmc_b200_ctx {
   // step buffers
   vb::DevBuf theta_dev, out_dev, R_dev, ent_partial, ent_partial2, glj_out, glj_part, glj_ticket;
   vb::DevBuf ent_tables;  // FP32 sweep: per-step tables (entmc_f32.cu)
+  // Cost-weighted schedule of the FP64 sweep (entmc2.cu): vp_unpack2_kernel estimates, per source component j, how many
+  // components survive the pruning test and cuts the K * tpc CTA-tiles into G ranges of equal estimated COST instead of equal
+  // count.  ent_plan: int tstart[G + 1] | jlo[K] | jhi[K].  ent_plan_req_*: request of the step being enqueued (consumed by
+  // launch_vp_unpack); ent_plan_active: the sweep and its reduction of this step read the table.
+  vb::DevBuf ent_plan;
+  bool ent_balance = true;          // VBMC_B200_ENTMC_BALANCE=0: equal-count ranges (round-2 schedule)
+  int ent_balance_c0 = 16;          // fixed cost of a tile in units of one scored component (VBMC_B200_ENTMC_C0)
+  bool ent_plan_req = false;
+  int ent_plan_req_tpc = 0, ent_plan_req_G = 0;
+  bool ent_plan_active = false;
   double* theta_pinned = nullptr;
   double* out_pinned = nullptr;
   size_t theta_pinned_cap = 0, out_pinned_cap = 0;
@@ -337,6 +349,7 @@ int gp_upload_derived(vbmc_b200_ctx* c, const vbmc_b200_gp_desc* g, int Ncov, in
 // ---- step pieces (each defined in its own .cu) ----
 int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta);
 int launch_entmc(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st);
+bool entmc2_balance_params(vbmc_b200_ctx* c, int Ns, int* tpc, int* G);
 int launch_entmc_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st);
 int launch_gplogjoint(vbmc_b200_ctx* c, int all_samples, cudaStream_t st);
 int launch_glj_reduce(vbmc_b200_ctx* c, cudaStream_t st, bool whole_step);
@@ -358,6 +371,8 @@ int run_factor_inverse(vbmc_b200_ctx* c, int N, int ld, const double* R, double*
 int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* isfac_dev, cudaStream_t st);
 int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st, const int* isfac_dev = nullptr);
 bool run_trsm_blocked(vbmc_b200_ctx* c, int T, double* Z, const int* isfac_dev, cudaStream_t st, int* rc, bool backward = false);
+bool run_trsv1(vbmc_b200_ctx* c, double* Z, const int* isfac_dev, cudaStream_t st, int* rc, bool backward);
+int trsv1_check(vbmc_b200_ctx* c);
 int pad_identity(double* L, int N, int Np, int S, cudaStream_t st);
 int entmc_num_tiles(vbmc_b200_ctx* c, int Ns, int* tiles_per_comp, int* pairs_per_tile, int* nwarps, size_t* smem);
 void shard_range(int total, int nranks, int rank, int* begin, int* end);

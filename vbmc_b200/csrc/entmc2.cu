@@ -38,6 +38,7 @@ struct Entmc2Args {
   int tpc;                   // CTA-tiles (nwarps groups) per component
   int ntiles;                // K * tpc
   int rmax;                  // partial slots per CTA (runs of equal j inside a CTA's tile range)
+  const int* tstart;         // cost-weighted schedule: CTA b sweeps tiles [tstart[b], tstart[b+1]) (vp_unpack2_kernel); null: equal counts
   int need;                  // NEED_* mask
   int pstride;               // 1 + 2*D + K doubles per partial
   double prune_c;
@@ -196,7 +197,8 @@ __device__ __forceinline__ void entmc2_body(const Entmc2Args& a, uint32_t tmem_b
 
   // this CTA's contiguous tile range: owner(t) = floor(t * G / T)
   const long long T = a.ntiles, G = gridDim.x, b = blockIdx.x;
-  const int t0 = static_cast<int>((b * T + G - 1) / G), t1 = static_cast<int>(((b + 1) * T + G - 1) / G);
+  const int t0 = a.tstart ? a.tstart[b] : static_cast<int>((b * T + G - 1) / G);
+  const int t1 = a.tstart ? a.tstart[b + 1] : static_cast<int>(((b + 1) * T + G - 1) / G);
   if (t0 >= t1) return;
 
   uint32_t phase = 0;
@@ -581,6 +583,7 @@ struct Entmc2Red {
   const double* partial;
   const int* form_flag;
   int G, tpc, ntiles, rmax, pstride, D, K, nb1;
+  const int* tstart;   // cost-weighted schedule (null: equal counts): tstart[G + 1], then jlo[K], jhi[K] = first / last CTA of component j
   const double* w;
   double* R;
   int oHs, oM, oE, oWc;
@@ -588,6 +591,16 @@ struct Entmc2Red {
 };
 
 __device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, int j, int i) {
+  if (a.tstart) {
+    const int b_lo = a.tstart[a.G + 1 + j], b_hi = a.tstart[a.G + 1 + a.K + j];
+    double s = 0.0;
+    for (int b = b_lo; b <= b_hi; ++b) {
+      const int t0 = a.tstart[b];
+      if (t0 >= a.tstart[b + 1]) continue;   // a CTA without tiles wrote nothing
+      s += a.partial[(static_cast<size_t>(b) * a.rmax + (j - t0 / a.tpc)) * a.pstride + i];
+    }
+    return s;
+  }
   const long long T = a.ntiles;
   const int b_lo = static_cast<int>((static_cast<long long>(j) * a.tpc * a.G) / T);
   const int b_hi = static_cast<int>(((static_cast<long long>(j + 1) * a.tpc - 1) * a.G) / T);
@@ -695,10 +708,25 @@ static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
   a.ntiles = a.tpc * K;
   pl->grid = a.ntiles < c->num_sms ? a.ntiles : c->num_sms;
   if (pl->grid > 0) {
-    const int per_cta = (a.ntiles + pl->grid - 1) / pl->grid;
+    int per_cta = (a.ntiles + pl->grid - 1) / pl->grid;
+    // cost-weighted ranges: a tile weighs between c0 and c0 + K, so a range holds at most (c0 + K) / c0 times the average count
+    if (c->ent_plan_active) per_cta = static_cast<int>((static_cast<long long>(per_cta) * (c->ent_balance_c0 + K) + c->ent_balance_c0 - 1) / c->ent_balance_c0) + 2;
     a.rmax = (per_cta + a.tpc - 1) / a.tpc + 1;
+    if (a.rmax > K + 1) a.rmax = K + 1;
   }
   pl->smem = a.off_warp + static_cast<size_t>(nw) * a.warp_bytes;
+  return true;
+}
+
+bool entmc2_enabled(vbmc_b200_ctx* c);
+// Shape of the sweep's schedule for the step being enqueued (api.cu asks before launching vp_unpack2_kernel, which builds the
+// cost-weighted tile ranges); false: this step's sweep does not take the FP64 second-generation kernel.
+bool entmc2_balance_params(vbmc_b200_ctx* c, int Ns, int* tpc, int* G) {
+  if (!c->ent_balance || !entmc2_enabled(c)) return false;
+  Entmc2Plan pl;
+  if (!make_plan2(c, Ns, &pl) || pl.a.ntiles == 0 || pl.grid < 2) return false;
+  *tpc = pl.a.tpc;
+  *G = pl.grid;
   return true;
 }
 
@@ -734,6 +762,7 @@ int launch_entmc2(vbmc_b200_ctx* c, int Ns, int need_mask, cudaStream_t st, bool
   a.eps = c->eps.d();
   a.mu = c->vp.mu; a.sigma = c->vp.sigma; a.lambda = c->vp.lambda; a.ck = c->vp.ck; a.ak = c->vp.ak;
   a.partial = c->ent_partial2.d();
+  a.tstart = c->ent_plan_active ? reinterpret_cast<const int*>(c->ent_plan.p) : nullptr;
   a.prune_c = c->entmc_prune_c;
   a.prune_stats = c->entmc_prune_stats_on ? reinterpret_cast<unsigned long long*>(c->entmc_prune_stats.p) : nullptr;
 #define VB_E2(dp)                                                                                                       \
@@ -756,6 +785,7 @@ int launch_entmc2_reduce(vbmc_b200_ctx* c, int Ns, int S_layout, cudaStream_t st
   rl.init(c->D, c->K, S_layout);
   Entmc2Red r;
   r.partial = c->ent_partial2.d();
+  r.tstart = c->ent_plan_active ? reinterpret_cast<const int*>(c->ent_plan.p) : nullptr;
   r.form_flag = c->vp.form_flag;
   r.G = pl.grid; r.tpc = pl.a.tpc; r.ntiles = pl.a.ntiles; r.rmax = pl.a.rmax; r.pstride = pl.a.pstride;
   r.D = c->D; r.K = c->K;

@@ -20,6 +20,11 @@ struct UnpackArgs {
   VpDev vp;
   double* cn;  // [K] nf/sigma_k^D ; cn[K] = nf
   double* scratch;  // [K*D]
+  // cost-weighted schedule of the FP64 entropy sweep (vp_unpack2_kernel only; null: none requested)
+  int* plan;          // tstart[G + 1] | jlo[K] | jhi[K]
+  int* plan_w;        // [K] scratch: estimated cost of one tile of component j
+  int plan_tpc, plan_G, plan_c0;
+  double plan_prune, plan_emax;   // pruning constant of the sweep, typical max ||eps|| of a warp's 32 draws
 };
 
 // One CTA.  Everything the later phases re-read (mu, sigma, lambda, 1/(sigma lambda)^2) is kept in shared memory, so the
@@ -180,9 +185,12 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
   double* s_sigma = usm;             // [K]
   double* s_lambda = s_sigma + K;    // [D]
   double* s_muj = s_lambda + D;      // [D]
+  double* s_lsig = s_muj + D;        // [K] log sigma_k
   __shared__ double part[128];
   __shared__ double s_es, s_nf;
+  __shared__ int s_cnt, s_last;
   const bool ht = a.have_theta != 0;
+  if (tid == 0) { s_cnt = 0; s_last = 0; }
   if (j == 0 && tid < 2 && a.dyn_src) a.vp.dyn_snap[tid] = a.dyn_src[tid];
   int idx = 0;
   const int o_mu = 0;
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
       ls = log(sg);
     }
     s_sigma[k] = sg;
+    s_lsig[k] = ls;
     const double et = (ht && a.opt[3]) ? a.theta[o_eta + k] : a.base_eta[k];
     es += exp(et);  // (:46-47) no max-shift, like the reference
     if (k == j) {
@@ -270,6 +279,15 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     const double r = s_sigma[j] * isg;
     const double v = fma(r * r, eemax, uu);
     m = (v > m || !(v == v)) ? v : m;
+    if (a.plan) {
+      // will component k survive the sweep's pruning test (entmc2.cu) for a typical warp of draws of component j?
+      // log(ck_k / ck_j) = log(w_k / w_j) + D (log sigma_j - log sigma_k)
+      const double lw = (ht && a.opt[3]) ? a.theta[o_eta + k] - a.theta[o_eta + j] : log(a.base_w[k] / a.base_w[j]);
+      const double tt = sqrt(uu) - r * a.plan_emax;
+      const double bb = tt > 0.0 ? -0.5 * tt * tt : 0.0;
+      const double lhs = bb + 0.5 * a.plan_emax * a.plan_emax + a.plan_prune + lw + D * (s_lsig[j] - s_lsig[k]) + 0.5;
+      if (!(lhs < 0.0) || a.plan_prune <= 0.0) atomicAdd(&s_cnt, 1);
+    }
   }
   part[tid] = m;
   __syncthreads();
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     __syncthreads();
   }
   if (tid == 0) {
+    if (a.plan) a.plan_w[j] = a.plan_c0 + (s_cnt < 1 ? 1 : s_cnt);
     // non-negative doubles order like their bit patterns; a NaN (0x7ff8...) is larger than every finite value
     unsigned long long* gmax = reinterpret_cast<unsigned long long*>(a.vp.form_flag) + 1;
     unsigned* ticket = reinterpret_cast<unsigned*>(a.vp.form_flag) + 1;
@@ -288,7 +307,77 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
       const double gm = __longlong_as_double(static_cast<long long>(atomicExch(gmax, 0ULL)));
       *a.vp.form_flag = a.force_form >= 0 ? a.force_form : ((gm <= 2.0e5) ? 2 : 1);
       *ticket = 0;
+      s_last = 1;
     }
+  }
+  if (!a.plan) return;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA to arrive: cut the K * tpc tiles of the sweep into G contiguous ranges of equal estimated cost ----
+  // (every tile of component j costs w_j; boundaries fall on tiles; sweep_plan_host in tests/ restates this arithmetic)
+  __shared__ long long s_pref[257];   // s_pref[j] = w_0 + ... + w_{j-1}
+  __shared__ int s_t[258];            // tstart
+  if (tid < 32) {
+    long long loc[8], run = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jj = 8 * tid + q;
+      run += jj < K ? static_cast<long long>(__ldcg(a.plan_w + jj)) : 0LL;
+      loc[q] = run;
+    }
+    long long inc = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const long long v = __shfl_up_sync(0xffffffffu, inc, off);
+      if (tid >= off) inc += v;
+    }
+    const long long base = inc - run;
+    if (tid == 0) s_pref[0] = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int jj = 8 * tid + q;
+      if (jj < K) s_pref[jj + 1] = base + loc[q];
+    }
+  }
+  __syncthreads();
+  const int G = a.plan_G, tpc = a.plan_tpc;
+  const long long Wtot = s_pref[K] * tpc;
+  for (int b = tid; b <= G; b += nt) {
+    const long long target = (Wtot * b) / G;
+    int lo = 0, hi = K;   // largest jj in [0, K] with s_pref[jj] * tpc <= target
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pref[mid] * tpc <= target) lo = mid; else hi = mid - 1;
+    }
+    int t;
+    if (lo >= K) {
+      t = K * tpc;
+    } else {
+      const long long wj = s_pref[lo + 1] - s_pref[lo];
+      long long q = (target - s_pref[lo] * tpc) / wj;
+      if (q > tpc) q = tpc;
+      t = lo * tpc + static_cast<int>(q);
+    }
+    if (b == 0) t = 0;
+    if (b == G) t = K * tpc;
+    s_t[b] = t;
+    a.plan[b] = t;
+  }
+  __syncthreads();
+  for (int jj = tid; jj < K; jj += nt) {
+    const int tlo = jj * tpc, thi = (jj + 1) * tpc;
+    int lo = 0, hi = G - 1;   // smallest b in [0, G) with s_t[b + 1] > tlo
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_t[mid + 1] > tlo) hi = mid; else lo = mid + 1;
+    }
+    a.plan[G + 1 + jj] = lo;
+    lo = 0; hi = G - 1;       // largest b in [0, G) with s_t[b] < thi
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_t[mid] < thi) lo = mid; else hi = mid - 1;
+    }
+    a.plan[G + 1 + K + jj] = lo;
   }
 }
 
@@ -721,10 +810,29 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   a.scratch = c->vp.scratch;
   a.want_cblob = c->entmc_form == 0 ? 1 : 0;
   static const bool v1 = getenv("VBMC_B200_UNPACK_V1") && atoi(getenv("VBMC_B200_UNPACK_V1")) != 0;
+  // cost-weighted sweep schedule requested by the step being enqueued (api.cu enqueue_step)
+  a.plan = nullptr; a.plan_w = nullptr;
+  a.plan_tpc = a.plan_G = a.plan_c0 = 0;
+  a.plan_prune = a.plan_emax = 0.0;
+  c->ent_plan_active = false;
+  if (c->ent_plan_req && !v1 && c->K <= 256 && c->ent_plan_req_G <= 256) {
+    const int G = c->ent_plan_req_G, K = c->K;
+    VB_TRY(c->ent_plan.reserve(sizeof(int) * (512 + 3 * 256 + 8)));
+    a.plan = reinterpret_cast<int*>(c->ent_plan.p);
+    a.plan_w = a.plan + (G + 1 + 2 * K);
+    a.plan_tpc = c->ent_plan_req_tpc; a.plan_G = G; a.plan_c0 = c->ent_balance_c0;
+    a.plan_prune = c->entmc_prune_c;
+    // expected maximum of ||eps|| over a warp's 32 draws: the 1 - 1/33 quantile of chi^2_D (Wilson-Hilferty)
+    const double D = c->D, z = 1.876;
+    const double wh = 1.0 - 2.0 / (9.0 * D) + z * sqrt(2.0 / (9.0 * D));
+    a.plan_emax = sqrt(D * wh * wh * wh);
+    c->ent_plan_active = true;
+  }
+  c->ent_plan_req = false;
   KernelScope ks(c, "vp_unpack", c->stream);
   if (!v1) {
     a.want_cblob = 0;
-    vp_unpack2_kernel<<<c->K, 128, sizeof(double) * (c->K + 2 * c->D), c->stream>>>(a);
+    vp_unpack2_kernel<<<c->K, 128, sizeof(double) * (2 * c->K + 2 * c->D), c->stream>>>(a);
     VB_CUDA(cudaGetLastError());
     return VBMC_B200_OK;
   }

@@ -219,6 +219,7 @@ extern "C" int vbmc_b200_gp_pred(vbmc_b200_ctx* c, int Nstar, const double* Xsta
     tmp.resize(static_cast<size_t>(S) * T);
     VB_CUDA(cudaMemcpyAsync(tmp.data(), d_fmu, sizeof(double) * S * T, cudaMemcpyDeviceToHost, st));
     VB_CUDA(cudaStreamSynchronize(st));
+    VB_TRY(trsv1_check(c));
     for (int s = 0; s < S; ++s) memcpy(&hf[static_cast<size_t>(s) * Nstar + t0], &tmp[static_cast<size_t>(s) * T], sizeof(double) * T);
     if (want_var) {
       VB_CUDA(cudaMemcpyAsync(tmp.data(), d_fs2, sizeof(double) * S * T, cudaMemcpyDeviceToHost, st));
@@ -404,6 +405,7 @@ extern "C" int vbmc_b200_gp_post_update1(vbmc_b200_ctx* c, const double* xstar, 
     VB_CUDA(cudaMemcpy2DAsync(Lcol_out, sizeof(double) * N1, c->gpL.d() + static_cast<size_t>(N) * ld, sizeof(double) * ld * ld,
                               sizeof(double) * N1, S, cudaMemcpyDeviceToHost, st));
   VB_CUDA(cudaStreamSynchronize(st));
+  VB_TRY(trsv1_check(c));
   if (sW_out) memcpy(sW_out, sw.data(), sizeof(double) * S);
   std::swap(c->gpAlpha, c->gpAlphaAlt);
   std::swap(c->gpX, c->gpXalt);

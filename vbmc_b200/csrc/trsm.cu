@@ -10,6 +10,8 @@
 // Every R tile is read once per 64 right-hand sides, all (j, column-tile, sample) work items of a step run in parallel.
 // The factors are read in place from the resident buffer (leading dimension ld >= Np, unit diagonal in the padding rows:
 // garbage in padding rows / columns only ever reaches padding rows of Z, which are dropped).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb {
@@ -318,6 +320,241 @@ bool run_trsm_blocked(vbmc_b200_ctx* c, int T, double* Z, const int* isfac_dev, 
     *rc = VBMC_B200_ECUDA;
   }
   return true;
+}
+
+// ---- ONE right-hand side per sample (the rank-one update, gplite_post.m:191,228-230; gplite_pred at a single point) ----------
+// The blocked sweep above is 2 nb dependent launches of (almost) empty grids for a single column: ~1 ms per direction at N = 2000.
+// Here one launch does the whole sweep: P CTAs per sample (P * S <= number of SMs, all resident), block J of the vector belongs
+// to CTA J mod P, which is the only one that ever writes z_J.  Per 64-block b, in sweep order:
+//   owner:   stage R_bb in shared memory, warp 0 substitutes through it (lane owns entries lane, lane+32; the pivot value is
+//            broadcast by shuffle, reciprocals of the diagonal are taken off the chain), store x_b in place, raise flag[s][b];
+//   others:  the factor entries of the step are loaded BEFORE the flag is awaited (their addresses do not depend on x);
+//   all:     z_J -= R(b, J)' x_b (forward) / R(J, b) x_b (backward) for the owned blocks not yet solved, four per pass.
+// `epoch` tells launches apart (flags are never reset).  A peer that does not arrive within ~2^22 polls poisons the sample's
+// vector with NaN and raises *err instead of hanging the GPU.
+__device__ __forceinline__ int t_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void t_st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(1024) trsv1_kernel(int N, int ld, const double* __restrict__ L, size_t Lstride, double* Z,
+                                                     const int* isfac, int* flags, int nbflag, int epoch, int* err) {
+  extern __shared__ __align__(16) double vsm[];
+  double (*Rk)[TT + 1] = reinterpret_cast<double (*)[TT + 1]>(vsm);   // Rk[c][r] = R_bb(r, c), r <= c; identity outside the N x N factor
+  double (*part)[TT] = reinterpret_cast<double (*)[TT]>(vsm + TT * (TT + 1));   // [16][64]
+  double* xk = vsm + TT * (TT + 1) + 16 * TT;                           // [64]
+  double* zown = xk + TT;                                               // [ceil(nbN / P)][64]: the blocks of z this CTA owns
+  __shared__ int timed_out;
+  const int s = blockIdx.y, me = blockIdx.x, P = gridDim.x, tid = threadIdx.x, lane = tid & 31;
+  if (isfac && !isfac[s]) return;
+  const int nbN = (N + TT - 1) / TT;
+  const double* Ls = L + static_cast<size_t>(s) * Lstride;
+  double* z = Z + static_cast<size_t>(s) * N;
+  int* fl = flags + static_cast<size_t>(s) * nbflag;
+  const int blk = tid >> 8, sub = (tid >> 6) & 3, r = tid & 63;
+  if (tid == 0) timed_out = 0;
+  for (int i = tid; me + P * (i >> 6) < nbN; i += 1024) {
+    const int g = (me + P * (i >> 6)) * TT + (i & 63);
+    zown[i] = g < N ? z[g] : 0.0;
+  }
+  auto stage_diag = [&](int b) {
+    const int b0 = b * TT;
+    for (int i = tid; i < TT * TT; i += 1024) {
+      const int c = i >> 6, rr = i & 63;
+      Rk[c][rr] = (b0 + c < N && b0 + rr < N && rr <= c) ? Ls[static_cast<size_t>(b0 + c) * ld + b0 + rr] : (c == rr ? 1.0 : 0.0);
+    }
+  };
+  int staged = -1;   // block whose diagonal tile sits in Rk
+  __syncthreads();
+  for (int step = 0; step < nbN; ++step) {
+    const int b = BACKWARD ? nbN - 1 - step : step;
+    const int bnext = BACKWARD ? b - 1 : b + 1;
+    const int b0 = b * TT;
+    // first owned block that still needs this step's update; the others follow at distance P
+    int Jfirst;
+    if (BACKWARD) {
+      Jfirst = b == 0 ? -1 : b - 1 - ((b - 1 - me) % P + P) % P;           // largest J < b, J == me (mod P); negative: none
+    } else {
+      Jfirst = b + 1 + ((me - (b + 1)) % P + P) % P;                        // smallest J > b, J == me (mod P)
+      if (Jfirst >= nbN) Jfirst = -1;
+    }
+    auto block_of = [&](int J0, int q) -> int {   // q-th block of a pass that starts at J0; -1: none
+      if (J0 < 0) return -1;
+      const int J = BACKWARD ? J0 - q * P : J0 + q * P;
+      return (J < 0 || J >= nbN) ? -1 : J;
+    };
+    // thread (blk, sub, r): backward -> row r of block J, columns 16 sub .. 16 sub + 15 of block b  (coalesced over r);
+    //                       forward  -> column r of block J, rows 16 sub .. 16 sub + 15 of block b    (128 contiguous bytes)
+    auto load16 = [&](int J, double* rv) {
+      if (BACKWARD) {
+        const double* col = Ls + static_cast<size_t>(b0 + 16 * sub) * ld + J * TT + r;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) rv[q] = __ldcs(col + static_cast<size_t>(q) * ld);
+      } else {
+        const double2* col = reinterpret_cast<const double2*>(Ls + static_cast<size_t>(J * TT + r) * ld + b0 + 16 * sub);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double2 v = __ldcs(col + q);
+          rv[2 * q] = v.x;
+          rv[2 * q + 1] = v.y;
+        }
+      }
+    };
+    double rv[16];
+    const int Jmine = block_of(Jfirst, blk);
+    if (Jmine >= 0) load16(Jmine, rv);
+    if (b % P == me) {
+      if (staged != b) {
+        stage_diag(b);
+        staged = b;
+        __syncthreads();
+      }
+      if (tid < 32) {
+        const double d0 = 1.0 / Rk[lane][lane], d1 = 1.0 / Rk[lane + 32][lane + 32];
+        const double* zb = zown + (b / P) * TT;
+        double x0 = zb[lane], x1 = zb[lane + 32];
+        if (BACKWARD) {
+#pragma unroll 8
+          for (int p = TT - 1; p >= 32; --p) {
+            const double xp = __shfl_sync(0xffffffffu, x1 * d1, p - 32);
+            if (lane == p - 32) x1 = xp;
+            if (lane + 32 < p) x1 = fma(-Rk[p][lane + 32], xp, x1);
+            x0 = fma(-Rk[p][lane], xp, x0);
+          }
+#pragma unroll 8
+          for (int p = 31; p >= 0; --p) {
+            const double xp = __shfl_sync(0xffffffffu, x0 * d0, p);
+            if (lane == p) x0 = xp;
+            if (lane < p) x0 = fma(-Rk[p][lane], xp, x0);
+          }
+        } else {
+#pragma unroll 8
+          for (int p = 0; p < 32; ++p) {
+            const double xp = __shfl_sync(0xffffffffu, x0 * d0, p);
+            if (lane == p) x0 = xp;
+            if (lane > p) x0 = fma(-Rk[lane][p], xp, x0);
+            x1 = fma(-Rk[lane + 32][p], xp, x1);
+          }
+#pragma unroll 8
+          for (int p = 32; p < TT; ++p) {
+            const double xp = __shfl_sync(0xffffffffu, x1 * d1, p - 32);
+            if (lane == p - 32) x1 = xp;
+            if (lane + 32 > p) x1 = fma(-Rk[lane + 32][p], xp, x1);
+          }
+        }
+        xk[lane] = x0;
+        xk[lane + 32] = x1;
+        if (b0 + lane < N) z[b0 + lane] = x0;
+        if (b0 + lane + 32 < N) z[b0 + lane + 32] = x1;
+        __threadfence();
+      }
+      __syncthreads();
+      if (tid == 0 && P > 1) t_st_release(fl + b, epoch);
+    } else {
+      // my turn comes next: fetch my diagonal tile while the current owner is still solving
+      if (bnext >= 0 && bnext < nbN && bnext % P == me) {
+        stage_diag(bnext);
+        staged = bnext;
+      }
+      if (tid == 0) {
+        int spins = 0;
+        while (t_ld_acquire(fl + b) != epoch) {
+          if (++spins > (1 << 22)) { timed_out = 1; break; }
+        }
+      }
+      __syncthreads();
+      if (timed_out) {
+        if (tid == 0) {
+          atomicExch(err, epoch);
+          z[0] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        return;
+      }
+      if (tid < TT) xk[tid] = (b0 + tid < N) ? __ldcg(z + b0 + tid) : 0.0;
+      __syncthreads();
+    }
+    // ---- update of the owned, not yet solved blocks, four per pass ----
+    for (int J0 = Jfirst; J0 >= 0 && J0 < nbN; J0 += BACKWARD ? -4 * P : 4 * P) {
+      const int J = block_of(J0, blk);
+      if (J0 != Jfirst && J >= 0) load16(J, rv);
+      double a0 = 0.0, a1 = 0.0;
+      if (J >= 0) {
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+          a0 = fma(rv[q], xk[16 * sub + q], a0);
+          a1 = fma(rv[q + 1], xk[16 * sub + q + 1], a1);
+        }
+      }
+      part[4 * blk + sub][r] = a0 + a1;
+      __syncthreads();
+      if (tid < 256) {
+        const int J2 = block_of(J0, tid >> 6);
+        if (J2 >= 0 && J2 * TT + r < N) {
+          const int q4 = 4 * (tid >> 6);
+          zown[(J2 / P) * TT + r] -= (part[q4][r] + part[q4 + 1][r]) + (part[q4 + 2][r] + part[q4 + 3][r]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Single right-hand side per sample, Z[S][N] in place.  Returns false (nothing done) when this path does not apply.
+bool run_trsv1(vbmc_b200_ctx* c, double* Z, const int* isfac_dev, cudaStream_t st, int* rc, bool backward) {
+  *rc = VBMC_B200_OK;
+  static const bool off = getenv("VBMC_B200_TRSV1") && atoi(getenv("VBMC_B200_TRSV1")) == 0;
+  const int N = c->gp.N, S = c->gp.S, ld = c->gpLd;
+  const int nbN = (N + TT - 1) / TT;
+  if (off || ld < nbN * TT || (ld & 1) || S > c->num_sms) return false;
+  const int nbflag = ld / TT + 1;
+  const size_t need = sizeof(int) * (static_cast<size_t>(S) * nbflag + 1);
+  if (c->trsvFlags.cap < need) {   // zeroed when (re)allocated; launches are told apart by an epoch; last word: error flag
+    if (c->trsvFlags.reserve(need + sizeof(int) * 8 * S) != VBMC_B200_OK || cudaMemsetAsync(c->trsvFlags.p, 0, c->trsvFlags.cap, st) != cudaSuccess) {
+      *rc = VBMC_B200_ECUDA;
+      return true;
+    }
+  }
+  int* flags = reinterpret_cast<int*>(c->trsvFlags.p);
+  int* err = flags + c->trsvFlags.cap / sizeof(int) - 1;
+  int P = c->num_sms / S;
+  P = P < 1 ? 1 : (P > nbN ? nbN : P);
+  if (P > 8) P = 8;
+  const int smem = static_cast<int>(sizeof(double)) * (TT * (TT + 1) + 16 * TT + TT + (nbN + P - 1) / P * TT);
+  if (smem > static_cast<int>(c->smem_optin) - 1024) return false;   // N beyond ~400 000 per CTA: the blocked sweep takes it
+  if (cudaFuncSetAttribute(trsv1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+      cudaFuncSetAttribute(trsv1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  KernelScope ks(c, "pred_trsm", st);
+  const int epoch = ++c->bsolve_epoch;
+  if (backward)
+    trsv1_kernel<true><<<dim3(P, S), 1024, smem, st>>>(N, ld, c->gpL.d(), static_cast<size_t>(ld) * ld, Z, isfac_dev, flags, nbflag, epoch, err);
+  else
+    trsv1_kernel<false><<<dim3(P, S), 1024, smem, st>>>(N, ld, c->gpL.d(), static_cast<size_t>(ld) * ld, Z, isfac_dev, flags, nbflag, epoch, err);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("trsv1: kernel launch failed");
+    *rc = VBMC_B200_ECUDA;
+  }
+  c->trsv1_pending = true;
+  return true;
+}
+
+// After the caller's stream synchronisation: did a CTA of a single-column sweep give up waiting for a peer?
+int trsv1_check(vbmc_b200_ctx* c) {
+  if (!c->trsv1_pending) return VBMC_B200_OK;
+  c->trsv1_pending = false;
+  int h = 0;
+  const int* err = reinterpret_cast<const int*>(c->trsvFlags.p) + c->trsvFlags.cap / sizeof(int) - 1;
+  VB_CUDA(cudaMemcpy(&h, err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h != 0) {
+    cudaMemset(const_cast<int*>(err), 0, sizeof(int));
+    VB_FAIL(VBMC_B200_ECUDA, "vbmc_b200:backsolve: a CTA of the single-column triangular sweep did not arrive (epoch %d)", h);
+  }
+  return VBMC_B200_OK;
 }
 
 // identity on the padding diagonal of factors attached from the host (rows/columns N .. Np-1)

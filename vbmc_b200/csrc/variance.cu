@@ -447,7 +447,9 @@ int run_rhs_solve(vbmc_b200_ctx* c, int ncols, double* Z, double* W, const int* 
   a.Z = Z; a.W = W; a.isfac = isfac_dev; a.unit_rhs = 0;
   static const bool blocked_off = getenv("VBMC_B200_TRSM_BLOCKED") && atoi(getenv("VBMC_B200_TRSM_BLOCKED")) == 0;
   int rc = VBMC_B200_OK;
-  if (!blocked_off && run_trsm_blocked(c, ncols, Z, isfac_dev, st, &rc)) {
+  if (!blocked_off && ncols == 1 && run_trsv1(c, Z, isfac_dev, st, &rc, false)) {
+    VB_TRY(rc);   // one column per sample: the whole sweep in one launch (trsm.cu)
+  } else if (!blocked_off && run_trsm_blocked(c, ncols, Z, isfac_dev, st, &rc)) {
     VB_TRY(rc);   // blocked DMMA forward substitution (trsm.cu)
   } else {
     KernelScope ks(c, "pred_trsm", st);
@@ -471,6 +473,7 @@ int run_rhs_backsolve(vbmc_b200_ctx* c, int ncols, double* Z, cudaStream_t st, c
   a.Z = Z; a.isfac = isfac_dev;
   static const bool blocked_off = getenv("VBMC_B200_TRSM_BLOCKED") && atoi(getenv("VBMC_B200_TRSM_BLOCKED")) == 0;
   int rc = VBMC_B200_OK;
+  if (!blocked_off && ncols == 1 && run_trsv1(c, Z, isfac_dev, st, &rc, true)) return rc;
   if (!blocked_off && run_trsm_blocked(c, ncols, Z, isfac_dev, st, &rc, true)) return rc;
   KernelScope ks(c, "pred_trsm", st);
   return launch_var_kernel(c, VK_BWD, a, ncols, c->gp.S, 64 * 65, 0, st, "gplite_post");
