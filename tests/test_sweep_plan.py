@@ -65,7 +65,7 @@ def test_plan_balances_the_c3_mixture():
 
 # ---------------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,over", [("c3", dict(N=200, S=2, Ns=8192)), ("c3", dict(N=120, S=2, Ns=2048, K=160)),
+@pytest.mark.parametrize("name,over", [("c3", dict(N=200, S=2, Ns=8192)), ("c3", dict(N=200, S=2, Ns=2048, K=160)),
                                        ("c2", dict(N=100, S=2, Ns=4096))])
 def test_device_plan_matches_host_restatement_and_results_do_not_depend_on_it(gpu_ctx, name, over):
     import vbmc_b200

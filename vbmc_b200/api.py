@@ -149,14 +149,54 @@ def _freeze_gp(gp):
 
 
 class _GpResident:
-    __slots__ = ("ident", "frozen", "content", "content_L", "has_L", "ref")
+    """What the device holds.  For a FrozenStruct produced by this module nothing is read at construction: the struct cannot
+    change, so its identity key and content probes are computed from it the first time a DIFFERENT object is compared with it
+    (0.5 ms of the 0.8 ms of Python per gplite_post call at S = 20, N = 2000 otherwise)."""
+    __slots__ = ("_ident", "_frozen", "_content", "_content_L", "_with_L", "has_L", "ref")
 
     def __init__(self, gp, has_L):
         self.ref = gp if isinstance(gp, FrozenStruct) else None   # strong reference: the id cannot be recycled while it is resident
-        self.ident, self.frozen = _gp_identity(gp)
-        self.content = _gp_content(gp, False)
-        self.content_L = _gp_content(gp, True) if (has_L and all(p.get("L") is not None for p in gp["post"])) else None
         self.has_L = has_L
+        self._with_L = has_L and all(p.get("L") is not None for p in gp["post"])
+        self._ident = self._frozen = self._content = self._content_L = None
+        if self.ref is None:
+            self._ident, self._frozen = _gp_identity(gp)
+            self._content = _gp_content(gp, False)
+            self._content_L = _gp_content(gp, True) if self._with_L else None
+
+    def _fill_ident(self):
+        if self._ident is None:
+            self._ident, self._frozen = _gp_identity(self.ref)
+
+    @property
+    def ident(self):
+        self._fill_ident()
+        return self._ident
+
+    @ident.setter
+    def ident(self, v):
+        self._ident = v
+
+    @property
+    def frozen(self):
+        self._fill_ident()
+        return self._frozen
+
+    @frozen.setter
+    def frozen(self, v):
+        self._frozen = v
+
+    @property
+    def content(self):
+        if self._content is None:
+            self._content = _gp_content(self.ref, False)
+        return self._content
+
+    @property
+    def content_L(self):
+        if self._content_L is None and self._with_L and self.ref is not None:
+            self._content_L = _gp_content(self.ref, True)
+        return self._content_L
 
 
 class _CallFrame:
@@ -743,7 +783,9 @@ def gplite_post(hyp, X, y, covfun=None, meanfun=None, noisefun=None, s2=None, *,
     Lchol = np.zeros(S, dtype=np.int32)
     _lib.check(ctx.lib.vbmc_b200_gp_post(ctx.handle, C.byref(d), dptr(alpha), dptr(L), dptr(sW1), dptr(mult),
                                          Lchol.ctypes.data_as(_lib.c_int_p)))
-    gp["post"] = [{"hyp": hyp[:, s].copy(), "alpha": alpha[s].copy(), "sW": np.full(N, sW1[s]),
+    # per-sample rows are views of the (frozen) result arrays; sW is a constant vector (gplite_core.m:281): a read-only broadcast
+    hypT = np.ascontiguousarray(hyp.T)
+    gp["post"] = [{"hyp": hypT[s], "alpha": alpha[s], "sW": np.broadcast_to(sW1[s:s + 1], (N,)),
                    "L": None if L is None else L[s].T.copy(), "sn2_mult": float(mult[s]), "Lchol": bool(Lchol[s])}
                   for s in range(S)]
     gp = _freeze_gp(gp)
