@@ -3,29 +3,34 @@ vp_unpack2_kernel; consumed by entmc2_kernel / entmc2_reduce_kernel).  Test help
 import numpy as np
 
 
-def typical_emax(D):
-    """1 - 1/33 quantile of chi^2_D (Wilson-Hilferty), square root: the expected largest ||eps|| of a warp's 32 draws."""
-    z = 1.876
-    wh = 1.0 - 2.0 / (9.0 * D) + z * np.sqrt(2.0 / (9.0 * D))
-    return float(np.sqrt(D * wh ** 3))
+def emax_quantiles(D):
+    """10 / 50 / 90 % quantiles of the largest ||eps|| among a warp's 32 draws (Wilson-Hilferty, as in launch_vp_unpack)."""
+    out = []
+    for z in (1.480, 2.026, 2.718):
+        wh = 1.0 - 2.0 / (9.0 * D) + z * np.sqrt(2.0 / (9.0 * D))
+        out.append(float(np.sqrt(D * wh ** 3)))
+    return out
 
 
-def survivors(mu, sigma, lam, w, prune_c, emax):
-    """cnt[j] = number of components k that pass the sweep's pruning test for source component j at ||eps||max = emax.
-    mu is (K, D)."""
+def survivors3(mu, sigma, lam, w, prune_c):
+    """cnt3[j] = sum over the three ||eps||max quantiles of the number of components k that pass the sweep's pruning test for
+    source component j (thirds of a component).  mu is (K, D)."""
     K, D = mu.shape
     cnt = np.zeros(K, dtype=np.int64)
     for j in range(K):
         u = (mu[j][None, :] - mu) / (sigma[:, None] * lam[None, :])
         un = np.sqrt((u * u).sum(1))
         r = sigma[j] / sigma
-        tt = un - r * emax
-        bb = np.where(tt > 0, -0.5 * tt * tt, 0.0)
         with np.errstate(divide="ignore", invalid="ignore"):
             lck = np.log(w / w[j]) + D * (np.log(sigma[j]) - np.log(sigma))
-        lhs = bb + 0.5 * emax * emax + prune_c + lck + 0.5
-        keep = ~(lhs < 0.0) if prune_c > 0 else np.ones(K, dtype=bool)
-        cnt[j] = max(1, int(keep.sum()))
+        tot = 0
+        for emax in emax_quantiles(D):
+            tt = un - r * emax
+            bb = np.where(tt > 0, -0.5 * tt * tt, 0.0)
+            lhs = bb + 0.5 * emax * emax + prune_c + lck + 0.5
+            keep = ~(lhs < 0.0) if prune_c > 0 else np.ones(K, dtype=bool)
+            tot += int(keep.sum())
+        cnt[j] = max(1, tot)
     return cnt
 
 

@@ -50,12 +50,12 @@ def test_plan_balances_the_c3_mixture():
     CTA 12-17 % above the mean; cost-weighted ranges bring it within tile granularity."""
     cfg, vp, mu, sigma, lam, w = _mixture("c3")
     K, D = cfg["K"], cfg["D"]
-    cnt = sp.survivors(mu, sigma, lam, w, 50.0, sp.typical_emax(D))
-    assert sorted(set(cnt.tolist())) == [17, 33]
+    cnt = sp.survivors3(mu, sigma, lam, w, 50.0)
+    assert sorted(set(cnt.tolist())) == [3 * 17, 3 * 33]
     tpc, G, c0 = 64, 148, 16
-    tstart, jlo, jhi = sp.plan(c0 + cnt, tpc, G)
+    tstart, jlo, jhi = sp.plan(3 * c0 + cnt, tpc, G)
     _check_invariants(tstart, jlo, jhi, K, tpc, G, c0)
-    cost = np.repeat(c0 + cnt, tpc).astype(float)
+    cost = np.repeat(3 * c0 + cnt, tpc).astype(float)
     eq = np.array([(b * K * tpc + G - 1) // G for b in range(G + 1)])
     load_eq = np.array([cost[eq[b]:eq[b + 1]].sum() for b in range(G)])
     load_w = np.array([cost[tstart[b]:tstart[b + 1]].sum() for b in range(G)])
@@ -90,9 +90,9 @@ def test_device_plan_matches_host_restatement_and_results_do_not_depend_on_it(gp
             _check_invariants(tstart.astype(np.int64), jlo, jhi, K, tpc, G, c0)
             mu = np.asarray(vp["mu"], float)
             mu = mu if mu.shape == (K, D) else mu.T
-            cnt = sp.survivors(np.ascontiguousarray(mu), np.asarray(vp["sigma"], float), np.asarray(vp["lambda"], float),
-                               np.asarray(vp["w"], float), 50.0, sp.typical_emax(D))
-            ts_h, jlo_h, jhi_h = sp.plan(c0 + cnt, tpc, G)
+            cnt = sp.survivors3(np.ascontiguousarray(mu), np.asarray(vp["sigma"], float), np.asarray(vp["lambda"], float),
+                                np.asarray(vp["w"], float), 50.0)
+            ts_h, jlo_h, jhi_h = sp.plan(3 * c0 + cnt, tpc, G)
             assert np.max(np.abs(ts_h - tstart)) <= 2, (ts_h, tstart)
             for i in (0, 1, 3, 5):   # F, dF, H, dH
                 assert rel(on[i], off[i]) < 1e-13, (c0, i)

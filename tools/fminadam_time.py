@@ -10,7 +10,7 @@ from vbmc_b200 import workloads
 
 
 def run(tag, env, prof=False, pre_profile=False):
-    for k in ("VBMC_B200_PREFETCH", "VBMC_B200_GLJ_FIRST", "VBMC_B200_GRAPHS"):
+    for k in ("VBMC_B200_PREFETCH", "VBMC_B200_GLJ_FIRST", "VBMC_B200_GRAPHS", "VBMC_B200_ENTMC_BALANCE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ctx = vbmc_b200.Context(0)
@@ -39,6 +39,8 @@ def run(tag, env, prof=False, pre_profile=False):
 
 if __name__ == "__main__":
     run("default", {})
+    run("balance=0", {"VBMC_B200_ENTMC_BALANCE": "0"})
+    run("balance=0 profiled (direct launches)", {"VBMC_B200_ENTMC_BALANCE": "0"}, prof=True)
     run("default+pre_profile", {}, pre_profile=True)
     run("glj_first=0", {"VBMC_B200_GLJ_FIRST": "0"})
     run("prefetch=0", {"VBMC_B200_PREFETCH": "0"})

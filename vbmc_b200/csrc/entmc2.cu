@@ -734,7 +734,9 @@ bool entmc2_enabled(vbmc_b200_ctx* c) {
   static const bool off = getenv("VBMC_B200_ENTMC_V1") && atoi(getenv("VBMC_B200_ENTMC_V1")) != 0;
   // D > 16: the 4*DP accumulator registers spill in both generations; the first-generation kernel measured 5 % faster
   // at c5 (D = 20, K = 100: 16.8 vs 17.7 ms), so it keeps those shapes while it can (K <= 128)
-  if (!off && c->precision == 64 && entmc_pick_dp(c->D) >= 20 && c->K <= 128) return false;
+  // (VBMC_B200_ENTMC_V2_D20=1 sends them to this kernel as well: A/B runs of the cost-weighted schedule)
+  static const bool d20 = getenv("VBMC_B200_ENTMC_V2_D20") && atoi(getenv("VBMC_B200_ENTMC_V2_D20")) != 0;
+  if (!off && !d20 && c->precision == 64 && entmc_pick_dp(c->D) >= 20 && c->K <= 128) return false;
   return !off && c->precision == 64;
 }
 

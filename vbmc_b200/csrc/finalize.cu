@@ -24,7 +24,7 @@ struct UnpackArgs {
   int* plan;          // tstart[G + 1] | jlo[K] | jhi[K]
   int* plan_w;        // [K] scratch: estimated cost of one tile of component j
   int plan_tpc, plan_G, plan_c0;
-  double plan_prune, plan_emax;   // pruning constant of the sweep, typical max ||eps|| of a warp's 32 draws
+  double plan_prune, plan_emax[3];   // pruning constant of the sweep; 10 / 50 / 90 % quantiles of the largest ||eps|| among a warp's 32 draws
 };
 
 // One CTA.  Everything the later phases re-read (mu, sigma, lambda, 1/(sigma lambda)^2) is kept in shared memory, so the
@@ -283,10 +283,16 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
       // will component k survive the sweep's pruning test (entmc2.cu) for a typical warp of draws of component j?
       // log(ck_k / ck_j) = log(w_k / w_j) + D (log sigma_j - log sigma_k)
       const double lw = (ht && a.opt[3]) ? a.theta[o_eta + k] - a.theta[o_eta + j] : log(a.base_w[k] / a.base_w[j]);
-      const double tt = sqrt(uu) - r * a.plan_emax;
-      const double bb = tt > 0.0 ? -0.5 * tt * tt : 0.0;
-      const double lhs = bb + 0.5 * a.plan_emax * a.plan_emax + a.plan_prune + lw + D * (s_lsig[j] - s_lsig[k]) + 0.5;
-      if (!(lhs < 0.0) || a.plan_prune <= 0.0) atomicAdd(&s_cnt, 1);
+      const double un = sqrt(uu), cst = a.plan_prune + lw + D * (s_lsig[j] - s_lsig[k]) + 0.5;
+      int hits = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {   // the test depends on the warp's largest ||eps||: average over its distribution
+        const double tt = un - r * a.plan_emax[q];
+        const double bb = tt > 0.0 ? -0.5 * tt * tt : 0.0;
+        const double lhs = bb + 0.5 * a.plan_emax[q] * a.plan_emax[q] + cst;
+        hits += (!(lhs < 0.0) || a.plan_prune <= 0.0) ? 1 : 0;
+      }
+      if (hits) atomicAdd(&s_cnt, hits);
     }
   }
   part[tid] = m;
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     __syncthreads();
   }
   if (tid == 0) {
-    if (a.plan) a.plan_w[j] = a.plan_c0 + (s_cnt < 1 ? 1 : s_cnt);
+    if (a.plan) a.plan_w[j] = 3 * a.plan_c0 + (s_cnt < 1 ? 1 : s_cnt);   // in thirds of a scored component
     // non-negative doubles order like their bit patterns; a NaN (0x7ff8...) is larger than every finite value
     unsigned long long* gmax = reinterpret_cast<unsigned long long*>(a.vp.form_flag) + 1;
     unsigned* ticket = reinterpret_cast<unsigned*>(a.vp.form_flag) + 1;
@@ -813,7 +819,8 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   // cost-weighted sweep schedule requested by the step being enqueued (api.cu enqueue_step)
   a.plan = nullptr; a.plan_w = nullptr;
   a.plan_tpc = a.plan_G = a.plan_c0 = 0;
-  a.plan_prune = a.plan_emax = 0.0;
+  a.plan_prune = 0.0;
+  a.plan_emax[0] = a.plan_emax[1] = a.plan_emax[2] = 0.0;
   c->ent_plan_active = false;
   if (c->ent_plan_req && !v1 && c->K <= 256 && c->ent_plan_req_G <= 256) {
     const int G = c->ent_plan_req_G, K = c->K;
@@ -822,10 +829,13 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
     a.plan_w = a.plan + (G + 1 + 2 * K);
     a.plan_tpc = c->ent_plan_req_tpc; a.plan_G = G; a.plan_c0 = c->ent_balance_c0;
     a.plan_prune = c->entmc_prune_c;
-    // expected maximum of ||eps|| over a warp's 32 draws: the 1 - 1/33 quantile of chi^2_D (Wilson-Hilferty)
-    const double D = c->D, z = 1.876;
-    const double wh = 1.0 - 2.0 / (9.0 * D) + z * sqrt(2.0 / (9.0 * D));
-    a.plan_emax = sqrt(D * wh * wh * wh);
+    // largest ||eps|| among a warp's 32 draws: P(max <= x) = F(x)^32, F the chi_D distribution; its 10 / 50 / 90 % quantiles are
+    // the 0.9306 / 0.9786 / 0.99671 quantiles of chi^2_D (Wilson-Hilferty with z = 1.480, 2.026, 2.718)
+    const double D = c->D, zq[3] = {1.480, 2.026, 2.718};
+    for (int q = 0; q < 3; ++q) {
+      const double wh = 1.0 - 2.0 / (9.0 * D) + zq[q] * sqrt(2.0 / (9.0 * D));
+      a.plan_emax[q] = sqrt(D * wh * wh * wh);
+    }
     c->ent_plan_active = true;
   }
   c->ent_plan_req = false;
