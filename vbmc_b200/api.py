@@ -822,13 +822,22 @@ def gplite_post_update1(gp, xstar, ystar, s2star=None, *, ctx=None):
     sWn = np.zeros(S)
     _lib.check(ctx.lib.vbmc_b200_gp_post_update1(ctx.handle, dptr(xs), ystar, dptr(alpha), dptr(Lcol), dptr(sWn)))
     new = dict(gp)
-    new["X"] = np.vstack([X, xs[None, :]])
-    new["y"] = np.append(y, ystar)
+    Xn = np.empty((N + 1, D))
+    Xn[:N] = X
+    Xn[N] = xs
+    yn = np.empty(N + 1)
+    yn[:N] = y
+    yn[N] = ystar
+    new["X"], new["y"] = Xn, yn
     new["post"] = []
+    sW_all = np.empty((S, N + 1))       # per-sample rows of the (frozen) result arrays are handed out as views
+    for s, p in enumerate(post):
+        sW_all[s, :N] = p["sW"]
+    sW_all[:, N] = sWn
     for s, p in enumerate(post):
         q = dict(p)
-        q["alpha"] = alpha[s].copy()
-        q["sW"] = np.append(np.ravel(p["sW"]), sWn[s])
+        q["alpha"] = alpha[s]
+        q["sW"] = sW_all[s]
         if have_L and not p.get("Lchol", True):
             # low noise (:234-238): every entry of L = -inv(K + diag) changes; the device hands the new matrix over (symmetric)
             Ln = np.zeros((N + 1, N + 1))
