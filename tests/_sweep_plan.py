@@ -47,7 +47,8 @@ def plan(weights, tpc, G):
         if lo >= K:
             t = K * tpc
         else:
-            q = (target - int(pref[lo]) * tpc) // int(weights[lo])
+            wj = int(weights[lo])
+            q = (2 * (target - int(pref[lo]) * tpc) + wj) // (2 * wj)   # nearest tile boundary
             t = lo * tpc + min(q, tpc)
         tstart[b] = t
     tstart[0], tstart[G] = 0, K * tpc

@@ -42,7 +42,7 @@ if __name__ == "__main__":
     run("balance=0", {"VBMC_B200_ENTMC_BALANCE": "0"})
     run("balance=0 profiled (direct launches)", {"VBMC_B200_ENTMC_BALANCE": "0"}, prof=True)
     run("default+pre_profile", {}, pre_profile=True)
-    run("glj_first=0", {"VBMC_B200_GLJ_FIRST": "0"})
+    run("glj_first=1", {"VBMC_B200_GLJ_FIRST": "1"})
     run("prefetch=0", {"VBMC_B200_PREFETCH": "0"})
     run("graphs=0", {"VBMC_B200_GRAPHS": "0"})
     run("profiled (direct launches)", {}, prof=True)

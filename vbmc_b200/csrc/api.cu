@@ -632,9 +632,11 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
   if (doH) {
     if (philox_now) VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_philox, 0));
     // The entropy sweep's persistent CTAs take a whole SM each (registers + shared memory), so the log-joint kernel cannot
-    // co-reside with them: when both become runnable together they race for the SMs and the loser waits for the winner's
-    // last CTA.  Without a generator in front of the sweep (its draws were produced ahead of time) the order is made
-    // explicit: log-joint first on the whole GPU, then the sweep.  VBMC_B200_GLJ_FIRST=0 leaves it to the block scheduler.
+    // co-reside with them.  Default: both are released together once the unpack kernel is done; the log-joint CTAs (enqueued
+    // first, two per SM, equal length) go first and the sweep's CTA of an SM starts as soon as THAT SM is free -- no grid-wide
+    // dependency between the two kernels (measured with the round's final kernels, same box, bench.py: value 2281 -> 2307,
+    // e2e 2131 -> 2176, resident loop 2373 -> 2443 steps/s against the explicit order).  VBMC_B200_GLJ_FIRST=1 makes the sweep
+    // wait for the whole log-joint kernel (the mid-round default, better with that round's slower sweep tail).
     if (doG && !philox_now && c->glj_first) {
       VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_glj, 0));  // the kernel itself; its small reduction may trail behind
     }

@@ -279,7 +279,7 @@ struct vbmc_b200_ctx {
   // right after the entropy sweep has consumed the current ones, in the shadow of the single-CTA tail of the step (reduce, finalize,
   // Adam update).  `eps_key` says which draws the buffer holds; a step whose (seed, stream) matches skips its own generation.
   bool prefetch_enabled = true;      // VBMC_B200_PREFETCH=0 turns the ahead-of-time generation off
-  bool glj_first = true;             // run the log-joint kernel before the entropy sweep when no generator precedes the sweep
+  bool glj_first = false;            // true (VBMC_B200_GLJ_FIRST=1): the sweep waits for the whole log-joint kernel; false: both are released together after the unpack kernel
   bool philox_trail = false;         // request: generate (seed, stream + 1) after the sweep of the step being enqueued
   bool trail_join_pending = false;   // stream3 carries an ahead-of-time generation that `stream` has not joined yet
   struct EpsKey {

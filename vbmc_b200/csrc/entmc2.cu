@@ -724,7 +724,8 @@ bool entmc2_enabled(vbmc_b200_ctx* c);
 bool entmc2_balance_params(vbmc_b200_ctx* c, int Ns, int* tpc, int* G) {
   if (!c->ent_balance || !entmc2_enabled(c)) return false;
   Entmc2Plan pl;
-  if (!make_plan2(c, Ns, &pl) || pl.a.ntiles == 0 || pl.grid < 2) return false;
+  // below two tiles per CTA a range cannot follow the weights (boundaries fall on tiles): equal counts are at least as good there
+  if (!make_plan2(c, Ns, &pl) || pl.a.ntiles == 0 || pl.grid < 2 || pl.a.ntiles < 2 * pl.grid) return false;
   *tpc = pl.a.tpc;
   *G = pl.grid;
   return true;

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
       t = K * tpc;
     } else {
       const long long wj = s_pref[lo + 1] - s_pref[lo];
-      long long q = (target - s_pref[lo] * tpc) / wj;
+      long long q = (2 * (target - s_pref[lo] * tpc) + wj) / (2 * wj);   // nearest tile boundary
       if (q > tpc) q = tpc;
       t = lo * tpc + static_cast<int>(q);
     }
