@@ -34,21 +34,24 @@ def survivors3(mu, sigma, lam, w, prune_c):
     return cnt
 
 
-def plan(weights, tpc, G):
-    """tstart[G+1], jlo[K], jhi[K] for tile weights `weights[j]` (every tile of component j weighs the same)."""
+def plan(weights, tpc, G, crun=0):
+    """tstart[G+1], jlo[K], jhi[K] for tile weights `weights[j]` (every tile of component j weighs the same) and a fixed cost
+    `crun` charged at the start of every component (same units as the weights)."""
     K = len(weights)
     pref = np.concatenate([[0], np.cumsum(np.asarray(weights, dtype=np.int64))])
-    Wtot = int(pref[K]) * tpc
+    C = pref * tpc + np.arange(K + 1, dtype=np.int64) * crun   # cumulative cost in front of component j
+    Wtot = int(C[K])
     tstart = np.zeros(G + 1, dtype=np.int64)
     for b in range(G + 1):
         target = (Wtot * b) // G
-        lo = int(np.searchsorted(pref * tpc, target, side="right")) - 1   # largest jj with pref[jj]*tpc <= target
+        lo = int(np.searchsorted(C, target, side="right")) - 1   # largest jj with C[jj] <= target
         lo = min(lo, K)
         if lo >= K:
             t = K * tpc
         else:
             wj = int(weights[lo])
-            q = (2 * (target - int(pref[lo]) * tpc) + wj) // (2 * wj)   # nearest tile boundary
+            off = target - int(C[lo]) - crun
+            q = 0 if off <= 0 else (2 * off + wj) // (2 * wj)   # nearest tile boundary
             t = lo * tpc + min(q, tpc)
         tstart[b] = t
     tstart[0], tstart[G] = 0, K * tpc
@@ -61,9 +64,9 @@ def plan(weights, tpc, G):
     return tstart, jlo, jhi
 
 
-def rmax_bound(K, tpc, G, c0):
-    """slots per CTA the host reserves (entmc2.cu make_plan2)"""
+def rmax_bound(K, tpc, G, c0, crun=0):
+    """slots per CTA the host reserves (entmc2.cu make_plan2); c0, crun in whole scored components"""
     T = K * tpc
     per = (T + G - 1) // G
-    per = (per * (c0 + K) + c0 - 1) // c0 + 2
+    per = (per * (c0 + K) + c0 - 1) // c0 + 3 + (K * crun) // (G * c0)
     return min(K + 1, (per + tpc - 1) // tpc + 1)

@@ -17,10 +17,10 @@ def _mixture(name="c3", **over):
     return cfg, vp, np.ascontiguousarray(mu), np.asarray(vp["sigma"], float), np.asarray(vp["lambda"], float), np.asarray(vp["w"], float)
 
 
-def _check_invariants(tstart, jlo, jhi, K, tpc, G, c0):
+def _check_invariants(tstart, jlo, jhi, K, tpc, G, c0, crun=0):
     assert tstart[0] == 0 and tstart[G] == K * tpc
     assert np.all(np.diff(tstart) >= 0)
-    rmax = sp.rmax_bound(K, tpc, G, c0)
+    rmax = sp.rmax_bound(K, tpc, G, c0, crun)
     for b in range(G):
         if tstart[b] < tstart[b + 1]:
             runs = (tstart[b + 1] - 1) // tpc - tstart[b] // tpc + 1
@@ -41,8 +41,9 @@ def test_plan_invariants_random_weights(K, tpc, G, c0):
     G = min(G, K * tpc)
     for trial in range(6):
         cnt = rs.integers(1, K + 1, K) if trial % 2 else np.where(rs.random(K) < 0.5, 1, K)
-        tstart, jlo, jhi = sp.plan(c0 + cnt, tpc, G)
-        _check_invariants(tstart, jlo, jhi, K, tpc, G, c0)
+        crun = (0, 40, 7)[trial % 3]
+        tstart, jlo, jhi = sp.plan(c0 + cnt, tpc, G, crun)
+        _check_invariants(tstart, jlo, jhi, K, tpc, G, c0, crun)
 
 
 def test_plan_balances_the_c3_mixture():
@@ -52,13 +53,20 @@ def test_plan_balances_the_c3_mixture():
     K, D = cfg["K"], cfg["D"]
     cnt = sp.survivors3(mu, sigma, lam, w, 50.0)
     assert sorted(set(cnt.tolist())) == [3 * 17, 3 * 33]
-    tpc, G, c0 = 64, 148, 16
-    tstart, jlo, jhi = sp.plan(3 * c0 + cnt, tpc, G)
-    _check_invariants(tstart, jlo, jhi, K, tpc, G, c0)
+    tpc, G, c0, crun = 64, 148, 16, 40
+    tstart, jlo, jhi = sp.plan(3 * c0 + cnt, tpc, G, 3 * crun)
+    _check_invariants(tstart, jlo, jhi, K, tpc, G, c0, crun)
     cost = np.repeat(3 * c0 + cnt, tpc).astype(float)
+
+    def loads(ts):   # tiles + one table build per source component a range touches
+        out = []
+        for b in range(G):
+            a, e = int(ts[b]), int(ts[b + 1])
+            out.append(cost[a:e].sum() + 3 * crun * ((e - 1) // tpc - a // tpc + 1) if a < e else 0.0)
+        return np.array(out)
+
     eq = np.array([(b * K * tpc + G - 1) // G for b in range(G + 1)])
-    load_eq = np.array([cost[eq[b]:eq[b + 1]].sum() for b in range(G)])
-    load_w = np.array([cost[tstart[b]:tstart[b + 1]].sum() for b in range(G)])
+    load_eq, load_w = loads(eq), loads(tstart)
     assert load_eq.max() / load_eq.mean() > 1.10
     assert load_w.max() / load_w.mean() < 1.05
 
@@ -87,12 +95,12 @@ def test_device_plan_matches_host_restatement_and_results_do_not_depend_on_it(gp
             assert got is not None
             tstart, jlo, jhi, tpc = got
             G = len(tstart) - 1
-            _check_invariants(tstart.astype(np.int64), jlo, jhi, K, tpc, G, c0)
+            _check_invariants(tstart.astype(np.int64), jlo, jhi, K, tpc, G, c0, 40)
             mu = np.asarray(vp["mu"], float)
             mu = mu if mu.shape == (K, D) else mu.T
             cnt = sp.survivors3(np.ascontiguousarray(mu), np.asarray(vp["sigma"], float), np.asarray(vp["lambda"], float),
                                 np.asarray(vp["w"], float), 50.0)
-            ts_h, jlo_h, jhi_h = sp.plan(3 * c0 + cnt, tpc, G)
+            ts_h, jlo_h, jhi_h = sp.plan(3 * c0 + cnt, tpc, G, 3 * 40)
             assert np.max(np.abs(ts_h - tstart)) <= 2, (ts_h, tstart)
             for i in (0, 1, 3, 5):   # F, dF, H, dH
                 assert rel(on[i], off[i]) < 1e-13, (c0, i)

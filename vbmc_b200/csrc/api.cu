@@ -134,6 +134,7 @@ int vbmc_b200_create(vbmc_b200_ctx** out, int device) {
   if (const char* g = getenv("VBMC_B200_GRAPHS")) c->graphs_enabled = strcmp(g, "0") != 0;
   if (const char* pc = getenv("VBMC_B200_ENTMC_PRUNE")) c->entmc_prune_c = atof(pc);
   if (const char* pb = getenv("VBMC_B200_ENTMC_BALANCE")) c->ent_balance = atoi(pb) != 0;
+  if (const char* pr = getenv("VBMC_B200_ENTMC_CRUN")) c->ent_balance_crun = atoi(pr) < 0 ? 0 : (atoi(pr) > 4096 ? 4096 : atoi(pr));
   if (const char* p0 = getenv("VBMC_B200_ENTMC_C0")) c->ent_balance_c0 = atoi(p0) < 1 ? 1 : (atoi(p0) > 4096 ? 4096 : atoi(p0));
   if (const char* f = getenv("VBMC_B200_ENTMC_FORM")) {
     if (!strcmp(f, "separable")) c->entmc_form = 0;
@@ -790,7 +791,7 @@ static std::vector<long long> step_signature(vbmc_b200_ctx* c, int Ns, int gmask
   key.push_back(c->rank);
   key.push_back(c->p2p_ready ? reinterpret_cast<long long>(c->xchg_peers.p) : 0);
   key.push_back(c->glj_first);
-  key.push_back(c->ent_balance ? c->ent_balance_c0 : 0);
+  key.push_back(c->ent_balance ? c->ent_balance_c0 + 8192LL * c->ent_balance_crun : 0);
   return key;
 }
 

@@ -710,7 +710,10 @@ static bool make_plan2(vbmc_b200_ctx* c, int Ns, Entmc2Plan* pl) {
   if (pl->grid > 0) {
     int per_cta = (a.ntiles + pl->grid - 1) / pl->grid;
     // cost-weighted ranges: a tile weighs between c0 and c0 + K, so a range holds at most (c0 + K) / c0 times the average count
-    if (c->ent_plan_active) per_cta = static_cast<int>((static_cast<long long>(per_cta) * (c->ent_balance_c0 + K) + c->ent_balance_c0 - 1) / c->ent_balance_c0) + 2;
+    // (+ the share of the per-component start costs, which only shortens ranges but is counted in the total)
+    if (c->ent_plan_active)
+      per_cta = static_cast<int>((static_cast<long long>(per_cta) * (c->ent_balance_c0 + K) + c->ent_balance_c0 - 1) / c->ent_balance_c0) + 3 +
+                static_cast<int>((static_cast<long long>(K) * c->ent_balance_crun) / (static_cast<long long>(pl->grid) * c->ent_balance_c0));
     a.rmax = (per_cta + a.tpc - 1) / a.tpc + 1;
     if (a.rmax > K + 1) a.rmax = K + 1;
   }

@@ -23,7 +23,7 @@ struct UnpackArgs {
   // cost-weighted schedule of the FP64 entropy sweep (vp_unpack2_kernel only; null: none requested)
   int* plan;          // tstart[G + 1] | jlo[K] | jhi[K]
   int* plan_w;        // [K] scratch: estimated cost of one tile of component j
-  int plan_tpc, plan_G, plan_c0;
+  int plan_tpc, plan_G, plan_c0, plan_crun;   // crun: fixed cost of starting a source component inside a range (table build, run result), in thirds of a scored component
   double plan_prune, plan_emax[3];   // pruning constant of the sweep; 10 / 50 / 90 % quantiles of the largest ||eps|| among a warp's 32 draws
 };
 
@@ -346,21 +346,25 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     }
   }
   __syncthreads();
+  // cumulative cost in front of component jj: C(jj) = tpc * s_pref[jj] + jj * crun -- every component also charges its start
+  // (a CTA pays one table build per source component it touches; the one at the head of its range is common to all CTAs)
   const int G = a.plan_G, tpc = a.plan_tpc;
-  const long long Wtot = s_pref[K] * tpc;
+  const long long crun = a.plan_crun;
+  const long long Wtot = s_pref[K] * tpc + K * crun;
   for (int b = tid; b <= G; b += nt) {
     const long long target = (Wtot * b) / G;
-    int lo = 0, hi = K;   // largest jj in [0, K] with s_pref[jj] * tpc <= target
+    int lo = 0, hi = K;   // largest jj in [0, K] with C(jj) <= target
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (s_pref[mid] * tpc <= target) lo = mid; else hi = mid - 1;
+      if (s_pref[mid] * tpc + mid * crun <= target) lo = mid; else hi = mid - 1;
     }
     int t;
     if (lo >= K) {
       t = K * tpc;
     } else {
       const long long wj = s_pref[lo + 1] - s_pref[lo];
-      long long q = (2 * (target - s_pref[lo] * tpc) + wj) / (2 * wj);   // nearest tile boundary
+      const long long off = target - (s_pref[lo] * tpc + lo * crun) - crun;
+      long long q = off <= 0 ? 0 : (2 * off + wj) / (2 * wj);   // nearest tile boundary
       if (q > tpc) q = tpc;
       t = lo * tpc + static_cast<int>(q);
     }
@@ -818,7 +822,7 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   static const bool v1 = getenv("VBMC_B200_UNPACK_V1") && atoi(getenv("VBMC_B200_UNPACK_V1")) != 0;
   // cost-weighted sweep schedule requested by the step being enqueued (api.cu enqueue_step)
   a.plan = nullptr; a.plan_w = nullptr;
-  a.plan_tpc = a.plan_G = a.plan_c0 = 0;
+  a.plan_tpc = a.plan_G = a.plan_c0 = a.plan_crun = 0;
   a.plan_prune = 0.0;
   a.plan_emax[0] = a.plan_emax[1] = a.plan_emax[2] = 0.0;
   c->ent_plan_active = false;
@@ -827,7 +831,7 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
     VB_TRY(c->ent_plan.reserve(sizeof(int) * (512 + 3 * 256 + 8)));
     a.plan = reinterpret_cast<int*>(c->ent_plan.p);
     a.plan_w = a.plan + (G + 1 + 2 * K);
-    a.plan_tpc = c->ent_plan_req_tpc; a.plan_G = G; a.plan_c0 = c->ent_balance_c0;
+    a.plan_tpc = c->ent_plan_req_tpc; a.plan_G = G; a.plan_c0 = c->ent_balance_c0; a.plan_crun = 3 * c->ent_balance_crun;
     a.plan_prune = c->entmc_prune_c;
     // largest ||eps|| among a warp's 32 draws: P(max <= x) = F(x)^32, F the chi_D distribution; its 10 / 50 / 90 % quantiles are
     // the 0.9306 / 0.9786 / 0.99671 quantiles of chi^2_D (Wilson-Hilferty with z = 1.480, 2.026, 2.718)
