@@ -76,7 +76,7 @@ int vbmc_b200_entmc_prune_stats(vbmc_b200_ctx* ctx, int enable, unsigned long lo
  * per warp, all of one source component j) are cut into one contiguous range per SM.  on != 0 (default): ranges of equal estimated
  * COST -- per source component the unpack kernel counts the components that survive the pruning test above for a typical warp
  * of draws, a tile of component j weighs c0 + that count and every component charges a fixed start cost (its table build;
- * VBMC_B200_ENTMC_CRUN, default 40); on == 0, or fewer than two tiles per CTA: ranges of equal tile count.  c0 <= 0 keeps the current
+ * VBMC_B200_ENTMC_CRUN, default 0: measured no gain); on == 0, or fewer than two tiles per CTA: ranges of equal tile count.  c0 <= 0 keeps the current
  * value (default 16).  Results are sums in a fixed order for a given theta either way; the two schedules differ by round-off.
  * Also VBMC_B200_ENTMC_BALANCE / VBMC_B200_ENTMC_C0 in the environment.  No counterpart in the reference (ent/entmc_vbmc.m:60-100
  * is one vectorised loop over components). */

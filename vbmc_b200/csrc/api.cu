@@ -638,7 +638,7 @@ static int enqueue_step(vbmc_b200_ctx* c, int Ns, int gmask, int use_bnd, int ja
     // dependency between the two kernels (measured with the round's final kernels, same box, bench.py: value 2281 -> 2307,
     // e2e 2131 -> 2176, resident loop 2373 -> 2443 steps/s against the explicit order).  VBMC_B200_GLJ_FIRST=1 makes the sweep
     // wait for the whole log-joint kernel (the mid-round default, better with that round's slower sweep tail).
-    if (doG && !philox_now && c->glj_first) {
+    if (doG && !philox_now && (c->glj_first || c->profiling)) {   // per-kernel event timing needs the serial order
       VB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_glj, 0));  // the kernel itself; its small reduction may trail behind
     }
     int need = 0;

@@ -301,7 +301,8 @@ struct vbmc_b200_ctx {
   vb::DevBuf ent_plan;
   bool ent_balance = true;          // VBMC_B200_ENTMC_BALANCE=0: equal-count ranges (round-2 schedule)
   int ent_balance_c0 = 16;          // fixed cost of a tile in units of one scored component (VBMC_B200_ENTMC_C0)
-  int ent_balance_crun = 40;        // fixed cost of a source component inside a range, same units (VBMC_B200_ENTMC_CRUN; from the per-SM active cycles of an ncu capture at c3)
+  int ent_balance_crun = 0;         // fixed cost of a source component inside a range, same units (VBMC_B200_ENTMC_CRUN; 40 would follow from the per-SM
+                                    // active cycles of the ncu capture at c3, but measured no gain: sweep 0.2539 / 0.2525 / 0.2520 ms at 0 / 40 / 80, c4 0.900 / 0.907)
   bool ent_plan_req = false;
   int ent_plan_req_tpc = 0, ent_plan_req_G = 0;
   bool ent_plan_active = false;
