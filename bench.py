@@ -550,7 +550,7 @@ def main():
     # ---- per-kernel CUDA-event timing of the same steps (roofline of the dominant kernel) ----
     ctx.profile_reset()
     ctx.profile_enable(True)
-    nprof = max(3, min(10, args.steps))
+    nprof = max(3, min(40, args.steps))
     for i in range(nprof):
         ctx.flush_l2()
         resident_step(10_000 + i)

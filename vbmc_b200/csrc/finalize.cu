@@ -320,52 +320,56 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
   __syncthreads();
   if (!s_last) return;
   // ---- last CTA to arrive: cut the K * tpc tiles of the sweep into G contiguous ranges of equal estimated cost ----
-  // (every tile of component j costs w_j; boundaries fall on tiles; sweep_plan_host in tests/ restates this arithmetic)
-  __shared__ long long s_pref[257];   // s_pref[j] = w_0 + ... + w_{j-1}
-  __shared__ int s_t[258];            // tstart
+  // (every tile of component j costs w_j; boundaries fall on tiles; tests/_sweep_plan.py restates this arithmetic in integers.
+  // All quantities are integers below 2^53 carried as doubles -- exact, and an order of magnitude less code than 64-bit integer
+  // division: this runs once per step in ONE CTA with a cold instruction cache, code size is what it pays for; loops not unrolled.)
+  __shared__ double s_pref[257];   // s_pref[j] = w_0 + ... + w_{j-1}
+  __shared__ int s_t[258];         // tstart
   if (tid < 32) {
-    long long loc[8], run = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    double run = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {   // lane: inclusive sums of its 8 consecutive components
       const int jj = 8 * tid + q;
-      run += jj < K ? static_cast<long long>(__ldcg(a.plan_w + jj)) : 0LL;
-      loc[q] = run;
+      if (jj < K) {
+        run += static_cast<double>(__ldcg(a.plan_w + jj));
+        s_pref[jj + 1] = run;
+      }
     }
-    long long inc = run;
-#pragma unroll
+    double inc = run;
+#pragma unroll 1
     for (int off = 1; off < 32; off <<= 1) {
-      const long long v = __shfl_up_sync(0xffffffffu, inc, off);
+      const double v = __shfl_up_sync(0xffffffffu, inc, off);
       if (tid >= off) inc += v;
     }
-    const long long base = inc - run;
-    if (tid == 0) s_pref[0] = 0;
-#pragma unroll
+    const double base = inc - run;
+    if (tid == 0) s_pref[0] = 0.0;
+#pragma unroll 1
     for (int q = 0; q < 8; ++q) {
       const int jj = 8 * tid + q;
-      if (jj < K) s_pref[jj + 1] = base + loc[q];
+      if (jj < K) s_pref[jj + 1] += base;
     }
   }
   __syncthreads();
   // cumulative cost in front of component jj: C(jj) = tpc * s_pref[jj] + jj * crun -- every component also charges its start
   // (a CTA pays one table build per source component it touches; the one at the head of its range is common to all CTAs)
   const int G = a.plan_G, tpc = a.plan_tpc;
-  const long long crun = a.plan_crun;
-  const long long Wtot = s_pref[K] * tpc + K * crun;
+  const double crun = a.plan_crun, dtpc = tpc;
+  const double Wtot = s_pref[K] * dtpc + K * crun;
+#pragma unroll 1
   for (int b = tid; b <= G; b += nt) {
-    const long long target = (Wtot * b) / G;
+    const double target = floor(Wtot * b / G);
     int lo = 0, hi = K;   // largest jj in [0, K] with C(jj) <= target
+#pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (s_pref[mid] * tpc + mid * crun <= target) lo = mid; else hi = mid - 1;
+      if (s_pref[mid] * dtpc + mid * crun <= target) lo = mid; else hi = mid - 1;
     }
-    int t;
-    if (lo >= K) {
-      t = K * tpc;
-    } else {
-      const long long wj = s_pref[lo + 1] - s_pref[lo];
-      const long long off = target - (s_pref[lo] * tpc + lo * crun) - crun;
-      long long q = off <= 0 ? 0 : (2 * off + wj) / (2 * wj);   // nearest tile boundary
-      if (q > tpc) q = tpc;
+    int t = K * tpc;
+    if (lo < K) {
+      const double wj = s_pref[lo + 1] - s_pref[lo];
+      const double off = target - (s_pref[lo] * dtpc + lo * crun) - crun;
+      double q = off <= 0.0 ? 0.0 : floor((2.0 * off + wj) / (2.0 * wj));   // nearest tile boundary
+      if (q > dtpc) q = dtpc;
       t = lo * tpc + static_cast<int>(q);
     }
     if (b == 0) t = 0;
@@ -374,15 +378,18 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     a.plan[b] = t;
   }
   __syncthreads();
+#pragma unroll 1
   for (int jj = tid; jj < K; jj += nt) {
     const int tlo = jj * tpc, thi = (jj + 1) * tpc;
     int lo = 0, hi = G - 1;   // smallest b in [0, G) with s_t[b + 1] > tlo
+#pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (s_t[mid + 1] > tlo) hi = mid; else lo = mid + 1;
     }
     a.plan[G + 1 + jj] = lo;
     lo = 0; hi = G - 1;       // largest b in [0, G) with s_t[b] < thi
+#pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_t[mid] < thi) lo = mid; else hi = mid - 1;
