@@ -90,7 +90,7 @@ __global__ void gp_minsn2_kernel(const double* sn2, int N, double* out) {
 }
 
 // ---- SE-ARD Gram, upper 64x64 tiles, + rhs column N, + identity padding -------------------------
-// grid (ntiles_upper, nact), 256 threads, each thread 4x4 entries.
+// grid (ntiles_upper, nact), 256 threads, each thread 4x4 entries (rows ty + 16 b, columns tx + 16 a).
 __global__ void __launch_bounds__(256) gp_gram_kernel(const GpBatch g) {
   extern __shared__ double sm[];
   const int s = g.active[blockIdx.y];
@@ -113,8 +113,31 @@ __global__ void __launch_bounds__(256) gp_gram_kernel(const GpBatch g) {
   __syncthreads();
   const double sf2 = exp(2.0 * h[D]) * g.scale[s];
   const double dsc = g.dscale[s];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // rows vary fastest across the threads of a warp: a store instruction covers 16 consecutive rows (128 contiguous bytes) of two
+  // columns (with columns fastest it touched 16 columns x 2 rows: 16 half-used sectors per instruction; the kernel ran at 1 TB/s)
+  const int tx = threadIdx.x >> 4, ty = threadIdx.x & 15;
   double* Ms = g.M + static_cast<size_t>(s) * Np * Np;
+  // squared distances of the thread's 4x4 patch, dimension by dimension: 8 shared-memory reads per 16 entries (the entry-by-entry
+  // loop read 2 per FMA and was bound by them); per entry the same operations in the same order
+  double sq[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sq[a][b] = 0.0;
+  for (int d = 0; d < D; ++d) {
+    double xr[4], xc[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xr[b] = xi[d * TB + ty + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xc[a] = xj[d * TB + tx + 16 * a];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double df = xr[b] - xc[a];
+        sq[a][b] = fma(df, df, sq[a][b]);
+      }
+  }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int c = tx + 16 * a;  // column inside tile
@@ -125,12 +148,7 @@ __global__ void __launch_bounds__(256) gp_gram_kernel(const GpBatch g) {
       const int gi = bi * TB + r;
       double v;
       if (gi < N && gj < N) {
-        double sq = 0.0;
-        for (int d = 0; d < D; ++d) {
-          const double df = xi[d * TB + r] - xj[d * TB + c];
-          sq = fma(df, df, sq);
-        }
-        v = sf2 * exp(-0.5 * sq);                                    // K_mat (:55-56), scaled
+        v = sf2 * exp(-0.5 * sq[a][b]);                              // K_mat (:55-56), scaled
         if (gi == gj) v += dsc * g.sn2[static_cast<size_t>(s) * N + gi];
       } else if (gj == N && gi < N) {
         v = g.y[gi] - g.mvec[static_cast<size_t>(s) * N + gi];      // rhs column b = y - m
