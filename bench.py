@@ -436,11 +436,13 @@ def main():
     if gp_source.startswith("vbmc_b200") and rank == 0:
         noisefun = [1, 1, 0] if w["s2"] is not None else [1, 0, 0]
         vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)  # warm
-        ctx.sync()
-        t0 = time.perf_counter()
-        vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
-        ctx.sync()
-        t_refit = time.perf_counter() - t0
+        t_refit = float("inf")
+        for _ in range(3):   # best of 3 whole calls, like the library bar below (a single call varies by +-0.2 ms with the host)
+            ctx.sync()
+            t0 = time.perf_counter()
+            vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
+            ctx.sync()
+            t_refit = min(t_refit, time.perf_counter() - t0)
         ctx.profile_reset(); ctx.profile_enable(True)
         gp = vbmc_b200.gplite_post(w["hyp"], w["X"], w["y"], 1, 4, noisefun, w["s2"], ctx=ctx, want_L=False)
         ctx.profile_enable(False)
