@@ -590,14 +590,28 @@ struct Entmc2Red {
   XchgDev xc;
 };
 
-__device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, int j, int i) {
-  if (a.tstart) {
-    const int b_lo = a.tstart[a.G + 1 + j], b_hi = a.tstart[a.G + 1 + a.K + j];
+// `plan`: the schedule table staged in shared memory by the kernel (tstart[G + 1] | jlo[K] | jhi[K]); four partial loads in flight per
+// iteration, added in CTA order (the table look-ups and the one-at-a-time loads were 74 % of the reduction kernel's samples)
+__device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, const int* plan, int j, int i) {
+  if (plan) {
+    const int b_lo = plan[a.G + 1 + j], b_hi = plan[a.G + 1 + a.K + j];
     double s = 0.0;
-    for (int b = b_lo; b <= b_hi; ++b) {
-      const int t0 = a.tstart[b];
-      if (t0 >= a.tstart[b + 1]) continue;   // a CTA without tiles wrote nothing
-      s += a.partial[(static_cast<size_t>(b) * a.rmax + (j - t0 / a.tpc)) * a.pstride + i];
+    for (int b = b_lo; b <= b_hi; b += 4) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int bq = b + q;
+        v[q] = 0.0;
+        if (bq <= b_hi) {
+          const int t0 = plan[bq];
+          if (t0 < plan[bq + 1])   // a CTA without tiles wrote nothing
+            v[q] = a.partial[(static_cast<size_t>(bq) * a.rmax + (j - t0 / a.tpc)) * a.pstride + i];
+        }
+      }
+      s += v[0];
+      s += v[1];
+      s += v[2];
+      s += v[3];
     }
     return s;
   }
@@ -613,12 +627,19 @@ __device__ __forceinline__ double entmc2_run_sum(const Entmc2Red& a, int j, int 
 }
 
 __global__ void __launch_bounds__(128) entmc2_reduce_kernel(const Entmc2Red a) {
+  __shared__ int s_plan[256 + 1 + 2 * 256];
   const int D = a.D, K = a.K, nv = 1 + 2 * D;
+  const int* plan = nullptr;
+  if (a.tstart) {   // (G <= 256, K <= 256: launch_vp_unpack only builds the table within these bounds)
+    for (int t = threadIdx.x; t < a.G + 1 + 2 * K; t += blockDim.x) s_plan[t] = a.tstart[t];
+    plan = s_plan;
+    __syncthreads();
+  }
   if (static_cast<int>(blockIdx.x) < a.nb1) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= K * nv) return;
     const int j = o / nv, i = o - j * nv;
-    const double s = entmc2_run_sum(a, j, i);
+    const double s = entmc2_run_sum(a, plan, j, i);
     const int at = i == 0 ? a.oHs + j : (i < 1 + D ? a.oM + j * D + (i - 1) : a.oE + j * D + (i - 1 - D));
     a.R[at] = s;
     xchg_push(a.xc, at, s);
@@ -626,7 +647,7 @@ __global__ void __launch_bounds__(128) entmc2_reduce_kernel(const Entmc2Red a) {
     const int l = (blockIdx.x - a.nb1) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (l >= K) return;
     double acc = 0.0;
-    for (int j = lane; j < K; j += 32) acc = fma(a.w[j], entmc2_run_sum(a, j, nv + l), acc);
+    for (int j = lane; j < K; j += 32) acc = fma(a.w[j], entmc2_run_sum(a, plan, j, nv + l), acc);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) {

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
   double* s_lambda = s_sigma + K;    // [D]
   double* s_muj = s_lambda + D;      // [D]
   double* s_lsig = s_muj + D;        // [K] log sigma_k
+  double* s_ilam = s_lsig + K;       // [D] 1 / lambda_d (guard rows and schedule weights only: no parity-relevant value uses it)
   __shared__ double part[128];
   __shared__ double s_es, s_nf;
   __shared__ int s_cnt, s_last;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
       ll = log(lm);
     }
     s_lambda[d] = lm;
+    s_ilam[d] = 1.0 / lm;
     if (j == 0) {
       a.vp.lnlambda[d] = ll;
       a.vp.lambda[d] = lm;
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(128) vp_unpack2_kernel(const UnpackArgs a) {
     const double isg = 1.0 / s_sigma[k];
     for (int d = 0; d < D; ++d) {
       const double mk = (ht && a.opt[0]) ? a.theta[o_mu + k * D + d] : a.base_mu[k * D + d];
-      const double u = (s_muj[d] - mk) * isg / s_lambda[d];
+      const double u = (s_muj[d] - mk) * isg * s_ilam[d];
       uu = fma(u, u, uu);
     }
     const double r = s_sigma[j] * isg;
@@ -853,7 +855,7 @@ int launch_vp_unpack(vbmc_b200_ctx* c, bool have_theta) {
   KernelScope ks(c, "vp_unpack", c->stream);
   if (!v1) {
     a.want_cblob = 0;
-    vp_unpack2_kernel<<<c->K, 128, sizeof(double) * (2 * c->K + 2 * c->D), c->stream>>>(a);
+    vp_unpack2_kernel<<<c->K, 128, sizeof(double) * (2 * c->K + 3 * c->D), c->stream>>>(a);
     VB_CUDA(cudaGetLastError());
     return VBMC_B200_OK;
   }

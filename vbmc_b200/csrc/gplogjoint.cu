@@ -291,14 +291,21 @@ __global__ void __launch_bounds__(128) glj_reduce_kernel(const double* __restric
   } else {
     const int d = (blockIdx.x - nb1) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (d >= D) return;
-    double acc = 0.0;
-    for (int k = lane; k < K; k += 32) {
-      const double* o = out + (static_cast<size_t>(s_begin) * K + k) * ostride + 2 + D + d;
-      const size_t step = static_cast<size_t>(K) * ostride;
-      double a2 = 0.0;
-      for (int s = 0; s < s_count; ++s) a2 += o[s * step];
-      acc = fma(w[k], a2, acc);
+    // lanes stride over the flattened (local s, k) pairs: ~ s_count*K/32 INDEPENDENT loads per lane, four in flight per iteration
+    // (the k-outer / s-inner loop made every lane wait for 2 x s_count dependent round trips to L2: 51 % of this kernel's samples)
+    const double* o = out + static_cast<size_t>(s_begin) * K * ostride + 2 + D + d;
+    const int npair = s_count * K;
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    int p = lane;
+    for (; p + 96 < npair; p += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int pq = p + 32 * q;
+        a4[q] = fma(w[pq % K], o[static_cast<size_t>(pq) * ostride], a4[q]);
+      }
     }
+    for (; p < npair; p += 32) a4[0] = fma(w[p % K], o[static_cast<size_t>(p) * ostride], a4[0]);
+    double acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) {
