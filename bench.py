@@ -204,8 +204,8 @@ def numpy_stand_in(w, cfg):
 
 
 
-TRAFFIC_C3_BYTES = 65.612e6 + 0.257e6
-TRAFFIC_C3_SOURCE = "ncu --set full capture r2_entmc2 (profiles/r2_ncu_summary.md): dram read 65.61 MB + write 0.26 MB per launch"
+TRAFFIC_C3_BYTES = 65.671e6 + 0.294e6
+TRAFFIC_C3_SOURCE = "ncu --set full capture r2b_entmc2 of the final round-2 build (profiles/r2_ncu_summary.md): dram read 65.67 MB + write 0.29 MB per launch; copied, not measured in this run"
 PARITY_TOL = 1e-10      # FP64 gate (BASELINE.json north_star); FP32 sweep: 1e-4
 
 
